@@ -1,0 +1,829 @@
+// abi.cu — implementation of include/voidray_cuda.h: scene builder, commit (flatten + upload), the
+// progressive wavefront driver behind vr_render_accumulate, resolve, and the gate entry points.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/voidray_cuda.h"
+#include "kernels.cuh"
+#include "layout.h"
+#include "scene_build.h"
+
+using namespace vr;
+
+namespace {
+
+thread_local std::string g_error;
+
+int32_t fail(int32_t code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+#define VR_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            return fail(_e == cudaErrorMemoryAllocation ? VR_ERR_OOM : VR_ERR_CUDA,                     \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                            \
+        }                                                                                               \
+    } while (0)
+
+struct DeviceBuffers {
+    std::vector<void*> ptrs;
+    cudaError_t alloc(void** p, size_t bytes) {
+        *p = nullptr;
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+}  // namespace
+
+struct vr_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    LaunchDims dims;
+};
+
+struct vr_scene {
+    vr_context* ctx = nullptr;
+    HostScene host;
+    FlatScene flat;
+    DeviceBuffers dev_mem;
+    DeviceScene dev;
+    std::vector<TextureRec> dev_textures;
+    bool committed = false;
+    uint64_t commit_serial = 0;
+};
+
+struct vr_render {
+    vr_scene* scene = nullptr;
+    uint32_t width = 0, height = 0, n_pixels = 0;
+    vr_render_settings settings;
+    DeviceBuffers dev_mem;
+    float4* accum = nullptr;
+    float4* partial = nullptr;
+    float4* resolved = nullptr;
+    Wavefront wf;
+    uint32_t samples_per_batch = 1;
+    uint32_t samples_done = 0;
+    std::atomic<int> cancel{0};
+    // statistics
+    std::mutex stats_mutex;
+    double seconds = 0.0, device_ms = 0.0, trace_ms = 0.0;
+    uint64_t trace_launches = 0, kernel_launches = 0;
+    unsigned long long segments_host = 0;
+    std::vector<cudaEvent_t> events;  // pairs around trace launches, reused call to call
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // gate scratch
+    uint32_t* dbg_surface = nullptr;
+    uint32_t* dbg_prim = nullptr;
+    float* dbg_t = nullptr;
+};
+
+namespace {
+
+FrameParams frame_params(const vr_render* r) {
+    FrameParams fp;
+    fp.width = r->width;
+    fp.height = r->height;
+    fp.pixel_mapping = r->settings.pixel_mapping;
+    fp.max_bounces = r->settings.max_bounces;
+    fp.firefly_clamp = r->settings.firefly_clamp;
+    fp.render_mode = r->settings.render_mode;
+    fp.seed = r->settings.seed;
+    return fp;
+}
+
+// One wavefront batch: ray generation, then per depth closest-hit + shade/compact. No host sync.
+void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool time_trace, size_t* event_cursor) {
+    vr_scene* sc = r->scene;
+    vr_context* ctx = sc->ctx;
+    const FrameParams fp = frame_params(r);
+    cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * (fp.max_bounces + 1), ctx->stream);
+    launch_raygen(sc->dev, r->wf, src, fp, n_paths, ctx->dims, ctx->stream);
+    r->kernel_launches += 1;
+    for (uint32_t depth = 0; depth < fp.max_bounces; ++depth) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (time_trace) {
+            while (r->events.size() < *event_cursor + 2) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                r->events.push_back(e);
+            }
+            e0 = r->events[(*event_cursor)++];
+            e1 = r->events[(*event_cursor)++];
+            cudaEventRecord(e0, ctx->stream);
+        }
+        launch_trace(sc->dev, r->wf, depth, n_paths, ctx->dims, ctx->stream);
+        if (time_trace) cudaEventRecord(e1, ctx->stream);
+        launch_shade(sc->dev, r->wf, src, fp, depth, n_paths, ctx->dims, ctx->stream);
+        r->kernel_launches += 2;
+        r->trace_launches += 1;
+    }
+}
+
+int32_t upload_texture(vr_scene* scene, const HostTexture& t, TextureRec* rec) {
+    const size_t n = (size_t)t.w * t.h;
+    std::vector<float> rgba(4 * n);
+    for (size_t i = 0; i < n; ++i) {
+        rgba[4 * i] = t.rgb[3 * i];
+        rgba[4 * i + 1] = t.rgb[3 * i + 1];
+        rgba[4 * i + 2] = t.rgb[3 * i + 2];
+        rgba[4 * i + 3] = 0.0f;
+    }
+    void* d = nullptr;
+    VR_CUDA(scene->dev_mem.alloc(&d, 16 * n));
+    VR_CUDA(cudaMemcpyAsync(d, rgba.data(), 16 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
+    VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));  // rgba goes out of scope
+    rec->texels = d;
+    rec->width = t.w;
+    rec->height = t.h;
+    rec->sample_type = t.sample_type;
+    rec->pad = 0;
+    return VR_OK;
+}
+
+template <typename T>
+int32_t upload_vector(vr_scene* scene, const std::vector<T>& v, const void** out) {
+    void* d = nullptr;
+    VR_CUDA(scene->dev_mem.alloc(&d, v.size() * sizeof(T)));
+    if (!v.empty())
+        VR_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, scene->ctx->stream));
+    *out = d;
+    return VR_OK;
+}
+
+int32_t check_scene(vr_scene* s) {
+    if (!s) return fail(VR_ERR_INVALID, "null scene");
+    return VR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vr_last_error(void) { return g_error.c_str(); }
+uint32_t vr_abi_version(void) { return 1; }
+
+int32_t vr_context_create(int32_t device, void* cuda_stream, vr_context** out) {
+    if (!out) return fail(VR_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(VR_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                     " (this library has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(VR_ERR_INVALID, "device index out of range");
+    VR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(VR_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                     std::to_string(prop.minor) + "; this library ships sm_100a code only");
+    vr_context* ctx = new (std::nothrow) vr_context();
+    if (!ctx) return fail(VR_ERR_OOM, "host allocation failed");
+    ctx->device = device;
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return fail(VR_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+        }
+        ctx->own_stream = true;
+    }
+    query_launch_dims(&ctx->dims);
+    *out = ctx;
+    return VR_OK;
+}
+
+int32_t vr_context_destroy(vr_context* ctx) {
+    if (!ctx) return VR_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VR_OK;
+}
+
+int32_t vr_scene_create(vr_context* ctx, vr_scene** out) {
+    if (!ctx || !out) return fail(VR_ERR_INVALID, "null argument");
+    vr_scene* s = new (std::nothrow) vr_scene();
+    if (!s) return fail(VR_ERR_OOM, "host allocation failed");
+    s->ctx = ctx;
+    // Scene::empty(), core/scene.rs:95-111
+    const float eye[3] = {1.0f, 0.0f, 10.0f}, center[3] = {0, 0, 0}, up[3] = {0, 1, 0};
+    HostCamera& c = s->host.camera;
+    std::memcpy(c.eye, eye, 12);
+    camera_look_at(eye, center, up, c.direction, c.up);
+    c.fov = 3.14159265358979323846f / 6.0f;
+    c.has_dof = 0;
+    c.aperture = 0.0f;
+    c.focal_point[0] = c.focal_point[1] = c.focal_point[2] = 0.0f;
+    *out = s;
+    return VR_OK;
+}
+
+int32_t vr_scene_destroy(vr_scene* scene) {
+    if (!scene) return VR_OK;
+    cudaSetDevice(scene->ctx->device);
+    scene->dev_mem.release();
+    delete scene;
+    return VR_OK;
+}
+
+int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t w, uint32_t h, int32_t sample_type,
+                                    uint32_t* texture) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!rgb || w == 0 || h == 0) return fail(VR_ERR_INVALID, "empty texture");
+    if ((uint64_t)w * h >= (1ull << 31)) return fail(VR_ERR_INVALID, "texture too large");
+    if (sample_type != 0 && sample_type != 1) return fail(VR_ERR_INVALID, "sample_type must be 0 (nearest) or 1 (bilinear)");
+    HostTexture t;
+    t.w = w;
+    t.h = h;
+    t.sample_type = sample_type;
+    t.rgb.assign(rgb, rgb + (size_t)3 * w * h);
+    scene->host.textures.push_back(std::move(t));
+    scene->committed = false;
+    if (texture) *texture = (uint32_t)scene->host.textures.size() - 1;
+    return VR_OK;
+}
+
+int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* uvs, const float* normals,
+                          uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, uint32_t* surface) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if ((!positions && n_vertices) || (!indices && n_indices)) return fail(VR_ERR_INVALID, "null mesh buffers");
+    const uint32_t n_idx = n_indices - n_indices % 3;  // chunks_exact(3), mesh.rs:79
+    for (uint32_t i = 0; i < n_idx; ++i)
+        if (indices[i] >= n_vertices) return fail(VR_ERR_INVALID, "mesh index out of range (the reference would panic)");
+    HostMesh m;
+    m.n_vertices = n_vertices;
+    m.pos.assign(positions, positions + (size_t)3 * n_vertices);
+    if (uvs) m.uv.assign(uvs, uvs + (size_t)2 * n_vertices);
+    else m.uv.assign((size_t)2 * n_vertices, 0.0f);
+    if (normals) m.nrm.assign(normals, normals + (size_t)3 * n_vertices);
+    else m.nrm.assign((size_t)3 * n_vertices, 0.0f);
+    m.idx.assign(indices, indices + n_idx);
+    scene->host.meshes.push_back(std::move(m));
+    HostSurface sf;
+    sf.kind = 0;
+    sf.mesh = (uint32_t)scene->host.meshes.size() - 1;
+    scene->host.surfaces.push_back(sf);
+    scene->committed = false;
+    if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
+    return VR_OK;
+}
+
+int32_t vr_scene_add_sphere(vr_scene* scene, const float center[3], float radius, uint32_t* surface) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!center) return fail(VR_ERR_INVALID, "null center");
+    HostSurface sf;
+    sf.kind = 1;
+    std::memcpy(sf.center, center, 12);
+    sf.radius_or_height = radius;
+    scene->host.surfaces.push_back(sf);
+    scene->committed = false;
+    if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
+    return VR_OK;
+}
+
+int32_t vr_scene_add_ground_plane(vr_scene* scene, float height, uint32_t* surface) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    HostSurface sf;
+    sf.kind = 2;
+    sf.radius_or_height = height;
+    scene->host.surfaces.push_back(sf);
+    scene->committed = false;
+    if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
+    return VR_OK;
+}
+
+int32_t vr_scene_add_material(vr_scene* scene, const vr_material_desc* desc, uint32_t* material) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!desc) return fail(VR_ERR_INVALID, "null material desc");
+    if (desc->kind < 0 || desc->kind > VR_MAT_LAMBERTIAN_BSDF) return fail(VR_ERR_INVALID, "unknown material kind");
+    MaterialRec m;
+    m.kind = desc->kind;
+    std::memcpy(m.color, desc->color, 12);
+    m.param = desc->param;
+    m.albedo_tex = desc->kind == VR_MAT_LAMBERTIAN ? desc->albedo_tex : -1;
+    m.normal_tex = desc->kind == VR_MAT_LAMBERTIAN ? desc->normal_tex : -1;
+    m.pad = 0;
+    if (desc->kind == VR_MAT_EMISSION) {  // Emission::new: color * strength, simple.rs:168-172
+        m.color[0] = desc->color[0] * desc->param;
+        m.color[1] = desc->color[1] * desc->param;
+        m.color[2] = desc->color[2] * desc->param;
+    }
+    scene->host.materials.push_back(m);
+    scene->committed = false;
+    if (material) *material = (uint32_t)scene->host.materials.size() - 1;
+    return VR_OK;
+}
+
+int32_t vr_scene_add_object(vr_scene* scene, uint32_t material, uint32_t surface, uint32_t* object) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (material >= scene->host.materials.size()) return fail(VR_ERR_INVALID, "unknown material handle");
+    if (surface >= scene->host.surfaces.size()) return fail(VR_ERR_INVALID, "unknown surface handle");
+    scene->host.objects.push_back(HostObject{surface, material});
+    scene->committed = false;
+    if (object) *object = (uint32_t)scene->host.objects.size() - 1;
+    return VR_OK;
+}
+
+int32_t vr_scene_set_camera(vr_scene* scene, const float eye[3], const float direction[3], const float up[3],
+                            float fov, int32_t has_dof, float aperture, const float focal_point[3]) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!eye || !direction || !up) return fail(VR_ERR_INVALID, "null camera vector");
+    if (has_dof && !focal_point) return fail(VR_ERR_INVALID, "has_dof needs a focal point");
+    HostCamera& c = scene->host.camera;
+    std::memcpy(c.eye, eye, 12);
+    std::memcpy(c.direction, direction, 12);
+    std::memcpy(c.up, up, 12);
+    c.fov = fov;
+    c.has_dof = has_dof ? 1 : 0;
+    c.aperture = aperture;
+    if (focal_point) std::memcpy(c.focal_point, focal_point, 12);
+    scene->committed = false;
+    return VR_OK;
+}
+
+int32_t vr_scene_set_camera_look_at(vr_scene* scene, const float eye[3], const float center[3], const float up[3],
+                                    float fov) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!eye || !center || !up) return fail(VR_ERR_INVALID, "null camera vector");
+    HostCamera& c = scene->host.camera;
+    std::memcpy(c.eye, eye, 12);
+    camera_look_at(eye, center, up, c.direction, c.up);
+    c.fov = fov;
+    c.has_dof = 0;
+    scene->committed = false;
+    return VR_OK;
+}
+
+int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!rgb) return fail(VR_ERR_INVALID, "null colour");
+    scene->host.env_kind = 1;
+    std::memcpy(scene->host.env_color, rgb, 12);
+    scene->host.env_image = HostTexture();
+    scene->committed = false;
+    return VR_OK;
+}
+
+int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, uint32_t w, uint32_t h) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!rgb || w == 0 || h == 0) return fail(VR_ERR_INVALID, "empty environment image");
+    if ((uint64_t)w * h >= (1ull << 31)) return fail(VR_ERR_INVALID, "environment image too large");
+    scene->host.env_kind = 2;
+    scene->host.env_image.w = w;
+    scene->host.env_image.h = h;
+    scene->host.env_image.sample_type = 1;
+    scene->host.env_image.rgb.assign(rgb, rgb + (size_t)3 * w * h);
+    scene->committed = false;
+    return VR_OK;
+}
+
+int32_t vr_scene_clear_environment(vr_scene* scene) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    scene->host.env_kind = 0;
+    scene->host.env_image = HostTexture();
+    scene->committed = false;
+    return VR_OK;
+}
+
+int32_t vr_scene_commit(vr_scene* scene) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    VR_CUDA(cudaSetDevice(scene->ctx->device));
+    std::string err;
+    if (!flatten_scene(scene->host, scene->flat, err)) return fail(VR_ERR_INVALID, err);
+    if (scene->flat.bvh_depth > 70) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
+    VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
+    scene->dev_mem.release();
+    scene->dev_textures.clear();
+
+    DeviceScene& d = scene->dev;
+    std::memset(&d, 0, sizeof(d));
+    const FlatScene& f = scene->flat;
+    int32_t rc;
+    if ((rc = upload_vector(scene, f.nodes, &d.nodes))) return rc;
+    if ((rc = upload_vector(scene, f.tri_isect, &d.tri_isect))) return rc;
+    if ((rc = upload_vector(scene, f.tri_shade, &d.tri_shade))) return rc;
+    if ((rc = upload_vector(scene, f.tri_surface, (const void**)&d.tri_surface))) return rc;
+    if ((rc = upload_vector(scene, f.tri_prim, (const void**)&d.tri_prim))) return rc;
+    if ((rc = upload_vector(scene, scene->host.materials, (const void**)&d.materials))) return rc;
+    if ((rc = upload_vector(scene, f.analytics, (const void**)&d.analytics))) return rc;
+    for (const HostTexture& t : scene->host.textures) {
+        TextureRec rec;
+        if ((rc = upload_texture(scene, t, &rec))) return rc;
+        scene->dev_textures.push_back(rec);
+    }
+    if ((rc = upload_vector(scene, scene->dev_textures, (const void**)&d.textures))) return rc;
+    d.n_tris = f.n_tris;
+    d.n_analytics = (uint32_t)f.analytics.size();
+    d.env_kind = scene->host.env_kind;
+    std::memcpy(d.env_color, scene->host.env_color, 12);
+    if (scene->host.env_kind == 2) {
+        if ((rc = upload_texture(scene, scene->host.env_image, &d.env_tex))) return rc;
+    }
+    d.camera = f.camera;
+    VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
+    scene->committed = true;
+    scene->commit_serial++;
+    return VR_OK;
+}
+
+int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const vr_render_settings* settings,
+                        vr_render** out) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!settings || !out) return fail(VR_ERR_INVALID, "null argument");
+    if (!scene->committed) return fail(VR_ERR_INVALID, "vr_scene_commit must be called before vr_render_begin");
+    if (width == 0 || height == 0 || (uint64_t)width * height >= (1ull << 31))
+        return fail(VR_ERR_INVALID, "bad target dimensions");
+    if (settings->total_samples == 0) return fail(VR_ERR_INVALID, "total_samples must be > 0");
+    if (settings->max_bounces > 64) return fail(VR_ERR_INVALID, "max_bounces > 64 is not supported");
+    if (settings->integrator != 0) return fail(VR_ERR_INVALID, "unknown integrator");
+    VR_CUDA(cudaSetDevice(scene->ctx->device));
+    vr_render* r = new (std::nothrow) vr_render();
+    if (!r) return fail(VR_ERR_OOM, "host allocation failed");
+    r->scene = scene;
+    r->width = width;
+    r->height = height;
+    r->n_pixels = width * height;
+    r->settings = *settings;
+
+    uint64_t capacity = settings->max_paths_in_flight ? settings->max_paths_in_flight : (8ull << 20);
+    if (capacity < r->n_pixels) capacity = r->n_pixels;
+    r->samples_per_batch = (uint32_t)(capacity / r->n_pixels);
+    capacity = (uint64_t)r->samples_per_batch * r->n_pixels;
+    if (capacity >= (1ull << 31)) {
+        delete r;
+        return fail(VR_ERR_INVALID, "max_paths_in_flight too large");
+    }
+    Wavefront& wf = r->wf;
+    wf.capacity = (uint32_t)capacity;
+    const size_t cap = capacity;
+    const uint32_t levels = settings->max_bounces ? settings->max_bounces : 1;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) {
+        if (e == cudaSuccess) e = r->dev_mem.alloc(p, bytes);
+    };
+    A((void**)&r->accum, 16ull * r->n_pixels);
+    A((void**)&r->partial, 16ull * r->n_pixels);
+    A((void**)&r->resolved, 16ull * r->n_pixels);
+    A((void**)&wf.ray_o, 16 * cap);
+    A((void**)&wf.ray_d, 16 * cap);
+    A((void**)&wf.hit, 16 * cap);
+    A((void**)&wf.radiance, 16 * cap);
+    A((void**)&wf.att, 16 * cap * levels);
+    A((void**)&wf.queue[0], 4 * cap);
+    A((void**)&wf.queue[1], 4 * cap);
+    A((void**)&wf.counts, 4 * (settings->max_bounces + 2));
+    A((void**)&wf.segments, 8);
+    A((void**)&r->dbg_surface, 4ull * r->n_pixels);
+    A((void**)&r->dbg_prim, 4ull * r->n_pixels);
+    A((void**)&r->dbg_t, 4ull * r->n_pixels);
+    if (e == cudaSuccess) e = cudaEventCreate(&r->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&r->ev_end);
+    cudaStream_t st = scene->ctx->stream;
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->accum, 0, 16ull * r->n_pixels, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r->partial, 0, 16ull * r->n_pixels, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(wf.segments, 0, 8, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        r->dev_mem.release();
+        delete r;
+        return fail(e == cudaErrorMemoryAllocation ? VR_ERR_OOM : VR_ERR_CUDA,
+                    std::string("vr_render_begin: ") + cudaGetErrorString(e));
+    }
+    *out = r;
+    return VR_OK;
+}
+
+int32_t vr_render_end(vr_render* r) {
+    if (!r) return VR_OK;
+    cudaSetDevice(r->scene->ctx->device);
+    cudaStreamSynchronize(r->scene->ctx->stream);
+    for (cudaEvent_t e : r->events) cudaEventDestroy(e);
+    if (r->ev_begin) cudaEventDestroy(r->ev_begin);
+    if (r->ev_end) cudaEventDestroy(r->ev_end);
+    r->dev_mem.release();
+    delete r;
+    return VR_OK;
+}
+
+int32_t vr_render_clear(vr_render* r) {
+    if (!r) return fail(VR_ERR_INVALID, "null render");
+    cudaStream_t st = r->scene->ctx->stream;
+    VR_CUDA(cudaSetDevice(r->scene->ctx->device));
+    VR_CUDA(cudaMemsetAsync(r->accum, 0, 16ull * r->n_pixels, st));
+    VR_CUDA(cudaMemsetAsync(r->partial, 0, 16ull * r->n_pixels, st));
+    VR_CUDA(cudaMemsetAsync(r->wf.segments, 0, 8, st));
+    VR_CUDA(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> lock(r->stats_mutex);
+    r->samples_done = 0;
+    r->seconds = r->device_ms = r->trace_ms = 0.0;
+    r->trace_launches = r->kernel_launches = 0;
+    r->segments_host = 0;
+    r->cancel = 0;
+    return VR_OK;
+}
+
+int32_t vr_render_accumulate(vr_render* r, uint32_t samples) {
+    if (!r) return fail(VR_ERR_INVALID, "null render");
+    if (!r->scene->committed) return fail(VR_ERR_INVALID, "scene was edited after commit");
+    if (samples == 0) return VR_OK;
+    vr_context* ctx = r->scene->ctx;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const float inv_total = 1.0f / (float)r->settings.total_samples;  // iterative.rs:45
+    VR_CUDA(cudaEventRecord(r->ev_begin, ctx->stream));
+    uint32_t done = 0;
+    size_t event_cursor = 0;
+    bool cancelled = false;
+    while (done < samples) {
+        if (r->cancel.load()) {
+            cancelled = true;
+            break;
+        }
+        const uint32_t nb = std::min(samples - done, r->samples_per_batch);
+        PathSource src;
+        src.pixel = nullptr;
+        src.sample = nullptr;
+        src.n_pixels = r->n_pixels;
+        src.sample_base = r->settings.sample_offset + r->samples_done + done;
+        run_wavefront(r, src, nb * r->n_pixels, true, &event_cursor);
+        done += nb;
+        launch_accumulate(r->wf, r->partial, r->accum, r->n_pixels, nb, done == samples ? 1 : 0, inv_total, ctx->stream);
+        r->kernel_launches += 1;
+    }
+    if (cancelled && done > 0) {
+        launch_accumulate(r->wf, r->partial, r->accum, r->n_pixels, 0, 1, inv_total, ctx->stream);
+        r->kernel_launches += 1;
+    }
+    VR_CUDA(cudaEventRecord(r->ev_end, ctx->stream));
+    VR_CUDA(cudaStreamSynchronize(ctx->stream));
+    VR_CUDA(cudaGetLastError());
+    float ms = 0.0f;
+    VR_CUDA(cudaEventElapsedTime(&ms, r->ev_begin, r->ev_end));
+    double trace_ms = 0.0;
+    for (size_t i = 0; i + 1 < event_cursor; i += 2) {
+        float t = 0.0f;
+        cudaEventElapsedTime(&t, r->events[i], r->events[i + 1]);
+        trace_ms += t;
+    }
+    unsigned long long seg = 0;
+    VR_CUDA(cudaMemcpy(&seg, r->wf.segments, 8, cudaMemcpyDeviceToHost));
+    const auto t1 = std::chrono::steady_clock::now();
+    {
+        std::lock_guard<std::mutex> lock(r->stats_mutex);
+        r->samples_done += done;
+        r->device_ms += ms;
+        r->trace_ms += trace_ms;
+        r->segments_host = seg;
+        r->seconds += std::chrono::duration<double>(t1 - t0).count();
+    }
+    if (cancelled) {
+        r->cancel = 0;
+        return fail(VR_ERR_CANCELLED, "accumulate cancelled");
+    }
+    return VR_OK;
+}
+
+int32_t vr_render_cancel(vr_render* r) {
+    if (!r) return fail(VR_ERR_INVALID, "null render");
+    r->cancel = 1;
+    return VR_OK;
+}
+
+int32_t vr_render_stats(vr_render* r, vr_stats* out) {
+    if (!r || !out) return fail(VR_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock(r->stats_mutex);
+    out->samples_done = r->samples_done;
+    out->total_samples = r->settings.total_samples;
+    out->camera_samples = (uint64_t)r->n_pixels * r->samples_done;
+    out->ray_segments = r->segments_host;
+    out->seconds = r->seconds;
+    out->device_ms = r->device_ms;
+    out->trace_ms = r->trace_ms;
+    out->trace_launches = r->trace_launches;
+    out->kernel_launches = r->kernel_launches;
+    return VR_OK;
+}
+
+int32_t vr_render_read_accum(vr_render* r, float* rgba) {
+    if (!r || !rgba) return fail(VR_ERR_INVALID, "null argument");
+    cudaStream_t st = r->scene->ctx->stream;
+    VR_CUDA(cudaSetDevice(r->scene->ctx->device));
+    VR_CUDA(cudaMemcpyAsync(rgba, r->accum, 16ull * r->n_pixels, cudaMemcpyDeviceToHost, st));
+    VR_CUDA(cudaStreamSynchronize(st));
+    return VR_OK;
+}
+
+int32_t vr_render_accum_device_ptr(vr_render* r, void** device_ptr) {
+    if (!r || !device_ptr) return fail(VR_ERR_INVALID, "null argument");
+    *device_ptr = r->accum;
+    return VR_OK;
+}
+
+int32_t vr_render_resolve(vr_render* r, float scale, float gamma, float exposure, int32_t tonemap, float* rgba_out) {
+    if (!r || !rgba_out) return fail(VR_ERR_INVALID, "null argument");
+    if (tonemap < 0 || tonemap > 4) return fail(VR_ERR_INVALID, "unknown tonemap");
+    cudaStream_t st = r->scene->ctx->stream;
+    VR_CUDA(cudaSetDevice(r->scene->ctx->device));
+    launch_resolve(r->accum, r->resolved, r->n_pixels, scale, std::pow(2.0f, exposure), 1.0f / gamma, tonemap, st);
+    r->kernel_launches += 1;
+    VR_CUDA(cudaMemcpyAsync(rgba_out, r->resolved, 16ull * r->n_pixels, cudaMemcpyDeviceToHost, st));
+    VR_CUDA(cudaStreamSynchronize(st));
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+// ---- gates ----------------------------------------------------------------------------------------
+
+int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface, uint32_t* prim, float* t) {
+    if (!r || !surface || !prim || !t) return fail(VR_ERR_INVALID, "null argument");
+    vr_context* ctx = r->scene->ctx;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    const FrameParams fp = frame_params(r);
+    PathSource src;
+    src.pixel = nullptr;
+    src.sample = nullptr;
+    src.n_pixels = r->n_pixels;
+    src.sample_base = sample;
+    VR_CUDA(cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * (fp.max_bounces + 1), ctx->stream));
+    launch_raygen(r->scene->dev, r->wf, src, fp, r->n_pixels, ctx->dims, ctx->stream);
+    launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, ctx->dims, ctx->stream);
+    launch_primary_ids(r->scene->dev, r->wf, r->n_pixels, r->dbg_surface, r->dbg_prim, r->dbg_t, ctx->stream);
+    VR_CUDA(cudaMemcpyAsync(surface, r->dbg_surface, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    VR_CUDA(cudaMemcpyAsync(prim, r->dbg_prim, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    VR_CUDA(cudaMemcpyAsync(t, r->dbg_t, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    VR_CUDA(cudaStreamSynchronize(ctx->stream));
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+int32_t vr_debug_trace_rays(vr_scene* scene, uint64_t n, const float* origins, const float* directions,
+                            uint32_t* surface, uint32_t* prim, float* t) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
+    if (n == 0) return VR_OK;
+    if (!origins || !directions || !surface || !prim || !t) return fail(VR_ERR_INVALID, "null argument");
+    vr_context* ctx = scene->ctx;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    DeviceBuffers tmp;
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    uint32_t *d_s = nullptr, *d_p = nullptr;
+    cudaError_t e = tmp.alloc((void**)&d_o, 12 * n);
+    if (e == cudaSuccess) e = tmp.alloc((void**)&d_d, 12 * n);
+    if (e == cudaSuccess) e = tmp.alloc((void**)&d_t, 4 * n);
+    if (e == cudaSuccess) e = tmp.alloc((void**)&d_s, 4 * n);
+    if (e == cudaSuccess) e = tmp.alloc((void**)&d_p, 4 * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, origins, 12 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, directions, 12 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        launch_trace_rays(scene->dev, d_o, d_d, n, d_s, d_p, d_t, ctx->stream);
+        e = cudaMemcpyAsync(surface, d_s, 4 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prim, d_p, 4 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t, d_t, 4 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    tmp.release();
+    if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_trace_rays: ") + cudaGetErrorString(e));
+    return VR_OK;
+}
+
+int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel, const uint32_t* sample, float* out) {
+    if (!r || !pixel || !sample || !out) return fail(VR_ERR_INVALID, "null argument");
+    vr_context* ctx = r->scene->ctx;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    for (uint64_t i = 0; i < n; ++i)
+        if (pixel[i] >= r->n_pixels) return fail(VR_ERR_INVALID, "pixel index out of range");
+    DeviceBuffers tmp;
+    const uint64_t chunk_max = r->wf.capacity;
+    uint32_t *d_px = nullptr, *d_sm = nullptr;
+    cudaError_t e = tmp.alloc((void**)&d_px, 4 * chunk_max);
+    if (e == cudaSuccess) e = tmp.alloc((void**)&d_sm, 4 * chunk_max);
+    std::vector<float4> host(chunk_max < n ? chunk_max : n);
+    for (uint64_t base = 0; base < n && e == cudaSuccess; base += chunk_max) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(chunk_max, n - base);
+        e = cudaMemcpyAsync(d_px, pixel + base, 4ull * m, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_sm, sample + base, 4ull * m, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) break;
+        PathSource src;
+        src.pixel = d_px;
+        src.sample = d_sm;
+        src.n_pixels = r->n_pixels;
+        src.sample_base = 0;
+        size_t cursor = 0;
+        run_wavefront(r, src, m, false, &cursor);
+        e = cudaMemcpyAsync(host.data(), r->wf.radiance, 16ull * m, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        for (uint32_t i = 0; i < m && e == cudaSuccess; ++i) {
+            out[3 * (base + i)] = host[i].x;
+            out[3 * (base + i) + 1] = host[i].y;
+            out[3 * (base + i) + 2] = host[i].z;
+        }
+    }
+    tmp.release();
+    if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_sample_radiance: ") + cudaGetErrorString(e));
+    return VR_OK;
+}
+
+int32_t vr_debug_tie_ranks(vr_scene* scene, uint32_t surface, uint32_t* out, uint32_t n) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
+    if (surface >= scene->flat.mesh_tie_rank.size()) return fail(VR_ERR_INVALID, "unknown surface");
+    const std::vector<uint32_t>& rank = scene->flat.mesh_tie_rank[surface];
+    if (n != rank.size()) return fail(VR_ERR_INVALID, "n must equal the surface's triangle count");
+    for (uint32_t i = 0; i < n; ++i) out[i] = scene->flat.surface_rank_base[surface] + rank[i];
+    return VR_OK;
+}
+
+int32_t vr_debug_texture_sample(vr_scene* scene, uint32_t texture, uint64_t n, const float* uv, float* rgb) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
+    if (texture >= scene->dev_textures.size()) return fail(VR_ERR_INVALID, "unknown texture");
+    if (n == 0) return VR_OK;
+    vr_context* ctx = scene->ctx;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    DeviceBuffers tmp;
+    float *d_uv = nullptr, *d_rgb = nullptr;
+    cudaError_t e = tmp.alloc((void**)&d_uv, 8 * n);
+    if (e == cudaSuccess) e = tmp.alloc((void**)&d_rgb, 12 * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_uv, uv, 8 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        launch_texture_sample(scene->dev_textures[texture], n, d_uv, d_rgb, ctx->stream);
+        e = cudaMemcpyAsync(rgb, d_rgb, 12 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    tmp.release();
+    if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_texture_sample: ") + cudaGetErrorString(e));
+    return VR_OK;
+}
+
+int32_t vr_debug_environment_sample(vr_scene* scene, uint64_t n, const float* directions, float* rgb) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
+    if (n == 0) return VR_OK;
+    vr_context* ctx = scene->ctx;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    DeviceBuffers tmp;
+    float *d_d = nullptr, *d_rgb = nullptr;
+    cudaError_t e = tmp.alloc((void**)&d_d, 12 * n);
+    if (e == cudaSuccess) e = tmp.alloc((void**)&d_rgb, 12 * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, directions, 12 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        launch_environment_sample(scene->dev, n, d_d, d_rgb, ctx->stream);
+        e = cudaMemcpyAsync(rgb, d_rgb, 12 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    tmp.release();
+    if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_environment_sample: ") + cudaGetErrorString(e));
+    return VR_OK;
+}
+
+static int32_t debug_draws(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, void* out,
+                           int floats_per_item) {
+    if (!ctx || !out) return fail(VR_ERR_INVALID, "null argument");
+    if (n == 0) return VR_OK;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    void* d = nullptr;
+    const size_t bytes = 4ull * n * floats_per_item;
+    VR_CUDA(cudaMalloc(&d, bytes));
+    if (floats_per_item == 1) launch_rng_draws(seed, pixel, sample, n, (uint32_t*)d, ctx->stream);
+    else launch_unit_sphere(seed, pixel, sample, n, (float*)d, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("debug draws: ") + cudaGetErrorString(e));
+    return VR_OK;
+}
+
+int32_t vr_debug_rng_draws(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out) {
+    return debug_draws(ctx, seed, pixel, sample, n, out, 1);
+}
+int32_t vr_debug_unit_sphere(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out) {
+    return debug_draws(ctx, seed, pixel, sample, n, out, 3);
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// device_math.cuh — f32 vector arithmetic in the operation order of cgmath 0.18 (the reference's
+// maths crate), the counter-based generator, and the rand / rand_distr distribution algorithms.
+//
+// This translation unit is compiled with -fmad=false: every `a*b+c` below is two IEEE roundings, in
+// source order, exactly like rustc emits for the reference. That is what makes hit distances,
+// barycentrics, normals and scatter directions bit-identical to a CPU evaluation of the same
+// expressions; FMA is used only where written explicitly (__fmaf_rn).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vr {
+
+struct f3 {
+    float x, y, z;
+};
+struct f2 {
+    float x, y;
+};
+
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 operator-(f3 a) { return f3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return f3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 operator/(f3 a, float s) { return f3{a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ f3 mul_elem(f3 a, f3 b) { return f3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+    return f3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float magnitude2(f3 a) { return dot(a, a); }
+__device__ __forceinline__ float magnitude(f3 a) { return sqrtf(magnitude2(a)); }
+__device__ __forceinline__ f3 normalize(f3 a) { return a * (1.0f / magnitude(a)); }
+// cgmath Vector3::angle
+__device__ __forceinline__ float angle_between(f3 a, f3 b) { return atan2f(magnitude(cross(a, b)), dot(a, b)); }
+
+__device__ __forceinline__ f3 xyz(float4 q) { return f3{q.x, q.y, q.z}; }
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+#define VR_PI_F 3.14159265358979323846f
+
+// compiler-rt __powisf2 (what f32::powi lowers to), specialised for exponent 5: a * (a^2)^2
+__device__ __forceinline__ float powi5(float a) {
+    const float a2 = a * a;
+    const float a4 = a2 * a2;
+    return a * a4;
+}
+
+// Rust `x as usize` then `.min(limit)`: saturating, NaN -> 0
+__device__ __forceinline__ uint32_t f32_as_index(float x, uint32_t limit) {
+    const uint32_t i = __float2uint_rz(x);  // saturates, NaN -> 0
+    return i < limit ? i : limit;
+}
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// One camera sample's draw stream: draw i is word (i & 3) of Philox(counter = (pixel, sample, i >> 2, 0)).
+// Only `n` (draws consumed) has to survive between wavefront stages.
+struct Rng {
+    uint32_t k0, k1, pixel, sample, n;
+    uint32_t b0, b1, b2, b3, block;
+    __device__ __forceinline__ Rng(uint64_t seed, uint32_t pixel_, uint32_t sample_, uint32_t n_)
+        : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), pixel(pixel_), sample(sample_), n(n_), b0(0), b1(0),
+          b2(0), b3(0), block(0xFFFFFFFFu) {}
+    __device__ __forceinline__ uint32_t next_u32() {
+        const uint32_t blk = n >> 2;
+        if (blk != block) {
+            uint32_t o[4];
+            philox4x32_10(pixel, sample, blk, 0u, k0, k1, o);
+            b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+            block = blk;
+        }
+        const uint32_t w = n & 3u;
+        ++n;
+        return w == 0 ? b0 : (w == 1 ? b1 : (w == 2 ? b2 : b3));
+    }
+    // rand 0.8.5 UniformFloat<f32>: 23 mantissa bits -> [1,2) - 1
+    __device__ __forceinline__ float v01() { return __uint_as_float((next_u32() >> 9) | 0x3f800000u) - 1.0f; }
+    // gen_range(low..high) — UniformFloat::sample_single
+    __device__ __forceinline__ float gen_range(float low, float high) {
+        const float scale = high - low;
+        while (true) {
+            const float res = v01() * scale + low;
+            if (res < high) return res;
+        }
+    }
+    // Uniform::new(-1.0, 1.0).sample
+    __device__ __forceinline__ float uniform_m1_1() { return v01() * 2.0f + -1.0f; }
+    // rand_distr 0.4.3 UnitSphere (Marsaglia 1972)
+    __device__ __forceinline__ f3 unit_sphere() {
+        while (true) {
+            const float x1 = uniform_m1_1();
+            const float x2 = uniform_m1_1();
+            const float sum = x1 * x1 + x2 * x2;
+            if (sum >= 1.0f) continue;
+            const float factor = 2.0f * sqrtf(1.0f - sum);
+            return f3{x1 * factor, x2 * factor, 1.0f - 2.0f * sum};
+        }
+    }
+    // rand_distr 0.4.3 UnitDisc
+    __device__ __forceinline__ f2 unit_disc() {
+        while (true) {
+            const float x1 = uniform_m1_1();
+            const float x2 = uniform_m1_1();
+            if (x1 * x1 + x2 * x2 <= 1.0f) return f2{x1, x2};
+        }
+    }
+};
+
+// util/math.rs
+__device__ __forceinline__ bool near_zero(f3 v) {
+    const float EPS = 1.0e-8f;
+    return fabsf(v.x) < EPS && fabsf(v.y) < EPS && fabsf(v.z) < EPS;
+}
+__device__ __forceinline__ f3 reflect(f3 v, f3 n) { return v - 2.0f * dot(v, n) * n; }
+__device__ __forceinline__ f3 refract(f3 uv, f3 n, float etai_over_etat) {
+    const float cos_theta = fminf(dot(n, -uv), 1.0f);
+    const f3 out_perp = etai_over_etat * (uv + cos_theta * n);
+    const f3 out_parallel = -sqrtf(fabsf(1.0f - magnitude2(out_perp))) * n;
+    return out_perp + out_parallel;
+}
+__device__ __forceinline__ f3 lerp3(f3 a, f3 b, float t) { return a * (1.0f - t) + b * t; }
+
+}  // namespace vr

@@ -1,0 +1,661 @@
+// kernels.cu — sm_100a wavefront path-tracing kernels: ray generation, closest-hit BVH traversal
+// (shared-memory short stack, Möller–Trumbore), shading with warp-aggregated queue compaction,
+// accumulation and resolve/tonemap. Compiled with -fmad=false (see device_math.cuh).
+//
+// Reference path being replaced: voidray_renderer/src/render/iterative.rs:11-55 -> core/tracer.rs:9-56
+// -> core/scene.rs:182-185 -> core/bvh.rs:132-160 -> core/mesh.rs:144-189 -> voidray_common/src/simple.rs,
+// environments.rs -> shaders/post_process.glsl.
+#include "device_math.cuh"
+#include "kernels.cuh"
+
+namespace vr {
+
+static constexpr int TRACE_THREADS = 128;
+static constexpr int SHADE_THREADS = 128;
+static constexpr int SMEM_STACK = 12;   // entries per thread kept in shared memory
+static constexpr int LOCAL_STACK = 64;  // overflow (local memory); flatten_scene bounds the BVH depth
+static constexpr float T_MIN = 0.00001f;  // core/scene.rs:183
+static constexpr int SENTINEL = 0x7FFFFFFF;
+
+// ------------------------------------------------------------------------------------------------
+// Closest hit: core/scene.rs:182-185 semantics — the smallest t > 1e-5 over every primitive whose
+// Möller–Trumbore / analytic test accepts the ray; equal t resolved by the reference's in-order rank
+// (largest wins). Box tests only cull: they are padded so that they never reject a primitive the
+// exact test would accept.
+// ------------------------------------------------------------------------------------------------
+struct HitResult {
+    float t;
+    int prim;  // GPU primitive: [0, n_tris) triangle, n_tris + k analytic k, -1 miss
+    float u, v;
+};
+
+__device__ __forceinline__ void intersect_triangle(const float4* __restrict__ tri_isect, int tri, f3 o, f3 d,
+                                                   HitResult& best, uint32_t& best_rank) {
+    const float4 q0 = ldg4(tri_isect + 3 * tri);
+    const float4 q1 = ldg4(tri_isect + 3 * tri + 1);
+    const float4 q2 = ldg4(tri_isect + 3 * tri + 2);
+    const f3 v0 = xyz(q0), e1 = xyz(q1), e2 = xyz(q2);
+    // core/mesh.rs:153-175, same operation order
+    const f3 h = cross(d, e2);
+    const float a = dot(e1, h);
+    if (a > -T_MIN && a < T_MIN) return;
+    const float f = 1.0f / a;
+    const f3 s = o - v0;
+    const float u = f * dot(s, h);
+    if (u < 0.0f || u > 1.0f) return;
+    const f3 q = cross(s, e1);
+    const float v = f * dot(d, q);
+    if (v < 0.0f || u + v > 1.0f) return;
+    const float t = f * dot(e2, q);
+    if (t > T_MIN) {
+        const uint32_t rank = __float_as_uint(q0.w);
+        if (t < best.t || (t == best.t && rank > best_rank)) {
+            best.t = t;
+            best.prim = tri;
+            best.u = u;
+            best.v = v;
+            best_rank = rank;
+        }
+    }
+}
+
+__device__ __forceinline__ void intersect_analytic(const AnalyticRec& a, int prim, f3 o, f3 d, HitResult& best,
+                                                   uint32_t& best_rank) {
+    float t;
+    if (a.kind == 0) {  // Sphere::hit, voidray_common/src/surfaces.rs:46-80 with (t_min, t_max) = (1e-5, inf)
+        const f3 oc = o - mk3(a.cx, a.cy, a.cz);
+        const float aa = magnitude2(d);
+        const float half_b = dot(oc, d);
+        const float c = magnitude2(oc) - a.radius * a.radius;
+        const float disc = half_b * half_b - aa * c;
+        if (disc < 0.0f) return;
+        const float sqrtd = sqrtf(disc);
+        float root = (-half_b - sqrtd) / aa;
+        if (root < T_MIN || INFINITY < root) {
+            root = (-half_b + sqrtd) / aa;
+            if (root < T_MIN || INFINITY < root) return;
+        }
+        t = root;
+    } else {  // GroundPlane::hit, surfaces.rs:87-105
+        t = (a.radius - o.y) / d.y;
+        if (t <= T_MIN || t >= INFINITY) return;
+    }
+    if (t < best.t || (t == best.t && a.rank > best_rank) || best.prim < 0) {
+        // (best.prim < 0 covers a NaN-free first hit at t == inf, which the tests above exclude anyway)
+        best.t = t;
+        best.prim = prim;
+        best.u = 0.0f;
+        best.v = 0.0f;
+        best_rank = a.rank;
+    }
+}
+
+// `sstack` points at this thread's column of the shared-memory stack (stride = blockDim.x).
+__device__ __forceinline__ HitResult closest_hit(const DeviceScene& sc, f3 o, f3 d, int* sstack, int sstride) {
+    HitResult best;
+    best.t = INFINITY;
+    best.prim = -1;
+    best.u = best.v = 0.0f;
+    uint32_t best_rank = 0;
+
+    const float4* __restrict__ nodes = (const float4*)sc.nodes;
+    const float4* __restrict__ tri_isect = (const float4*)sc.tri_isect;
+
+    // reciprocal direction for the slab tests only (never feeds a reported value)
+    const float tiny = 1e-20f;
+    const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+    const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+    const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+
+    int lstack[LOCAL_STACK];
+    int sp = 0;
+    int cur = sc.n_tris > 0 ? 0 : SENTINEL;
+
+    while (cur != SENTINEL) {
+        if (cur >= 0) {
+            const float4 q0 = ldg4(nodes + 4 * cur);
+            const float4 q1 = ldg4(nodes + 4 * cur + 1);
+            const float4 q2 = ldg4(nodes + 4 * cur + 2);
+            const float4 q3 = ldg4(nodes + 4 * cur + 3);
+            // child 0: lo (q0.x q0.y q0.z) hi (q0.w q1.x q1.y); child 1: lo (q1.z q1.w q2.x) hi (q2.y q2.z q2.w)
+            const float ax0 = (q0.x - o.x) * idx, ax1 = (q0.w - o.x) * idx;
+            const float ay0 = (q0.y - o.y) * idy, ay1 = (q1.x - o.y) * idy;
+            const float az0 = (q0.z - o.z) * idz, az1 = (q1.y - o.z) * idz;
+            const float bx0 = (q1.z - o.x) * idx, bx1 = (q2.y - o.x) * idx;
+            const float by0 = (q1.w - o.y) * idy, by1 = (q2.z - o.y) * idy;
+            const float bz0 = (q2.x - o.z) * idz, bz1 = (q2.w - o.z) * idz;
+            const float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
+            const float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best.t));
+            const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));
+            const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), best.t));
+            // conservative: widen the exit by a few ulps (Ize, "Robust BVH ray traversal", 2013)
+            const bool hit_a = an <= af * 1.0000005f;
+            const bool hit_b = bn <= bf * 1.0000005f;
+            int ca = __float_as_int(q3.x), cb = __float_as_int(q3.y);
+            if (hit_a && hit_b) {
+                if (bn < an) { const int tmp = ca; ca = cb; cb = tmp; }
+                if (sp < SMEM_STACK) sstack[sp * sstride] = cb;
+                else lstack[sp - SMEM_STACK] = cb;
+                ++sp;
+                cur = ca;
+            } else if (hit_a) {
+                cur = ca;
+            } else if (hit_b) {
+                cur = cb;
+            } else {
+                if (sp == 0) break;
+                --sp;
+                cur = sp < SMEM_STACK ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
+            }
+        } else {
+            const int code = ~cur;
+            const int first = code >> 3, count = code & 7;
+            for (int k = 0; k < count; ++k) intersect_triangle(tri_isect, first + k, o, d, best, best_rank);
+            if (sp == 0) break;
+            --sp;
+            cur = sp < SMEM_STACK ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
+        }
+    }
+
+    for (uint32_t k = 0; k < sc.n_analytics; ++k)
+        intersect_analytic(sc.analytics[k], (int)(sc.n_tris + k), o, d, best, best_rank);
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Textures and environment (core/texture.rs:52-98, voidray_common/src/environments.rs:57-86)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 texel(const TextureRec& tex, uint32_t idx, uint32_t len) {
+    if (idx >= len) idx -= len;  // `% len`: idx < 2*len always
+    return xyz(ldg4((const float4*)tex.texels + idx));
+}
+__device__ __forceinline__ f3 bilinear_sample(const TextureRec& tex, float x, float y) {
+    const uint32_t len = tex.width * tex.height;
+    const uint32_t x0 = f32_as_index(x, tex.width - 1);
+    const uint32_t y0 = f32_as_index(y, tex.height - 1);
+    const float ax = x - (float)x0;
+    const float ay = y - (float)y0;
+    const f3 c00 = texel(tex, y0 * tex.width + x0, len);
+    const f3 c01 = texel(tex, y0 * tex.width + x0 + 1, len);
+    const f3 c10 = texel(tex, (y0 + 1) * tex.width + x0, len);
+    const f3 c11 = texel(tex, (y0 + 1) * tex.width + x0 + 1, len);
+    return lerp3(lerp3(c00, c01, ax), lerp3(c10, c11, ax), ay);
+}
+__device__ __forceinline__ f3 texture_sample(const TextureRec& tex, float u, float v) {
+    if (u < 0.0f) u -= truncf(u) - 1.0f;
+    if (v < 0.0f) v -= truncf(v) - 1.0f;
+    const float x = fmodf(u, 1.0f) * (float)tex.width;
+    const float y = (1.0f - fmodf(v, 1.0f)) * (float)tex.height;
+    if (tex.sample_type == 0) {
+        const uint32_t xi = f32_as_index(x, tex.width - 1);
+        const uint32_t yi = f32_as_index(y, tex.height - 1);
+        return texel(tex, yi * tex.width + xi, tex.width * tex.height);
+    }
+    return bilinear_sample(tex, x, y);
+}
+__device__ __forceinline__ f3 environment_sample(const DeviceScene& sc, f3 dir) {
+    if (sc.env_kind == 1) return mk3(sc.env_color[0], sc.env_color[1], sc.env_color[2]);
+    if (sc.env_kind != 2) return mk3(0.0f, 0.0f, 0.0f);
+    const f3 d = normalize(dir);
+    const float sx = acosf(-d.y);                   // util/math.rs:24-29
+    const float sy = atan2f(-d.z, d.x) + VR_PI_F;
+    const float u = sx / VR_PI_F;
+    const float v = sy / (2.0f * VR_PI_F);
+    const float x = v * (float)sc.env_tex.width;
+    const float y = (float)(sc.env_tex.height - 1) - (u * (float)sc.env_tex.height);
+    return bilinear_sample(sc.env_tex, x, y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray generation: render/iterative.rs:25-42 + core/camera.rs:69-82
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slot_source(const PathSource& src, uint32_t slot, uint32_t& pixel, uint32_t& sample) {
+    if (src.pixel) {
+        pixel = src.pixel[slot];
+        sample = src.sample[slot];
+    } else {
+        pixel = slot % src.n_pixels;
+        sample = src.sample_base + slot / src.n_pixels;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp,
+                                                uint32_t n_paths) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[0] = n_paths;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+        uint32_t pixel, sample;
+        slot_source(src, slot, pixel, sample);
+        const uint32_t W = fp.width, H = fp.height;
+        const uint32_t px = pixel % W;
+        const uint32_t py = fp.pixel_mapping == 1 ? pixel / H : pixel / W;
+        const float dd = (float)(W > H ? W : H);
+        const float x = ((float)(2u * px + 1u) - (float)W) / dd;
+        const float y = ((float)(2u * (H - py) - 1u) - (float)H) / dd;
+        Rng rng(fp.seed, pixel, sample, 0);
+        const float dx = rng.gen_range(-1.0f / dd, 1.0f / dd);
+        const float dy = rng.gen_range(-1.0f / dd, 1.0f / dd);
+        const float cx = x + dx, cy = y + dy;
+
+        const CameraRec& cam = sc.camera;
+        const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
+        const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
+        f3 origin = mk3(cam.origin[0], cam.origin[1], cam.origin[2]);
+        f3 new_dir = cam.d * mk3(cam.direction[0], cam.direction[1], cam.direction[2]) + cx * right + cy * up;
+        if (cam.has_dof) {
+            const f3 focal_point = origin + normalize(new_dir) * cam.focal_length;
+            const f2 s = rng.unit_disc();
+            origin = origin + (s.x * right + s.y * up) * cam.aperture;
+            new_dir = focal_point - origin;
+        }
+        const f3 dir = normalize(normalize(new_dir));  // camera.rs:81 then Ray::new, util/ray.rs:15
+        wf.ray_o[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n));
+        wf.ray_d[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Closest-hit kernel: one ray per thread, queue of slots
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
+    __shared__ int s_stack[SMEM_STACK * TRACE_THREADS];
+    const uint32_t n = wf.counts[depth];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wf.segments, (unsigned long long)n);
+    const uint32_t* __restrict__ queue = depth == 0 ? nullptr : wf.queue[depth & 1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue ? queue[i] : i;
+        const float4 ro = wf.ray_o[slot];
+        const float4 rd = wf.ray_d[slot];
+        const HitResult h = closest_hit(sc, xyz(ro), xyz(rd), s_stack + threadIdx.x, TRACE_THREADS);
+        wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shading: core/tracer.rs:19-56 unrolled over the wavefront. The reference recursion
+//   L_d = 0 + min(att_d * L_{d+1}, clamp)      (tracer.rs:44-50, util/color.rs:30-36)
+// is evaluated exactly: every level's attenuation is parked in wf.att and the product is unwound from
+// the terminal value back to level 0 when the path ends, in the reference's own operation order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 clamp_color(f3 c, float mx) { return mk3(fminf(c.x, mx), fminf(c.y, mx), fminf(c.z, mx)); }
+
+// L_level = value; fold levels level-1 .. 0
+__device__ __forceinline__ f3 unwind(const Wavefront& wf, uint32_t slot, uint32_t level, f3 value, float clampv) {
+    for (uint32_t d = level; d-- > 0;) {
+        const f3 att = xyz(wf.att[(size_t)d * wf.capacity + slot]);
+        value = mk3(0.0f, 0.0f, 0.0f) + clamp_color(mul_elem(att, value), clampv);
+    }
+    return value;
+}
+
+__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefront wf, PathSource src,
+                                                         FrameParams fp, uint32_t depth) {
+    const uint32_t n = wf.counts[depth];
+    const uint32_t* __restrict__ queue = depth == 0 ? nullptr : wf.queue[depth & 1];
+    uint32_t* __restrict__ queue_out = wf.queue[(depth + 1) & 1];
+    const float4* __restrict__ tri_shade = (const float4*)sc.tri_shade;
+    const uint32_t lane = threadIdx.x & 31u;
+
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        bool alive = false;
+        uint32_t slot = 0;
+        if (i < n) {
+            slot = queue ? queue[i] : i;
+            const float4 ro = wf.ray_o[slot];
+            const float4 rd = wf.ray_d[slot];
+            const float4 hr = wf.hit[slot];
+            const f3 o = xyz(ro), d = xyz(rd);
+            const int prim = __float_as_int(hr.y);
+
+            if (prim < 0) {
+                // tracer.rs:30-33: a miss returns the environment sample unclamped at this level
+                const f3 env = environment_sample(sc, d);
+                const f3 L = unwind(wf, slot, depth, env, fp.firefly_clamp);
+                wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+            } else {
+                const float t = hr.x;
+                const f3 point = o + d * t;  // Ray::at, util/ray.rs:19-21
+                f3 outward;
+                f2 uv;
+                uint32_t material;
+                if ((uint32_t)prim < sc.n_tris) {
+                    const float u = hr.z, v = hr.w;
+                    const float4 s0 = ldg4(tri_shade + 5 * prim), s1 = ldg4(tri_shade + 5 * prim + 1),
+                                 s2 = ldg4(tri_shade + 5 * prim + 2), s3 = ldg4(tri_shade + 5 * prim + 3),
+                                 s4 = ldg4(tri_shade + 5 * prim + 4);
+                    const f3 n0 = xyz(s0), n1 = xyz(s1), n2 = xyz(s2), ng = xyz(s3);
+                    const float w = 1.0f - u - v;
+                    // mesh.rs:176-181
+                    outward = u * n1 + v * n2 + w * n0;
+                    uv.x = u * s2.w + v * s4.x + w * s0.w;
+                    uv.y = u * s3.w + v * s4.y + w * s1.w;
+                    if (angle_between(outward, ng) > 30.0f * VR_PI_F / 180.0f) outward = ng;
+                    material = __float_as_uint(s4.z);
+                } else {
+                    const AnalyticRec a = sc.analytics[prim - sc.n_tris];
+                    if (a.kind == 0) {
+                        outward = (point - mk3(a.cx, a.cy, a.cz)) / a.radius;  // surfaces.rs:69-70
+                        uv.x = 0.0f;
+                        uv.y = 0.0f;
+                    } else {
+                        outward = mk3(0.0f, 1.0f, 0.0f);  // surfaces.rs:93-101
+                        uv.x = point.x;
+                        uv.y = point.z;
+                    }
+                    material = a.material;
+                }
+                // HitRecord::new, util/ray.rs:34-49
+                const bool front_face = dot(d, outward) < 0.0f;
+                const f3 normal = front_face ? outward : -outward;
+
+                const MaterialRec m = sc.materials[material];
+                f3 attenuation;
+                bool scattered = false;
+                f3 new_o = point, new_d = d;
+                uint32_t pixel, sample;
+                slot_source(src, slot, pixel, sample);
+                Rng rng(fp.seed, pixel, sample, __float_as_uint(ro.w));
+
+                if (fp.render_mode == 1) {
+                    // tracer.rs:40: RenderMode::Normal
+                    attenuation = 0.5f * normalize(normal) + mk3(1.0f, 1.0f, 1.0f) * 0.5f;
+                } else if (m.kind == 0) {
+                    // Lambertian::scatter, simple.rs:103-132
+                    const f3 sn = m.normal_tex >= 0 ? texture_sample(sc.textures[m.normal_tex], uv.x, uv.y) : normal;
+                    f3 dir = sn + rng.unit_sphere();
+                    if (near_zero(dir)) dir = sn;
+                    new_d = normalize(dir);
+                    scattered = true;
+                    attenuation = m.albedo_tex >= 0 ? texture_sample(sc.textures[m.albedo_tex], uv.x, uv.y)
+                                                    : mk3(m.color[0], m.color[1], m.color[2]);
+                } else if (m.kind == 1) {
+                    // Metal::scatter, simple.rs:141-160 (rejection loop bounded at 64 draws)
+                    const f3 reflected = normalize(reflect(d, normal));
+                    attenuation = mk3(m.color[0], m.color[1], m.color[2]);
+                    for (int k = 0; k < 64; ++k) {
+                        const f3 cand = normalize(reflected + m.param * rng.unit_sphere());
+                        if (dot(cand, normal) > 0.0f) {
+                            new_d = cand;
+                            scattered = true;
+                            break;
+                        }
+                    }
+                } else if (m.kind == 2) {
+                    // Dielectric::scatter, simple.rs:201-231
+                    const float ratio = front_face ? 1.0f / m.param : m.param;
+                    const f3 unit_direction = normalize(d);
+                    const float cos_theta = fminf(dot(normal, -unit_direction), 1.0f);
+                    const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+                    bool do_reflect = (ratio * sin_theta) > 1.0f;
+                    if (!do_reflect) {
+                        float r0 = (1.0f - ratio) / (1.0f + ratio);
+                        r0 = r0 * r0;
+                        const float refl = r0 + (1.0f - r0) * powi5(1.0f - cos_theta);
+                        do_reflect = refl > rng.gen_range(0.0f, 1.0f);
+                    }
+                    const f3 dir = do_reflect ? reflect(unit_direction, normal) : refract(unit_direction, normal, ratio);
+                    new_d = normalize(dir);
+                    scattered = true;
+                    attenuation = mk3(1.0f, 1.0f, 1.0f);
+                } else if (m.kind == 3) {
+                    // Emission::scatter, simple.rs:176-184 (colour * strength folded on the host)
+                    attenuation = mk3(m.color[0], m.color[1], m.color[2]);
+                } else {
+                    // LambertianBSDF through the blanket impl, core/traits.rs:23-40 + simple.rs:64-81
+                    const f3 wi = normalize(rng.unit_sphere());
+                    const f3 f = mk3(m.color[0], m.color[1], m.color[2]) / VR_PI_F;
+                    attenuation = f * fabsf(dot(wi, normal)) * (1.0f / 1.0f);
+                    new_d = normalize(wi);
+                    scattered = true;
+                }
+
+                if (!scattered) {
+                    // tracer.rs:44-50 with no scattered ray: delta = attenuation
+                    const f3 Lk = mk3(0.0f, 0.0f, 0.0f) + clamp_color(attenuation, fp.firefly_clamp);
+                    const f3 L = unwind(wf, slot, depth, Lk, fp.firefly_clamp);
+                    wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+                } else if (depth + 1 >= fp.max_bounces) {
+                    // the scattered ray would be traced at depth == max_bounces and return BLACK (tracer.rs:28)
+                    const f3 Lk = mk3(0.0f, 0.0f, 0.0f) +
+                                  clamp_color(mul_elem(attenuation, mk3(0.0f, 0.0f, 0.0f)), fp.firefly_clamp);
+                    const f3 L = unwind(wf, slot, depth, Lk, fp.firefly_clamp);
+                    wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+                } else {
+                    wf.att[(size_t)depth * wf.capacity + slot] = make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f);
+                    wf.ray_o[slot] = make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng.n));
+                    wf.ray_d[slot] = make_float4(new_d.x, new_d.y, new_d.z, 0.0f);
+                    alive = true;
+                }
+            }
+        }
+        // warp-aggregated compaction: one atomic per warp
+        __syncwarp();
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, alive);
+        if (ballot) {
+            uint32_t warp_base = 0;
+            const int leader = __ffs(ballot) - 1;
+            if ((int)lane == leader) warp_base = atomicAdd(&wf.counts[depth + 1], (uint32_t)__popc(ballot));
+            warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, leader);
+            if (alive) queue_out[warp_base + __popc(ballot & ((1u << lane) - 1u))] = slot;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Accumulation: render/iterative.rs:35-51
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_accumulate(Wavefront wf, float4* partial, float4* accum, uint32_t n_pixels,
+                                                    uint32_t samples_in_batch, int finish, float inv_total) {
+    for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += gridDim.x * blockDim.x) {
+        float4 p = partial[px];
+        for (uint32_t s = 0; s < samples_in_batch; ++s) {
+            const float4 L = wf.radiance[(size_t)s * n_pixels + px];
+            p.x += L.x;
+            p.y += L.y;
+            p.z += L.z;
+        }
+        if (finish) {
+            float4 a = accum[px];
+            a.x += p.x * inv_total;
+            a.y += p.y * inv_total;
+            a.z += p.z * inv_total;
+            a.w += 1.0f;  // Color::a() == 1.0 per call, util/color.rs:54 / iterative.rs:51
+            accum[px] = a;
+            p = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        partial[px] = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resolve: shaders/post_process.glsl:23-49 + shaders/tonemapping.glsl:2-40 (GLSL mat3 is column-major)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 mat3_mul(const float* m, f3 v) {
+    return mk3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z,
+               m[2] * v.x + m[5] * v.y + m[8] * v.z);
+}
+__device__ __forceinline__ float aces_fit(float c) {
+    return (c * (c + 0.0245786f) - 0.000090537f) / (c * (0.983729f * c + 0.432951f) + 0.238081f);
+}
+__device__ __forceinline__ float filmic_fit(float c) { return (c * (6.2f * c + 0.5f)) / (c * (6.2f * c + 1.7f) + 0.06f); }
+__device__ __forceinline__ float uncharted_fit(float c) {
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((c * (A * c + C * B) + D * E) / (c * (A * c + B) + D * F)) - E / F;
+}
+
+__global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accum, float4* __restrict__ out,
+                                                 uint32_t n_pixels, float scale, float exposure_mul, float inv_gamma,
+                                                 int32_t tonemap) {
+    const float ACES_IN[9] = {0.59719f, 0.076f, 0.0284f, 0.35458f, 0.90834f, 0.13383f, 0.04823f, 0.01566f, 0.83777f};
+    const float ACES_OUT[9] = {1.60475f, -0.10208f, -0.00327f, -0.53108f, 1.10813f, -0.07276f, -0.07367f, -0.00605f, 1.07602f};
+    for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += gridDim.x * blockDim.x) {
+        const float4 a = accum[px];
+        f3 c = mk3(a.x * scale, a.y * scale, a.z * scale) * exposure_mul;
+        if (tonemap == 1) {
+            c = mat3_mul(ACES_IN, c);
+            c = mk3(aces_fit(c.x), aces_fit(c.y), aces_fit(c.z));
+            c = mat3_mul(ACES_OUT, c);
+        } else if (tonemap == 2) {
+            const float white = 2.0f;
+            const float luma = (c.x * 0.2126f + c.y * 0.7152f) + c.z * 0.0722f;
+            const float tm = luma * (1.0f + luma / (white * white)) / (1.0f + luma);
+            c = c * (tm / luma);
+        } else if (tonemap == 3) {
+            c = mk3(fmaxf(0.0f, c.x - 0.004f), fmaxf(0.0f, c.y - 0.004f), fmaxf(0.0f, c.z - 0.004f));
+            c = mk3(filmic_fit(c.x), filmic_fit(c.y), filmic_fit(c.z));
+        } else if (tonemap == 4) {
+            c = c * 2.0f;
+            c = mk3(uncharted_fit(c.x), uncharted_fit(c.y), uncharted_fit(c.z));
+            c = c / uncharted_fit(11.2f);
+        }
+        out[px] = make_float4(powf(c.x, inv_gamma), powf(c.y, inv_gamma), powf(c.z, inv_gamma), 1.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gate / debug kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void export_hit(const DeviceScene& sc, const HitResult& h, uint32_t* surface, uint32_t* prim,
+                                           float* t, uint64_t i) {
+    if (h.prim < 0) {
+        surface[i] = 0xFFFFFFFFu;
+        prim[i] = 0xFFFFFFFFu;
+        t[i] = INFINITY;
+    } else if ((uint32_t)h.prim < sc.n_tris) {
+        surface[i] = sc.tri_surface[h.prim];
+        prim[i] = sc.tri_prim[h.prim];
+        t[i] = h.t;
+    } else {
+        surface[i] = sc.analytics[h.prim - sc.n_tris].surface;
+        prim[i] = 0xFFFFFFFFu;
+        t[i] = h.t;
+    }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DeviceScene sc, const float* origins, const float* dirs,
+                                                              uint64_t n, uint32_t* surface, uint32_t* prim, float* t) {
+    __shared__ int s_stack[SMEM_STACK * TRACE_THREADS];
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const f3 o = mk3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        const f3 d = normalize(mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));  // Ray::new
+        const HitResult h = closest_hit(sc, o, d, s_stack + threadIdx.x, TRACE_THREADS);
+        export_hit(sc, h, surface, prim, t, i);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_primary_ids(DeviceScene sc, Wavefront wf, uint32_t n, uint32_t* surface,
+                                                     uint32_t* prim, float* t) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 hr = wf.hit[i];
+        HitResult h;
+        h.t = hr.x;
+        h.prim = __float_as_int(hr.y);
+        h.u = hr.z;
+        h.v = hr.w;
+        export_hit(sc, h, surface, prim, t, i);
+    }
+}
+
+__global__ void k_rng_draws(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Rng rng(seed, pixel, sample, 0);
+        for (uint32_t i = 0; i < n; ++i) out[i] = rng.next_u32();
+    }
+}
+__global__ void k_unit_sphere(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Rng rng(seed, pixel, sample, 0);
+        for (uint32_t i = 0; i < n; ++i) {
+            const f3 v = rng.unit_sphere();
+            out[3 * i] = v.x;
+            out[3 * i + 1] = v.y;
+            out[3 * i + 2] = v.z;
+        }
+    }
+}
+__global__ void k_texture_sample(TextureRec tex, uint64_t n, const float* uv, float* rgb) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const f3 c = texture_sample(tex, uv[2 * i], uv[2 * i + 1]);
+        rgb[3 * i] = c.x;
+        rgb[3 * i + 1] = c.y;
+        rgb[3 * i + 2] = c.z;
+    }
+}
+__global__ void k_environment_sample(DeviceScene sc, uint64_t n, const float* dirs, float* rgb) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const f3 c = environment_sample(sc, mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+        rgb[3 * i] = c.x;
+        rgb[3 * i + 1] = c.y;
+        rgb[3 * i + 2] = c.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch wrappers. Grids are persistent-style: a multiple of the SM count x resident blocks, with
+// grid-stride loops; the live queue length is read on the device, so no host round trip per depth.
+// ------------------------------------------------------------------------------------------------
+void query_launch_dims(LaunchDims* dims) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&dims->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->trace_blocks_per_sm, k_trace, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_blocks_per_sm, k_shade, SHADE_THREADS, 0);
+    if (dims->trace_blocks_per_sm < 1) dims->trace_blocks_per_sm = 1;
+    if (dims->shade_blocks_per_sm < 1) dims->shade_blocks_per_sm = 1;
+}
+
+static inline uint32_t grid_for(uint64_t n, int threads, int sm_count, int blocks_per_sm) {
+    const uint64_t need = (n + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)sm_count * blocks_per_sm;
+    const uint64_t g = need < cap ? need : cap;
+    return (uint32_t)(g < 1 ? 1 : g);
+}
+
+void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
+                   uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream) {
+    k_raygen<<<grid_for(n_paths, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, src, fp, n_paths);
+}
+void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, const LaunchDims& ld,
+                  cudaStream_t stream) {
+    k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(sc, wf, depth);
+}
+void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
+                  uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {
+    k_shade<<<grid_for(n_upper, SHADE_THREADS, ld.sm_count, ld.shade_blocks_per_sm), SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+}
+void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t n_pixels, uint32_t samples_in_batch,
+                       int finish, float inv_total_samples, cudaStream_t stream) {
+    const uint32_t grid = (n_pixels + 255) / 256;
+    k_accumulate<<<grid, 256, 0, stream>>>(wf, partial, accum, n_pixels, samples_in_batch, finish, inv_total_samples);
+}
+void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul, float inv_gamma,
+                    int32_t tonemap, cudaStream_t stream) {
+    const uint32_t grid = (n_pixels + 255) / 256;
+    k_resolve<<<grid, 256, 0, stream>>>(accum, out, n_pixels, scale, exposure_mul, inv_gamma, tonemap);
+}
+void launch_trace_rays(const DeviceScene& sc, const float* origins, const float* dirs, uint64_t n, uint32_t* surface,
+                       uint32_t* prim, float* t, cudaStream_t stream) {
+    const uint32_t grid = (uint32_t)((n + TRACE_THREADS - 1) / TRACE_THREADS);
+    k_trace_rays<<<grid < 1 ? 1 : (grid > 148 * 8 ? 148 * 8 : grid), TRACE_THREADS, 0, stream>>>(sc, origins, dirs, n, surface, prim, t);
+}
+void launch_primary_ids(const DeviceScene& sc, const Wavefront& wf, uint32_t n, uint32_t* surface, uint32_t* prim,
+                        float* t, cudaStream_t stream) {
+    k_primary_ids<<<(n + 255) / 256, 256, 0, stream>>>(sc, wf, n, surface, prim, t);
+}
+void launch_rng_draws(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out, cudaStream_t stream) {
+    k_rng_draws<<<1, 32, 0, stream>>>(seed, pixel, sample, n, out);
+}
+void launch_unit_sphere(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, cudaStream_t stream) {
+    k_unit_sphere<<<1, 32, 0, stream>>>(seed, pixel, sample, n, out);
+}
+void launch_texture_sample(TextureRec tex, uint64_t n, const float* uv, float* rgb, cudaStream_t stream) {
+    const uint32_t grid = (uint32_t)((n + 255) / 256);
+    k_texture_sample<<<grid < 1 ? 1 : (grid > 4096 ? 4096 : grid), 256, 0, stream>>>(tex, n, uv, rgb);
+}
+void launch_environment_sample(const DeviceScene& sc, uint64_t n, const float* dirs, float* rgb, cudaStream_t stream) {
+    const uint32_t grid = (uint32_t)((n + 255) / 256);
+    k_environment_sample<<<grid < 1 ? 1 : (grid > 4096 ? 4096 : grid), 256, 0, stream>>>(sc, n, dirs, rgb);
+}
+
+}  // namespace vr

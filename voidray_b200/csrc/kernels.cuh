@@ -1,0 +1,70 @@
+// kernels.cuh — launch interface of the wavefront integrator (kernels.cu) used by abi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace vr {
+
+// Wavefront state, structure-of-arrays over `capacity` path slots.
+struct Wavefront {
+    float4* ray_o;   // origin.xyz, draws consumed so far (uint bits)
+    float4* ray_d;   // direction.xyz (unit), unused
+    float4* hit;     // t, GPU primitive index (int bits, -1 miss), u, v
+    float4* att;     // [max_bounces][capacity] attenuation of every level (rgb, unused)
+    float4* radiance;  // [capacity] finished radiance of the slot's camera sample
+    uint32_t* queue[2];  // compacted slot lists, ping-pong by depth parity
+    uint32_t* counts;    // [max_bounces + 1] queue lengths
+    unsigned long long* segments;  // scene.hit calls, whole render
+    uint32_t capacity;
+};
+
+// slot -> (pixel, global sample): implicit (slot % n_pixels, sample_base + slot / n_pixels) or explicit lists
+struct PathSource {
+    const uint32_t* pixel;   // null: implicit
+    const uint32_t* sample;
+    uint32_t n_pixels;
+    uint32_t sample_base;
+};
+
+struct FrameParams {
+    uint32_t width, height;
+    int32_t pixel_mapping;
+    uint32_t max_bounces;
+    float firefly_clamp;
+    int32_t render_mode;
+    uint64_t seed;
+};
+
+struct LaunchDims {
+    int sm_count;
+    int trace_blocks_per_sm;
+    int shade_blocks_per_sm;
+};
+void query_launch_dims(LaunchDims* dims);
+
+void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
+                   uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream);
+void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper,
+                  const LaunchDims& ld, cudaStream_t stream);
+void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
+                  uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
+// partial[pixel] += sum over the batch's samples (in sample order); when `finish`, fold
+// partial * (1/total_samples) into accum (alpha += 1) and clear partial.
+void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t n_pixels,
+                       uint32_t samples_in_batch, int finish, float inv_total_samples, cudaStream_t stream);
+void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul,
+                    float inv_gamma, int32_t tonemap, cudaStream_t stream);
+
+// debug / gate kernels
+void launch_trace_rays(const DeviceScene& sc, const float* origins, const float* dirs, uint64_t n,
+                       uint32_t* surface, uint32_t* prim, float* t, cudaStream_t stream);
+void launch_primary_ids(const DeviceScene& sc, const Wavefront& wf, uint32_t n, uint32_t* surface, uint32_t* prim,
+                        float* t, cudaStream_t stream);
+void launch_rng_draws(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out, cudaStream_t stream);
+void launch_unit_sphere(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, cudaStream_t stream);
+void launch_texture_sample(TextureRec tex, uint64_t n, const float* uv, float* rgb, cudaStream_t stream);
+void launch_environment_sample(const DeviceScene& sc, uint64_t n, const float* dirs, float* rgb, cudaStream_t stream);
+
+}  // namespace vr

@@ -1,0 +1,82 @@
+// layout.h — packed device layouts of the flattened scene and of the wavefront state.
+// Everything the kernels fetch is a 16-byte float4 (one LDG.128 per lane); see DESIGN.md §3.
+#pragma once
+#include <stdint.h>
+
+namespace vr {
+
+// BVH2 node, 64 B = 4 x float4. A node stores the boxes of BOTH children so that one 64-byte fetch
+// decides the descent (two slab tests, ordered by entry distance).
+//   q0 = (lo0.x, lo0.y, lo0.z, hi0.x)
+//   q1 = (hi0.y, hi0.z, lo1.x, lo1.y)
+//   q2 = (lo1.z, hi1.x, hi1.y, hi1.z)
+//   q3 = (child0, child1, 0, 0) as int bits: >= 0 inner node index; < 0 leaf, ~c = (first_tri << 3) | count
+static const int NODE_QUADS = 4;
+static const int LEAF_MAX_TRIS = 4;
+
+// Intersection record, 48 B = 3 x float4 (pre-subtracted edges: e1 = v1 - v0, e2 = v2 - v0 are the
+// same f32 subtractions core/mesh.rs:150-151 performs per test, done once on the host).
+//   q0 = (v0.xyz, tie rank as uint bits)
+//   q1 = (e1.xyz, 0)
+//   q2 = (e2.xyz, 0)
+static const int TRI_ISECT_QUADS = 3;
+
+// Shading record, 80 B = 5 x float4, fetched once per closest hit.
+//   q0 = (n0.xyz, uv0.x)   q1 = (n1.xyz, uv0.y)   q2 = (n2.xyz, uv1.x)
+//   q3 = (ng.xyz, uv1.y)   q4 = (uv2.x, uv2.y, material index bits, 0)
+static const int TRI_SHADE_QUADS = 5;
+
+struct MaterialRec {  // 32 B
+    int32_t kind;
+    float color[3];
+    float param;
+    int32_t albedo_tex;
+    int32_t normal_tex;
+    int32_t pad;
+};
+
+struct TextureRec {  // texels are RGBA f32 (w unused) so one tap is one 16-byte load
+    const void* texels;  // float4*
+    uint32_t width, height;
+    int32_t sample_type;
+    uint32_t pad;
+};
+
+struct AnalyticRec {  // 32 B; tested linearly after the triangle BVH (scenes have a handful)
+    int32_t kind;     // 0 sphere, 1 ground plane
+    float cx, cy, cz; // sphere centre
+    float radius;     // sphere radius | plane height
+    uint32_t rank;    // tie rank in the reference's in-order sequence
+    uint32_t material;
+    uint32_t surface;
+};
+
+struct CameraRec {
+    float origin[3];
+    float direction[3];
+    float right[3];
+    float up[3];
+    float d;
+    int32_t has_dof;
+    float aperture;
+    float focal_length;
+};
+
+struct DeviceScene {
+    const void* nodes;      // float4*
+    const void* tri_isect;  // float4*
+    const void* tri_shade;  // float4*
+    const uint32_t* tri_surface;  // GPU triangle -> surface handle
+    const uint32_t* tri_prim;     // GPU triangle -> triangle index inside its mesh
+    const MaterialRec* materials;
+    const TextureRec* textures;
+    const AnalyticRec* analytics;
+    uint32_t n_tris;
+    uint32_t n_analytics;
+    int32_t env_kind;  // 0 none, 1 uniform, 2 hdri
+    float env_color[3];
+    TextureRec env_tex;
+    CameraRec camera;
+};
+
+}  // namespace vr

@@ -1,0 +1,462 @@
+// scene_build.cpp — flatten a HostScene into the packed device layout: world-space triangle records,
+// a binned-SAH BVH2 whose nodes carry both child boxes, and the tie ranks that make the closest hit
+// identical to the reference's (DESIGN.md §4 "Tie rule").
+#include "scene_build.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace vr {
+namespace {
+
+struct V3 {
+    float x, y, z;
+};
+inline V3 sub(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 scale(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+// cgmath 0.18 operation order: dot = (x*x' + y*y') + z*z'
+inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline V3 normalize(V3 a) { return scale(a, 1.0f / std::sqrt(dot(a, a))); }
+inline V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
+
+// f32::total_cmp key
+inline int32_t total_key(float f) {
+    int32_t i;
+    std::memcpy(&i, &f, 4);
+    i ^= (int32_t)(((uint32_t)(i >> 31)) >> 1);
+    return i;
+}
+inline float bits_f(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+}  // namespace
+
+void camera_look_at(const float eye[3], const float center[3], const float up_in[3], float direction[3],
+                    float up[3]) {
+    const V3 dir = normalize(sub(ld3(center), ld3(eye)));
+    const V3 u0 = ld3(up_in);
+    const V3 u = normalize(sub(u0, scale(dir, dot(u0, dir))));
+    direction[0] = dir.x; direction[1] = dir.y; direction[2] = dir.z;
+    up[0] = u.x; up[1] = u.y; up[2] = u.z;
+}
+
+// core/bvh.rs:48-130 restated on index ranges: a range of >= 2 items is stably sorted by the centroid
+// coordinate of the axis with the strictly largest centroid spread (else Z) and cut at len/2. The left
+// half precedes the right half, so after the recursion the array itself is the in-order leaf sequence.
+void reference_leaf_order(const std::vector<float>& boxes6, std::vector<uint32_t>& order) {
+    const size_t n = boxes6.size() / 6;
+    order.resize(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    if (n < 2) return;
+    // centroid = (min + max) / 2.0 (util/aabb.rs:33-35)
+    std::vector<float> cen(3 * n);
+    for (size_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) cen[3 * i + a] = (boxes6[6 * i + a] + boxes6[6 * i + 3 + a]) / 2.0f;
+
+    struct Range {
+        size_t lo, hi;
+    };
+    std::vector<Range> stack;
+    stack.push_back(Range{0, n});
+    std::vector<std::pair<int32_t, uint32_t>> keyed;
+    while (!stack.empty()) {
+        const Range r = stack.back();
+        stack.pop_back();
+        const size_t len = r.hi - r.lo;
+        if (len < 2) continue;
+        float cmin[3], cmax[3];
+        for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = cen[3 * order[r.lo] + a];
+        for (size_t i = r.lo + 1; i < r.hi; ++i)
+            for (int a = 0; a < 3; ++a) {
+                cmin[a] = std::fmin(cmin[a], cen[3 * order[i] + a]);
+                cmax[a] = std::fmax(cmax[a], cen[3 * order[i] + a]);
+            }
+        const float sx = cmax[0] - cmin[0], sy = cmax[1] - cmin[1], sz = cmax[2] - cmin[2];
+        int axis;
+        if (sx > sy && sx > sz) axis = 0;
+        else if (sy > sx && sy > sz) axis = 1;
+        else axis = 2;
+        keyed.resize(len);
+        for (size_t i = 0; i < len; ++i) {
+            keyed[i].first = total_key(cen[3 * order[r.lo + i] + axis]);
+            keyed[i].second = order[r.lo + i];
+        }
+        std::stable_sort(keyed.begin(), keyed.end(),
+                         [](const std::pair<int32_t, uint32_t>& a, const std::pair<int32_t, uint32_t>& b) {
+                             return a.first < b.first;
+                         });
+        for (size_t i = 0; i < len; ++i) order[r.lo + i] = keyed[i].second;
+        const size_t half = len / 2;
+        stack.push_back(Range{r.lo, r.lo + half});
+        stack.push_back(Range{r.lo + half, r.hi});
+    }
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Binned-SAH BVH2 builder
+// ------------------------------------------------------------------------------------------------
+struct Box {
+    float lo[3], hi[3];
+    void reset() {
+        for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; }
+    }
+    void grow(const float* p) {
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); }
+    }
+    void grow(const Box& b) {
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
+    }
+    float half_area() const {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.0f;
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct Prim {
+    Box box;
+    float cen[3];
+    uint32_t id;
+};
+
+struct Builder {
+    std::vector<Prim>& prims;
+    std::vector<Quad>& nodes;
+    std::atomic<uint32_t> next_node{0};
+    std::atomic<uint32_t> max_depth{0};
+    std::atomic<int> threads_left{0};
+    static const int BINS = 32;
+
+    Builder(std::vector<Prim>& p, std::vector<Quad>& n) : prims(p), nodes(n) {}
+
+    static int32_t leaf_code(uint32_t first, uint32_t count) { return ~(int32_t)((first << 3) | count); }
+
+    void note_depth(uint32_t d) {
+        uint32_t cur = max_depth.load();
+        while (d > cur && !max_depth.compare_exchange_weak(cur, d)) {}
+    }
+
+    // Builds the subtree over prims[lo, hi); returns its child code and box.
+    int32_t build(uint32_t lo, uint32_t hi, Box& out_box, uint32_t depth) {
+        const uint32_t n = hi - lo;
+        Box bounds, cbounds;
+        bounds.reset();
+        cbounds.reset();
+        for (uint32_t i = lo; i < hi; ++i) {
+            bounds.grow(prims[i].box);
+            cbounds.grow(prims[i].cen);
+        }
+        out_box = bounds;
+        if (n == 1) {
+            note_depth(depth);
+            return leaf_code(lo, n);
+        }
+
+        // binned SAH over the three axes
+        float best_cost = FLT_MAX;
+        int best_axis = -1, best_bin = -1;
+        const float parent_area = std::max(bounds.half_area(), 1e-30f);
+        for (int axis = 0; axis < 3; ++axis) {
+            const float cmin = cbounds.lo[axis], cmax = cbounds.hi[axis];
+            if (!(cmax > cmin)) continue;
+            const float k = (float)BINS * (1.0f - 1e-6f) / (cmax - cmin);
+            Box bin_box[BINS];
+            uint32_t bin_count[BINS];
+            for (int b = 0; b < BINS; ++b) { bin_box[b].reset(); bin_count[b] = 0; }
+            for (uint32_t i = lo; i < hi; ++i) {
+                int b = (int)((prims[i].cen[axis] - cmin) * k);
+                b = std::min(std::max(b, 0), BINS - 1);
+                bin_box[b].grow(prims[i].box);
+                bin_count[b]++;
+            }
+            float right_area[BINS];
+            Box acc;
+            acc.reset();
+            for (int b = BINS - 1; b > 0; --b) {
+                acc.grow(bin_box[b]);
+                right_area[b] = acc.half_area();
+            }
+            acc.reset();
+            uint32_t left_n = 0;
+            for (int b = 0; b < BINS - 1; ++b) {
+                acc.grow(bin_box[b]);
+                left_n += bin_count[b];
+                if (left_n == 0 || left_n == n) continue;
+                const float cost = (acc.half_area() * (float)left_n + right_area[b + 1] * (float)(n - left_n)) / parent_area;
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            }
+        }
+
+        const float TRAVERSAL_COST = 1.0f;
+        if (n <= (uint32_t)LEAF_MAX_TRIS && (best_axis < 0 || (float)n <= TRAVERSAL_COST + best_cost)) {
+            note_depth(depth);
+            return leaf_code(lo, n);
+        }
+
+        uint32_t mid;
+        if (best_axis < 0) {
+            mid = lo + n / 2;  // identical centroids: split by position
+        } else {
+            const float cmin = cbounds.lo[best_axis], cmax = cbounds.hi[best_axis];
+            const float k = (float)BINS * (1.0f - 1e-6f) / (cmax - cmin);
+            Prim* first = prims.data() + lo;
+            Prim* last = prims.data() + hi;
+            Prim* m = std::partition(first, last, [&](const Prim& p) {
+                int b = (int)((p.cen[best_axis] - cmin) * k);
+                b = std::min(std::max(b, 0), BINS - 1);
+                return b <= best_bin;
+            });
+            mid = (uint32_t)(m - prims.data());
+            if (mid == lo || mid == hi) mid = lo + n / 2;
+        }
+
+        const uint32_t node = next_node.fetch_add(1);
+        Box lbox, rbox;
+        int32_t lcode, rcode;
+        bool spawned = false;
+        if (n > 200000 && threads_left.fetch_sub(1) > 0) {
+            spawned = true;
+            std::thread t([&]() { lcode = build(lo, mid, lbox, depth + 1); });
+            rcode = build(mid, hi, rbox, depth + 1);
+            t.join();
+            threads_left.fetch_add(1);
+        } else if (n > 200000) {
+            threads_left.fetch_add(1);
+        }
+        if (!spawned) {
+            lcode = build(lo, mid, lbox, depth + 1);
+            rcode = build(mid, hi, rbox, depth + 1);
+        }
+        write_node(node, lcode, lbox, rcode, rbox);
+        return (int32_t)node;
+    }
+
+    void write_node(uint32_t node, int32_t c0, const Box& b0, int32_t c1, const Box& b1) {
+        Quad* q = nodes.data() + (size_t)node * NODE_QUADS;
+        q[0] = Quad{b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]};
+        q[1] = Quad{b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]};
+        q[2] = Quad{b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]};
+        q[3] = Quad{bits_f((uint32_t)c0), bits_f((uint32_t)c1), 0.0f, 0.0f};
+    }
+};
+
+}  // namespace
+
+bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
+    out = FlatScene();
+    const size_t n_surfaces = in.surfaces.size();
+    // scene.rs:183-184 resolves a hit's material through objects[surface index]
+    if (in.objects.size() < n_surfaces) {
+        err = "every surface needs an object at its own index: the reference looks the material of surface s up as "
+              "objects[s] (core/scene.rs:183-184) and would panic on the first hit of surface " +
+              std::to_string(in.objects.size());
+        return false;
+    }
+    for (size_t s = 0; s < in.objects.size(); ++s) {
+        if (in.objects[s].material >= in.materials.size()) { err = "object refers to an unknown material"; return false; }
+        if (in.objects[s].surface >= n_surfaces) { err = "object refers to an unknown surface"; return false; }
+    }
+    for (const MaterialRec& m : in.materials) {
+        if (m.albedo_tex >= (int32_t)in.textures.size() || m.normal_tex >= (int32_t)in.textures.size()) {
+            err = "material refers to an unknown texture";
+            return false;
+        }
+    }
+
+    // ---- camera (core/camera.rs:38-54) ----
+    {
+        const HostCamera& c = in.camera;
+        CameraRec& r = out.camera;
+        const V3 dir = ld3(c.direction), up = ld3(c.up), eye = ld3(c.eye);
+        r.d = 1.0f / std::tan(c.fov / 2.0f);
+        const V3 right = normalize(cross(dir, up));
+        std::memcpy(r.origin, c.eye, 12);
+        std::memcpy(r.direction, c.direction, 12);
+        std::memcpy(r.up, c.up, 12);
+        r.right[0] = right.x; r.right[1] = right.y; r.right[2] = right.z;
+        r.has_dof = c.has_dof;
+        r.aperture = c.aperture;
+        r.focal_length = c.has_dof ? dot(sub(ld3(c.focal_point), eye), dir) : 0.0f;
+    }
+
+    // ---- per-surface bounds (scene.rs:72-79) and per-mesh tie ranks ----
+    std::vector<float> surface_boxes(6 * n_surfaces);
+    out.mesh_tie_rank.resize(n_surfaces);
+    uint64_t total_tris = 0;
+    for (size_t s = 0; s < n_surfaces; ++s) {
+        const HostSurface& sf = in.surfaces[s];
+        float* b = &surface_boxes[6 * s];
+        if (sf.kind == 0) {
+            const HostMesh& m = in.meshes[sf.mesh];
+            // mesh.rs:93-102: AABB::default() grown by every vertex
+            b[0] = b[1] = b[2] = INFINITY;
+            b[3] = b[4] = b[5] = -INFINITY;
+            for (uint32_t v = 0; v < m.n_vertices; ++v)
+                for (int a = 0; a < 3; ++a) {
+                    b[a] = std::fmin(b[a], m.pos[3 * v + a]);
+                    b[3 + a] = std::fmax(b[3 + a], m.pos[3 * v + a]);
+                }
+            const size_t nt = m.idx.size() / 3;
+            total_tris += nt;
+            std::vector<uint32_t>& rank = out.mesh_tie_rank[s];
+            rank.resize(nt);
+            if (m.idx.size() > 4 * 3) {  // SMALL_MESH, mesh.rs:43,112
+                // per-triangle boxes, mesh.rs:193-205: vertex bounds, epsilon_expand(0.001)
+                std::vector<float> boxes(6 * nt);
+                for (size_t t = 0; t < nt; ++t) {
+                    float* tb = &boxes[6 * t];
+                    for (int a = 0; a < 3; ++a) {
+                        const float p0 = m.pos[3 * m.idx[3 * t] + a], p1 = m.pos[3 * m.idx[3 * t + 1] + a],
+                                    p2 = m.pos[3 * m.idx[3 * t + 2] + a];
+                        tb[a] = std::fmin(p0, std::fmin(p1, p2));
+                        tb[3 + a] = std::fmax(p0, std::fmax(p1, p2));
+                    }
+                    for (int a = 0; a < 3; ++a) {  // util/aabb.rs:62-83
+                        const float dim = tb[3 + a] - tb[a];
+                        const float c = (tb[a] + tb[3 + a]) / 2.0f;
+                        if (dim < 0.001f) { tb[a] = c - 0.001f; tb[3 + a] = c + 0.001f; }
+                    }
+                }
+                std::vector<uint32_t> order;
+                reference_leaf_order(boxes, order);
+                for (size_t i = 0; i < nt; ++i) rank[order[i]] = (uint32_t)i;
+            } else {
+                // linear loop, first index wins a tie (mesh.rs:129-135)
+                for (size_t t = 0; t < nt; ++t) rank[t] = (uint32_t)(nt - 1 - t);
+            }
+        } else if (sf.kind == 1) {  // surfaces.rs:36-43
+            for (int a = 0; a < 3; ++a) {
+                b[a] = sf.center[a] - sf.radius_or_height;
+                b[3 + a] = sf.center[a] + sf.radius_or_height;
+            }
+        } else {  // surfaces.rs:107-114
+            b[0] = -INFINITY; b[1] = sf.radius_or_height - 0.0001f; b[2] = -INFINITY;
+            b[3] = INFINITY; b[4] = sf.radius_or_height + 0.0001f; b[5] = INFINITY;
+        }
+    }
+    if (total_tris >= (1u << 28)) { err = "too many triangles (limit 2^28)"; return false; }
+
+    // ---- scene-level in-order sequence -> global rank base of every surface ----
+    std::vector<uint32_t> surface_order;
+    reference_leaf_order(surface_boxes, surface_order);
+    out.surface_rank_base.assign(n_surfaces, 0);
+    {
+        uint32_t base = 0;
+        for (size_t i = 0; i < n_surfaces; ++i) {
+            const uint32_t s = surface_order[i];
+            out.surface_rank_base[s] = base;
+            const HostSurface& sf = in.surfaces[s];
+            base += sf.kind == 0 ? (uint32_t)(in.meshes[sf.mesh].idx.size() / 3) : 1u;
+        }
+    }
+
+    // ---- analytic surfaces ----
+    for (size_t s = 0; s < n_surfaces; ++s) {
+        const HostSurface& sf = in.surfaces[s];
+        if (sf.kind == 0) continue;
+        AnalyticRec a;
+        a.kind = sf.kind == 1 ? 0 : 1;
+        a.cx = sf.center[0]; a.cy = sf.center[1]; a.cz = sf.center[2];
+        a.radius = sf.radius_or_height;
+        a.rank = out.surface_rank_base[s];
+        a.material = in.objects[s].material;
+        a.surface = (uint32_t)s;
+        out.analytics.push_back(a);
+    }
+
+    // ---- triangles ----
+    const uint32_t n_tris = (uint32_t)total_tris;
+    out.n_tris = n_tris;
+    std::vector<Prim> prims(n_tris);
+    struct Src {
+        uint32_t surface, prim;
+    };
+    std::vector<Src> src(n_tris);
+    {
+        uint32_t g = 0;
+        for (size_t s = 0; s < n_surfaces; ++s) {
+            const HostSurface& sf = in.surfaces[s];
+            if (sf.kind != 0) continue;
+            const HostMesh& m = in.meshes[sf.mesh];
+            const size_t nt = m.idx.size() / 3;
+            for (size_t t = 0; t < nt; ++t, ++g) {
+                Prim& p = prims[g];
+                p.box.reset();
+                for (int k = 0; k < 3; ++k) p.box.grow(&m.pos[3 * m.idx[3 * t + k]]);
+                for (int a = 0; a < 3; ++a) p.cen[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
+                p.id = g;
+                src[g] = Src{(uint32_t)s, (uint32_t)t};
+            }
+        }
+    }
+
+    // ---- BVH ----
+    out.nodes.assign((size_t)std::max<uint32_t>(n_tris, 2) * NODE_QUADS, Quad{0, 0, 0, 0});
+    Builder builder(prims, out.nodes);
+    Box empty;
+    empty.reset();
+    if (n_tris == 0) {
+        builder.next_node = 1;
+        builder.write_node(0, Builder::leaf_code(0, 0), empty, Builder::leaf_code(0, 0), empty);
+    } else {
+        builder.threads_left = (int)std::max(1u, std::thread::hardware_concurrency()) - 1;
+        builder.next_node = 1;  // reserve the root
+        // build the root by hand so that it is node 0 even when the whole scene fits one leaf
+        Box root_box;
+        // Temporarily build into a subtree; if it returns an inner node we move it to slot 0.
+        const int32_t code = builder.build(0, n_tris, root_box, 1);
+        if (code < 0) {
+            builder.write_node(0, code, root_box, Builder::leaf_code(0, 0), empty);
+        } else {
+            // copy the subtree root into slot 0 (children indices are absolute, so this is a plain copy)
+            for (int q = 0; q < NODE_QUADS; ++q) out.nodes[q] = out.nodes[(size_t)code * NODE_QUADS + q];
+        }
+    }
+    out.nodes.resize((size_t)builder.next_node.load() * NODE_QUADS);
+    out.bvh_depth = builder.max_depth.load();
+
+    // ---- packed records in BVH leaf order ----
+    out.tri_isect.resize((size_t)n_tris * TRI_ISECT_QUADS);
+    out.tri_shade.resize((size_t)n_tris * TRI_SHADE_QUADS);
+    out.tri_surface.resize(n_tris);
+    out.tri_prim.resize(n_tris);
+    for (uint32_t i = 0; i < n_tris; ++i) {
+        const Src sp = src[prims[i].id];
+        const HostMesh& m = in.meshes[in.surfaces[sp.surface].mesh];
+        const uint32_t i0 = m.idx[3 * sp.prim], i1 = m.idx[3 * sp.prim + 1], i2 = m.idx[3 * sp.prim + 2];
+        const V3 p0 = ld3(&m.pos[3 * i0]), p1 = ld3(&m.pos[3 * i1]), p2 = ld3(&m.pos[3 * i2]);
+        const V3 e1 = sub(p1, p0), e2 = sub(p2, p0);  // mesh.rs:150-151
+        const uint32_t rank = out.surface_rank_base[sp.surface] + out.mesh_tie_rank[sp.surface][sp.prim];
+        Quad* qi = &out.tri_isect[(size_t)i * TRI_ISECT_QUADS];
+        qi[0] = Quad{p0.x, p0.y, p0.z, bits_f(rank)};
+        qi[1] = Quad{e1.x, e1.y, e1.z, 0.0f};
+        qi[2] = Quad{e2.x, e2.y, e2.z, 0.0f};
+        // geometric normal, mesh.rs:80-84
+        const V3 ng = normalize(cross(sub(p2, p1), sub(p0, p1)));
+        const V3 n0 = ld3(&m.nrm[3 * i0]), n1 = ld3(&m.nrm[3 * i1]), n2 = ld3(&m.nrm[3 * i2]);
+        const float* t0 = &m.uv[2 * i0];
+        const float* t1 = &m.uv[2 * i1];
+        const float* t2 = &m.uv[2 * i2];
+        Quad* qs = &out.tri_shade[(size_t)i * TRI_SHADE_QUADS];
+        qs[0] = Quad{n0.x, n0.y, n0.z, t0[0]};
+        qs[1] = Quad{n1.x, n1.y, n1.z, t0[1]};
+        qs[2] = Quad{n2.x, n2.y, n2.z, t1[0]};
+        qs[3] = Quad{ng.x, ng.y, ng.z, t1[1]};
+        qs[4] = Quad{t2[0], t2[1], bits_f(in.objects[sp.surface].material), 0.0f};
+        out.tri_surface[i] = sp.surface;
+        out.tri_prim[i] = sp.prim;
+    }
+    return true;
+}
+
+}  // namespace vr

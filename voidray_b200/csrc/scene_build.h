@@ -1,0 +1,83 @@
+// scene_build.h — host-side scene description and flattening (the `build_acceleration` half of the
+// boundary, core/scene.rs:163-179). Pure host C++; no CUDA types.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "layout.h"
+
+namespace vr {
+
+struct Quad {
+    float x, y, z, w;
+};
+
+struct HostMesh {
+    std::vector<float> pos, uv, nrm;  // 3n, 2n, 3n
+    std::vector<uint32_t> idx;        // 3 per triangle (trailing partial chunk already dropped)
+    uint32_t n_vertices = 0;
+};
+
+struct HostSurface {
+    int kind = 0;  // 0 mesh, 1 sphere, 2 ground plane
+    uint32_t mesh = 0;
+    float center[3] = {0, 0, 0};
+    float radius_or_height = 0;
+};
+
+struct HostTexture {
+    std::vector<float> rgb;  // 3*w*h
+    uint32_t w = 0, h = 0;
+    int32_t sample_type = 0;
+};
+
+struct HostObject {
+    uint32_t surface, material;
+};
+
+struct HostCamera {
+    float eye[3], direction[3], up[3];
+    float fov;
+    int32_t has_dof;
+    float aperture;
+    float focal_point[3];
+};
+
+struct HostScene {
+    std::vector<HostMesh> meshes;
+    std::vector<HostSurface> surfaces;
+    std::vector<HostTexture> textures;
+    std::vector<MaterialRec> materials;
+    std::vector<HostObject> objects;
+    HostCamera camera;
+    int32_t env_kind = 0;
+    float env_color[3] = {0, 0, 0};
+    HostTexture env_image;
+};
+
+struct FlatScene {
+    std::vector<Quad> nodes;      // NODE_QUADS per node; node 0 is the root
+    std::vector<Quad> tri_isect;  // TRI_ISECT_QUADS per triangle, BVH leaf order
+    std::vector<Quad> tri_shade;  // TRI_SHADE_QUADS per triangle
+    std::vector<uint32_t> tri_surface, tri_prim;
+    std::vector<AnalyticRec> analytics;
+    std::vector<std::vector<uint32_t>> mesh_tie_rank;  // per surface (empty for analytic): rank inside the mesh
+    std::vector<uint32_t> surface_rank_base;           // per surface: first global rank
+    CameraRec camera;
+    uint32_t n_tris = 0;
+    uint32_t bvh_depth = 0;
+};
+
+// In-order leaf sequence of the reference's median-split tree (core/bvh.rs:48-130) over items with
+// the given boxes (6 floats each: min xyz, max xyz). order[i] = item at in-order position i.
+void reference_leaf_order(const std::vector<float>& boxes6, std::vector<uint32_t>& order);
+
+// Camera::look_at, core/camera.rs:26-36
+void camera_look_at(const float eye[3], const float center[3], const float up_in[3], float direction[3],
+                    float up[3]);
+
+bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err);
+
+}  // namespace vr
