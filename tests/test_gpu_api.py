@@ -1,0 +1,149 @@
+"""-m gpu: behaviour of the C ABI / host mirror: call-order errors, accumulation semantics, batching
+invariance, cancel, the progressive driver, sample-range sharding on one device."""
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from voidray_b200 import _lib, scenes
+from voidray_b200.distributed import shard_samples
+from voidray_b200.render import (Context, PostProcessingData, PostProcessingPass, RenderAction, Renderer,
+                                 RenderTarget, iterative_render)
+from voidray_b200.scene import Environments, Materials, RenderSettings, Scene, Settings, Surfaces, Tonemap
+
+from test_oracle_shading import sphere_scene
+from util import F32
+
+pytestmark = pytest.mark.gpu
+
+
+def test_errors_are_statuses_not_crashes(ctx):
+    lib = _lib.load()
+    import ctypes as C
+    # surfaces without objects: the reference would panic at the first hit (scene.rs:183-184)
+    s = Scene.empty()
+    s.add_analytic_surface(Surfaces.sphere((0, 0, 0), 1))
+    with pytest.raises(_lib.VoidrayError) as e:
+        s.build_acceleration(ctx)
+    assert e.value.status == _lib.VR_ERR_INVALID and "objects[s]" in str(e.value)
+    # render before commit, bad handles, bad settings
+    h = C.c_void_p()
+    _lib.check(lib.vr_scene_create(ctx.handle, C.byref(h)))
+    out = C.c_uint32()
+    assert lib.vr_scene_add_object(h, 3, 0, C.byref(out)) == _lib.VR_ERR_INVALID
+    cs = _lib.RenderSettingsC(4, 4, 3.0, 0, 0, 0, 1, 0, 0)
+    r = C.c_void_p()
+    assert lib.vr_render_begin(h, 8, 8, C.byref(cs), C.byref(r)) == _lib.VR_ERR_INVALID
+    assert b"commit" in lib.vr_last_error()
+    _lib.check(lib.vr_scene_commit(h))
+    assert lib.vr_render_begin(h, 0, 8, C.byref(cs), C.byref(r)) == _lib.VR_ERR_INVALID
+    cs.total_samples = 0
+    assert lib.vr_render_begin(h, 8, 8, C.byref(cs), C.byref(r)) == _lib.VR_ERR_INVALID
+    idx = np.array([0, 1, 5], np.uint32)
+    pos = np.zeros((3, 3), F32)
+    assert lib.vr_scene_add_mesh(h, _lib.fptr(pos), None, None, 3, _lib.uptr(idx), 3, C.byref(out)) == _lib.VR_ERR_INVALID
+    lib.vr_scene_destroy(h)
+    with pytest.raises(_lib.VoidrayError):
+        Context(99)
+
+
+def test_accumulation_semantics_match_iterative_render(oracle, ctx):
+    # two calls of 3 and 5 samples against total_samples = 8: alpha counts calls, values are sums / total
+    scene, st, _ = scenes.config1_mushroom(96, 72, 8)
+    rs = st.render
+    osc = oracle.OracleScene(scene)
+    ref, _ = osc.render(96, 72, rs, 3)
+    ref, _ = osc.render(96, 72, rs, 5, accum=ref, sample_offset=3)
+    accel = scene.build_acceleration(ctx)
+    tgt = RenderTarget(accel, (96, 72), rs)
+    iterative_render(tgt, accel, rs, 3)
+    iterative_render(tgt, accel, rs, 5)
+    img = tgt.read()
+    assert np.all(img[..., 3] == 2.0)
+    assert np.abs(img - ref).max() <= 2e-4
+    st_ = tgt.stats()
+    assert (st_.samples_done, st_.total_samples, st_.camera_samples) == (8, 8, 96 * 72 * 8)
+    assert st_.kernel_launches > 0 and st_.trace_launches == 16 and st_.device_ms > 0 and st_.trace_ms > 0
+    tgt.clear()
+    assert not tgt.read().any() and tgt.stats().samples_done == 0
+
+
+def test_wavefront_batching_is_invisible(ctx):
+    # the number of paths in flight changes how a call is cut into wavefront batches, never the result
+    scene, st, _ = scenes.config5_combined(128, 72, 12)
+    accel = scene.build_acceleration(ctx)
+    imgs = []
+    for cap in (128 * 72, 128 * 72 * 5, 0):
+        rs = RenderSettings(total_samples=12, max_bounces=8, max_paths_in_flight=cap)
+        tgt = RenderTarget(accel, (128, 72), rs)
+        tgt.accumulate(12)
+        imgs.append(tgt.read())
+    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    # and the render is deterministic run to run
+    tgt = RenderTarget(accel, (128, 72), RenderSettings(total_samples=12, max_bounces=8))
+    tgt.accumulate(12)
+    assert np.array_equal(tgt.read(), imgs[0])
+
+
+def test_sample_range_sharding_on_one_device(ctx):
+    # N renders owning disjoint sample ranges, summed, equal one render of all samples (up to f32 summation order)
+    w, h, spp = 128, 72, 16
+    scene, st, _ = scenes.config1_mushroom(w, h, spp)
+    accel = scene.build_acceleration(ctx)
+    full = RenderTarget(accel, (w, h), RenderSettings(total_samples=spp, max_bounces=8))
+    full.accumulate(spp)
+    want = full.read()
+    for world in (2, 4):
+        total = np.zeros_like(want)
+        for rank in range(world):
+            off, cnt = shard_samples(spp, world, rank)
+            t = RenderTarget(accel, (w, h), RenderSettings(total_samples=spp, max_bounces=8, sample_offset=off))
+            t.accumulate(cnt)
+            total += t.read()
+        assert np.abs(total[..., :3] - want[..., :3]).max() <= 2e-6
+        assert np.all(total[..., 3] == world)
+    # the accumulation buffer is reachable as a torch tensor for NCCL reduces
+    import torch
+    ten = full.as_torch()
+    assert ten.is_cuda and ten.numel() == w * h * 4
+    assert np.array_equal(ten.cpu().numpy().reshape(h, w, 4), want)
+
+
+def test_cancel_leaves_whole_samples(ctx):
+    scene, st, _ = scenes.config5_combined(640, 360, 4096)
+    rs = RenderSettings(total_samples=4096, max_bounces=8, max_paths_in_flight=640 * 360)
+    accel = scene.build_acceleration(ctx)
+    tgt = RenderTarget(accel, (640, 360), rs)
+    timer = threading.Timer(0.05, tgt.cancel)
+    timer.start()
+    with pytest.raises(_lib.RenderCancelled):
+        tgt.accumulate(4096)
+    timer.join()
+    done = tgt.stats().samples_done
+    assert 0 < done < 4096
+    img = tgt.read()
+    assert np.all(img[..., 3] == 1.0) and np.all(np.isfinite(img))
+    # what is in the buffer is exactly `done` samples
+    ref = RenderTarget(accel, (640, 360), rs)
+    ref.accumulate(done)
+    assert np.array_equal(ref.read(), img)
+    tgt.accumulate(1)     # usable again after a cancel
+    assert tgt.stats().samples_done == done + 1
+
+
+def test_renderer_one_shot_driver(ctx):
+    # RenderThread::one_shot (renderer.rs:35-125): 1-spp probe, batches, stats, post-process scale = total/done
+    scene, st, dims = scenes.config1_mushroom(160, 120, 40)
+    st.render.update_frequency = 0.005
+    r = Renderer(scene, st, dims, ctx)
+    with pytest.raises(RuntimeError):
+        r.execute(RenderAction.Cancel)          # nothing running: the reference panics (renderer.rs:229-231)
+    r.execute(RenderAction.Render)
+    r.join()
+    assert r.samples() == (40, 40) and not r.currently_rendering()
+    assert r.elapsed_time() > 0 and r.remaining_time() is None
+    img = r.post_process()
+    assert img.shape == (120, 160, 4) and np.all(np.isfinite(img)) and img[..., :3].max() > 0.1
+    want = PostProcessingPass().render(r.target, PostProcessingData(1.0, 1.0, 1.0, int(Tonemap.ACES)))
+    assert np.array_equal(img, want)

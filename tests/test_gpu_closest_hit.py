@@ -1,0 +1,150 @@
+"""-m gpu: closest-hit parity of the CUDA path (through the C ABI) with the oracle.
+Gate (BASELINE.json north_star): primary-ray hit triangle ids bit-exact, distances within 1e-5
+relative. The implementation evaluates Möller–Trumbore in the reference's operation order, so the
+distances are asserted bit-equal as well."""
+import numpy as np
+import pytest
+
+from voidray_b200 import scenes
+from voidray_b200.render import RenderTarget
+from voidray_b200.scene import (Camera, Environments, Materials, MeshData, PixelMapping, RenderSettings, Scene,
+                                Surfaces)
+
+from util import F32, MISS, obj_scene, random_rays, scene_bounds, single_mesh_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def check_primary(oracle, ctx, scene, rs, w, h, samples=(0,)):
+    osc = oracle.OracleScene(scene)
+    accel = scene.build_acceleration(ctx)
+    tgt = RenderTarget(accel, (w, h), rs)
+    for smp in samples:
+        _, _, s_ref, p_ref, t_ref, _ = osc.trace_primary(w, h, rs, smp)
+        s, p, t = tgt.trace_primary(smp)
+        assert np.array_equal(s, s_ref), f"surface ids differ at {int((s != s_ref).sum())} pixels"
+        assert np.array_equal(p, p_ref), f"triangle ids differ at {int((p != p_ref).sum())} pixels"
+        hit = s_ref != MISS
+        assert np.all(np.abs(t[hit] - t_ref[hit]) <= 1e-5 * t_ref[hit])
+        assert np.array_equal(t, t_ref)
+    return float((s_ref != MISS).mean())
+
+
+def test_primary_config1_full_size(oracle, ctx):
+    # configs[0] at its full 800x600, with the depth-of-field camera (lens + jitter drawn from the stream)
+    scene, st, (w, h) = scenes.config1_mushroom()
+    frac = check_primary(oracle, ctx, scene, st.render, w, h, samples=(0, 63))
+    assert 0.2 < frac < 0.4
+
+
+def test_primary_config1_square_reference_mapping(oracle, ctx):
+    # the reference's own pixel mapping (iterative.rs:26,33) on a square 600x600 target
+    scene, st, _ = scenes.config1_mushroom(600, 600, dof=False)
+    st.render.pixel_mapping = PixelMapping.Reference
+    check_primary(oracle, ctx, scene, st.render, 600, 600)
+
+
+def test_primary_non_square_reference_mapping(oracle, ctx):
+    # W > H with the reference mapping: sheared rows and u32 wrap-around, reproduced as is
+    scene, st, _ = scenes.config1_mushroom(96, 64, dof=False)
+    st.render.pixel_mapping = PixelMapping.Reference
+    check_primary(oracle, ctx, scene, st.render, 96, 64)
+    check_primary(oracle, ctx, scene, st.render, 64, 96)
+
+
+def test_primary_two_surfaces_and_materials_scene(oracle, ctx):
+    scene, st, _ = scenes.config5_combined(480, 270)
+    assert check_primary(oracle, ctx, scene, st.render, 480, 270) > 0.7
+    scene, st, _ = scenes.config3_materials(480, 270)
+    check_primary(oracle, ctx, scene, st.render, 480, 270)
+    scene, st, _ = scenes.config2_mossy_ground(480, 270)
+    check_primary(oracle, ctx, scene, st.render, 480, 270)
+
+
+def test_primary_analytic_and_small_meshes(oracle, ctx):
+    for fn in (scenes.example_cornell, scenes.example_spheres, scenes.example_material):
+        scene, st, _ = fn()
+        check_primary(oracle, ctx, scene, RenderSettings(total_samples=4, max_bounces=4), 200, 200, samples=(0, 2))
+
+
+@pytest.mark.parametrize("name,n", [("cube.obj", 200000), ("mushroom.obj", 200000), ("mossy_ground.obj", 100000),
+                                    ("material_testing_stand.obj", 100000), ("fancy_monkey.obj", 100000)])
+def test_incoherent_rays(oracle, ctx, name, n):
+    # secondary-ray-like workload: random origins and directions around each mesh
+    scene = obj_scene(name)
+    osc = oracle.OracleScene(scene)
+    accel = scene.build_acceleration(ctx)
+    o, d = random_rays(n, *scene_bounds(scene), seed=21)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d)
+    s, p, t = accel.trace_rays(o, d)
+    assert np.array_equal(s, s_ref) and np.array_equal(p, p_ref) and np.array_equal(t, t_ref)
+    assert 0.1 < (s_ref != MISS).mean()
+    # rays that start on a surface (like every scattered ray) must not re-hit it below t = 1e-5
+    hit = s_ref != MISS
+    dn = d / np.linalg.norm(d, axis=1, keepdims=True)
+    o2 = (o[hit] + dn[hit] * t_ref[hit, None]).astype(F32)
+    d2 = np.random.default_rng(5).normal(size=o2.shape).astype(F32)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o2, d2)
+    s, p, t = accel.trace_rays(o2, d2)
+    assert np.array_equal(s, s_ref) and np.array_equal(p, p_ref) and np.array_equal(t, t_ref)
+
+
+def test_tie_rule_matches_reference_order(oracle, ctx):
+    # coincident triangles: the reference returns the right-most leaf of its median-split tree
+    # (bvh.rs:171); small meshes return the first index (mesh.rs:131); between surfaces the scene tree decides
+    base = np.array([[-1, -1, 2], [1, -1, 2], [0, 1, 2]], F32)
+    vs = [base] + [base + np.array([3.0 * k, 0, 0], F32) for k in range(1, 5)] + [base]
+    big = MeshData.from_buffers(np.concatenate(vs), np.arange(18))
+    small = MeshData.from_buffers(np.concatenate([base, base]), [0, 1, 2, 3, 4, 5])
+    o = np.zeros((1, 3), F32)
+    d = np.array([[0, 0, 1]], F32)
+    for mesh in (big, small):
+        scene = single_mesh_scene(mesh)
+        osc = oracle.OracleScene(scene)
+        accel = scene.build_acceleration(ctx)
+        assert np.array_equal(accel.tie_ranks(0), osc.global_tie_rank(0))
+        s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d)
+        s, p, t = accel.trace_rays(o, d)
+        assert (s[0], p[0], t[0]) == (s_ref[0], p_ref[0], t_ref[0])
+    # two surfaces with coincident geometry + a sphere tangent at the same t
+    scene = Scene.empty()
+    m = scene.add_material(Materials.lambertian((0.5, 0.5, 0.5)))
+    for mesh in (small, big, small):
+        scene.add_object(m, scene.add_mesh(mesh))
+    scene.add_object(m, scene.add_analytic_surface(Surfaces.sphere((0, 0, 3), 1.0)))
+    osc = oracle.OracleScene(scene)
+    accel = scene.build_acceleration(ctx)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d)
+    s, p, t = accel.trace_rays(o, d)
+    assert (s[0], p[0], t[0]) == (s_ref[0], p_ref[0], t_ref[0])
+    for sf in range(3):
+        assert np.array_equal(accel.tie_ranks(sf), osc.global_tie_rank(sf))
+
+
+def test_tie_ranks_on_real_meshes(oracle, ctx):
+    for name in ("mushroom.obj", "mossy_ground.obj"):
+        scene = obj_scene(name)
+        assert np.array_equal(scene.build_acceleration(ctx).tie_ranks(0), oracle.OracleScene(scene).global_tie_rank(0))
+
+
+def test_degenerate_inputs(oracle, ctx):
+    # empty scene, zero-area triangles, axis-parallel rays, rays inside flat boxes
+    empty = Scene.empty()
+    accel = empty.build_acceleration(ctx)
+    s, p, t = accel.trace_rays(np.zeros((4, 3), F32), np.eye(3, dtype=F32)[[0, 1, 2, 0]])
+    assert np.all(s == MISS) and np.all(np.isinf(t))
+    quad = Surfaces.quad((0, 0, 0), (0, 0, 1), (1, 0, 1), (1, 0, 0))
+    degenerate = MeshData.from_buffers(np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1, 0], [1, 1, 0], [0, 2, 0]], F32),
+                                       [0, 1, 2, 3, 4, 5])
+    scene = Scene.empty()
+    m = scene.add_material(Materials.lambertian((0.5, 0.5, 0.5)))
+    scene.add_object(m, scene.add_mesh(quad))
+    scene.add_object(m, scene.add_mesh(degenerate))
+    osc = oracle.OracleScene(scene)
+    accel = scene.build_acceleration(ctx)
+    o = np.array([[0.25, 1, 0.5], [0.25, 1, 0.5], [0.5, 0.0, -1], [0.3, 0.3, 1], [0.5, 1, 0.5]], F32)
+    d = np.array([[0, -1, 0], [0, 1, 0], [0, 0, 1], [0, 0, -1], [1, 0, 0]], F32)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d)
+    s, p, t = accel.trace_rays(o, d)
+    assert np.array_equal(s, s_ref) and np.array_equal(p, p_ref) and np.array_equal(t, t_ref)
+    assert s_ref[0] == 0 and t_ref[0] == F32(1.0)

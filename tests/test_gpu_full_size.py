@@ -1,0 +1,70 @@
+"""-m gpu: size-independent properties at BASELINE.json's full resolutions (the oracle would take
+minutes there): determinism, additivity of accumulation, sharding invariance, alpha = call count,
+finiteness, clamp bound, and the closed-form furnace value."""
+import numpy as np
+import pytest
+
+from voidray_b200 import scenes
+from voidray_b200.render import RenderTarget
+from voidray_b200.scene import Environments, Materials, RenderSettings
+
+from util import F32
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_full_resolution_properties(ctx):
+    scene, st, (w, h) = scenes.config2_mossy_ground()        # 1920x1080, textured + normal-mapped, indoor HDRI
+    assert (w, h) == (1920, 1080)
+    accel = scene.build_acceleration(ctx)
+    rs = RenderSettings(total_samples=8, max_bounces=8)
+    a = RenderTarget(accel, (w, h), rs)
+    a.accumulate(8)
+    img = a.read()
+    assert np.all(np.isfinite(img)) and np.all(img[..., 3] == 1.0)
+    # firefly clamp: a pixel mean is bounded by max(clamp, peak environment radiance) = 15 (primary misses are unclamped)
+    assert img[..., :3].max() <= 15.0 + 1e-3 and img[..., :3].min() >= 0.0
+    b = RenderTarget(accel, (w, h), rs)
+    b.accumulate(8)
+    assert np.array_equal(img, b.read())                      # deterministic
+    # additivity: 3 + 5 samples == the same sample set
+    c = RenderTarget(accel, (w, h), rs)
+    c.accumulate(3)
+    c.accumulate(5)
+    img_c = c.read()
+    assert np.all(img_c[..., 3] == 2.0)
+    assert np.abs(img_c[..., :3] - img[..., :3]).max() <= 4e-6
+    st_ = a.stats()
+    assert st_.camera_samples == w * h * 8 and w * h * 8 <= st_.ray_segments <= w * h * 8 * 8
+
+
+def test_config5_4k_sharding_invariance(ctx):
+    scene, st, (w, h) = scenes.config5_combined()             # 3840x2160
+    assert (w, h) == (3840, 2160)
+    accel = scene.build_acceleration(ctx)
+    one = RenderTarget(accel, (w, h), RenderSettings(total_samples=4, max_bounces=8))
+    one.accumulate(4)
+    want = one.read()
+    del one
+    total = np.zeros_like(want)
+    for rank in range(2):
+        t = RenderTarget(accel, (w, h), RenderSettings(total_samples=4, max_bounces=8, sample_offset=2 * rank))
+        t.accumulate(2)
+        total += t.read()
+        del t
+    assert np.abs(total[..., :3] - want[..., :3]).max() <= 2e-6
+    assert np.all(np.isfinite(want)) and want[..., :3].mean() > 0.01
+
+
+def test_furnace_at_full_hd(ctx):
+    # closed-form: convex-free check — with max_bounces = 1 every hit pixel is black and every miss is E,
+    # with a white dielectric the whole 1920x1080 image equals E bit for bit
+    scene, st, (w, h) = scenes.config1_mushroom(1920, 1080, dof=False)
+    scene.environment = Environments.uniform((0.25, 0.5, 0.75))
+    scene.materials[0] = Materials.dielectric(1.5)
+    tgt = RenderTarget(scene.build_acceleration(ctx), (w, h), RenderSettings(total_samples=2, max_bounces=64))
+    tgt.accumulate(2)
+    img = tgt.read()
+    bad = np.any(img[..., :3] != np.array([0.25, 0.5, 0.75], F32), axis=2)
+    # only paths still inside the glass after 64 bounces can differ
+    assert bad.mean() < 1e-3

@@ -141,13 +141,13 @@ def synth_hdri(name: str, width: int = 2048, height: int = 1024) -> np.ndarray:
     return out
 
 
-def transform_mesh(mesh, rotate_y: float = 0.0, translate=(0.0, 0.0, 0.0)):
+def transform_mesh(mesh, rotate_y: float = 0.0, translate=(0.0, 0.0, 0.0), scale: float = 1.0):
     """Baked world-space copy (the reference has no instancing or transforms, core/traits.rs:59-63)."""
     from .scene import MeshData
 
     c, s = np.cos(rotate_y), np.sin(rotate_y)
     R = np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]], dtype=np.float64)
-    pos = (mesh.positions.astype(np.float64) @ R.T + np.asarray(translate, dtype=np.float64)).astype(F32)
+    pos = (mesh.positions.astype(np.float64) @ R.T * scale + np.asarray(translate, dtype=np.float64)).astype(F32)
     nrm = (mesh.normals.astype(np.float64) @ R.T).astype(F32)
     return MeshData(np.ascontiguousarray(pos), mesh.uvs, np.ascontiguousarray(nrm), mesh.indices)
 

@@ -95,11 +95,9 @@ def config3_materials(width: int = 1920, height: int = 1080, spp: int = 1024, ma
         Materials.lambertian_texture(wood_albedo, wood_normal),
     ]
     monkey = _mesh("fancy_monkey.obj")
-    offsets = [(-1.2, 0.9, 0.0), (-0.4, 0.9, 0.6), (0.4, 0.9, 0.6), (1.2, 0.9, 0.0)]
+    offsets = [(-1.0, 0.3, 0.4), (-0.55, 0.3, 1.0), (0.6, 0.3, 1.0), (1.05, 0.3, 0.4)]
     for mat, off in zip(mats, offsets):
-        m = transform_mesh(monkey, 0.0, off)
-        m = type(m)((m.positions * F32(0.35) + np.array(off, F32) * F32(0.65)).astype(F32), m.uvs, m.normals, m.indices)
-        s = scene.add_mesh(m)
+        s = scene.add_mesh(transform_mesh(monkey, 0.0, off, scale=0.2))
         scene.add_object(scene.add_material(mat), s)
     scene.camera = Camera.look_at((0.5, 0.6, 5.0), (0.0, 0.5, 0.0), (0.0, 1.0, 0.0), float(F32(np.pi) / F32(6.0)))
     scene.environment = Environments.hdri(synth_hdri("indoor"))
