@@ -117,6 +117,20 @@ int32_t vr_scene_clear_environment(vr_scene* scene);
  * again after any edit. */
 int32_t vr_scene_commit(vr_scene* scene);
 
+/* What the last vr_scene_commit built and uploaded (println! on load in the reference, core/mesh.rs:67). */
+typedef struct vr_scene_info {
+    uint32_t n_triangles;
+    uint32_t n_bvh_nodes;
+    uint32_t bvh_depth;
+    uint32_t n_analytic_surfaces;
+    uint32_t n_textures;
+    uint32_t reserved;
+    uint64_t h2d_bytes;   /* bytes copied host -> device by the commit (geometry, BVH, textures, environment) */
+    double flatten_ms;    /* host: tie ranks + BVH build + packing */
+    double upload_ms;     /* host -> device copies */
+} vr_scene_info;
+int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out);
+
 /* ---- render: render/iterative.rs:11-55, core/tracer.rs, core/settings.rs:15-33 ------------- */
 typedef struct vr_render_settings {
     uint32_t total_samples; /* RenderSettings.total_samples: accumulated values are divided by this */

@@ -38,6 +38,12 @@ class StatsC(C.Structure):
                 ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class SceneInfoC(C.Structure):
+    _fields_ = [("n_triangles", C.c_uint32), ("n_bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32),
+                ("n_analytic_surfaces", C.c_uint32), ("n_textures", C.c_uint32), ("reserved", C.c_uint32),
+                ("h2d_bytes", C.c_uint64), ("flatten_ms", C.c_double), ("upload_ms", C.c_double)]
+
+
 _P = C.c_void_p
 _FP = C.POINTER(C.c_float)
 _UP = C.POINTER(C.c_uint32)
@@ -61,6 +67,7 @@ SIGNATURES = {
     "vr_scene_set_environment_hdri_rgb32f": [_P, _FP, _U32, _U32],
     "vr_scene_clear_environment": [_P],
     "vr_scene_commit": [_P],
+    "vr_scene_get_info": [_P, C.POINTER(SceneInfoC)],
     "vr_render_begin": [_P, _U32, _U32, C.POINTER(RenderSettingsC), C.POINTER(_P)],
     "vr_render_end": [_P],
     "vr_render_clear": [_P],

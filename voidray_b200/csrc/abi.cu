@@ -68,6 +68,8 @@ struct vr_scene {
     std::vector<TextureRec> dev_textures;
     bool committed = false;
     uint64_t commit_serial = 0;
+    uint64_t h2d_bytes = 0;
+    double flatten_ms = 0.0, upload_ms = 0.0;
 };
 
 struct vr_render {
@@ -150,6 +152,7 @@ int32_t upload_texture(vr_scene* scene, const HostTexture& t, TextureRec* rec) {
     VR_CUDA(scene->dev_mem.alloc(&d, 16 * n));
     VR_CUDA(cudaMemcpyAsync(d, rgba.data(), 16 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));  // rgba goes out of scope
+    scene->h2d_bytes += 16 * n;
     rec->texels = d;
     rec->width = t.w;
     rec->height = t.h;
@@ -164,6 +167,7 @@ int32_t upload_vector(vr_scene* scene, const std::vector<T>& v, const void** out
     VR_CUDA(scene->dev_mem.alloc(&d, v.size() * sizeof(T)));
     if (!v.empty())
         VR_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, scene->ctx->stream));
+    scene->h2d_bytes += v.size() * sizeof(T);
     *out = d;
     return VR_OK;
 }
@@ -410,7 +414,10 @@ int32_t vr_scene_commit(vr_scene* scene) {
     if (check_scene(scene)) return VR_ERR_INVALID;
     VR_CUDA(cudaSetDevice(scene->ctx->device));
     std::string err;
+    const auto t_begin = std::chrono::steady_clock::now();
     if (!flatten_scene(scene->host, scene->flat, err)) return fail(VR_ERR_INVALID, err);
+    const auto t_flat = std::chrono::steady_clock::now();
+    scene->h2d_bytes = 0;
     if (scene->flat.bvh_depth > 70) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
     scene->dev_mem.release();
@@ -442,8 +449,27 @@ int32_t vr_scene_commit(vr_scene* scene) {
     }
     d.camera = f.camera;
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
+    const auto t_up = std::chrono::steady_clock::now();
+    scene->flatten_ms = std::chrono::duration<double, std::milli>(t_flat - t_begin).count();
+    scene->upload_ms = std::chrono::duration<double, std::milli>(t_up - t_flat).count();
     scene->committed = true;
     scene->commit_serial++;
+    return VR_OK;
+}
+
+int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!out) return fail(VR_ERR_INVALID, "null argument");
+    if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
+    out->n_triangles = scene->flat.n_tris;
+    out->n_bvh_nodes = (uint32_t)(scene->flat.nodes.size() / NODE_QUADS);
+    out->bvh_depth = scene->flat.bvh_depth;
+    out->n_analytic_surfaces = (uint32_t)scene->flat.analytics.size();
+    out->n_textures = (uint32_t)scene->host.textures.size();
+    out->reserved = 0;
+    out->h2d_bytes = scene->h2d_bytes;
+    out->flatten_ms = scene->flatten_ms;
+    out->upload_ms = scene->upload_ms;
     return VR_OK;
 }
 

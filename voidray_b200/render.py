@@ -117,6 +117,11 @@ class SceneAcceleration:
         check(self._lib.vr_scene_commit(self.handle))
         self.commit_seconds = time.perf_counter() - t0
 
+    def info(self) -> dict:
+        i = _lib.SceneInfoC()
+        check(self._lib.vr_scene_get_info(self.handle, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in _lib.SceneInfoC._fields_ if k != "reserved"}
+
     # ---- gates ----
     def trace_rays(self, origins: np.ndarray, directions: np.ndarray):
         o = np.ascontiguousarray(origins, dtype=F32).reshape(-1, 3)
