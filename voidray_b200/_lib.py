@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvoidray_cuda.so")
+LIB_PATH = os.environ.get("VOIDRAY_CUDA_LIB") or os.path.join(_HERE, "libvoidray_cuda.so")
 
 VR_OK, VR_ERR_INVALID, VR_ERR_CUDA, VR_ERR_OOM, VR_ERR_CANCELLED = 0, -1, -2, -3, -4
 

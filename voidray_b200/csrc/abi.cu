@@ -116,7 +116,7 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
     vr_scene* sc = r->scene;
     vr_context* ctx = sc->ctx;
     const FrameParams fp = frame_params(r);
-    cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * (fp.max_bounces + 1), ctx->stream);
+    cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * 2 * (fp.max_bounces + 2), ctx->stream);  // counts + cursors
     launch_raygen(sc->dev, r->wf, src, fp, n_paths, ctx->dims, ctx->stream);
     r->kernel_launches += 1;
     for (uint32_t depth = 0; depth < fp.max_bounces; ++depth) {
@@ -518,11 +518,12 @@ int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const 
     A((void**)&wf.att, 16 * cap * levels);
     A((void**)&wf.queue[0], 4 * cap);
     A((void**)&wf.queue[1], 4 * cap);
-    A((void**)&wf.counts, 4 * (settings->max_bounces + 2));
+    A((void**)&wf.counts, 4 * 2 * (settings->max_bounces + 2));
     A((void**)&wf.segments, 8);
     A((void**)&r->dbg_surface, 4ull * r->n_pixels);
     A((void**)&r->dbg_prim, 4ull * r->n_pixels);
     A((void**)&r->dbg_t, 4ull * r->n_pixels);
+    wf.cursors = wf.counts ? wf.counts + (settings->max_bounces + 2) : nullptr;
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_end);
     cudaStream_t st = scene->ctx->stream;
@@ -591,14 +592,16 @@ int32_t vr_render_accumulate(vr_render* r, uint32_t samples) {
         src.pixel = nullptr;
         src.sample = nullptr;
         src.n_pixels = r->n_pixels;
+        src.width = r->width;
+        src.height = r->height;
         src.sample_base = r->settings.sample_offset + r->samples_done + done;
         run_wavefront(r, src, nb * r->n_pixels, true, &event_cursor);
         done += nb;
-        launch_accumulate(r->wf, r->partial, r->accum, r->n_pixels, nb, done == samples ? 1 : 0, inv_total, ctx->stream);
+        launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, nb, done == samples ? 1 : 0, inv_total, ctx->stream);
         r->kernel_launches += 1;
     }
     if (cancelled && done > 0) {
-        launch_accumulate(r->wf, r->partial, r->accum, r->n_pixels, 0, 1, inv_total, ctx->stream);
+        launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, 0, 1, inv_total, ctx->stream);
         r->kernel_launches += 1;
     }
     VR_CUDA(cudaEventRecord(r->ev_end, ctx->stream));
@@ -690,11 +693,13 @@ int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface,
     src.pixel = nullptr;
     src.sample = nullptr;
     src.n_pixels = r->n_pixels;
+    src.width = r->width;
+    src.height = r->height;
     src.sample_base = sample;
-    VR_CUDA(cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * (fp.max_bounces + 1), ctx->stream));
+    VR_CUDA(cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * 2 * (fp.max_bounces + 2), ctx->stream));
     launch_raygen(r->scene->dev, r->wf, src, fp, r->n_pixels, ctx->dims, ctx->stream);
     launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, ctx->dims, ctx->stream);
-    launch_primary_ids(r->scene->dev, r->wf, r->n_pixels, r->dbg_surface, r->dbg_prim, r->dbg_t, ctx->stream);
+    launch_primary_ids(r->scene->dev, r->wf, r->width, r->height, r->dbg_surface, r->dbg_prim, r->dbg_t, ctx->stream);
     VR_CUDA(cudaMemcpyAsync(surface, r->dbg_surface, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
     VR_CUDA(cudaMemcpyAsync(prim, r->dbg_prim, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
     VR_CUDA(cudaMemcpyAsync(t, r->dbg_t, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
@@ -755,6 +760,8 @@ int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel
         src.pixel = d_px;
         src.sample = d_sm;
         src.n_pixels = r->n_pixels;
+        src.width = r->width;
+        src.height = r->height;
         src.sample_base = 0;
         size_t cursor = 0;
         run_wavefront(r, src, m, false, &cursor);

@@ -39,6 +39,20 @@ __device__ __forceinline__ float angle_between(f3 a, f3 b) { return atan2f(magni
 __device__ __forceinline__ f3 xyz(float4 q) { return f3{q.x, q.y, q.z}; }
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// 256-bit read-only load (PTX ISA 8.8, sm_100+: SASS LDG.E.ENL2.256.CONSTANT). One instruction per
+// 32 bytes halves the L1 tag traffic of the scattered node / triangle fetches; `p` must be 32-byte aligned.
+struct __align__(32) float8 {
+    float4 lo, hi;
+};
+__device__ __forceinline__ float8 ldg8(const float4* p) {
+    float8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
+                   "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+
 #define VR_PI_F 3.14159265358979323846f
 
 // compiler-rt __powisf2 (what f32::powi lowers to), specialised for exponent 5: a * (a^2)^2

@@ -10,9 +10,18 @@
 
 namespace vr {
 
-static constexpr int TRACE_THREADS = 128;
+#ifndef VR_TRACE_THREADS
+#define VR_TRACE_THREADS 128
+#endif
+#ifndef VR_TRACE_MIN_BLOCKS
+#define VR_TRACE_MIN_BLOCKS 1
+#endif
+#ifndef VR_REFILL_THRESHOLD
+#define VR_REFILL_THRESHOLD 16
+#endif
+static constexpr int TRACE_THREADS = VR_TRACE_THREADS;
 static constexpr int SHADE_THREADS = 128;
-static constexpr int SMEM_STACK = 12;   // entries per thread kept in shared memory
+static constexpr int SMEM_STACK = 16;   // entries per thread kept in shared memory
 static constexpr int LOCAL_STACK = 64;  // overflow (local memory); flatten_scene bounds the BVH depth
 static constexpr float T_MIN = 0.00001f;  // core/scene.rs:183
 static constexpr int SENTINEL = 0x7FFFFFFF;
@@ -31,10 +40,10 @@ struct HitResult {
 
 __device__ __forceinline__ void intersect_triangle(const float4* __restrict__ tri_isect, int tri, f3 o, f3 d,
                                                    HitResult& best, uint32_t& best_rank) {
-    const float4 q0 = ldg4(tri_isect + 3 * tri);
-    const float4 q1 = ldg4(tri_isect + 3 * tri + 1);
-    const float4 q2 = ldg4(tri_isect + 3 * tri + 2);
-    const f3 v0 = xyz(q0), e1 = xyz(q1), e2 = xyz(q2);
+    const float8 r0 = ldg8(tri_isect + TRI_ISECT_QUADS * tri);      // v0 | e1
+    const float8 r1 = ldg8(tri_isect + TRI_ISECT_QUADS * tri + 2);  // e2 | -
+    const float4 q0 = r0.lo;
+    const f3 v0 = xyz(r0.lo), e1 = xyz(r0.hi), e2 = xyz(r1.lo);
     // core/mesh.rs:153-175, same operation order
     const f3 h = cross(d, e2);
     const float a = dot(e1, h);
@@ -90,76 +99,103 @@ __device__ __forceinline__ void intersect_analytic(const AnalyticRec& a, int pri
     }
 }
 
-// `sstack` points at this thread's column of the shared-memory stack (stride = blockDim.x).
-__device__ __forceinline__ HitResult closest_hit(const DeviceScene& sc, f3 o, f3 d, int* sstack, int sstride) {
+// Per-lane traversal state. The stack keeps its first SMEM_STACK entries in shared memory (one column per
+// thread, stride = blockDim.x, conflict-free) and spills deeper entries to local memory.
+struct Traversal {
+    f3 o, d;
+    float idx, idy, idz;  // reciprocal direction, slab tests only (never feeds a reported value)
     HitResult best;
-    best.t = INFINITY;
-    best.prim = -1;
-    best.u = best.v = 0.0f;
-    uint32_t best_rank = 0;
+    uint32_t best_rank;
+    int cur, sp;
+};
 
+__device__ __forceinline__ void trav_begin(Traversal& tr, const DeviceScene& sc, f3 o, f3 d) {
+    tr.o = o;
+    tr.d = d;
+    const float tiny = 1e-20f;
+    tr.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+    tr.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+    tr.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+    tr.best.t = INFINITY;
+    tr.best.prim = -1;
+    tr.best.u = tr.best.v = 0.0f;
+    tr.best_rank = 0;
+    tr.sp = 0;
+    tr.cur = sc.n_tris > 0 ? 0 : SENTINEL;
+}
+
+__device__ __forceinline__ int trav_pop(Traversal& tr, const int* sstack, int sstride, const int* lstack) {
+    if (tr.sp == 0) return SENTINEL;
+    --tr.sp;
+    return tr.sp < SMEM_STACK ? sstack[tr.sp * sstride] : lstack[tr.sp - SMEM_STACK];
+}
+__device__ __forceinline__ void trav_push(Traversal& tr, int* sstack, int sstride, int* lstack, int v) {
+    if (tr.sp < SMEM_STACK) sstack[tr.sp * sstride] = v;
+    else lstack[tr.sp - SMEM_STACK] = v;
+    ++tr.sp;
+}
+
+__device__ __forceinline__ bool is_inner(int cur) { return (unsigned)cur < (unsigned)SENTINEL; }  // leaf codes are negative
+
+// One inner node: two slab tests from a single 64-byte record, near child first, far child pushed.
+__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride,
+                                          int* lstack) {
+    const int cur = tr.cur;
+    const f3 o = tr.o;
+    const float8 n0 = ldg8(nodes + 4 * cur);
+    const float8 n1 = ldg8(nodes + 4 * cur + 2);
+    const float4 q0 = n0.lo, q1 = n0.hi, q2 = n1.lo, q3 = n1.hi;
+    // child 0: lo (q0.x q0.y q0.z) hi (q0.w q1.x q1.y); child 1: lo (q1.z q1.w q2.x) hi (q2.y q2.z q2.w)
+    const float ax0 = (q0.x - o.x) * tr.idx, ax1 = (q0.w - o.x) * tr.idx;
+    const float ay0 = (q0.y - o.y) * tr.idy, ay1 = (q1.x - o.y) * tr.idy;
+    const float az0 = (q0.z - o.z) * tr.idz, az1 = (q1.y - o.z) * tr.idz;
+    const float bx0 = (q1.z - o.x) * tr.idx, bx1 = (q2.y - o.x) * tr.idx;
+    const float by0 = (q1.w - o.y) * tr.idy, by1 = (q2.z - o.y) * tr.idy;
+    const float bz0 = (q2.x - o.z) * tr.idz, bz1 = (q2.w - o.z) * tr.idz;
+    const float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
+    const float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tr.best.t));
+    const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));
+    const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), tr.best.t));
+    // conservative: widen the exit by a few ulps (Ize, "Robust BVH ray traversal", 2013)
+    const bool hit_a = an <= af * 1.0000005f;
+    const bool hit_b = bn <= bf * 1.0000005f;
+    const int ca = __float_as_int(q3.x), cb = __float_as_int(q3.y);
+    // branch-free child selection: the divergent if/else ladder ran at 2-3 lanes per instruction
+    const bool b_first = hit_b && (!hit_a || bn < an);
+    const int near_c = b_first ? cb : ca;
+    const int far_c = b_first ? ca : cb;
+    if (hit_a && hit_b) trav_push(tr, sstack, sstride, lstack, far_c);
+    tr.cur = (hit_a || hit_b) ? near_c : trav_pop(tr, sstack, sstride, lstack);
+}
+
+__device__ __forceinline__ void trav_leaf(Traversal& tr, const float4* __restrict__ tri_isect, int leaf) {
+    const int code = ~leaf;
+    const int first = code >> 3, count = code & 7;
+    for (int k = 0; k < count; ++k) intersect_triangle(tri_isect, first + k, tr.o, tr.d, tr.best, tr.best_rank);
+}
+
+__device__ __forceinline__ HitResult trav_finish(Traversal& tr, const DeviceScene& sc) {
+    for (uint32_t k = 0; k < sc.n_analytics; ++k)
+        intersect_analytic(sc.analytics[k], (int)(sc.n_tris + k), tr.o, tr.d, tr.best, tr.best_rank);
+    return tr.best;
+}
+
+// One ray, start to finish (gate kernels).
+__device__ __forceinline__ HitResult closest_hit(const DeviceScene& sc, f3 o, f3 d, int* sstack, int sstride) {
+    int lstack[LOCAL_STACK];
+    Traversal tr;
+    trav_begin(tr, sc, o, d);
     const float4* __restrict__ nodes = (const float4*)sc.nodes;
     const float4* __restrict__ tri_isect = (const float4*)sc.tri_isect;
-
-    // reciprocal direction for the slab tests only (never feeds a reported value)
-    const float tiny = 1e-20f;
-    const float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-
-    int lstack[LOCAL_STACK];
-    int sp = 0;
-    int cur = sc.n_tris > 0 ? 0 : SENTINEL;
-
-    while (cur != SENTINEL) {
-        if (cur >= 0) {
-            const float4 q0 = ldg4(nodes + 4 * cur);
-            const float4 q1 = ldg4(nodes + 4 * cur + 1);
-            const float4 q2 = ldg4(nodes + 4 * cur + 2);
-            const float4 q3 = ldg4(nodes + 4 * cur + 3);
-            // child 0: lo (q0.x q0.y q0.z) hi (q0.w q1.x q1.y); child 1: lo (q1.z q1.w q2.x) hi (q2.y q2.z q2.w)
-            const float ax0 = (q0.x - o.x) * idx, ax1 = (q0.w - o.x) * idx;
-            const float ay0 = (q0.y - o.y) * idy, ay1 = (q1.x - o.y) * idy;
-            const float az0 = (q0.z - o.z) * idz, az1 = (q1.y - o.z) * idz;
-            const float bx0 = (q1.z - o.x) * idx, bx1 = (q2.y - o.x) * idx;
-            const float by0 = (q1.w - o.y) * idy, by1 = (q2.z - o.y) * idy;
-            const float bz0 = (q2.x - o.z) * idz, bz1 = (q2.w - o.z) * idz;
-            const float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
-            const float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best.t));
-            const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));
-            const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), best.t));
-            // conservative: widen the exit by a few ulps (Ize, "Robust BVH ray traversal", 2013)
-            const bool hit_a = an <= af * 1.0000005f;
-            const bool hit_b = bn <= bf * 1.0000005f;
-            int ca = __float_as_int(q3.x), cb = __float_as_int(q3.y);
-            if (hit_a && hit_b) {
-                if (bn < an) { const int tmp = ca; ca = cb; cb = tmp; }
-                if (sp < SMEM_STACK) sstack[sp * sstride] = cb;
-                else lstack[sp - SMEM_STACK] = cb;
-                ++sp;
-                cur = ca;
-            } else if (hit_a) {
-                cur = ca;
-            } else if (hit_b) {
-                cur = cb;
-            } else {
-                if (sp == 0) break;
-                --sp;
-                cur = sp < SMEM_STACK ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
-            }
+    while (tr.cur != SENTINEL) {
+        if (is_inner(tr.cur)) {
+            trav_node(tr, nodes, sstack, sstride, lstack);
         } else {
-            const int code = ~cur;
-            const int first = code >> 3, count = code & 7;
-            for (int k = 0; k < count; ++k) intersect_triangle(tri_isect, first + k, o, d, best, best_rank);
-            if (sp == 0) break;
-            --sp;
-            cur = sp < SMEM_STACK ? sstack[sp * sstride] : lstack[sp - SMEM_STACK];
+            trav_leaf(tr, tri_isect, tr.cur);
+            tr.cur = trav_pop(tr, sstack, sstride, lstack);
         }
     }
-
-    for (uint32_t k = 0; k < sc.n_analytics; ++k)
-        intersect_analytic(sc.analytics[k], (int)(sc.n_tris + k), o, d, best, best_rank);
-    return best;
+    return trav_finish(tr, sc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -209,12 +245,40 @@ __device__ __forceinline__ f3 environment_sample(const DeviceScene& sc, f3 dir) 
 // ------------------------------------------------------------------------------------------------
 // Ray generation: render/iterative.rs:25-42 + core/camera.rs:69-82
 // ------------------------------------------------------------------------------------------------
+// Within one sample the slots enumerate the frame in 8x4-pixel tiles, so the 32 primary rays of a warp
+// cover a compact screen tile instead of a 32x1 strip (coherent node fetches at depth 0). Pixels right of
+// the last full tile column / below the last full tile row follow in row order. Pure enumeration: the
+// pixel index itself (and with it the camera mapping and the random stream) is unchanged.
+__device__ __forceinline__ uint32_t tile_slot_to_pixel(uint32_t j, uint32_t W, uint32_t H) {
+    const uint32_t W8 = W & ~7u, H4 = H & ~3u;
+    const uint32_t n_tiled = W8 * H4;
+    if (j < n_tiled) {
+        const uint32_t tile = j >> 5, within = j & 31u;
+        const uint32_t tiles_per_row = W8 >> 3;
+        const uint32_t tx = tile % tiles_per_row, ty = tile / tiles_per_row;
+        return (ty * 4 + (within >> 3)) * W + tx * 8 + (within & 7u);
+    }
+    uint32_t r = j - n_tiled;
+    const uint32_t RW = W - W8;
+    if (r < RW * H4) return (r / RW) * W + W8 + r % RW;
+    r -= RW * H4;
+    return (H4 + r / W) * W + r % W;
+}
+__device__ __forceinline__ uint32_t tile_pixel_to_slot(uint32_t pixel, uint32_t W, uint32_t H) {
+    const uint32_t W8 = W & ~7u, H4 = H & ~3u;
+    const uint32_t x = pixel % W, y = pixel / W;
+    if (x < W8 && y < H4) return (((y >> 2) * (W8 >> 3) + (x >> 3)) << 5) + ((y & 3u) << 3) + (x & 7u);
+    const uint32_t n_tiled = W8 * H4, RW = W - W8;
+    if (y < H4) return n_tiled + y * RW + (x - W8);
+    return n_tiled + RW * H4 + (y - H4) * W + x;
+}
+
 __device__ __forceinline__ void slot_source(const PathSource& src, uint32_t slot, uint32_t& pixel, uint32_t& sample) {
     if (src.pixel) {
         pixel = src.pixel[slot];
         sample = src.sample[slot];
     } else {
-        pixel = slot % src.n_pixels;
+        pixel = tile_slot_to_pixel(slot % src.n_pixels, src.width, src.height);
         sample = src.sample_base + slot / src.n_pixels;
     }
 }
@@ -257,17 +321,78 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, Pa
 // ------------------------------------------------------------------------------------------------
 // Closest-hit kernel: one ray per thread, queue of slots
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
+// Closest-hit kernel: persistent warps, one ray per lane, two mechanisms against SIMT divergence
+// (ncu before: 6.8 of 32 threads active per instruction at depth >= 1, profiles/r1_trace_baseline.md):
+//  1. dynamic ray replacement (Aila & Laine 2009): ray lengths inside a warp differ by an order of
+//     magnitude once paths are incoherent, so a warp whose live lanes drop below REFILL_THRESHOLD pulls
+//     fresh rays from the depth's queue (one atomicAdd per refill) instead of idling until its longest ray ends;
+//  2. majority-vote stepping: a lane is either at an inner node or at a leaf. Each warp iteration executes
+//     the state that holds more lanes (one vote each), the other lanes wait; waiting leaf lanes pile up
+//     until they outvote the node lanes. At least half of the live lanes work in every iteration and, unlike
+//     speculative traversal, no lane walks nodes that a pending leaf would have culled.
+static constexpr int REFILL_THRESHOLD = VR_REFILL_THRESHOLD;
+
+__global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
     __shared__ int s_stack[SMEM_STACK * TRACE_THREADS];
+    int lstack[LOCAL_STACK];
     const uint32_t n = wf.counts[depth];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wf.segments, (unsigned long long)n);
     const uint32_t* __restrict__ queue = depth == 0 ? nullptr : wf.queue[depth & 1];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = queue ? queue[i] : i;
-        const float4 ro = wf.ray_o[slot];
-        const float4 rd = wf.ray_d[slot];
-        const HitResult h = closest_hit(sc, xyz(ro), xyz(rd), s_stack + threadIdx.x, TRACE_THREADS);
-        wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+    const float4* __restrict__ nodes = (const float4*)sc.nodes;
+    const float4* __restrict__ tri_isect = (const float4*)sc.tri_isect;
+    uint32_t* cursor = wf.cursors + depth;
+    int* sstack = s_stack + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    Traversal tr;
+    tr.cur = SENTINEL;
+    bool have = false;
+    bool exhausted = false;  // warp-uniform: the queue has no more rays
+    uint32_t slot = 0;
+
+    while (true) {
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xFFFFFFFFu, !have);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                const uint32_t cnt = (uint32_t)__popc(need);
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(cursor, cnt);
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (!have) {
+                    const uint32_t i = base + (uint32_t)__popc(need & lt_mask);
+                    if (i < n) {
+                        slot = queue ? queue[i] : i;
+                        const float4 ro = wf.ray_o[slot];
+                        const float4 rd = wf.ray_d[slot];
+                        trav_begin(tr, sc, xyz(ro), xyz(rd));
+                        have = true;
+                    }
+                }
+                if (base + cnt >= n) exhausted = true;
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, have)) break;
+        while (true) {
+            if (have && tr.cur == SENTINEL) {
+                const HitResult h = trav_finish(tr, sc);
+                wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+                have = false;
+            }
+            const bool at_node = have && is_inner(tr.cur);
+            const bool at_leaf = have && tr.cur < 0;
+            const unsigned m_node = __ballot_sync(0xFFFFFFFFu, at_node);
+            const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, at_leaf);
+            const int live = __popc(m_node | m_leaf);
+            if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
+            if (__popc(m_node) >= __popc(m_leaf)) {
+                if (at_node) trav_node(tr, nodes, sstack, TRACE_THREADS, lstack);
+            } else if (at_leaf) {
+                trav_leaf(tr, tri_isect, tr.cur);
+                tr.cur = trav_pop(tr, sstack, TRACE_THREADS, lstack);
+            }
+        }
     }
 }
 
@@ -445,12 +570,16 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
 // ------------------------------------------------------------------------------------------------
 // Accumulation: render/iterative.rs:35-51
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_accumulate(Wavefront wf, float4* partial, float4* accum, uint32_t n_pixels,
-                                                    uint32_t samples_in_batch, int finish, float inv_total) {
-    for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) k_accumulate(Wavefront wf, float4* partial, float4* accum, uint32_t width,
+                                                    uint32_t height, uint32_t samples_in_batch, int finish,
+                                                    float inv_total) {
+    const uint32_t n_pixels = width * height;
+    // one thread per slot-in-sample j (coalesced radiance reads); it owns pixel tile_slot_to_pixel(j)
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pixels; j += gridDim.x * blockDim.x) {
+        const uint32_t px = tile_slot_to_pixel(j, width, height);
         float4 p = partial[px];
         for (uint32_t s = 0; s < samples_in_batch; ++s) {
-            const float4 L = wf.radiance[(size_t)s * n_pixels + px];
+            const float4 L = wf.radiance[(size_t)s * n_pixels + j];
             p.x += L.x;
             p.y += L.y;
             p.z += L.z;
@@ -544,8 +673,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DeviceScene sc, co
     }
 }
 
-__global__ void __launch_bounds__(256) k_primary_ids(DeviceScene sc, Wavefront wf, uint32_t n, uint32_t* surface,
-                                                     uint32_t* prim, float* t) {
+__global__ void __launch_bounds__(256) k_primary_ids(DeviceScene sc, Wavefront wf, uint32_t n, uint32_t width,
+                                                     uint32_t height, uint32_t* surface, uint32_t* prim, float* t) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 hr = wf.hit[i];
         HitResult h;
@@ -553,7 +682,7 @@ __global__ void __launch_bounds__(256) k_primary_ids(DeviceScene sc, Wavefront w
         h.prim = __float_as_int(hr.y);
         h.u = hr.z;
         h.v = hr.w;
-        export_hit(sc, h, surface, prim, t, i);
+        export_hit(sc, h, surface, prim, t, tile_slot_to_pixel(i, width, height));
     }
 }
 
@@ -624,10 +753,10 @@ void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& 
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {
     k_shade<<<grid_for(n_upper, SHADE_THREADS, ld.sm_count, ld.shade_blocks_per_sm), SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
 }
-void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t n_pixels, uint32_t samples_in_batch,
-                       int finish, float inv_total_samples, cudaStream_t stream) {
-    const uint32_t grid = (n_pixels + 255) / 256;
-    k_accumulate<<<grid, 256, 0, stream>>>(wf, partial, accum, n_pixels, samples_in_batch, finish, inv_total_samples);
+void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t width, uint32_t height,
+                       uint32_t samples_in_batch, int finish, float inv_total_samples, cudaStream_t stream) {
+    const uint32_t grid = (width * height + 255) / 256;
+    k_accumulate<<<grid, 256, 0, stream>>>(wf, partial, accum, width, height, samples_in_batch, finish, inv_total_samples);
 }
 void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul, float inv_gamma,
                     int32_t tonemap, cudaStream_t stream) {
@@ -639,9 +768,10 @@ void launch_trace_rays(const DeviceScene& sc, const float* origins, const float*
     const uint32_t grid = (uint32_t)((n + TRACE_THREADS - 1) / TRACE_THREADS);
     k_trace_rays<<<grid < 1 ? 1 : (grid > 148 * 8 ? 148 * 8 : grid), TRACE_THREADS, 0, stream>>>(sc, origins, dirs, n, surface, prim, t);
 }
-void launch_primary_ids(const DeviceScene& sc, const Wavefront& wf, uint32_t n, uint32_t* surface, uint32_t* prim,
-                        float* t, cudaStream_t stream) {
-    k_primary_ids<<<(n + 255) / 256, 256, 0, stream>>>(sc, wf, n, surface, prim, t);
+void launch_primary_ids(const DeviceScene& sc, const Wavefront& wf, uint32_t width, uint32_t height, uint32_t* surface,
+                        uint32_t* prim, float* t, cudaStream_t stream) {
+    const uint32_t n = width * height;
+    k_primary_ids<<<(n + 255) / 256, 256, 0, stream>>>(sc, wf, n, width, height, surface, prim, t);
 }
 void launch_rng_draws(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out, cudaStream_t stream) {
     k_rng_draws<<<1, 32, 0, stream>>>(seed, pixel, sample, n, out);

@@ -16,6 +16,7 @@ struct Wavefront {
     float4* radiance;  // [capacity] finished radiance of the slot's camera sample
     uint32_t* queue[2];  // compacted slot lists, ping-pong by depth parity
     uint32_t* counts;    // [max_bounces + 1] queue lengths
+    uint32_t* cursors;   // [max_bounces + 1] next unclaimed queue entry (dynamic ray fetch)
     unsigned long long* segments;  // scene.hit calls, whole render
     uint32_t capacity;
 };
@@ -26,6 +27,7 @@ struct PathSource {
     const uint32_t* sample;
     uint32_t n_pixels;
     uint32_t sample_base;
+    uint32_t width, height;  // implicit mode enumerates pixels in 8x4 tiles
 };
 
 struct FrameParams {
@@ -52,7 +54,7 @@ void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& 
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
 // partial[pixel] += sum over the batch's samples (in sample order); when `finish`, fold
 // partial * (1/total_samples) into accum (alpha += 1) and clear partial.
-void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t n_pixels,
+void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t width, uint32_t height,
                        uint32_t samples_in_batch, int finish, float inv_total_samples, cudaStream_t stream);
 void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul,
                     float inv_gamma, int32_t tonemap, cudaStream_t stream);
@@ -60,8 +62,8 @@ void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float s
 // debug / gate kernels
 void launch_trace_rays(const DeviceScene& sc, const float* origins, const float* dirs, uint64_t n,
                        uint32_t* surface, uint32_t* prim, float* t, cudaStream_t stream);
-void launch_primary_ids(const DeviceScene& sc, const Wavefront& wf, uint32_t n, uint32_t* surface, uint32_t* prim,
-                        float* t, cudaStream_t stream);
+void launch_primary_ids(const DeviceScene& sc, const Wavefront& wf, uint32_t width, uint32_t height,
+                        uint32_t* surface, uint32_t* prim, float* t, cudaStream_t stream);
 void launch_rng_draws(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out, cudaStream_t stream);
 void launch_unit_sphere(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, cudaStream_t stream);
 void launch_texture_sample(TextureRec tex, uint64_t n, const float* uv, float* rgb, cudaStream_t stream);

@@ -14,12 +14,13 @@ namespace vr {
 static const int NODE_QUADS = 4;
 static const int LEAF_MAX_TRIS = 4;
 
-// Intersection record, 48 B = 3 x float4 (pre-subtracted edges: e1 = v1 - v0, e2 = v2 - v0 are the
-// same f32 subtractions core/mesh.rs:150-151 performs per test, done once on the host).
+// Intersection record, 64 B = 4 x float4 = two 256-bit loads (pre-subtracted edges: e1 = v1 - v0,
+// e2 = v2 - v0 are the same f32 subtractions core/mesh.rs:150-151 performs per test, done once on the host).
 //   q0 = (v0.xyz, tie rank as uint bits)
 //   q1 = (e1.xyz, 0)
 //   q2 = (e2.xyz, 0)
-static const int TRI_ISECT_QUADS = 3;
+//   q3 = padding to the 32-byte alignment the 256-bit loads need
+static const int TRI_ISECT_QUADS = 4;
 
 // Shading record, 80 B = 5 x float4, fetched once per closest hit.
 //   q0 = (n0.xyz, uv0.x)   q1 = (n1.xyz, uv0.y)   q2 = (n2.xyz, uv1.x)

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -136,6 +137,8 @@ struct Builder {
     std::atomic<uint32_t> max_depth{0};
     std::atomic<int> threads_left{0};
     static const int BINS = 32;
+    uint32_t leaf_max = LEAF_MAX_TRIS;
+    float node_cost = 1.0f;
 
     Builder(std::vector<Prim>& p, std::vector<Quad>& n) : prims(p), nodes(n) {}
 
@@ -197,8 +200,8 @@ struct Builder {
             }
         }
 
-        const float TRAVERSAL_COST = 1.0f;
-        if (n <= (uint32_t)LEAF_MAX_TRIS && (best_axis < 0 || (float)n <= TRAVERSAL_COST + best_cost)) {
+        // SAH in units of one triangle test: a node visit (two slab tests + stack work) costs node_cost
+        if (n <= leaf_max && (best_axis < 0 || (float)n <= node_cost + best_cost)) {
             note_depth(depth);
             return leaf_code(lo, n);
         }
@@ -403,6 +406,9 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     // ---- BVH ----
     out.nodes.assign((size_t)std::max<uint32_t>(n_tris, 2) * NODE_QUADS, Quad{0, 0, 0, 0});
     Builder builder(prims, out.nodes);
+    // tuning knobs for experiments (defaults are the shipped configuration)
+    if (const char* e = std::getenv("VOIDRAY_LEAF_MAX")) builder.leaf_max = (uint32_t)std::min(7, std::max(1, atoi(e)));
+    if (const char* e = std::getenv("VOIDRAY_NODE_COST")) builder.node_cost = (float)atof(e);
     Box empty;
     empty.reset();
     if (n_tris == 0) {
@@ -441,6 +447,7 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         qi[0] = Quad{p0.x, p0.y, p0.z, bits_f(rank)};
         qi[1] = Quad{e1.x, e1.y, e1.z, 0.0f};
         qi[2] = Quad{e2.x, e2.y, e2.z, 0.0f};
+        qi[3] = Quad{0.0f, 0.0f, 0.0f, 0.0f};
         // geometric normal, mesh.rs:80-84
         const V3 ng = normalize(cross(sub(p2, p1), sub(p0, p1)));
         const V3 n0 = ld3(&m.nrm[3 * i0]), n1 = ld3(&m.nrm[3 * i1]), n2 = ld3(&m.nrm[3 * i2]);
