@@ -281,6 +281,7 @@ def run_ours(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
+    info = accel.info()
 
     samples_total = float(w) * h * spp * world * args.steps
     seg_total = sum_over_ranks(float(stats_acc["seg"]))
@@ -367,6 +368,7 @@ def run_ours(args):
         "e2e": {"value": samples_total / e2e_s / 1e6, "unit": "Msamples/s",
                 "h2d_bytes_per_step": int(info["h2d_bytes"]) * world, "d2h_bytes_per_step": w * h * 16,
                 "ms_per_step": e2e_s / args.steps * 1e3,
+                "commit_ms": {"flatten_and_bvh": info["flatten_ms"], "upload": info["upload_ms"]},
                 "what": "vr_scene_commit (flatten + BVH + H2D) + clear + accumulate + reduce + read_accum to pinned host"},
         "gpu_launches": int(launches_total),
         "roofline": roofline,

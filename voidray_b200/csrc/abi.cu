@@ -59,11 +59,45 @@ struct vr_context {
     LaunchDims dims;
 };
 
+// Device allocations of a scene are kept across commits and handed out again in the same order, so a
+// re-commit of an unchanged-size scene performs no cudaMalloc / cudaFree.
+struct DeviceArena {
+    struct Slot {
+        void* ptr;
+        size_t capacity;
+    };
+    std::vector<Slot> slots;
+    size_t cursor = 0;
+    cudaError_t get(void** p, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        if (cursor == slots.size()) slots.push_back(Slot{nullptr, 0});
+        Slot& s = slots[cursor++];
+        if (s.capacity < bytes) {
+            if (s.ptr) cudaFree(s.ptr);
+            s.ptr = nullptr;
+            s.capacity = 0;
+            cudaError_t e = cudaMalloc(&s.ptr, bytes);
+            if (e != cudaSuccess) return e;
+            s.capacity = bytes;
+        }
+        *p = s.ptr;
+        return cudaSuccess;
+    }
+    void rewind() { cursor = 0; }
+    void release() {
+        for (Slot& s : slots)
+            if (s.ptr) cudaFree(s.ptr);
+        slots.clear();
+        cursor = 0;
+    }
+};
+
 struct vr_scene {
     vr_context* ctx = nullptr;
     HostScene host;
     FlatScene flat;
-    DeviceBuffers dev_mem;
+    DeviceArena dev_mem;
+    std::vector<const void*> pinned;  // host texture storage registered with cudaHostRegister
     DeviceScene dev;
     std::vector<TextureRec> dev_textures;
     bool committed = false;
@@ -139,20 +173,32 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
     }
 }
 
-int32_t upload_texture(vr_scene* scene, const HostTexture& t, TextureRec* rec) {
+// Page-lock the scene's own copy of a texture so that commits DMA straight from it.
+void pin_host(vr_scene* scene, const std::vector<float>& v) {
+    if (v.empty()) return;
+    if (cudaHostRegister((void*)v.data(), v.size() * sizeof(float), cudaHostRegisterDefault) == cudaSuccess)
+        scene->pinned.push_back(v.data());
+    else
+        cudaGetLastError();  // pageable copies still work, just slower
+}
+void unpin_host(vr_scene* scene, const std::vector<float>& v) {
+    for (size_t i = 0; i < scene->pinned.size(); ++i)
+        if (scene->pinned[i] == v.data()) {
+            cudaHostUnregister((void*)v.data());
+            scene->pinned.erase(scene->pinned.begin() + i);
+            return;
+        }
+}
+
+// The RGB f32 texels go over the bus as they are (12 B/texel) and are widened to the 16-byte RGBA
+// records the kernels fetch by a device kernel. `stage` is a device scratch buffer of >= 12 * n bytes.
+int32_t upload_texture(vr_scene* scene, const HostTexture& t, void* stage, TextureRec* rec) {
     const size_t n = (size_t)t.w * t.h;
-    std::vector<float> rgba(4 * n);
-    for (size_t i = 0; i < n; ++i) {
-        rgba[4 * i] = t.rgb[3 * i];
-        rgba[4 * i + 1] = t.rgb[3 * i + 1];
-        rgba[4 * i + 2] = t.rgb[3 * i + 2];
-        rgba[4 * i + 3] = 0.0f;
-    }
     void* d = nullptr;
-    VR_CUDA(scene->dev_mem.alloc(&d, 16 * n));
-    VR_CUDA(cudaMemcpyAsync(d, rgba.data(), 16 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
-    VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));  // rgba goes out of scope
-    scene->h2d_bytes += 16 * n;
+    VR_CUDA(scene->dev_mem.get(&d, 16 * n));
+    VR_CUDA(cudaMemcpyAsync(stage, t.rgb.data(), 12 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
+    launch_expand_rgb((const float*)stage, (float4*)d, n, scene->ctx->stream);
+    scene->h2d_bytes += 12 * n;
     rec->texels = d;
     rec->width = t.w;
     rec->height = t.h;
@@ -164,7 +210,7 @@ int32_t upload_texture(vr_scene* scene, const HostTexture& t, TextureRec* rec) {
 template <typename T>
 int32_t upload_vector(vr_scene* scene, const std::vector<T>& v, const void** out) {
     void* d = nullptr;
-    VR_CUDA(scene->dev_mem.alloc(&d, v.size() * sizeof(T)));
+    VR_CUDA(scene->dev_mem.get(&d, v.size() * sizeof(T)));
     if (!v.empty())
         VR_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, scene->ctx->stream));
     scene->h2d_bytes += v.size() * sizeof(T);
@@ -246,7 +292,9 @@ int32_t vr_scene_create(vr_context* ctx, vr_scene** out) {
 int32_t vr_scene_destroy(vr_scene* scene) {
     if (!scene) return VR_OK;
     cudaSetDevice(scene->ctx->device);
+    cudaStreamSynchronize(scene->ctx->stream);
     scene->dev_mem.release();
+    for (const void* p : scene->pinned) cudaHostUnregister((void*)p);
     delete scene;
     return VR_OK;
 }
@@ -263,6 +311,8 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
     t.sample_type = sample_type;
     t.rgb.assign(rgb, rgb + (size_t)3 * w * h);
     scene->host.textures.push_back(std::move(t));
+    cudaSetDevice(scene->ctx->device);
+    pin_host(scene, scene->host.textures.back().rgb);
     scene->committed = false;
     if (texture) *texture = (uint32_t)scene->host.textures.size() - 1;
     return VR_OK;
@@ -384,6 +434,7 @@ int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]) {
     if (!rgb) return fail(VR_ERR_INVALID, "null colour");
     scene->host.env_kind = 1;
     std::memcpy(scene->host.env_color, rgb, 12);
+    unpin_host(scene, scene->host.env_image.rgb);
     scene->host.env_image = HostTexture();
     scene->committed = false;
     return VR_OK;
@@ -394,10 +445,13 @@ int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, 
     if (!rgb || w == 0 || h == 0) return fail(VR_ERR_INVALID, "empty environment image");
     if ((uint64_t)w * h >= (1ull << 31)) return fail(VR_ERR_INVALID, "environment image too large");
     scene->host.env_kind = 2;
+    cudaSetDevice(scene->ctx->device);
+    unpin_host(scene, scene->host.env_image.rgb);
     scene->host.env_image.w = w;
     scene->host.env_image.h = h;
     scene->host.env_image.sample_type = 1;
     scene->host.env_image.rgb.assign(rgb, rgb + (size_t)3 * w * h);
+    pin_host(scene, scene->host.env_image.rgb);
     scene->committed = false;
     return VR_OK;
 }
@@ -405,6 +459,7 @@ int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, 
 int32_t vr_scene_clear_environment(vr_scene* scene) {
     if (check_scene(scene)) return VR_ERR_INVALID;
     scene->host.env_kind = 0;
+    unpin_host(scene, scene->host.env_image.rgb);
     scene->host.env_image = HostTexture();
     scene->committed = false;
     return VR_OK;
@@ -420,7 +475,7 @@ int32_t vr_scene_commit(vr_scene* scene) {
     scene->h2d_bytes = 0;
     if (scene->flat.bvh_depth > 70) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
-    scene->dev_mem.release();
+    scene->dev_mem.rewind();
     scene->dev_textures.clear();
 
     DeviceScene& d = scene->dev;
@@ -434,9 +489,13 @@ int32_t vr_scene_commit(vr_scene* scene) {
     if ((rc = upload_vector(scene, f.tri_prim, (const void**)&d.tri_prim))) return rc;
     if ((rc = upload_vector(scene, scene->host.materials, (const void**)&d.materials))) return rc;
     if ((rc = upload_vector(scene, f.analytics, (const void**)&d.analytics))) return rc;
+    size_t max_texels = scene->host.env_kind == 2 ? (size_t)scene->host.env_image.w * scene->host.env_image.h : 0;
+    for (const HostTexture& t : scene->host.textures) max_texels = std::max(max_texels, (size_t)t.w * t.h);
+    void* stage = nullptr;
+    VR_CUDA(scene->dev_mem.get(&stage, 12 * max_texels));
     for (const HostTexture& t : scene->host.textures) {
         TextureRec rec;
-        if ((rc = upload_texture(scene, t, &rec))) return rc;
+        if ((rc = upload_texture(scene, t, stage, &rec))) return rc;
         scene->dev_textures.push_back(rec);
     }
     if ((rc = upload_vector(scene, scene->dev_textures, (const void**)&d.textures))) return rc;
@@ -445,7 +504,7 @@ int32_t vr_scene_commit(vr_scene* scene) {
     d.env_kind = scene->host.env_kind;
     std::memcpy(d.env_color, scene->host.env_color, 12);
     if (scene->host.env_kind == 2) {
-        if ((rc = upload_texture(scene, scene->host.env_image, &d.env_tex))) return rc;
+        if ((rc = upload_texture(scene, scene->host.env_image, stage, &d.env_tex))) return rc;
     }
     d.camera = f.camera;
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));

@@ -642,6 +642,12 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accu
     }
 }
 
+// RGB f32 texels as uploaded -> the 16-byte RGBA records the lookups fetch (w = 0)
+__global__ void __launch_bounds__(256) k_expand_rgb(const float* __restrict__ rgb, float4* __restrict__ rgba, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        rgba[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Gate / debug kernels
 // ------------------------------------------------------------------------------------------------
@@ -762,6 +768,11 @@ void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float s
                     int32_t tonemap, cudaStream_t stream) {
     const uint32_t grid = (n_pixels + 255) / 256;
     k_resolve<<<grid, 256, 0, stream>>>(accum, out, n_pixels, scale, exposure_mul, inv_gamma, tonemap);
+}
+void launch_expand_rgb(const float* rgb, float4* rgba, size_t n_texels, cudaStream_t stream) {
+    if (n_texels == 0) return;
+    const size_t grid = (n_texels + 255) / 256;
+    k_expand_rgb<<<(unsigned)(grid > 148 * 16 ? 148 * 16 : grid), 256, 0, stream>>>(rgb, rgba, n_texels);
 }
 void launch_trace_rays(const DeviceScene& sc, const float* origins, const float* dirs, uint64_t n, uint32_t* surface,
                        uint32_t* prim, float* t, cudaStream_t stream) {

@@ -59,6 +59,9 @@ void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint
 void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul,
                     float inv_gamma, int32_t tonemap, cudaStream_t stream);
 
+// RGB f32 (as uploaded) -> RGBA f32 texel records
+void launch_expand_rgb(const float* rgb, float4* rgba, size_t n_texels, cudaStream_t stream);
+
 // debug / gate kernels
 void launch_trace_rays(const DeviceScene& sc, const float* origins, const float* dirs, uint64_t n,
                        uint32_t* surface, uint32_t* prim, float* t, cudaStream_t stream);
