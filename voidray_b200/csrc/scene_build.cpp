@@ -49,6 +49,110 @@ void camera_look_at(const float eye[3], const float center[3], const float up_in
     up[0] = u.x; up[1] = u.y; up[2] = u.z;
 }
 
+namespace {
+
+typedef std::pair<int32_t, uint32_t> KeyIdx;  // (total_cmp key of the centroid coordinate, item)
+
+// fn(begin, end) over [0, n) in contiguous chunks, one per hardware thread (inline when n is small)
+template <typename Fn>
+void parallel_for(size_t n, Fn fn) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t T = n < 65536 ? 1 : std::min<size_t>(hw, 32);
+    if (T == 1) {
+        fn((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + T - 1) / T;
+    for (size_t t = 0; t < T; ++t) {
+        const size_t b = t * chunk, e = std::min(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([=]() { fn(b, e); });
+    }
+    for (std::thread& x : th) x.join();
+}
+
+// Stable sort by key: LSD radix sort (stable by construction) for large ranges, std::stable_sort otherwise.
+void stable_sort_by_key(KeyIdx* v, size_t n, std::vector<KeyIdx>& tmp) {
+    if (n < (1u << 15)) {
+        std::stable_sort(v, v + n, [](const KeyIdx& a, const KeyIdx& b) { return a.first < b.first; });
+        return;
+    }
+    tmp.resize(n);
+    KeyIdx* src = v;
+    KeyIdx* dst = tmp.data();
+    for (int pass = 0; pass < 3; ++pass) {  // 11 + 11 + 10 bits of the sign-flipped key
+        const int shift = pass * 11;
+        const uint32_t mask = pass == 2 ? 0x3FFu : 0x7FFu;
+        size_t count[2048] = {0};
+        for (size_t i = 0; i < n; ++i) count[(((uint32_t)src[i].first ^ 0x80000000u) >> shift) & mask]++;
+        size_t sum = 0;
+        for (uint32_t b = 0; b <= mask; ++b) {
+            const size_t c = count[b];
+            count[b] = sum;
+            sum += c;
+        }
+        for (size_t i = 0; i < n; ++i) dst[count[(((uint32_t)src[i].first ^ 0x80000000u) >> shift) & mask]++] = src[i];
+        std::swap(src, dst);
+    }
+    // three passes: the result is in tmp
+    std::memcpy(v, tmp.data(), n * sizeof(KeyIdx));
+}
+
+struct LeafOrderJob {
+    const std::vector<float>& cen;
+    std::vector<uint32_t>& order;
+    std::atomic<int> threads_left;
+    LeafOrderJob(const std::vector<float>& c, std::vector<uint32_t>& o, int t) : cen(c), order(o), threads_left(t) {}
+
+    void run(size_t lo, size_t hi) {
+        std::vector<KeyIdx> keyed, tmp;
+        std::vector<std::pair<size_t, size_t>> stack;
+        std::vector<std::thread> spawned;
+        stack.emplace_back(lo, hi);
+        while (!stack.empty()) {
+            const std::pair<size_t, size_t> r = stack.back();
+            stack.pop_back();
+            const size_t len = r.second - r.first;
+            if (len < 2) continue;
+            float cmin[3], cmax[3];
+            for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = cen[3 * order[r.first] + a];
+            for (size_t i = r.first + 1; i < r.second; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    cmin[a] = std::fmin(cmin[a], cen[3 * order[i] + a]);
+                    cmax[a] = std::fmax(cmax[a], cen[3 * order[i] + a]);
+                }
+            const float sx = cmax[0] - cmin[0], sy = cmax[1] - cmin[1], sz = cmax[2] - cmin[2];
+            int axis;  // bvh.rs:71-77: strictly largest spread, else Z
+            if (sx > sy && sx > sz) axis = 0;
+            else if (sy > sx && sy > sz) axis = 1;
+            else axis = 2;
+            keyed.resize(len);
+            for (size_t i = 0; i < len; ++i) {
+                keyed[i].first = total_key(cen[3 * order[r.first + i] + axis]);
+                keyed[i].second = order[r.first + i];
+            }
+            stable_sort_by_key(keyed.data(), len, tmp);  // Vec::sort_by(total_cmp) is stable, bvh.rs:80-108
+            for (size_t i = 0; i < len; ++i) order[r.first + i] = keyed[i].second;
+            const size_t mid = r.first + len / 2;  // bvh.rs:111-120
+            // the halves are independent: hand the left one to another thread while any are free
+            if (len > 100000 && threads_left.fetch_sub(1) > 0) {
+                spawned.emplace_back([this, r, mid]() {
+                    run(r.first, mid);
+                    threads_left.fetch_add(1);
+                });
+            } else {
+                if (len > 100000) threads_left.fetch_add(1);
+                stack.emplace_back(r.first, mid);
+            }
+            stack.emplace_back(mid, r.second);
+        }
+        for (std::thread& t : spawned) t.join();
+    }
+};
+
+}  // namespace
+
 // core/bvh.rs:48-130 restated on index ranges: a range of >= 2 items is stably sorted by the centroid
 // coordinate of the axis with the strictly largest centroid spread (else Z) and cut at len/2. The left
 // half precedes the right half, so after the recursion the array itself is the in-order leaf sequence.
@@ -61,44 +165,8 @@ void reference_leaf_order(const std::vector<float>& boxes6, std::vector<uint32_t
     std::vector<float> cen(3 * n);
     for (size_t i = 0; i < n; ++i)
         for (int a = 0; a < 3; ++a) cen[3 * i + a] = (boxes6[6 * i + a] + boxes6[6 * i + 3 + a]) / 2.0f;
-
-    struct Range {
-        size_t lo, hi;
-    };
-    std::vector<Range> stack;
-    stack.push_back(Range{0, n});
-    std::vector<std::pair<int32_t, uint32_t>> keyed;
-    while (!stack.empty()) {
-        const Range r = stack.back();
-        stack.pop_back();
-        const size_t len = r.hi - r.lo;
-        if (len < 2) continue;
-        float cmin[3], cmax[3];
-        for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = cen[3 * order[r.lo] + a];
-        for (size_t i = r.lo + 1; i < r.hi; ++i)
-            for (int a = 0; a < 3; ++a) {
-                cmin[a] = std::fmin(cmin[a], cen[3 * order[i] + a]);
-                cmax[a] = std::fmax(cmax[a], cen[3 * order[i] + a]);
-            }
-        const float sx = cmax[0] - cmin[0], sy = cmax[1] - cmin[1], sz = cmax[2] - cmin[2];
-        int axis;
-        if (sx > sy && sx > sz) axis = 0;
-        else if (sy > sx && sy > sz) axis = 1;
-        else axis = 2;
-        keyed.resize(len);
-        for (size_t i = 0; i < len; ++i) {
-            keyed[i].first = total_key(cen[3 * order[r.lo + i] + axis]);
-            keyed[i].second = order[r.lo + i];
-        }
-        std::stable_sort(keyed.begin(), keyed.end(),
-                         [](const std::pair<int32_t, uint32_t>& a, const std::pair<int32_t, uint32_t>& b) {
-                             return a.first < b.first;
-                         });
-        for (size_t i = 0; i < len; ++i) order[r.lo + i] = keyed[i].second;
-        const size_t half = len / 2;
-        stack.push_back(Range{r.lo, r.lo + half});
-        stack.push_back(Range{r.lo + half, r.hi});
-    }
+    LeafOrderJob job(cen, order, (int)std::max(1u, std::thread::hardware_concurrency()) - 1);
+    job.run(0, n);
 }
 
 namespace {
@@ -227,13 +295,13 @@ struct Builder {
         Box lbox, rbox;
         int32_t lcode, rcode;
         bool spawned = false;
-        if (n > 200000 && threads_left.fetch_sub(1) > 0) {
+        if (n > 50000 && threads_left.fetch_sub(1) > 0) {
             spawned = true;
             std::thread t([&]() { lcode = build(lo, mid, lbox, depth + 1); });
             rcode = build(mid, hi, rbox, depth + 1);
             t.join();
             threads_left.fetch_add(1);
-        } else if (n > 200000) {
+        } else if (n > 50000) {
             threads_left.fetch_add(1);
         }
         if (!spawned) {
@@ -316,7 +384,8 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
             if (m.idx.size() > 4 * 3) {  // SMALL_MESH, mesh.rs:43,112
                 // per-triangle boxes, mesh.rs:193-205: vertex bounds, epsilon_expand(0.001)
                 std::vector<float> boxes(6 * nt);
-                for (size_t t = 0; t < nt; ++t) {
+                parallel_for(nt, [&](size_t t_begin, size_t t_end) {
+                for (size_t t = t_begin; t < t_end; ++t) {
                     float* tb = &boxes[6 * t];
                     for (int a = 0; a < 3; ++a) {
                         const float p0 = m.pos[3 * m.idx[3 * t] + a], p1 = m.pos[3 * m.idx[3 * t + 1] + a],
@@ -330,9 +399,12 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                         if (dim < 0.001f) { tb[a] = c - 0.001f; tb[3 + a] = c + 0.001f; }
                     }
                 }
+                });
                 std::vector<uint32_t> order;
                 reference_leaf_order(boxes, order);
-                for (size_t i = 0; i < nt; ++i) rank[order[i]] = (uint32_t)i;
+                parallel_for(nt, [&](size_t b, size_t e) {
+                    for (size_t i = b; i < e; ++i) rank[order[i]] = (uint32_t)i;
+                });
             } else {
                 // linear loop, first index wins a tie (mesh.rs:129-135)
                 for (size_t t = 0; t < nt; ++t) rank[t] = (uint32_t)(nt - 1 - t);
@@ -392,14 +464,19 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
             if (sf.kind != 0) continue;
             const HostMesh& m = in.meshes[sf.mesh];
             const size_t nt = m.idx.size() / 3;
-            for (size_t t = 0; t < nt; ++t, ++g) {
-                Prim& p = prims[g];
-                p.box.reset();
-                for (int k = 0; k < 3; ++k) p.box.grow(&m.pos[3 * m.idx[3 * t + k]]);
-                for (int a = 0; a < 3; ++a) p.cen[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
-                p.id = g;
-                src[g] = Src{(uint32_t)s, (uint32_t)t};
-            }
+            const uint32_t g0 = g;
+            parallel_for(nt, [&](size_t t_begin, size_t t_end) {
+                for (size_t t = t_begin; t < t_end; ++t) {
+                    const uint32_t gi = g0 + (uint32_t)t;
+                    Prim& p = prims[gi];
+                    p.box.reset();
+                    for (int k = 0; k < 3; ++k) p.box.grow(&m.pos[3 * m.idx[3 * t + k]]);
+                    for (int a = 0; a < 3; ++a) p.cen[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
+                    p.id = gi;
+                    src[gi] = Src{(uint32_t)s, (uint32_t)t};
+                }
+            });
+            g += (uint32_t)nt;
         }
     }
 
@@ -436,7 +513,8 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     out.tri_shade.resize((size_t)n_tris * TRI_SHADE_QUADS);
     out.tri_surface.resize(n_tris);
     out.tri_prim.resize(n_tris);
-    for (uint32_t i = 0; i < n_tris; ++i) {
+    parallel_for(n_tris, [&](size_t i_begin, size_t i_end) {
+    for (size_t i = i_begin; i < i_end; ++i) {
         const Src sp = src[prims[i].id];
         const HostMesh& m = in.meshes[in.surfaces[sp.surface].mesh];
         const uint32_t i0 = m.idx[3 * sp.prim], i1 = m.idx[3 * sp.prim + 1], i2 = m.idx[3 * sp.prim + 2];
@@ -463,6 +541,7 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         out.tri_surface[i] = sp.surface;
         out.tri_prim[i] = sp.prim;
     }
+    });
     return true;
 }
 
