@@ -79,7 +79,9 @@ typedef enum vr_material_kind {
     VR_MAT_METAL = 1,           /* Materials::metal(albedo, fuzz), simple.rs:135-160; param = fuzz */
     VR_MAT_DIELECTRIC = 2,      /* Materials::dielectric(ir), simple.rs:187-231; param = ir */
     VR_MAT_EMISSION = 3,        /* Materials::colored_emissive(color, strength), simple.rs:163-184; param = strength */
-    VR_MAT_LAMBERTIAN_BSDF = 4  /* Materials::lambertian_bsdf(albedo), simple.rs:60-81 via core/traits.rs:23-40 */
+    VR_MAT_LAMBERTIAN_BSDF = 4, /* Materials::lambertian_bsdf(albedo), simple.rs:60-81 via core/traits.rs:23-40 */
+    VR_MAT_MICROFACET = 5       /* MicrofacetBSDF{color,index,roughness,metallic,emittance,transparent},
+                                   voidray_common/src/microfacet.rs:9-313 via core/traits.rs:23-40 */
 } vr_material_kind;
 
 typedef struct vr_material_desc {
@@ -88,6 +90,10 @@ typedef struct vr_material_desc {
     float param;        /* fuzz | ir | strength */
     int32_t albedo_tex; /* texture handle, or -1: use `color` (ColorType, simple.rs:83-86) */
     int32_t normal_tex; /* texture handle, or -1 (Lambertian.normal, simple.rs:90) */
+    /* VR_MAT_MICROFACET only (microfacet.rs:9-27); `emittance` is carried but, as in the reference, unused by
+       bsdf()/sample() */
+    float index, roughness, metallic, emittance;
+    int32_t transparent;
 } vr_material_desc;
 
 /* Scene::add_material (scene.rs:113-119) */

@@ -26,7 +26,8 @@ MODE_FAITHFUL, MODE_EARLY_OUT, MODE_BRUTE = 0, 1, 2
 
 class _MaterialDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("color", C.c_float * 3), ("param", C.c_float), ("albedo_tex", C.c_int32),
-                ("normal_tex", C.c_int32)]
+                ("normal_tex", C.c_int32), ("index", C.c_float), ("roughness", C.c_float), ("metallic", C.c_float),
+                ("emittance", C.c_float), ("transparent", C.c_int32)]
 
 
 class _Settings(C.Structure):
@@ -106,7 +107,9 @@ class OracleScene:
             else:
                 raise TypeError(surf)
         for m in scene.materials:
-            d = _MaterialDesc(int(m.kind), (C.c_float * 3)(*m.color), float(m.param), int(m.albedo_tex), int(m.normal_tex))
+            d = _MaterialDesc(int(m.kind), (C.c_float * 3)(*m.color), float(m.param), int(m.albedo_tex), int(m.normal_tex),
+                              float(m.index), float(m.roughness), float(m.metallic), float(m.emittance),
+                              1 if m.transparent else 0)
             if lib.vo_add_material(h, C.byref(d)) < 0:
                 raise ValueError(f"oracle: unknown material kind {m.kind}")
         for o in scene.objects:

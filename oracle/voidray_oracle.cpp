@@ -173,6 +173,33 @@ struct Rng {
             return V3{x1 * factor, x2 * factor, 1.0f - 2.0f * sum};
         }
     }
+    // rand 0.8.5 Standard f32: 24 random bits * 2^-24
+    F gen_f32() { return (F)(next_u32() >> 8) * (1.0f / 16777216.0f); }
+    // BlockRng::next_u64: two consecutive words, low word first
+    uint64_t next_u64() {
+        const uint64_t lo = next_u32();
+        const uint64_t hi = next_u32();
+        return (hi << 32) | lo;
+    }
+    // rng.gen_bool(p) = Bernoulli::new(p).sample: p_int = (p * 2^64) as u64, true iff next_u64 < p_int;
+    // p == 1 is always true without a draw. (Bernoulli::new panics for p outside [0, 1]; p > 1 is treated as 1.)
+    bool gen_bool(double p) {
+        if (p >= 1.0) return true;
+        const uint64_t p_int = p > 0.0 ? (uint64_t)(p * 18446744073709551616.0) : 0;
+        return next_u64() < p_int;
+    }
+    // rand_distr 0.4.3 UnitCircle
+    V2 unit_circle() {
+        F x1, x2, sum;
+        while (true) {
+            x1 = uniform_m1_1();
+            x2 = uniform_m1_1();
+            sum = x1 * x1 + x2 * x2;
+            if (sum < 1.0f) break;
+        }
+        const F diff = x1 * x1 - x2 * x2;
+        return V2{diff / sum, 2.0f * x1 * x2 / sum};
+    }
     // rand_distr::UnitDisc
     V2 unit_disc() {
         while (true) {
@@ -871,6 +898,154 @@ struct LambertianBSDF : Material {
     }
 };
 
+// util/math.rs:50-60 — note Matrix3::new is column-major, so the product below evaluates
+// (ns . h, nss . h, normal . h): the transpose of a local-to-world basis. Reproduced as written.
+struct M3 {
+    V3 c0, c1, c2;
+};
+inline V3 m3_mul(const M3& m, V3 v) { return m.c0 * v.x + m.c1 * v.y + m.c2 * v.z; }
+inline M3 local_to_world(V3 normal) {
+    const V3 ns = std::isnormal(normal.x) ? normalize(v3(normal.y, -normal.x, 0.0f)) : normalize(v3(0.0f, -normal.z, normal.y));
+    const V3 nss = cross(normal, ns);
+    return M3{v3(ns.x, nss.x, normal.x), v3(ns.y, nss.y, normal.y), v3(ns.z, nss.z, normal.z)};
+}
+inline V3 lerp_v(V3 a, V3 b, F t) { return a * (1.0f - t) + b * t; }
+inline bool sign_positive(F x) { return !std::signbit(x); }
+inline F signum(F x) { return std::isnan(x) ? x : (std::signbit(x) ? -1.0f : 1.0f); }
+
+// voidray_common/src/microfacet.rs through the blanket impl core/traits.rs:23-40
+struct MicrofacetBSDF : Material {
+    Color color;
+    F index, roughness, metallic, emittance;
+    bool transparent;
+
+    // microfacet.rs:120-208
+    Color bsdf(V3 n, V3 wo, V3 wi) const {
+        const F n_dot_wi = dot(n, wi);
+        const F n_dot_wo = dot(n, wo);
+        const bool wi_outside = sign_positive(n_dot_wi);
+        const bool wo_outside = sign_positive(n_dot_wo);
+        if (!transparent && (!wi_outside || !wo_outside)) return BLACK;
+        if (wi_outside == wo_outside) {
+            const V3 h = normalize(wi + wo);
+            const F wo_dot_h = dot(wo, h);
+            const F n_dot_h = dot(n, h);
+            const F nh2 = powi(n_dot_h, 2);
+            const F m2 = roughness * roughness;
+            const F d = std::exp((nh2 - 1.0f) / (m2 * nh2)) / (m2 * PI_F * nh2 * nh2);
+            V3 f;
+            if (!wi_outside && std::sqrt(1.0f - wo_dot_h * wo_dot_h) * index > 1.0f) {
+                f = v3(1.0f, 1.0f, 1.0f);
+            } else {
+                const F f0s = powi((index - 1.0f) / (index + 1.0f), 2);
+                const V3 f0 = lerp_v(v3(f0s, f0s, f0s), color, metallic);
+                f = f0 + (v3(1.0f, 1.0f, 1.0f) - f0) * powi(1.0f - wo_dot_h, 5);
+            }
+            F g = rmin(n_dot_wi * n_dot_h, n_dot_wo * n_dot_h);
+            g = (2.0f * g) / wo_dot_h;
+            g = rmin(g, 1.0f);
+            const V3 specular = d * f * g / (4.0f * n_dot_wo * n_dot_wi);
+            if (transparent) return specular;
+            const V3 diffuse = mul_elem(v3(1.0f, 1.0f, 1.0f) - f, color) / PI_F;
+            return specular + diffuse;
+        }
+        const F eta_t = wo_outside ? index : 1.0f / index;
+        const V3 h = normalize(wi * eta_t + wo);
+        const F wi_dot_h = dot(wi, h);
+        const F wo_dot_h = dot(wo, h);
+        const F n_dot_h = dot(n, h);
+        const F nh2 = powi(n_dot_h, 2);
+        const F m2 = roughness * roughness;
+        const F d = std::exp((nh2 - 1.0f) / (m2 * nh2)) / (m2 * PI_F * nh2 * nh2);
+        const F f0s = powi((index - 1.0f) / (index + 1.0f), 2);
+        const V3 f0 = lerp_v(v3(f0s, f0s, f0s), color, metallic);
+        const V3 f = f0 + (v3(1.0f, 1.0f, 1.0f) - f0) * powi(1.0f - std::fabs(wi_dot_h), 5);
+        F g = rmin(std::fabs(n_dot_wi * n_dot_h), std::fabs(n_dot_wo * n_dot_h));
+        g = (2.0f * g) / std::fabs(wo_dot_h);
+        g = rmin(g, 1.0f);
+        const V3 btdf = std::fabs(wi_dot_h * wo_dot_h / (n_dot_wi * n_dot_wo)) *
+                        (d * (v3(1.0f, 1.0f, 1.0f) - f) * g / powi(eta_t * wi_dot_h + wo_dot_h, 2));
+        return mul_elem(btdf, color);
+    }
+
+    V3 beckmann(V3 n, F m2, Rng& rng) const {  // :239-249
+        const F theta = std::atan(std::sqrt(m2 * -std::log(rng.gen_f32())));
+        const F sin_t = std::sin(theta), cos_t = std::cos(theta);
+        const V2 c = rng.unit_circle();
+        return m3_mul(local_to_world(n), v3(c.x * sin_t, c.y * sin_t, cos_t));
+    }
+    F beckmann_pdf(V3 h, V3 n, F m2) const {  // :251-256
+        const F cos_t = std::fabs(dot(h, n));
+        const F sin_t = std::sqrt(1.0f - cos_t * cos_t);
+        return (1.0f / (PI_F * m2 * powi(cos_t, 3))) * std::exp(-powi(sin_t / cos_t, 2) / m2);
+    }
+
+    // microfacet.rs:222-313; returns false for None
+    bool sample(V3 n, V3 wo, Rng& rng, V3& wi_out, F& pdf_out) const {
+        const F m2 = roughness * roughness;
+        const F f0 = powi((index - 1.0f) / (index + 1.0f), 2);
+        F f = (1.0f - metallic) * f0 + metallic * ((color.x + color.y + color.z) / 3.0f);
+        f = f * (1.0f - 0.2f) + 1.0f * 0.2f;  // lerp(f, 1.0, 0.2)
+        const F eta_t = dot(wo, n) > 0.0f ? index : 1.0f / index;
+        V3 wi;
+        if (rng.gen_bool((double)f)) {
+            const V3 h = beckmann(n, m2, rng);
+            wi = -reflect(wo, h);
+        } else if (!transparent) {
+            const V2 dsk = rng.unit_disc();
+            const F z = std::sqrt(1.0f - dsk.x * dsk.x - dsk.y * dsk.y);
+            wi = m3_mul(local_to_world(n), v3(dsk.x, dsk.y, z));
+        } else {
+            const V3 h = beckmann(n, m2, rng);
+            const F cos_to = dot(h, wo);
+            const V3 wo_perp = wo - h * cos_to;
+            const V3 wi_perp = -wo_perp / eta_t;
+            const F sin2_ti = magnitude2(wi_perp);
+            if (sin2_ti > 1.0f) return false;
+            const F cos_ti = std::sqrt(1.0f - sin2_ti);
+            wi = -signum(cos_to) * cos_ti * h + wi_perp;
+        }
+        F p = 0.0f;
+        {
+            const V3 h = normalize(wi + wo);
+            const F p_h = beckmann_pdf(h, n, m2);
+            p += f * p_h / (4.0f * std::fabs(dot(h, wo)));
+        }
+        if (!transparent) {
+            p += (1.0f - f) * rmax(dot(wi, n), 0.0f) / PI_F;
+        } else if (sign_positive(dot(wo, n)) != sign_positive(dot(wi, n))) {
+            const V3 h = normalize(wi * eta_t + wo);
+            const F p_h = beckmann_pdf(h, n, m2);
+            const F h_dot_wo = dot(h, wo);
+            const F h_dot_wi = dot(h, wi);
+            const F jacobian = std::fabs(h_dot_wo) / powi(eta_t * h_dot_wi + h_dot_wo, 2);
+            p += (1.0f - f) * p_h * jacobian;
+        } else {
+            p += 0.0f;
+        }
+        if (p == 0.0f) return false;
+        wi_out = wi;
+        pdf_out = p;
+        return true;
+    }
+
+    // the blanket `impl<M: BSDFMaterial> Material for M`, core/traits.rs:23-40 (wo is the *incoming* direction)
+    Color scatter(const Scene&, const Ray& ray, const HitRecord& hit, Rng& rng, bool& has_scattered,
+                  Ray& scattered) const override {
+        const V3 wo = normalize(ray.direction);
+        V3 wi;
+        F pdf;
+        if (sample(hit.normal, wo, rng, wi, pdf)) {
+            const Color f = bsdf(hit.normal, wo, wi);
+            scattered = Ray(ray.at(hit.t), wi);
+            has_scattered = true;
+            return f * std::fabs(dot(wi, hit.normal)) * (1.0f / pdf);
+        }
+        has_scattered = false;
+        return BLACK;  // hex_color(0x000000)
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // core/tracer.rs
 // ---------------------------------------------------------------------------------------------
@@ -936,11 +1111,13 @@ inline Ray camera_sample_ray(const Scene& scene, F x, F y, F d, Rng& rng) {
 extern "C" {
 
 struct vo_material_desc {
-    int32_t kind;  // 0 lambertian, 1 metal, 2 dielectric, 3 emission, 4 lambertian_bsdf
+    int32_t kind;  // 0 lambertian, 1 metal, 2 dielectric, 3 emission, 4 lambertian_bsdf, 5 microfacet
     float color[3];
     float param;          // metal: fuzz; dielectric: ir; emission: strength
     int32_t albedo_tex;   // -1: use color
     int32_t normal_tex;   // -1: none
+    float index, roughness, metallic, emittance;  // microfacet (voidray_common/src/microfacet.rs:9-27)
+    int32_t transparent;
 };
 
 struct vo_settings {
@@ -1057,6 +1234,17 @@ int32_t vo_add_material(void* p, const vo_material_desc* d) {
         case 4: {
             LambertianBSDF* t = new LambertianBSDF();
             t->albedo = col;
+            m.reset(t);
+            break;
+        }
+        case 5: {
+            MicrofacetBSDF* t = new MicrofacetBSDF();
+            t->color = col;
+            t->index = d->index;
+            t->roughness = d->roughness;
+            t->metallic = d->metallic;
+            t->emittance = d->emittance;
+            t->transparent = d->transparent != 0;
             m.reset(t);
             break;
         }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared_functions():
         assert hasattr(lib, name), f"libvoidray_cuda.so does not export {name}"
-    assert lib.vr_abi_version() == 1
+    assert lib.vr_abi_version() == 2
     # the ctypes table binds exactly the declared functions
     bound = set(_lib.SIGNATURES) | set(_lib.NON_STATUS)
     assert bound == set(declared_functions())
@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     from voidray_b200 import _lib
-    assert C.sizeof(_lib.MaterialDescC) == 28
+    assert C.sizeof(_lib.MaterialDescC) == 48
     assert C.sizeof(_lib.RenderSettingsC) == 40 and _lib.RenderSettingsC.seed.offset == 24
     assert C.sizeof(_lib.StatsC) == 64
 

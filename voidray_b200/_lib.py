@@ -23,7 +23,8 @@ class RenderCancelled(VoidrayError):
 
 class MaterialDescC(C.Structure):
     _fields_ = [("kind", C.c_int32), ("color", C.c_float * 3), ("param", C.c_float), ("albedo_tex", C.c_int32),
-                ("normal_tex", C.c_int32)]
+                ("normal_tex", C.c_int32), ("index", C.c_float), ("roughness", C.c_float), ("metallic", C.c_float),
+                ("emittance", C.c_float), ("transparent", C.c_int32)]
 
 
 class RenderSettingsC(C.Structure):

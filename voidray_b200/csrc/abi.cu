@@ -228,7 +228,7 @@ int32_t check_scene(vr_scene* s) {
 extern "C" {
 
 const char* vr_last_error(void) { return g_error.c_str(); }
-uint32_t vr_abi_version(void) { return 1; }
+uint32_t vr_abi_version(void) { return 2; }
 
 int32_t vr_context_create(int32_t device, void* cuda_stream, vr_context** out) {
     if (!out) return fail(VR_ERR_INVALID, "out is null");
@@ -370,14 +370,18 @@ int32_t vr_scene_add_ground_plane(vr_scene* scene, float height, uint32_t* surfa
 int32_t vr_scene_add_material(vr_scene* scene, const vr_material_desc* desc, uint32_t* material) {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!desc) return fail(VR_ERR_INVALID, "null material desc");
-    if (desc->kind < 0 || desc->kind > VR_MAT_LAMBERTIAN_BSDF) return fail(VR_ERR_INVALID, "unknown material kind");
+    if (desc->kind < 0 || desc->kind > VR_MAT_MICROFACET) return fail(VR_ERR_INVALID, "unknown material kind");
     MaterialRec m;
     m.kind = desc->kind;
     std::memcpy(m.color, desc->color, 12);
     m.param = desc->param;
     m.albedo_tex = desc->kind == VR_MAT_LAMBERTIAN ? desc->albedo_tex : -1;
     m.normal_tex = desc->kind == VR_MAT_LAMBERTIAN ? desc->normal_tex : -1;
-    m.pad = 0;
+    m.transparent = desc->transparent ? 1 : 0;
+    m.index = desc->index;
+    m.roughness = desc->roughness;
+    m.metallic = desc->metallic;
+    m.emittance = desc->emittance;
     if (desc->kind == VR_MAT_EMISSION) {  // Emission::new: color * strength, simple.rs:168-172
         m.color[0] = desc->color[0] * desc->param;
         m.color[1] = desc->color[1] * desc->param;

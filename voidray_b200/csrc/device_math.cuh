@@ -127,6 +127,33 @@ struct Rng {
             return f3{x1 * factor, x2 * factor, 1.0f - 2.0f * sum};
         }
     }
+    // rand 0.8.5 Standard f32: 24 random bits * 2^-24
+    __device__ __forceinline__ float gen_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
+    // BlockRng::next_u64: two consecutive words, low word first
+    __device__ __forceinline__ unsigned long long next_u64() {
+        const unsigned long long lo = next_u32();
+        const unsigned long long hi = next_u32();
+        return (hi << 32) | lo;
+    }
+    // rng.gen_bool(p as f64) = Bernoulli: p_int = (p * 2^64) as u64; p == 1 is always true without a draw
+    __device__ __forceinline__ bool gen_bool(float pf) {
+        const double p = (double)pf;
+        if (p >= 1.0) return true;
+        const unsigned long long p_int = p > 0.0 ? __double2ull_rz(p * 18446744073709551616.0) : 0ull;
+        return next_u64() < p_int;
+    }
+    // rand_distr 0.4.3 UnitCircle
+    __device__ __forceinline__ f2 unit_circle() {
+        float x1, x2, sum;
+        while (true) {
+            x1 = uniform_m1_1();
+            x2 = uniform_m1_1();
+            sum = x1 * x1 + x2 * x2;
+            if (sum < 1.0f) break;
+        }
+        const float diff = x1 * x1 - x2 * x2;
+        return f2{diff / sum, 2.0f * x1 * x2 / sum};
+    }
     // rand_distr 0.4.3 UnitDisc
     __device__ __forceinline__ f2 unit_disc() {
         while (true) {

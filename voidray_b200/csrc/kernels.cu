@@ -406,6 +406,132 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
 // is evaluated exactly: every level's attenuation is parked in wf.att and the product is unwound from
 // the terminal value back to level 0 when the path ends, in the reference's own operation order.
 // ------------------------------------------------------------------------------------------------
+// ---- MicrofacetBSDF, voidray_common/src/microfacet.rs (same operation order as the reference) ----
+__device__ __forceinline__ f3 lerp_v(f3 a, f3 b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float powi2(float a) { return a * a; }
+__device__ __forceinline__ float powi3(float a) { return a * (a * a); }  // __powisf2(a, 3): r = a; a *= a; r *= a
+__device__ __forceinline__ bool sign_positive(float x) { return (__float_as_uint(x) >> 31) == 0u; }
+
+// util/math.rs:50-60: Matrix3::new is column-major, so `local_to_world(n) * h` evaluates
+// (ns . h, nss . h, n . h) — the transpose of a local-to-world basis. Reproduced as written.
+__device__ __forceinline__ f3 local_to_world_mul(f3 normal, f3 h) {
+    const bool is_normal = isfinite(normal.x) && fabsf(normal.x) >= 1.17549435e-38f;
+    const f3 ns = is_normal ? normalize(mk3(normal.y, -normal.x, 0.0f)) : normalize(mk3(0.0f, -normal.z, normal.y));
+    const f3 nss = cross(normal, ns);
+    const f3 c0 = mk3(ns.x, nss.x, normal.x), c1 = mk3(ns.y, nss.y, normal.y), c2 = mk3(ns.z, nss.z, normal.z);
+    return c0 * h.x + c1 * h.y + c2 * h.z;
+}
+
+__device__ __noinline__ f3 microfacet_bsdf(const MaterialRec& m, f3 n, f3 wo, f3 wi) {  // microfacet.rs:120-208
+    const f3 color = mk3(m.color[0], m.color[1], m.color[2]);
+    const f3 one = mk3(1.0f, 1.0f, 1.0f);
+    const float n_dot_wi = dot(n, wi);
+    const float n_dot_wo = dot(n, wo);
+    const bool wi_outside = sign_positive(n_dot_wi);
+    const bool wo_outside = sign_positive(n_dot_wo);
+    if (!m.transparent && (!wi_outside || !wo_outside)) return mk3(0.0f, 0.0f, 0.0f);
+    const float m2 = m.roughness * m.roughness;
+    const float f0s = powi2((m.index - 1.0f) / (m.index + 1.0f));
+    if (wi_outside == wo_outside) {
+        const f3 h = normalize(wi + wo);
+        const float wo_dot_h = dot(wo, h);
+        const float n_dot_h = dot(n, h);
+        const float nh2 = powi2(n_dot_h);
+        const float dd = expf((nh2 - 1.0f) / (m2 * nh2)) / (m2 * VR_PI_F * nh2 * nh2);
+        f3 f;
+        if (!wi_outside && sqrtf(1.0f - wo_dot_h * wo_dot_h) * m.index > 1.0f) {
+            f = one;
+        } else {
+            const f3 f0 = lerp_v(mk3(f0s, f0s, f0s), color, m.metallic);
+            f = f0 + (one - f0) * powi5(1.0f - wo_dot_h);
+        }
+        float g = fminf(n_dot_wi * n_dot_h, n_dot_wo * n_dot_h);
+        g = (2.0f * g) / wo_dot_h;
+        g = fminf(g, 1.0f);
+        const f3 specular = dd * f * g / (4.0f * n_dot_wo * n_dot_wi);
+        if (m.transparent) return specular;
+        const f3 diffuse = mul_elem(one - f, color) / VR_PI_F;
+        return specular + diffuse;
+    }
+    const float eta_t = wo_outside ? m.index : 1.0f / m.index;
+    const f3 h = normalize(wi * eta_t + wo);
+    const float wi_dot_h = dot(wi, h);
+    const float wo_dot_h = dot(wo, h);
+    const float n_dot_h = dot(n, h);
+    const float nh2 = powi2(n_dot_h);
+    const float dd = expf((nh2 - 1.0f) / (m2 * nh2)) / (m2 * VR_PI_F * nh2 * nh2);
+    const f3 f0 = lerp_v(mk3(f0s, f0s, f0s), color, m.metallic);
+    const f3 f = f0 + (one - f0) * powi5(1.0f - fabsf(wi_dot_h));
+    float g = fminf(fabsf(n_dot_wi * n_dot_h), fabsf(n_dot_wo * n_dot_h));
+    g = (2.0f * g) / fabsf(wo_dot_h);
+    g = fminf(g, 1.0f);
+    const f3 btdf = fabsf(wi_dot_h * wo_dot_h / (n_dot_wi * n_dot_wo)) *
+                    (dd * (one - f) * g / powi2(eta_t * wi_dot_h + wo_dot_h));
+    return mul_elem(btdf, color);
+}
+
+__device__ __forceinline__ f3 microfacet_beckmann(f3 n, float m2, Rng& rng) {  // microfacet.rs:239-249
+    const float theta = atanf(sqrtf(m2 * -logf(rng.gen_f32())));
+    const float sin_t = sinf(theta), cos_t = cosf(theta);
+    const f2 c = rng.unit_circle();
+    return local_to_world_mul(n, mk3(c.x * sin_t, c.y * sin_t, cos_t));
+}
+__device__ __forceinline__ float microfacet_beckmann_pdf(f3 h, f3 n, float m2) {  // microfacet.rs:251-256
+    const float cos_t = fabsf(dot(h, n));
+    const float sin_t = sqrtf(1.0f - cos_t * cos_t);
+    return (1.0f / (VR_PI_F * m2 * powi3(cos_t))) * expf(-powi2(sin_t / cos_t) / m2);
+}
+
+// microfacet.rs:222-313; false = None
+__device__ __noinline__ bool microfacet_sample(const MaterialRec& m, f3 n, f3 wo, Rng& rng, f3& wi_out, float& pdf_out) {
+    const float m2 = m.roughness * m.roughness;
+    const float f0 = powi2((m.index - 1.0f) / (m.index + 1.0f));
+    float f = (1.0f - m.metallic) * f0 + m.metallic * ((m.color[0] + m.color[1] + m.color[2]) / 3.0f);
+    f = f * (1.0f - 0.2f) + 1.0f * 0.2f;
+    const float eta_t = dot(wo, n) > 0.0f ? m.index : 1.0f / m.index;
+    f3 wi;
+    if (rng.gen_bool(f)) {
+        const f3 h = microfacet_beckmann(n, m2, rng);
+        wi = -reflect(wo, h);
+    } else if (!m.transparent) {
+        const f2 dsk = rng.unit_disc();
+        const float z = sqrtf(1.0f - dsk.x * dsk.x - dsk.y * dsk.y);
+        wi = local_to_world_mul(n, mk3(dsk.x, dsk.y, z));
+    } else {
+        const f3 h = microfacet_beckmann(n, m2, rng);
+        const float cos_to = dot(h, wo);
+        const f3 wo_perp = wo - h * cos_to;
+        const f3 wi_perp = -wo_perp / eta_t;
+        const float sin2_ti = magnitude2(wi_perp);
+        if (sin2_ti > 1.0f) return false;
+        const float cos_ti = sqrtf(1.0f - sin2_ti);
+        const float sg = isnan(cos_to) ? cos_to : (sign_positive(cos_to) ? 1.0f : -1.0f);
+        wi = -sg * cos_ti * h + wi_perp;
+    }
+    float p = 0.0f;
+    {
+        const f3 h = normalize(wi + wo);
+        const float p_h = microfacet_beckmann_pdf(h, n, m2);
+        p += f * p_h / (4.0f * fabsf(dot(h, wo)));
+    }
+    if (!m.transparent) {
+        p += (1.0f - f) * fmaxf(dot(wi, n), 0.0f) / VR_PI_F;
+    } else if (sign_positive(dot(wo, n)) != sign_positive(dot(wi, n))) {
+        const f3 h = normalize(wi * eta_t + wo);
+        const float p_h = microfacet_beckmann_pdf(h, n, m2);
+        const float h_dot_wo = dot(h, wo);
+        const float h_dot_wi = dot(h, wi);
+        const float jacobian = fabsf(h_dot_wo) / powi2(eta_t * h_dot_wi + h_dot_wo);
+        p += (1.0f - f) * p_h * jacobian;
+    } else {
+        p += 0.0f;
+    }
+    if (p == 0.0f) return false;
+    wi_out = wi;
+    pdf_out = p;
+    return true;
+}
+
 __device__ __forceinline__ f3 clamp_color(f3 c, float mx) { return mk3(fminf(c.x, mx), fminf(c.y, mx), fminf(c.z, mx)); }
 
 // L_level = value; fold levels level-1 .. 0
@@ -530,6 +656,18 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
                 } else if (m.kind == 3) {
                     // Emission::scatter, simple.rs:176-184 (colour * strength folded on the host)
                     attenuation = mk3(m.color[0], m.color[1], m.color[2]);
+                } else if (m.kind == 5) {
+                    // MicrofacetBSDF through the blanket impl, core/traits.rs:23-40 + microfacet.rs:120-313
+                    const f3 wo = normalize(d);  // the *incoming* direction, as in the reference
+                    f3 wi;
+                    float pdf;
+                    attenuation = mk3(0.0f, 0.0f, 0.0f);
+                    if (microfacet_sample(m, normal, wo, rng, wi, pdf)) {
+                        const f3 f = microfacet_bsdf(m, normal, wo, wi);
+                        attenuation = f * fabsf(dot(wi, normal)) * (1.0f / pdf);
+                        new_d = normalize(wi);
+                        scattered = true;
+                    }
                 } else {
                     // LambertianBSDF through the blanket impl, core/traits.rs:23-40 + simple.rs:64-81
                     const f3 wi = normalize(rng.unit_sphere());

@@ -27,13 +27,14 @@ static const int TRI_ISECT_QUADS = 4;
 //   q3 = (ng.xyz, uv1.y)   q4 = (uv2.x, uv2.y, material index bits, 0)
 static const int TRI_SHADE_QUADS = 5;
 
-struct MaterialRec {  // 32 B
+struct MaterialRec {  // 48 B
     int32_t kind;
     float color[3];
     float param;
     int32_t albedo_tex;
     int32_t normal_tex;
-    int32_t pad;
+    int32_t transparent;
+    float index, roughness, metallic, emittance;  // microfacet
 };
 
 struct TextureRec {  // texels are RGBA f32 (w unused) so one tap is one 16-byte load

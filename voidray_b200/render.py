@@ -92,7 +92,8 @@ class SceneAcceleration:
                 raise TypeError(f"unknown surface {surf!r}")
         for m in scene.materials:
             desc = MaterialDescC(int(m.kind), (C.c_float * 3)(*m.color), float(m.param), int(m.albedo_tex),
-                                 int(m.normal_tex))
+                                 int(m.normal_tex), float(m.index), float(m.roughness), float(m.metallic),
+                                 float(m.emittance), 1 if m.transparent else 0)
             check(lib.vr_scene_add_material(self.handle, C.byref(desc), C.byref(out)))
         for o in scene.objects:
             check(lib.vr_scene_add_object(self.handle, o.material, o.surface, C.byref(out)))

@@ -88,7 +88,7 @@ class Settings:  # settings.rs:3-7
 
 
 # ---- materials ------------------------------------------------------------------------------------
-MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_EMISSION, MAT_LAMBERTIAN_BSDF = range(5)
+MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_EMISSION, MAT_LAMBERTIAN_BSDF, MAT_MICROFACET = range(6)
 
 
 @dataclass
@@ -98,6 +98,12 @@ class MaterialDesc:
     param: float = 0.0
     albedo_tex: int = -1
     normal_tex: int = -1
+    # MicrofacetBSDF fields (voidray_common/src/microfacet.rs:9-27)
+    index: float = 1.5
+    roughness: float = 1.0
+    metallic: float = 0.0
+    emittance: float = 0.0
+    transparent: bool = False
 
 
 class Materials:
@@ -134,6 +140,39 @@ class Materials:
     @staticmethod
     def colored_emissive(color, strength: float) -> MaterialDesc:
         return MaterialDesc(MAT_EMISSION, tuple(color), float(strength))
+
+
+class MicrofacetBSDF:
+    """voidray_common/src/microfacet.rs:29-101 (constructors of the Beckmann / Cook-Torrance BSDF)."""
+
+    @staticmethod
+    def _mk(color, index, roughness, metallic=0.0, emittance=0.0, transparent=False) -> MaterialDesc:
+        return MaterialDesc(MAT_MICROFACET, tuple(color), index=float(index), roughness=float(roughness),
+                            metallic=float(metallic), emittance=float(emittance), transparent=bool(transparent))
+
+    @staticmethod
+    def diffuse(color) -> MaterialDesc:
+        return MicrofacetBSDF._mk(color, 1.5, 1.0)
+
+    @staticmethod
+    def specular(color, roughness: float) -> MaterialDesc:
+        return MicrofacetBSDF._mk(color, 1.5, roughness)
+
+    @staticmethod
+    def clear(index: float, roughness: float) -> MaterialDesc:
+        return MicrofacetBSDF._mk(hex_color(0xFFFFFF), index, roughness, transparent=True)
+
+    @staticmethod
+    def transparent(color, index: float, roughness: float) -> MaterialDesc:
+        return MicrofacetBSDF._mk(color, index, roughness, transparent=True)
+
+    @staticmethod
+    def metallic(color, roughness: float) -> MaterialDesc:
+        return MicrofacetBSDF._mk(color, 1.5, roughness, metallic=1.0)
+
+    @staticmethod
+    def light(color, emittance: float) -> MaterialDesc:
+        return MicrofacetBSDF._mk(color, 1.0, 1.0, emittance=emittance)
 
 
 # ---- surfaces -------------------------------------------------------------------------------------
