@@ -145,7 +145,11 @@ typedef struct vr_render_settings {
     int32_t render_mode;    /* 0 RenderMode::Full, 1 RenderMode::Normal (settings.rs:9-13) */
     int32_t pixel_mapping;  /* 0: y = index / width (intended); 1: the reference's y = index / height with
                                u32 wrapping (iterative.rs:26,33) — identical for square targets */
-    int32_t integrator;     /* 0: the reference estimator (parity). Others reserved. */
+    int32_t integrator;     /* 0: the reference estimator (parity). 1: "fast" — the same integrand, but Lambertian
+                               directions are drawn by one-sample MIS between the reference's normal + UnitSphere
+                               density and an HDRI luminance table, and paths play Russian roulette from depth 3.
+                               Not in the reference (core/tracer.rs:19-56 has neither); equal in expectation to
+                               integrator 0 only without the firefly clamp. */
     uint64_t seed;          /* Philox4x32-10 key. The reference's thread_rng() is unseedable (iterative.rs:29) */
     uint32_t sample_offset; /* global index of this render's first camera sample: rank r of an N-GPU job
                                renders [sample_offset, sample_offset + its share) of every pixel */

@@ -33,7 +33,7 @@ class _MaterialDesc(C.Structure):
 class _Settings(C.Structure):
     _fields_ = [("total_samples", C.c_uint32), ("max_bounces", C.c_uint32), ("firefly_clamp", C.c_float),
                 ("render_mode", C.c_int32), ("pixel_mapping", C.c_int32), ("traverse_mode", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("integrator", C.c_int32), ("reserved", C.c_int32)]
 
 
 class _Counters(C.Structure):
@@ -139,7 +139,7 @@ class OracleScene:
     @staticmethod
     def _settings(rs: RenderSettings, traverse_mode: int) -> _Settings:
         return _Settings(int(rs.total_samples), int(rs.max_bounces), float(rs.firefly_clamp), int(rs.render_mode),
-                         int(rs.pixel_mapping), int(traverse_mode), int(rs.seed))
+                         int(rs.pixel_mapping), int(traverse_mode), int(rs.seed), int(rs.integrator), 0)
 
     def trace_rays(self, origins, directions, mode: int = MODE_FAITHFUL, details: bool = False):
         o = np.ascontiguousarray(origins, dtype=F32).reshape(-1, 3)

@@ -681,6 +681,82 @@ struct UniformEnvironment : Environment {  // environments.rs:19-33
 struct HDRIEnvironment : Environment {  // environments.rs:35-86
     std::vector<Color> image;
     size_t width, height;
+
+    // ---- integrator 1 ("fast") only; not in the reference: luminance x sin(theta) sampling tables ----
+    // marginal[j] = P(row < j), cond[j * (W + 1) + i] = P(col < i | row j). A texel's weight is
+    // (luminance + 5 % of the mean luminance) * sin(polar angle of the row centre); the polar angle follows the
+    // lookup's own mapping, environments.rs:80-86: y = (H - 1) - acos(-d.y) / pi * H.
+    std::vector<float> marginal, cond;
+    void build_sampling_tables() {
+        const size_t W = width, H = height;
+        std::vector<double> lum(W * H), sinw(H);
+        double mean = 0.0;
+        for (size_t k = 0; k < W * H; ++k) {
+            lum[k] = 0.2126 * (double)image[k].x + 0.7152 * (double)image[k].y + 0.0722 * (double)image[k].z;
+            mean += lum[k];
+        }
+        mean /= (double)(W * H);
+        for (size_t j = 0; j < H; ++j) {
+            const double sx = 3.14159265358979323846 * ((double)(H - 1) - ((double)j + 0.5)) / (double)H;
+            sinw[j] = sx > 0.0 ? std::sin(sx) : 0.0;
+        }
+        std::vector<double> row_sum(H);
+        double total = 0.0;
+        for (size_t j = 0; j < H; ++j) {
+            double rs = 0.0;
+            for (size_t i = 0; i < W; ++i) rs += (lum[j * W + i] + 0.05 * mean) * sinw[j];
+            row_sum[j] = rs;
+            total += rs;
+        }
+        marginal.assign(H + 1, 0.0f);
+        cond.assign(H * (W + 1), 0.0f);
+        double acc = 0.0;
+        for (size_t j = 0; j < H; ++j) {
+            marginal[j] = (float)(total > 0.0 ? acc / total : (double)j / (double)H);
+            acc += row_sum[j];
+            double c = 0.0;
+            for (size_t i = 0; i < W; ++i) {
+                cond[j * (W + 1) + i] = (float)(row_sum[j] > 0.0 ? c / row_sum[j] : (double)i / (double)W);
+                c += (lum[j * W + i] + 0.05 * mean) * sinw[j];
+            }
+            cond[j * (W + 1) + W] = 1.0f;
+        }
+        marginal[H] = 1.0f;
+    }
+    // largest k in [0, n) with cdf[k] <= xi (cdf has n + 1 entries, cdf[0] = 0, cdf[n] = 1)
+    static size_t cdf_find(const float* cdf, size_t n, F xi) {
+        size_t lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const size_t mid = (lo + hi) / 2;
+            if (cdf[mid] <= xi) lo = mid; else hi = mid;
+        }
+        return lo;
+    }
+    V3 sample_direction(Rng& rng) const {
+        const size_t W = width, H = height;
+        const size_t j = cdf_find(marginal.data(), H, rng.v01());
+        const size_t i = cdf_find(cond.data() + j * (W + 1), W, rng.v01());
+        const F x = (F)i + rng.v01();
+        const F y = (F)j + rng.v01();
+        F sx = ((F)(H - 1) - y) / (F)H * PI_F;
+        if (!(sx > 1.0e-6f)) sx = 1.0e-6f;
+        const F ang = x / (F)W * (2.0f * PI_F) - PI_F;
+        const F r = std::sin(sx);
+        return v3(r * std::cos(ang), -std::cos(sx), -(r * std::sin(ang)));
+    }
+    F pdf_direction(V3 dir) const {
+        const size_t W = width, H = height;
+        const V3 d = normalize(dir);
+        const F sx = std::acos(-d.y);
+        const F sy = std::atan2(-d.z, d.x) + PI_F;
+        const F x = sy / (2.0f * PI_F) * (F)W;
+        const F y = (F)(H - 1) - (sx / PI_F * (F)H);
+        if (!(y >= 0.0f)) return 0.0f;
+        const size_t i = std::min(f32_as_usize(x), W - 1);
+        const size_t j = std::min(f32_as_usize(y), H - 1);
+        const F p_tex = (marginal[j + 1] - marginal[j]) * (cond[j * (W + 1) + i + 1] - cond[j * (W + 1) + i]);
+        return p_tex * ((F)W * (F)H) / (2.0f * PI_F * PI_F * rmax(std::sin(sx), 1.0e-6f));
+    }
     Color bilinear_sample(F x, F y) const {  // :57-76
         const size_t len = image.size();
         const size_t x0 = std::min(f32_as_usize(x), width - 1);
@@ -1057,7 +1133,32 @@ struct RenderSettings {  // core/settings.rs:15-33 + oracle-only switches
     int32_t pixel_mapping;  // 0 = fixed (y = index / width), 1 = reference (iterative.rs:26,33)
     uint64_t seed;
     int32_t traverse_mode;
+    int32_t integrator;  // 0 = the reference estimator; 1 = "fast" (not in the reference)
 };
+
+// Density (per solid angle) of the reference's Lambertian direction normalize(n + UnitSphere)
+// (simple.rs:116) for an arbitrary, possibly non-unit n: the points n + s lie on the unit sphere around n;
+// a ray from the origin along w meets it at r = a c +- sqrt(a^2 c^2 - a^2 + 1) (a = |n|, c = cos(w, n)), and
+// projecting the uniform surface measure gives sum over positive roots of r^2 / (4 pi |r - a c|).
+// For |n| = 1 this is cos/pi.
+inline F lambert_reference_pdf(V3 w_unit, V3 n) {
+    const F a = magnitude(n);
+    if (!(a > 1.0e-6f)) return 1.0f / (4.0f * PI_F);
+    const F ac = dot(w_unit, n);
+    const F disc = ac * ac - a * a + 1.0f;
+    if (!(disc >= 0.0f)) return 0.0f;
+    const F sq = rmax(std::sqrt(disc), 1.0e-6f);
+    const F r1 = ac + sq, r2 = ac - sq;
+    F sum = 0.0f;
+    if (r1 > 0.0f) sum += r1 * r1;
+    if (r2 > 0.0f) sum += r2 * r2;
+    return sum / (4.0f * PI_F * sq);
+}
+
+// integrator 1, Lambertian: same integrand as simple.rs:103-132 (albedo x the density above), sampled by
+// one-sample MIS between that density and the HDRI table. Returns the attenuation albedo * p_ref / p_mix.
+Color lambertian_fast(const Scene& scene, const Lambertian& m, const HitRecord& hit, Rng& rng, bool& has_scattered,
+                      Ray& scattered);
 
 Color trace_ray_internal(const Scene& scene, const RenderSettings& st, const Ray& ray, uint32_t depth,
                          Rng& rng, Counters& c) {  // tracer.rs:19-56
@@ -1074,17 +1175,53 @@ Color trace_ray_internal(const Scene& scene, const RenderSettings& st, const Ray
         Color attenuation;
         bool has_scattered = false;
         Ray scattered;
-        if (st.render_mode == 0) {
+        const Lambertian* lam = st.integrator == 1 ? dynamic_cast<const Lambertian*>(&material) : nullptr;
+        if (st.render_mode == 0 && lam) {
+            attenuation = lambertian_fast(scene, *lam, hit, rng, has_scattered, scattered);
+        } else if (st.render_mode == 0) {
             attenuation = material.scatter(scene, ray, hit, rng, has_scattered, scattered);
         } else {
             attenuation = 0.5f * normalize(hit.normal) + v3(1.0f, 1.0f, 1.0f) * 0.5f;
         }
+        // integrator 1: Russian roulette from the fourth segment on. Survival probability = the largest
+        // attenuation channel clamped to [0.05, 1]; survivors are divided by it, the rest see BLACK.
+        bool killed = false;
+        if (st.integrator == 1 && has_scattered && depth >= 3) {
+            const F q = rmin(rmax(rmax(attenuation.x, rmax(attenuation.y, attenuation.z)), 0.05f), 1.0f);
+            if (rng.v01() < q) attenuation = attenuation / q;
+            else killed = true;
+        }
         Color delta;
-        if (has_scattered) delta = mul_elem(attenuation, trace_ray_internal(scene, st, scattered, depth + 1, rng, c));
+        if (has_scattered && killed) delta = mul_elem(attenuation, BLACK);
+        else if (has_scattered) delta = mul_elem(attenuation, trace_ray_internal(scene, st, scattered, depth + 1, rng, c));
         else delta = attenuation;
         color = color + color_clamp(delta, st.firefly_clamp);
     }
     return color;
+}
+
+Color lambertian_fast(const Scene& scene, const Lambertian& m, const HitRecord& hit, Rng& rng, bool& has_scattered,
+                      Ray& scattered) {
+    const V3 normal = m.has_normal_tex ? scene.textures[m.normal_tex].sample(hit.uv.x, hit.uv.y) : hit.normal;
+    const Color albedo = m.albedo_is_texture ? scene.textures[m.albedo_tex].sample(hit.uv.x, hit.uv.y) : m.albedo;
+    const HDRIEnvironment* env = dynamic_cast<const HDRIEnvironment*>(scene.environment.get());
+    V3 w;
+    if (env && rng.v01() >= 0.5f) {
+        w = normalize(env->sample_direction(rng));
+    } else {
+        V3 dir = normal + rng.unit_sphere();
+        if (near_zero(dir)) dir = normal;
+        w = normalize(dir);
+    }
+    scattered = Ray(hit.point, w);
+    const F p_ref = lambert_reference_pdf(scattered.direction, normal);
+    const F p_mix = env ? 0.5f * p_ref + 0.5f * env->pdf_direction(scattered.direction) : p_ref;
+    if (!(p_mix > 0.0f) || !(p_ref > 0.0f)) {
+        has_scattered = false;
+        return BLACK;
+    }
+    has_scattered = true;
+    return albedo * (p_ref / p_mix);
 }
 
 // render/iterative.rs:25-33 — pixel index -> camera-plane coordinates
@@ -1128,6 +1265,8 @@ struct vo_settings {
     int32_t pixel_mapping;
     int32_t traverse_mode;
     uint64_t seed;
+    int32_t integrator;
+    int32_t reserved;
 };
 
 struct vo_counters {
@@ -1292,6 +1431,7 @@ void vo_set_environment_hdri(void* p, const float* rgb, uint32_t w, uint32_t h) 
     e->height = h;
     e->image.resize((size_t)w * h);
     for (size_t i = 0; i < e->image.size(); ++i) e->image[i] = v3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+    e->build_sampling_tables();
     s->environment = e;
 }
 void vo_clear_environment(void* p) { ((Scene*)p)->environment.reset(); }
@@ -1327,6 +1467,7 @@ static RenderSettings to_settings(const vo_settings* v) {
     st.pixel_mapping = v->pixel_mapping;
     st.seed = v->seed;
     st.traverse_mode = v->traverse_mode;
+    st.integrator = v->integrator;
     return st;
 }
 

@@ -141,6 +141,7 @@ FrameParams frame_params(const vr_render* r) {
     fp.max_bounces = r->settings.max_bounces;
     fp.firefly_clamp = r->settings.firefly_clamp;
     fp.render_mode = r->settings.render_mode;
+    fp.integrator = r->settings.integrator;
     fp.seed = r->settings.seed;
     return fp;
 }
@@ -215,6 +216,18 @@ int32_t upload_vector(vr_scene* scene, const std::vector<T>& v, const void** out
         VR_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, scene->ctx->stream));
     scene->h2d_bytes += v.size() * sizeof(T);
     *out = d;
+    return VR_OK;
+}
+
+// Sampling tables of integrator 1, built and uploaded the first time a render asks for them after a commit.
+int32_t ensure_env_tables(vr_scene* scene) {
+    if (scene->host.env_kind != 2 || scene->dev.env_marginal) return VR_OK;
+    std::vector<float> marginal, cond;
+    build_env_tables(scene->host.env_image, marginal, cond);
+    int32_t rc;
+    if ((rc = upload_vector(scene, marginal, (const void**)&scene->dev.env_marginal))) return rc;
+    if ((rc = upload_vector(scene, cond, (const void**)&scene->dev.env_cond))) return rc;
+    VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));  // the host vectors go out of scope
     return VR_OK;
 }
 
@@ -503,12 +516,16 @@ int32_t vr_scene_commit(vr_scene* scene) {
         scene->dev_textures.push_back(rec);
     }
     if ((rc = upload_vector(scene, scene->dev_textures, (const void**)&d.textures))) return rc;
+    d.has_microfacet = 0;
+    for (const MaterialRec& m : scene->host.materials)
+        if (m.kind == VR_MAT_MICROFACET) d.has_microfacet = 1;
     d.n_tris = f.n_tris;
     d.n_analytics = (uint32_t)f.analytics.size();
     d.env_kind = scene->host.env_kind;
     std::memcpy(d.env_color, scene->host.env_color, 12);
     if (scene->host.env_kind == 2) {
         if ((rc = upload_texture(scene, scene->host.env_image, stage, &d.env_tex))) return rc;
+        // the sampling tables of integrator 1 are built on demand by vr_render_begin (ensure_env_tables)
     }
     d.camera = f.camera;
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
@@ -545,8 +562,12 @@ int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const 
         return fail(VR_ERR_INVALID, "bad target dimensions");
     if (settings->total_samples == 0) return fail(VR_ERR_INVALID, "total_samples must be > 0");
     if (settings->max_bounces > 64) return fail(VR_ERR_INVALID, "max_bounces > 64 is not supported");
-    if (settings->integrator != 0) return fail(VR_ERR_INVALID, "unknown integrator");
+    if (settings->integrator != 0 && settings->integrator != 1) return fail(VR_ERR_INVALID, "unknown integrator");
     VR_CUDA(cudaSetDevice(scene->ctx->device));
+    if (settings->integrator == 1) {
+        const int32_t rc = ensure_env_tables(scene);
+        if (rc) return rc;
+    }
     vr_render* r = new (std::nothrow) vr_render();
     if (!r) return fail(VR_ERR_OOM, "host allocation failed");
     r->scene = scene;

@@ -406,6 +406,63 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
 // is evaluated exactly: every level's attenuation is parked in wf.att and the product is unwound from
 // the terminal value back to level 0 when the path ends, in the reference's own operation order.
 // ------------------------------------------------------------------------------------------------
+// ---- integrator 1 ("fast"; not in the reference) ----------------------------------------------------
+// Density per solid angle of the reference's Lambertian direction normalize(n + UnitSphere) (simple.rs:116)
+// for an arbitrary, possibly non-unit n: the points n + s lie on the unit sphere around n; a ray from the
+// origin along w meets it at r = a c +- sqrt(a^2 c^2 - a^2 + 1) (a = |n|, c = cos(w, n)); projecting the uniform
+// surface measure gives the sum over positive roots of r^2 / (4 pi |r - a c|). For |n| = 1 this is cos / pi.
+__device__ __forceinline__ float lambert_reference_pdf(f3 w_unit, f3 n) {
+    const float a = magnitude(n);
+    if (!(a > 1.0e-6f)) return 1.0f / (4.0f * VR_PI_F);
+    const float ac = dot(w_unit, n);
+    const float disc = ac * ac - a * a + 1.0f;
+    if (!(disc >= 0.0f)) return 0.0f;
+    const float sq = fmaxf(sqrtf(disc), 1.0e-6f);
+    const float r1 = ac + sq, r2 = ac - sq;
+    float sum = 0.0f;
+    if (r1 > 0.0f) sum += r1 * r1;
+    if (r2 > 0.0f) sum += r2 * r2;
+    return sum / (4.0f * VR_PI_F * sq);
+}
+// largest k in [0, n) with cdf[k] <= xi (cdf has n + 1 entries)
+__device__ __forceinline__ uint32_t cdf_find(const float* __restrict__ cdf, uint32_t n, float xi) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (__ldg(cdf + mid) <= xi) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+// HDRI luminance x sin(theta) table sampling; the texel <-> direction mapping is the lookup's own
+// (environments.rs:80-86): x = phi / 2pi * W, y = (H - 1) - acos(-d.y) / pi * H.
+__device__ __noinline__ f3 env_sample_direction(const DeviceScene& sc, Rng& rng) {
+    const uint32_t W = sc.env_tex.width, H = sc.env_tex.height;
+    const uint32_t j = cdf_find(sc.env_marginal, H, rng.v01());
+    const uint32_t i = cdf_find(sc.env_cond + (size_t)j * (W + 1), W, rng.v01());
+    const float x = (float)i + rng.v01();
+    const float y = (float)j + rng.v01();
+    float sx = ((float)(H - 1) - y) / (float)H * VR_PI_F;
+    if (!(sx > 1.0e-6f)) sx = 1.0e-6f;
+    const float ang = x / (float)W * (2.0f * VR_PI_F) - VR_PI_F;
+    const float r = sinf(sx);
+    return mk3(r * cosf(ang), -cosf(sx), -(r * sinf(ang)));
+}
+__device__ __noinline__ float env_pdf_direction(const DeviceScene& sc, f3 dir) {
+    const uint32_t W = sc.env_tex.width, H = sc.env_tex.height;
+    const f3 d = normalize(dir);
+    const float sx = acosf(-d.y);
+    const float sy = atan2f(-d.z, d.x) + VR_PI_F;
+    const float x = sy / (2.0f * VR_PI_F) * (float)W;
+    const float y = (float)(H - 1) - (sx / VR_PI_F * (float)H);
+    if (!(y >= 0.0f)) return 0.0f;
+    const uint32_t i = f32_as_index(x, W - 1);
+    const uint32_t j = f32_as_index(y, H - 1);
+    const float* row = sc.env_cond + (size_t)j * (W + 1);
+    const float p_tex = (__ldg(sc.env_marginal + j + 1) - __ldg(sc.env_marginal + j)) * (__ldg(row + i + 1) - __ldg(row + i));
+    return p_tex * ((float)W * (float)H) / (2.0f * VR_PI_F * VR_PI_F * fmaxf(sinf(sx), 1.0e-6f));
+}
+
 // ---- MicrofacetBSDF, voidray_common/src/microfacet.rs (same operation order as the reference) ----
 __device__ __forceinline__ f3 lerp_v(f3 a, f3 b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float powi2(float a) { return a * a; }
@@ -543,6 +600,9 @@ __device__ __forceinline__ f3 unwind(const Wavefront& wf, uint32_t slot, uint32_
     return value;
 }
 
+// FAST = integrator 1 compiled in, MICROFACET = the scene has a MicrofacetBSDF material; the common
+// kernel (parity integrator, simple materials) carries neither code path
+template <bool FAST, bool MICROFACET>
 __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefront wf, PathSource src,
                                                          FrameParams fp, uint32_t depth) {
     const uint32_t n = wf.counts[depth];
@@ -615,6 +675,30 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
                 if (fp.render_mode == 1) {
                     // tracer.rs:40: RenderMode::Normal
                     attenuation = 0.5f * normalize(normal) + mk3(1.0f, 1.0f, 1.0f) * 0.5f;
+                } else if (FAST && m.kind == 0) {
+                    // integrator 1: the integrand of Lambertian::scatter (albedo x the density of
+                    // normalize(n + UnitSphere)), sampled by one-sample MIS with the HDRI luminance table
+                    const f3 sn = m.normal_tex >= 0 ? texture_sample(sc.textures[m.normal_tex], uv.x, uv.y) : normal;
+                    const f3 albedo = m.albedo_tex >= 0 ? texture_sample(sc.textures[m.albedo_tex], uv.x, uv.y)
+                                                        : mk3(m.color[0], m.color[1], m.color[2]);
+                    const bool has_env = sc.env_kind == 2;
+                    f3 w;
+                    if (has_env && rng.v01() >= 0.5f) {
+                        w = normalize(env_sample_direction(sc, rng));
+                    } else {
+                        f3 dir = sn + rng.unit_sphere();
+                        if (near_zero(dir)) dir = sn;
+                        w = normalize(dir);
+                    }
+                    new_d = normalize(w);  // Ray::new
+                    const float p_ref = lambert_reference_pdf(new_d, sn);
+                    const float p_mix = has_env ? 0.5f * p_ref + 0.5f * env_pdf_direction(sc, new_d) : p_ref;
+                    if (!(p_mix > 0.0f) || !(p_ref > 0.0f)) {
+                        attenuation = mk3(0.0f, 0.0f, 0.0f);
+                    } else {
+                        attenuation = albedo * (p_ref / p_mix);
+                        scattered = true;
+                    }
                 } else if (m.kind == 0) {
                     // Lambertian::scatter, simple.rs:103-132
                     const f3 sn = m.normal_tex >= 0 ? texture_sample(sc.textures[m.normal_tex], uv.x, uv.y) : normal;
@@ -656,7 +740,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
                 } else if (m.kind == 3) {
                     // Emission::scatter, simple.rs:176-184 (colour * strength folded on the host)
                     attenuation = mk3(m.color[0], m.color[1], m.color[2]);
-                } else if (m.kind == 5) {
+                } else if (MICROFACET && m.kind == 5) {
                     // MicrofacetBSDF through the blanket impl, core/traits.rs:23-40 + microfacet.rs:120-313
                     const f3 wo = normalize(d);  // the *incoming* direction, as in the reference
                     f3 wi;
@@ -677,12 +761,21 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
                     scattered = true;
                 }
 
+                // integrator 1: Russian roulette from the fourth segment on; survival probability = the largest
+                // attenuation channel clamped to [0.05, 1], survivors are divided by it, the rest see BLACK
+                bool killed = false;
+                if (FAST && scattered && depth >= 3) {
+                    const float q = fminf(fmaxf(fmaxf(attenuation.x, fmaxf(attenuation.y, attenuation.z)), 0.05f), 1.0f);
+                    if (rng.v01() < q) attenuation = attenuation / q;
+                    else killed = true;
+                }
+
                 if (!scattered) {
                     // tracer.rs:44-50 with no scattered ray: delta = attenuation
                     const f3 Lk = mk3(0.0f, 0.0f, 0.0f) + clamp_color(attenuation, fp.firefly_clamp);
                     const f3 L = unwind(wf, slot, depth, Lk, fp.firefly_clamp);
                     wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
-                } else if (depth + 1 >= fp.max_bounces) {
+                } else if (killed || depth + 1 >= fp.max_bounces) {
                     // the scattered ray would be traced at depth == max_bounces and return BLACK (tracer.rs:28)
                     const f3 Lk = mk3(0.0f, 0.0f, 0.0f) +
                                   clamp_color(mul_elem(attenuation, mk3(0.0f, 0.0f, 0.0f)), fp.firefly_clamp);
@@ -877,7 +970,7 @@ void query_launch_dims(LaunchDims* dims) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&dims->sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->trace_blocks_per_sm, k_trace, TRACE_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_blocks_per_sm, k_shade, SHADE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_blocks_per_sm, k_shade<false, false>, SHADE_THREADS, 0);
     if (dims->trace_blocks_per_sm < 1) dims->trace_blocks_per_sm = 1;
     if (dims->shade_blocks_per_sm < 1) dims->shade_blocks_per_sm = 1;
 }
@@ -899,7 +992,12 @@ void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, ui
 }
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {
-    k_shade<<<grid_for(n_upper, SHADE_THREADS, ld.sm_count, ld.shade_blocks_per_sm), SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+    const uint32_t grid = grid_for(n_upper, SHADE_THREADS, ld.sm_count, ld.shade_blocks_per_sm);
+    const bool fast = fp.integrator == 1, mf = sc.has_microfacet != 0;
+    if (fast && mf) k_shade<true, true><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+    else if (fast) k_shade<true, false><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+    else if (mf) k_shade<false, true><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+    else k_shade<false, false><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
 }
 void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t width, uint32_t height,
                        uint32_t samples_in_batch, int finish, float inv_total_samples, cudaStream_t stream) {

@@ -36,6 +36,7 @@ struct FrameParams {
     uint32_t max_bounces;
     float firefly_clamp;
     int32_t render_mode;
+    int32_t integrator;
     uint64_t seed;
 };
 

@@ -75,9 +75,12 @@ struct DeviceScene {
     const AnalyticRec* analytics;
     uint32_t n_tris;
     uint32_t n_analytics;
+    int32_t has_microfacet;  // some material is a MicrofacetBSDF (selects the shading kernel variant)
     int32_t env_kind;  // 0 none, 1 uniform, 2 hdri
     float env_color[3];
     TextureRec env_tex;
+    const float* env_marginal;  // integrator 1: P(row < j), H + 1 entries
+    const float* env_cond;      // integrator 1: P(col < i | row j), H x (W + 1) entries
     CameraRec camera;
 };
 

@@ -545,4 +545,44 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     return true;
 }
 
+// A texel weighs (luminance + 5 % of the mean luminance) x sin(polar angle of its row centre), with the polar
+// angle of row j taken from the lookup's own mapping y = (H - 1) - acos(-d.y) / pi * H
+// (voidray_common/src/environments.rs:80-86); the last row maps to no direction and gets weight 0.
+void build_env_tables(const HostTexture& env, std::vector<float>& marginal, std::vector<float>& cond) {
+    const size_t W = env.w, H = env.h;
+    std::vector<double> weight(W * H), row_sum(H, 0.0);
+    double mean = 0.0;
+    for (size_t k = 0; k < W * H; ++k) {
+        weight[k] = 0.2126 * (double)env.rgb[3 * k] + 0.7152 * (double)env.rgb[3 * k + 1] + 0.0722 * (double)env.rgb[3 * k + 2];
+        mean += weight[k];
+    }
+    mean /= (double)(W * H);
+    double total = 0.0;
+    for (size_t j = 0; j < H; ++j) {
+        const double sx = 3.14159265358979323846 * ((double)(H - 1) - ((double)j + 0.5)) / (double)H;
+        const double sinw = sx > 0.0 ? std::sin(sx) : 0.0;
+        double rs = 0.0;
+        for (size_t i = 0; i < W; ++i) {
+            weight[j * W + i] = (weight[j * W + i] + 0.05 * mean) * sinw;
+            rs += weight[j * W + i];
+        }
+        row_sum[j] = rs;
+        total += rs;
+    }
+    marginal.assign(H + 1, 0.0f);
+    cond.assign(H * (W + 1), 0.0f);
+    double acc = 0.0;
+    for (size_t j = 0; j < H; ++j) {
+        marginal[j] = (float)(total > 0.0 ? acc / total : (double)j / (double)H);
+        acc += row_sum[j];
+        double c = 0.0;
+        for (size_t i = 0; i < W; ++i) {
+            cond[j * (W + 1) + i] = (float)(row_sum[j] > 0.0 ? c / row_sum[j] : (double)i / (double)W);
+            c += weight[j * W + i];
+        }
+        cond[j * (W + 1) + W] = 1.0f;
+    }
+    marginal[H] = 1.0f;
+}
+
 }  // namespace vr

@@ -187,7 +187,8 @@ class RenderTarget:
         self.dimensions = (int(dimensions[0]), int(dimensions[1]))
         self.settings = settings
         cs = RenderSettingsC(int(settings.total_samples), int(settings.max_bounces), float(settings.firefly_clamp),
-                             int(settings.render_mode), int(settings.pixel_mapping), 0, int(settings.seed),
+                             int(settings.render_mode), int(settings.pixel_mapping), int(settings.integrator),
+                             int(settings.seed),
                              int(settings.sample_offset), int(settings.max_paths_in_flight))
         self.handle = C.c_void_p()
         check(self._lib.vr_render_begin(scene.handle, self.dimensions[0], self.dimensions[1], C.byref(cs),

@@ -71,6 +71,9 @@ class RenderSettings:  # settings.rs:15-33
     pixel_mapping: PixelMapping = PixelMapping.Fixed
     sample_offset: int = 0
     max_paths_in_flight: int = 0
+    # 0 = the reference estimator (parity); 1 = "fast": the same integrand sampled with one-sample MIS between the
+    # reference's Lambertian density and an HDRI luminance table, plus Russian roulette from depth 3
+    integrator: int = 0
 
 
 @dataclass
