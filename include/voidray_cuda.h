@@ -61,6 +61,13 @@ int32_t vr_scene_destroy(vr_scene* scene);
 int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t w, uint32_t h,
                                     int32_t sample_type, uint32_t* texture);
 
+/* The same for decoded 8- / 16-bit images: `to_rgb32f` is channel / 255 resp. / 65535, alpha dropped
+ * (image 0.24.3). `channels` is 3 or 4 (RGBA: the fourth channel is skipped). */
+int32_t vr_scene_add_texture_rgb8(vr_scene* scene, const uint8_t* pixels, uint32_t w, uint32_t h, uint32_t channels,
+                                  int32_t sample_type, uint32_t* texture);
+int32_t vr_scene_add_texture_rgb16(vr_scene* scene, const uint16_t* pixels, uint32_t w, uint32_t h, uint32_t channels,
+                                   int32_t sample_type, uint32_t* texture);
+
 /* Scene::add_mesh(Arc::new(Mesh::from_buffers(vertices, indices))) (scene.rs:128-135,
  * core/mesh.rs:76-116). positions 3*n_vertices, uvs 2*n_vertices, normals 3*n_vertices (uvs /
  * normals may be NULL = zeros, like Vertex::position, mesh.rs:26-32); indices: n_indices u32,
@@ -68,6 +75,13 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
 int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* uvs, const float* normals,
                           uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
                           uint32_t* surface);
+/* Scene::add_mesh_from_file(path) (scene.rs:137-144 -> Mesh::from_file, core/mesh.rs:46-74): Wavefront OBJ with
+ * obj-rs 0.7.0 `load_obj::<TexturedVertex, u32>` semantics — every face must be a triangle of v/vt/vn triples,
+ * each distinct triple becomes one vertex in first-seen order, (u, v) = the first two texture coordinates.
+ * n_vertices / n_triangles (may be NULL) receive what the reference prints (mesh.rs:67-72). */
+int32_t vr_scene_add_mesh_from_obj_file(vr_scene* scene, const char* path, uint32_t* surface, uint32_t* n_vertices,
+                                        uint32_t* n_triangles);
+
 /* Scene::add_analytic_surface(Surfaces::sphere(center, radius)) — voidray_common/src/surfaces.rs:18-20,31-80 */
 int32_t vr_scene_add_sphere(vr_scene* scene, const float center[3], float radius, uint32_t* surface);
 /* Scene::add_analytic_surface(Surfaces::ground_plane(height)) — surfaces.rs:22-24,82-114 */

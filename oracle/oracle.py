@@ -14,8 +14,8 @@ from typing import Optional
 
 import numpy as np
 
-from voidray_b200.scene import (GroundPlaneDesc, HDRIEnvironment, MeshData, RenderSettings, Scene, SphereDesc,
-                                UniformEnvironment)
+from voidray_b200.scene import (GroundPlaneDesc, HDRIEnvironment, MeshData, ObjFile, RenderSettings, Scene,
+                                SphereDesc, UniformEnvironment)
 
 F32 = np.float32
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -94,6 +94,8 @@ class OracleScene:
             img = np.ascontiguousarray(tex.image, dtype=F32)
             lib.vo_add_texture(h, _fp(img), C.c_uint32(img.shape[1]), C.c_uint32(img.shape[0]), C.c_int32(int(tex.sample_type)))
         for surf in scene.surfaces:
+            if isinstance(surf, ObjFile):
+                surf = surf.mesh()      # the oracle gets the Python loader's arrays (assets.load_obj)
             if isinstance(surf, MeshData):
                 pos = np.ascontiguousarray(surf.positions, dtype=F32)
                 uvs = np.ascontiguousarray(surf.uvs, dtype=F32)
@@ -221,7 +223,7 @@ class OracleScene:
             surf = self.scene.surfaces[s]
             if s == surface:
                 return (self.mesh_tie_rank(surface) + np.uint32(base)).astype(np.uint32)
-            base += surf.n_triangles if isinstance(surf, MeshData) else 1
+            base += surf.n_triangles if isinstance(surf, (MeshData, ObjFile)) else 1
         raise IndexError(surface)
 
     def texture_sample(self, texture: int, uv) -> np.ndarray:

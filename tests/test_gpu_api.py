@@ -147,3 +147,44 @@ def test_renderer_one_shot_driver(ctx):
     assert img.shape == (120, 160, 4) and np.all(np.isfinite(img)) and img[..., :3].max() > 0.1
     want = PostProcessingPass().render(r.target, PostProcessingData(1.0, 1.0, 1.0, int(Tonemap.ACES)))
     assert np.array_equal(img, want)
+
+
+def test_native_obj_loader_and_integer_textures(oracle, ctx):
+    # vr_scene_add_mesh_from_obj_file (obj-rs semantics in C++) against the Python loader feeding the oracle, and
+    # vr_scene_add_texture_rgb8 (`to_rgb32f` = byte / 255) against the f32 entry point
+    import ctypes as C
+    from PIL import Image
+    from voidray_b200.assets import asset_path, load_obj
+    from voidray_b200.scene import Camera
+    from util import random_rays, scene_bounds
+    lib = _lib.load()
+    for name in ("cube.obj", "mushroom.obj", "fancy_monkey.obj"):
+        scene = Scene.empty()
+        sf = scene.add_mesh_from_file(asset_path(name))
+        scene.add_object(scene.add_material(Materials.lambertian((0.5, 0.5, 0.5))), sf)
+        accel = scene.build_acceleration(ctx)
+        mesh = load_obj(asset_path(name))
+        assert accel.info()["n_triangles"] == mesh.n_triangles
+        osc = oracle.OracleScene(scene)
+        assert np.array_equal(accel.tie_ranks(0), osc.global_tie_rank(0))
+        o, d = random_rays(50000, mesh.positions.min(0), mesh.positions.max(0), seed=2)
+        s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d)
+        s, p, t = accel.trace_rays(o, d)
+        assert np.array_equal(s, s_ref) and np.array_equal(p, p_ref) and np.array_equal(t, t_ref)
+    h = C.c_void_p()
+    _lib.check(lib.vr_scene_create(ctx.handle, C.byref(h)))
+    out = C.c_uint32()
+    assert lib.vr_scene_add_mesh_from_obj_file(h, b"/nonexistent.obj", C.byref(out), None, None) == _lib.VR_ERR_INVALID
+    img8 = np.ascontiguousarray(np.asarray(Image.open(asset_path("uv_test.png")).convert("RGBA")))
+    _lib.check(lib.vr_scene_add_texture_rgb8(h, img8.ctypes.data_as(C.POINTER(C.c_uint8)), img8.shape[1], img8.shape[0],
+                                             4, 1, C.byref(out)))
+    f32 = np.ascontiguousarray(img8[..., :3].astype(F32) / F32(255.0))
+    _lib.check(lib.vr_scene_add_texture_rgb32f(h, _lib.fptr(f32), f32.shape[1], f32.shape[0], 1, C.byref(out)))
+    _lib.check(lib.vr_scene_commit(h))
+    uv = np.random.default_rng(3).uniform(-1, 2, (5000, 2)).astype(F32)
+    a = np.empty((5000, 3), F32)
+    b = np.empty((5000, 3), F32)
+    _lib.check(lib.vr_debug_texture_sample(h, 0, 5000, _lib.fptr(uv), _lib.fptr(a)))
+    _lib.check(lib.vr_debug_texture_sample(h, 1, 5000, _lib.fptr(uv), _lib.fptr(b)))
+    assert np.array_equal(a, b)
+    lib.vr_scene_destroy(h)

@@ -231,6 +231,17 @@ int32_t ensure_env_tables(vr_scene* scene) {
     return VR_OK;
 }
 
+template <typename T>
+int32_t add_texture_int(vr_scene* scene, const T* pixels, uint32_t w, uint32_t h, uint32_t channels,
+                               int32_t sample_type, float denom, uint32_t* texture) {
+    if (!pixels || w == 0 || h == 0) return fail(VR_ERR_INVALID, "empty texture");
+    if (channels != 3 && channels != 4) return fail(VR_ERR_INVALID, "channels must be 3 or 4");
+    std::vector<float> rgb((size_t)3 * w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i)
+        for (int c = 0; c < 3; ++c) rgb[3 * i + c] = (float)pixels[channels * i + c] / denom;  // to_rgb32f
+    return vr_scene_add_texture_rgb32f(scene, rgb.data(), w, h, sample_type, texture);
+}
+
 int32_t check_scene(vr_scene* s) {
     if (!s) return fail(VR_ERR_INVALID, "null scene");
     return VR_OK;
@@ -331,6 +342,17 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
     return VR_OK;
 }
 
+int32_t vr_scene_add_texture_rgb8(vr_scene* scene, const uint8_t* pixels, uint32_t w, uint32_t h, uint32_t channels,
+                                  int32_t sample_type, uint32_t* texture) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    return add_texture_int(scene, pixels, w, h, channels, sample_type, 255.0f, texture);
+}
+int32_t vr_scene_add_texture_rgb16(vr_scene* scene, const uint16_t* pixels, uint32_t w, uint32_t h, uint32_t channels,
+                                   int32_t sample_type, uint32_t* texture) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    return add_texture_int(scene, pixels, w, h, channels, sample_type, 65535.0f, texture);
+}
+
 int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* uvs, const float* normals,
                           uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, uint32_t* surface) {
     if (check_scene(scene)) return VR_ERR_INVALID;
@@ -346,6 +368,25 @@ int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* 
     if (normals) m.nrm.assign(normals, normals + (size_t)3 * n_vertices);
     else m.nrm.assign((size_t)3 * n_vertices, 0.0f);
     m.idx.assign(indices, indices + n_idx);
+    scene->host.meshes.push_back(std::move(m));
+    HostSurface sf;
+    sf.kind = 0;
+    sf.mesh = (uint32_t)scene->host.meshes.size() - 1;
+    scene->host.surfaces.push_back(sf);
+    scene->committed = false;
+    if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
+    return VR_OK;
+}
+
+int32_t vr_scene_add_mesh_from_obj_file(vr_scene* scene, const char* path, uint32_t* surface, uint32_t* n_vertices,
+                                        uint32_t* n_triangles) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!path) return fail(VR_ERR_INVALID, "null path");
+    HostMesh m;
+    std::string err;
+    if (!load_obj_file(path, m, err)) return fail(VR_ERR_INVALID, std::string(path) + ": " + err);
+    if (n_vertices) *n_vertices = m.n_vertices;
+    if (n_triangles) *n_triangles = (uint32_t)(m.idx.size() / 3);
     scene->host.meshes.push_back(std::move(m));
     HostSurface sf;
     sf.kind = 0;

@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 #include <thread>
+#include <unordered_map>
 
 namespace vr {
 namespace {
@@ -583,6 +585,98 @@ void build_env_tables(const HostTexture& env, std::vector<float>& marginal, std:
         cond[j * (W + 1) + W] = 1.0f;
     }
     marginal[H] = 1.0f;
+}
+
+// obj-rs 0.7.0 `load_obj::<TexturedVertex, u32>` (what Mesh::from_file calls, core/mesh.rs:46-48): positions,
+// texture coordinates and normals are indexed per face corner as v/vt/vn; every polygon must be a triangle
+// with all three indices; identical index triples share one output vertex, created in first-seen order.
+bool load_obj_file(const char* path, HostMesh& out, std::string& err) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) {
+        err = std::string("cannot open ") + path;
+        return false;
+    }
+    std::vector<float> pos, tex, nrm;
+    struct Key {
+        int64_t p, t, n;
+        bool operator==(const Key& o) const { return p == o.p && t == o.t && n == o.n; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key& k) const {
+            return (size_t)(k.p * 73856093) ^ (size_t)(k.t * 19349663) ^ (size_t)(k.n * 83492791);
+        }
+    };
+    std::unordered_map<Key, uint32_t, KeyHash> seen;
+    std::vector<Key> order;
+    out = HostMesh();
+    char line[1024];
+    bool ok = true;
+    while (ok && std::fgets(line, sizeof line, f)) {
+        char* s = line;
+        while (*s == ' ' || *s == '\t') ++s;
+        if (s[0] == 'v' && (s[1] == ' ' || s[1] == '\t')) {
+            float x = 0, y = 0, z = 0;
+            if (std::sscanf(s + 1, "%f %f %f", &x, &y, &z) < 3) { err = "malformed v line"; ok = false; break; }
+            pos.push_back(x); pos.push_back(y); pos.push_back(z);
+        } else if (s[0] == 'v' && s[1] == 't') {
+            float u = 0, v = 0;
+            if (std::sscanf(s + 2, "%f %f", &u, &v) < 1) { err = "malformed vt line"; ok = false; break; }
+            tex.push_back(u); tex.push_back(v);
+        } else if (s[0] == 'v' && s[1] == 'n') {
+            float x = 0, y = 0, z = 0;
+            if (std::sscanf(s + 2, "%f %f %f", &x, &y, &z) < 3) { err = "malformed vn line"; ok = false; break; }
+            nrm.push_back(x); nrm.push_back(y); nrm.push_back(z);
+        } else if (s[0] == 'f' && (s[1] == ' ' || s[1] == '\t')) {
+            int corners = 0;
+            char* p = s + 1;
+            while (true) {
+                while (*p == ' ' || *p == '\t') ++p;
+                if (*p == 0 || *p == '\n' || *p == '\r') break;
+                long long a = 0, b = 0, c = 0;
+                int consumed = 0;
+                if (std::sscanf(p, "%lld/%lld/%lld%n", &a, &b, &c, &consumed) < 3) {
+                    err = "TexturedVertex needs position/texture/normal on every face corner";
+                    ok = false;
+                    break;
+                }
+                p += consumed;
+                if (++corners > 3) { err = "model should be triangulated first to be loaded properly"; ok = false; break; }
+                // negative indices are relative to the elements read so far
+                Key k;
+                k.p = a > 0 ? a - 1 : (int64_t)(pos.size() / 3) + a;
+                k.t = b > 0 ? b - 1 : (int64_t)(tex.size() / 2) + b;
+                k.n = c > 0 ? c - 1 : (int64_t)(nrm.size() / 3) + c;
+                if (k.p < 0 || k.t < 0 || k.n < 0) { err = "face index out of range"; ok = false; break; }
+                auto it = seen.find(k);
+                uint32_t idx;
+                if (it == seen.end()) {
+                    idx = (uint32_t)order.size();
+                    seen.emplace(k, idx);
+                    order.push_back(k);
+                } else {
+                    idx = it->second;
+                }
+                out.idx.push_back(idx);
+            }
+            if (ok && corners != 3) { err = "model should be triangulated first to be loaded properly"; ok = false; }
+        }
+    }
+    std::fclose(f);
+    if (!ok) return false;
+    out.n_vertices = (uint32_t)order.size();
+    out.pos.resize(3 * order.size());
+    out.uv.resize(2 * order.size());
+    out.nrm.resize(3 * order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        const Key& k = order[i];
+        if ((size_t)k.p * 3 + 2 >= pos.size() + 0 && (size_t)k.p * 3 + 2 > pos.size() - 1) { err = "face refers to a missing position"; return false; }
+        if ((size_t)k.t * 2 + 1 > tex.size() - 1 || tex.empty()) { err = "face refers to a missing texture coordinate"; return false; }
+        if ((size_t)k.n * 3 + 2 > nrm.size() - 1 || nrm.empty()) { err = "face refers to a missing normal"; return false; }
+        for (int a = 0; a < 3; ++a) out.pos[3 * i + a] = pos[3 * k.p + a];
+        for (int a = 0; a < 2; ++a) out.uv[2 * i + a] = tex[2 * k.t + a];
+        for (int a = 0; a < 3; ++a) out.nrm[3 * i + a] = nrm[3 * k.n + a];
+    }
+    return true;
 }
 
 }  // namespace vr

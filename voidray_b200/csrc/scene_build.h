@@ -80,6 +80,9 @@ void camera_look_at(const float eye[3], const float center[3], const float up_in
 
 bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err);
 
+// Wavefront OBJ with obj-rs 0.7.0 `load_obj::<TexturedVertex, u32>` semantics (core/mesh.rs:46-74).
+bool load_obj_file(const char* path, HostMesh& out, std::string& err);
+
 // integrator 1: luminance x sin(polar angle) sampling tables of a lat-long environment image.
 // marginal: H + 1 entries, P(row < j); cond: H x (W + 1) entries, P(col < i | row j).
 void build_env_tables(const HostTexture& env, std::vector<float>& marginal, std::vector<float>& cond);

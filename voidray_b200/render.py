@@ -19,8 +19,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import MaterialDescC, RenderSettingsC, StatsC, check, fptr, uptr
-from .scene import (GroundPlaneDesc, HDRIEnvironment, MeshData, RenderSettings, Scene, Settings, SphereDesc,
-                    UniformEnvironment)
+from .scene import (GroundPlaneDesc, HDRIEnvironment, MeshData, ObjFile, RenderSettings, Scene, Settings,
+                    SphereDesc, UniformEnvironment)
 
 F32 = np.float32
 
@@ -84,6 +84,8 @@ class SceneAcceleration:
                 idx = np.ascontiguousarray(surf.indices, dtype=np.uint32)
                 check(lib.vr_scene_add_mesh(self.handle, fptr(pos), fptr(uvs), fptr(nrm), pos.shape[0], uptr(idx),
                                             idx.size, C.byref(out)))
+            elif isinstance(surf, ObjFile):
+                check(lib.vr_scene_add_mesh_from_obj_file(self.handle, surf.path.encode(), C.byref(out), None, None))
             elif isinstance(surf, SphereDesc):
                 check(lib.vr_scene_add_sphere(self.handle, _f3(surf.center), float(surf.radius), C.byref(out)))
             elif isinstance(surf, GroundPlaneDesc):

@@ -218,6 +218,22 @@ class MeshData:
         return self.indices.size // 3
 
 
+@dataclass
+class ObjFile:
+    """A mesh surface that stays a path until the scene is committed (Mesh::from_file, core/mesh.rs:46-74)."""
+    path: str
+    _mesh: Optional["MeshData"] = None
+
+    def mesh(self) -> "MeshData":
+        if self._mesh is None:
+            self._mesh = MeshData.from_file(self.path)
+        return self._mesh
+
+    @property
+    def n_triangles(self) -> int:
+        return self.mesh().n_triangles
+
+
 class Surfaces:
     """voidray_common/src/surfaces.rs:9-29"""
 
@@ -302,7 +318,7 @@ class Object:  # scene.rs:31-34
     material: int
 
 
-SurfaceDesc = Union[MeshData, SphereDesc, GroundPlaneDesc]
+SurfaceDesc = Union[MeshData, "ObjFile", SphereDesc, GroundPlaneDesc]
 
 
 class Scene:
@@ -334,7 +350,10 @@ class Scene:
         return len(self.surfaces) - 1
 
     def add_mesh_from_file(self, path: str) -> int:
-        return self.add_mesh(MeshData.from_file(path))
+        """scene.rs:137-144. The OBJ file is parsed by the library's native loader at build_acceleration
+        (vr_scene_add_mesh_from_obj_file); `assets.load_obj` is the same loader in Python for host-side use."""
+        self.surfaces.append(ObjFile(path))
+        return len(self.surfaces) - 1
 
     def add_object(self, material: int, surface: int) -> int:
         self.objects.append(Object(surface=int(surface), material=int(material)))
@@ -357,4 +376,4 @@ class Scene:
 
     # convenience for statistics
     def n_triangles(self) -> int:
-        return sum(s.n_triangles for s in self.surfaces if isinstance(s, MeshData))
+        return sum(s.n_triangles for s in self.surfaces if isinstance(s, (MeshData, ObjFile)))
