@@ -531,7 +531,7 @@ int32_t vr_scene_commit(vr_scene* scene) {
     if (!flatten_scene(scene->host, scene->flat, err)) return fail(VR_ERR_INVALID, err);
     const auto t_flat = std::chrono::steady_clock::now();
     scene->h2d_bytes = 0;
-    if (scene->flat.bvh_depth > 70) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
+    if (scene->flat.bvh_depth > 32) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
     scene->dev_mem.rewind();
     scene->dev_textures.clear();
@@ -560,6 +560,8 @@ int32_t vr_scene_commit(vr_scene* scene) {
     d.has_microfacet = 0;
     for (const MaterialRec& m : scene->host.materials)
         if (m.kind == VR_MAT_MICROFACET) d.has_microfacet = 1;
+    std::memcpy(d.grid_min, f.grid_min, 12);
+    std::memcpy(d.grid_extent, f.grid_extent, 12);
     d.n_tris = f.n_tris;
     d.n_analytics = (uint32_t)f.analytics.size();
     d.env_kind = scene->host.env_kind;

@@ -14,15 +14,14 @@ namespace vr {
 #define VR_TRACE_THREADS 128
 #endif
 #ifndef VR_TRACE_MIN_BLOCKS
-#define VR_TRACE_MIN_BLOCKS 1
+#define VR_TRACE_MIN_BLOCKS 8
 #endif
 #ifndef VR_REFILL_THRESHOLD
 #define VR_REFILL_THRESHOLD 16
 #endif
 static constexpr int TRACE_THREADS = VR_TRACE_THREADS;
 static constexpr int SHADE_THREADS = 128;
-static constexpr int SMEM_STACK = 16;   // entries per thread kept in shared memory
-static constexpr int LOCAL_STACK = 64;  // overflow (local memory); flatten_scene bounds the BVH depth
+static constexpr int SMEM_STACK = 32;  // per-thread traversal stack, all in shared memory; the builder caps the BVH depth at 32
 static constexpr float T_MIN = 0.00001f;  // core/scene.rs:183
 static constexpr int SENTINEL = 0x7FFFFFFF;
 
@@ -103,23 +102,37 @@ __device__ __forceinline__ void intersect_analytic(const AnalyticRec& a, int pri
 // thread, stride = blockDim.x, conflict-free) and spills deeper entries to local memory.
 struct Traversal {
     f3 o, d;
-    // Reciprocal direction, slab tests only (never feeds a reported value). The planes are tested as
-    // (plane - o) * id: the FMA form plane * id - o * id saves 12 instructions per node but its error is
-    // absolute (u * |o * id|), and covering it with a per-ray slack switches culling off for rays with one
-    // tiny direction component — measured 12x slower on the 10 M-triangle scene for +1.6 % on config 2.
-    float idx, idy, idz;
+    // Slab tests on the quantised nodes (layout.h), never feeding a reported value:
+    //   t = fma(f, a, b),  f = 1 + q / 32768 (decoded by one PRMT),  a = extent * id,  b = (grid_min - o) * id - a.
+    // The near plane (q_lo if id >= 0, else q_hi) uses bn = b - err, the far plane bf = b + err, where err bounds the
+    // rounding of b per axis (it only ever touches that axis' distances, so a ray with a tiny direction component
+    // keeps culling on the other two axes — unlike a per-ray slack). No min / max per axis is needed.
+    float ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz;
+    uint32_t selx, sely, selz;  // PRMT selector of the near plane's half-word; far = sel ^ 0x0220
     HitResult best;
     uint32_t best_rank;
     int cur, sp;
 };
 
+__device__ __forceinline__ void trav_axis(float o, float d, float gmin, float extent, float& a, float& bn, float& bf,
+                                          uint32_t& sel) {
+    const float tiny = 1e-20f;
+    const float id = 1.0f / (fabsf(d) > tiny ? d : copysignf(tiny, d));
+    a = extent * id;
+    const float g = (gmin - o) * id;
+    const float b = g - a;
+    const float err = 2.4e-7f * (fabsf(g) + fabsf(a)) + 1e-30f;
+    bn = b - err;
+    bf = b + err;
+    sel = id >= 0.0f ? 0x7104u : 0x7324u;  // bytes (0x00, q.b0, q.b1, 0x3F) of the low / high half-word
+}
+
 __device__ __forceinline__ void trav_begin(Traversal& tr, const DeviceScene& sc, f3 o, f3 d) {
     tr.o = o;
     tr.d = d;
-    const float tiny = 1e-20f;
-    tr.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-    tr.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-    tr.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+    trav_axis(o.x, d.x, sc.grid_min[0], sc.grid_extent[0], tr.ax, tr.bnx, tr.bfx, tr.selx);
+    trav_axis(o.y, d.y, sc.grid_min[1], sc.grid_extent[1], tr.ay, tr.bny, tr.bfy, tr.sely);
+    trav_axis(o.z, d.z, sc.grid_min[2], sc.grid_extent[2], tr.az, tr.bnz, tr.bfz, tr.selz);
     tr.best.t = INFINITY;
     tr.best.prim = -1;
     tr.best.u = tr.best.v = 0.0f;
@@ -128,54 +141,63 @@ __device__ __forceinline__ void trav_begin(Traversal& tr, const DeviceScene& sc,
     tr.cur = sc.n_tris > 0 ? 0 : SENTINEL;
 }
 
-__device__ __forceinline__ int trav_pop(Traversal& tr, const int* sstack, int sstride, const int* lstack) {
-    if (tr.sp == 0) return SENTINEL;
-    --tr.sp;
-    return tr.sp < SMEM_STACK ? sstack[tr.sp * sstride] : lstack[tr.sp - SMEM_STACK];
-}
-__device__ __forceinline__ void trav_push(Traversal& tr, int* sstack, int sstride, int* lstack, int v) {
-    if (tr.sp < SMEM_STACK) sstack[tr.sp * sstride] = v;
-    else lstack[tr.sp - SMEM_STACK] = v;
-    ++tr.sp;
+// The stack lives entirely in shared memory (one column per thread, stride = blockDim.x: conflict-free).
+// Push and pop are written so that they compile to predicated STS / LDS instead of branches.
+__device__ __forceinline__ int trav_pop(Traversal& tr, const int* sstack, int sstride) {
+    const bool empty = tr.sp == 0;
+    tr.sp -= empty ? 0 : 1;
+    const int v = sstack[tr.sp * sstride];
+    return empty ? SENTINEL : v;
 }
 
 __device__ __forceinline__ bool is_inner(int cur) { return (unsigned)cur < (unsigned)SENTINEL; }  // leaf codes are negative
 
-// One inner node: two slab tests from a single 64-byte record, near child first, far child pushed.
-__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride,
-                                          int* lstack) {
-    const int cur = tr.cur;
-    const f3 o = tr.o;
-    const float8 n0 = ldg8(nodes + 4 * cur);
-    const float8 n1 = ldg8(nodes + 4 * cur + 2);
-    const float4 q0 = n0.lo, q1 = n0.hi, q2 = n1.lo, q3 = n1.hi;
-    // child 0: lo (q0.x q0.y q0.z) hi (q0.w q1.x q1.y); child 1: lo (q1.z q1.w q2.x) hi (q2.y q2.z q2.w)
-    const float ax0 = (q0.x - o.x) * tr.idx, ax1 = (q0.w - o.x) * tr.idx;
-    const float ay0 = (q0.y - o.y) * tr.idy, ay1 = (q1.x - o.y) * tr.idy;
-    const float az0 = (q0.z - o.z) * tr.idz, az1 = (q1.y - o.z) * tr.idz;
-    const float bx0 = (q1.z - o.x) * tr.idx, bx1 = (q2.y - o.x) * tr.idx;
-    const float by0 = (q1.w - o.y) * tr.idy, by1 = (q2.z - o.y) * tr.idy;
-    const float bz0 = (q2.x - o.z) * tr.idz, bz1 = (q2.w - o.z) * tr.idz;
-    const float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.0f));
-    const float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), tr.best.t));
-    const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.0f));
-    const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), tr.best.t));
-    // conservative: widen the exit by a few ulps (Ize, "Robust BVH ray traversal", 2013)
+// Plane distance from a packed (q_lo | q_hi << 16) word: PRMT builds f = 1 + q / 32768, one FFMA maps it to t.
+__device__ __forceinline__ float plane_t(uint32_t pair, uint32_t sel, float a, float b) {
+    return __fmaf_rn(__uint_as_float(__byte_perm(pair, 0x3F000000u, sel)), a, b);
+}
+
+// One inner node: two slab tests from a single 32-byte record, near child first, far child pushed.
+__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride) {
+    const float8 n = ldg8(nodes + 2 * tr.cur);
+    const uint32_t w0 = __float_as_uint(n.lo.x), w1 = __float_as_uint(n.lo.y), w2 = __float_as_uint(n.lo.z),
+                   w3 = __float_as_uint(n.lo.w), w4 = __float_as_uint(n.hi.x), w5 = __float_as_uint(n.hi.y);
+    const uint32_t fx = tr.selx ^ 0x0220u, fy = tr.sely ^ 0x0220u, fz = tr.selz ^ 0x0220u;
+    const float an = fmaxf(fmaxf(plane_t(w0, tr.selx, tr.ax, tr.bnx), plane_t(w1, tr.sely, tr.ay, tr.bny)),
+                           fmaxf(plane_t(w2, tr.selz, tr.az, tr.bnz), 0.0f));
+    const float af = fminf(fminf(plane_t(w0, fx, tr.ax, tr.bfx), plane_t(w1, fy, tr.ay, tr.bfy)),
+                           fminf(plane_t(w2, fz, tr.az, tr.bfz), tr.best.t));
+    const float bn = fmaxf(fmaxf(plane_t(w3, tr.selx, tr.ax, tr.bnx), plane_t(w4, tr.sely, tr.ay, tr.bny)),
+                           fmaxf(plane_t(w5, tr.selz, tr.az, tr.bnz), 0.0f));
+    const float bf = fminf(fminf(plane_t(w3, fx, tr.ax, tr.bfx), plane_t(w4, fy, tr.ay, tr.bfy)),
+                           fminf(plane_t(w5, fz, tr.az, tr.bfz), tr.best.t));
+    // conservative: the boxes carry a guard cell, bn / bf carry the addend's rounding, and the exit is widened
+    // by a few ulps for the FFMA's own rounding (Ize, "Robust BVH ray traversal", 2013)
     const bool hit_a = an <= af * 1.0000005f;
     const bool hit_b = bn <= bf * 1.0000005f;
-    const int ca = __float_as_int(q3.x), cb = __float_as_int(q3.y);
+    const int ca = __float_as_int(n.hi.z), cb = __float_as_int(n.hi.w);
     // branch-free child selection: the divergent if/else ladder ran at 2-3 lanes per instruction
     const bool b_first = hit_b && (!hit_a || bn < an);
     const int near_c = b_first ? cb : ca;
     const int far_c = b_first ? ca : cb;
-    if (hit_a && hit_b) trav_push(tr, sstack, sstride, lstack, far_c);
-    tr.cur = (hit_a || hit_b) ? near_c : trav_pop(tr, sstack, sstride, lstack);
+    const bool both = hit_a && hit_b, any = hit_a || hit_b;
+    if (both) sstack[tr.sp * sstride] = far_c;
+    tr.sp += both ? 1 : 0;
+    int next = near_c;
+    if (!any) next = trav_pop(tr, sstack, sstride);
+    tr.cur = next;
 }
 
-__device__ __forceinline__ void trav_leaf(Traversal& tr, const float4* __restrict__ tri_isect, int leaf) {
-    const int code = ~leaf;
+// One triangle of the current leaf; the leaf code counts down so that lanes with short leaves do not idle
+// through a neighbour's longer one.
+__device__ __forceinline__ void trav_leaf_step(Traversal& tr, const float4* __restrict__ tri_isect, int* sstack,
+                                               int sstride) {
+    const int code = ~tr.cur;
     const int first = code >> 3, count = code & 7;
-    for (int k = 0; k < count; ++k) intersect_triangle(tri_isect, first + k, tr.o, tr.d, tr.best, tr.best_rank);
+    if (count > 0) intersect_triangle(tri_isect, first, tr.o, tr.d, tr.best, tr.best_rank);
+    int next = ~(((first + 1) << 3) | (count - 1));
+    if (count <= 1) next = trav_pop(tr, sstack, sstride);
+    tr.cur = next;
 }
 
 __device__ __forceinline__ HitResult trav_finish(Traversal& tr, const DeviceScene& sc) {
@@ -186,18 +208,13 @@ __device__ __forceinline__ HitResult trav_finish(Traversal& tr, const DeviceScen
 
 // One ray, start to finish (gate kernels).
 __device__ __forceinline__ HitResult closest_hit(const DeviceScene& sc, f3 o, f3 d, int* sstack, int sstride) {
-    int lstack[LOCAL_STACK];
     Traversal tr;
     trav_begin(tr, sc, o, d);
     const float4* __restrict__ nodes = (const float4*)sc.nodes;
     const float4* __restrict__ tri_isect = (const float4*)sc.tri_isect;
     while (tr.cur != SENTINEL) {
-        if (is_inner(tr.cur)) {
-            trav_node(tr, nodes, sstack, sstride, lstack);
-        } else {
-            trav_leaf(tr, tri_isect, tr.cur);
-            tr.cur = trav_pop(tr, sstack, sstride, lstack);
-        }
+        if (is_inner(tr.cur)) trav_node(tr, nodes, sstack, sstride);
+        else trav_leaf_step(tr, tri_isect, sstack, sstride);
     }
     return trav_finish(tr, sc);
 }
@@ -338,7 +355,6 @@ static constexpr int REFILL_THRESHOLD = VR_REFILL_THRESHOLD;
 
 __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
     __shared__ int s_stack[SMEM_STACK * TRACE_THREADS];
-    int lstack[LOCAL_STACK];
     const uint32_t n = wf.counts[depth];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wf.segments, (unsigned long long)n);
     const uint32_t* __restrict__ queue = depth == 0 ? nullptr : wf.queue[depth & 1];
@@ -390,11 +406,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
             const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, at_leaf);
             const int live = __popc(m_node | m_leaf);
             if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
-            if (__popc(m_node) >= __popc(m_leaf)) {
-                if (at_node) trav_node(tr, nodes, sstack, TRACE_THREADS, lstack);
+            const int n_node = __popc(m_node), n_leaf = __popc(m_leaf);
+            if (n_node >= n_leaf) {
+                if (at_node) trav_node(tr, nodes, sstack, TRACE_THREADS);
+                // when inner nodes clearly dominate, take a second step on one vote (the loop control is ~25
+                // instructions at full width, a third of a node step)
+                if (n_node >= 3 * n_leaf && have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS);
             } else if (at_leaf) {
-                trav_leaf(tr, tri_isect, tr.cur);
-                tr.cur = trav_pop(tr, sstack, TRACE_THREADS, lstack);
+                trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS);
             }
         }
     }

@@ -5,13 +5,15 @@
 
 namespace vr {
 
-// BVH2 node, 64 B = 4 x float4. A node stores the boxes of BOTH children so that one 64-byte fetch
-// decides the descent (two slab tests, ordered by entry distance).
-//   q0 = (lo0.x, lo0.y, lo0.z, hi0.x)
-//   q1 = (hi0.y, hi0.z, lo1.x, lo1.y)
-//   q2 = (lo1.z, hi1.x, hi1.y, hi1.z)
-//   q3 = (child0, child1, 0, 0) as int bits: >= 0 inner node index; < 0 leaf, ~c = (first_tri << 3) | count
-static const int NODE_QUADS = 4;
+// BVH2 node, 32 B = one 256-bit load. A node stores the boxes of BOTH children, quantised to a 15-bit grid
+// over the scene bounds (cell = extent / 32768; lo rounded down, hi rounded up, plus one guard cell):
+//   w0..w2 = child 0 (x, y, z), w3..w5 = child 1 (x, y, z): each word = (0x8000 | q_lo) | (0x8000 | q_hi) << 16
+//   w6, w7 = child codes: >= 0 inner node index; < 0 leaf, ~c = (first_tri << 3) | count
+// The stored 16-bit value already carries the float's implicit-one position: PRMT drops its two bytes into bytes
+// 1..2 of 0x3F000000, giving f = 1 + q / 32768 exactly, and the slab distance is one FFMA per plane,
+//   t = f * (extent * id) + ((grid_min - o) * id - extent * id),
+// with the near / far plane picked by the ray's sign (PRMT selector) instead of min / max.
+static const int NODE_QUADS = 2;
 static const int LEAF_MAX_TRIS = 4;
 
 // Intersection record, 64 B = 4 x float4 = two 256-bit loads (pre-subtracted edges: e1 = v1 - v0,
@@ -73,6 +75,8 @@ struct DeviceScene {
     const MaterialRec* materials;
     const TextureRec* textures;
     const AnalyticRec* analytics;
+    float grid_min[3];     // node quantisation grid: plane(q) = grid_min + grid_extent * q / 32768
+    float grid_extent[3];
     uint32_t n_tris;
     uint32_t n_analytics;
     int32_t has_microfacet;  // some material is a MicrofacetBSDF (selects the shading kernel variant)

@@ -207,6 +207,7 @@ struct Builder {
     std::atomic<uint32_t> max_depth{0};
     std::atomic<int> threads_left{0};
     static const int BINS = 32;
+    static const uint32_t MAX_DEPTH = 32;  // == the kernel's shared-memory stack depth
     uint32_t leaf_max = LEAF_MAX_TRIS;
     float node_cost = 1.0f;
 
@@ -276,8 +277,19 @@ struct Builder {
             return leaf_code(lo, n);
         }
 
+        // depth cap: the traversal stack holds MAX_DEPTH entries. Once the remaining levels only just suffice
+        // for a balanced tree over n primitives, split at the median (by position) instead of by SAH.
+        uint32_t levels_needed = 0;
+        while ((1u << levels_needed) < n) ++levels_needed;
+        const bool force_median = depth + levels_needed + 1 >= MAX_DEPTH;
         uint32_t mid;
-        if (best_axis < 0) {
+        if (force_median && best_axis >= 0) {
+            Prim* first = prims.data() + lo;
+            Prim* nth = first + n / 2;
+            const int ax = best_axis;
+            std::nth_element(first, nth, prims.data() + hi, [ax](const Prim& a, const Prim& b) { return a.cen[ax] < b.cen[ax]; });
+            mid = lo + n / 2;
+        } else if (best_axis < 0) {
             mid = lo + n / 2;  // identical centroids: split by position
         } else {
             const float cmin = cbounds.lo[best_axis], cmax = cbounds.hi[best_axis];
@@ -314,12 +326,26 @@ struct Builder {
         return (int32_t)node;
     }
 
+    // Quantisation grid (layout.h): 15-bit cells over the scene bounds, set before the build.
+    double grid_min[3] = {0, 0, 0}, grid_inv_cell[3] = {1, 1, 1};
+
+    // lo rounded down, hi rounded up, one more cell outwards for the decoder's rounding; an empty box
+    // (lo > hi) becomes the inverted pair (32767, 0), which no ray enters.
+    uint32_t quantize_pair(float lo, float hi, int axis) const {
+        if (!(lo <= hi)) return (0x8000u | 32767u) | ((0x8000u | 0u) << 16);
+        long long ql = (long long)std::floor(((double)lo - grid_min[axis]) * grid_inv_cell[axis]) - 1;
+        long long qh = (long long)std::ceil(((double)hi - grid_min[axis]) * grid_inv_cell[axis]) + 1;
+        ql = std::min<long long>(std::max<long long>(ql, 0), 32767);
+        qh = std::min<long long>(std::max<long long>(qh, 0), 32767);
+        return (0x8000u | (uint32_t)ql) | ((0x8000u | (uint32_t)qh) << 16);
+    }
+
     void write_node(uint32_t node, int32_t c0, const Box& b0, int32_t c1, const Box& b1) {
         Quad* q = nodes.data() + (size_t)node * NODE_QUADS;
-        q[0] = Quad{b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]};
-        q[1] = Quad{b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]};
-        q[2] = Quad{b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]};
-        q[3] = Quad{bits_f((uint32_t)c0), bits_f((uint32_t)c1), 0.0f, 0.0f};
+        q[0] = Quad{bits_f(quantize_pair(b0.lo[0], b0.hi[0], 0)), bits_f(quantize_pair(b0.lo[1], b0.hi[1], 1)),
+                    bits_f(quantize_pair(b0.lo[2], b0.hi[2], 2)), bits_f(quantize_pair(b1.lo[0], b1.hi[0], 0))};
+        q[1] = Quad{bits_f(quantize_pair(b1.lo[1], b1.hi[1], 1)), bits_f(quantize_pair(b1.lo[2], b1.hi[2], 2)),
+                    bits_f((uint32_t)c0), bits_f((uint32_t)c1)};
     }
 };
 
@@ -485,6 +511,24 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     // ---- BVH ----
     out.nodes.assign((size_t)std::max<uint32_t>(n_tris, 2) * NODE_QUADS, Quad{0, 0, 0, 0});
     Builder builder(prims, out.nodes);
+    {
+        // quantisation grid = bounds of all triangles; a flat axis gets a token extent so the cell size is not 0
+        Box scene_box;
+        scene_box.reset();
+        for (uint32_t i = 0; i < n_tris; ++i) scene_box.grow(prims[i].box);
+        float max_extent = 0.0f;
+        for (int a = 0; a < 3; ++a) max_extent = std::max(max_extent, n_tris ? scene_box.hi[a] - scene_box.lo[a] : 0.0f);
+        if (!(max_extent > 0.0f)) max_extent = 1.0f;
+        for (int a = 0; a < 3; ++a) {
+            const float lo = n_tris ? scene_box.lo[a] : 0.0f;
+            float extent = n_tris ? scene_box.hi[a] - scene_box.lo[a] : 0.0f;
+            extent = std::max(extent, 1e-6f * max_extent) * 1.0001f;
+            out.grid_min[a] = lo;
+            out.grid_extent[a] = extent;
+            builder.grid_min[a] = (double)lo;
+            builder.grid_inv_cell[a] = 32768.0 / (double)extent;
+        }
+    }
     // tuning knobs for experiments (defaults are the shipped configuration)
     if (const char* e = std::getenv("VOIDRAY_LEAF_MAX")) builder.leaf_max = (uint32_t)std::min(7, std::max(1, atoi(e)));
     if (const char* e = std::getenv("VOIDRAY_NODE_COST")) builder.node_cost = (float)atof(e);

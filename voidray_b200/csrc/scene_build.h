@@ -66,6 +66,7 @@ struct FlatScene {
     std::vector<std::vector<uint32_t>> mesh_tie_rank;  // per surface (empty for analytic): rank inside the mesh
     std::vector<uint32_t> surface_rank_base;           // per surface: first global rank
     CameraRec camera;
+    float grid_min[3] = {0, 0, 0}, grid_extent[3] = {1, 1, 1};  // node quantisation grid
     uint32_t n_tris = 0;
     uint32_t bvh_depth = 0;
 };
