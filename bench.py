@@ -205,7 +205,8 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     ctx = Context(local, stream.cuda_stream)
     rs = RenderSettings(total_samples=spp * world, max_bounces=settings.render.max_bounces,
-                        firefly_clamp=settings.render.firefly_clamp, sample_offset=rank * spp)
+                        firefly_clamp=settings.render.firefly_clamp, sample_offset=rank * spp,
+                        max_paths_in_flight=args.paths)
     accel = scene.build_acceleration(ctx)
     info = accel.info()
     target = RenderTarget(accel, (w, h), rs)
@@ -409,6 +410,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per GPU per step (default: the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=5.0, help="--impl reference: CPU work per step")
+    ap.add_argument("--paths", type=int, default=0, help="wavefront capacity (paths in flight); 0 = library default")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

@@ -619,7 +619,10 @@ int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const 
     r->n_pixels = width * height;
     r->settings = *settings;
 
-    uint64_t capacity = settings->max_paths_in_flight ? settings->max_paths_in_flight : (8ull << 20);
+    // Paths in flight per wavefront batch. More is better for the deep, sparse depths (measured: +27 % on
+    // config 1, +7 % on config 2 going from 8 Mi to 32 Mi); 32 Mi slots are 6.7 GB of the 180 GB of HBM at 8 bounces.
+    uint64_t capacity = settings->max_paths_in_flight ? settings->max_paths_in_flight : (32ull << 20);
+    capacity = std::min<uint64_t>(capacity, (uint64_t)r->n_pixels * settings->total_samples);
     if (capacity < r->n_pixels) capacity = r->n_pixels;
     r->samples_per_batch = (uint32_t)(capacity / r->n_pixels);
     capacity = (uint64_t)r->samples_per_batch * r->n_pixels;
