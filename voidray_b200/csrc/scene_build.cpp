@@ -34,6 +34,9 @@ inline int32_t total_key(float f) {
     i ^= (int32_t)(((uint32_t)(i >> 31)) >> 1);
     return i;
 }
+// f32::min / f32::max (NaN loses), inlined: std::fmin / std::fmax are libm calls at -O2
+inline float fmin_(float a, float b) { return (a < b || b != b) ? a : b; }
+inline float fmax_(float a, float b) { return (a > b || b != b) ? a : b; }
 inline float bits_f(uint32_t u) {
     float f;
     std::memcpy(&f, &u, 4);
@@ -76,6 +79,15 @@ void parallel_for(size_t n, Fn fn) {
 
 // Stable sort by key: LSD radix sort (stable by construction) for large ranges, std::stable_sort otherwise.
 void stable_sort_by_key(KeyIdx* v, size_t n, std::vector<KeyIdx>& tmp) {
+    if (n <= 24) {  // most ranges of the recursion are tiny: stable insertion sort, no allocation
+        for (size_t i = 1; i < n; ++i) {
+            const KeyIdx x = v[i];
+            size_t j = i;
+            while (j > 0 && v[j - 1].first > x.first) { v[j] = v[j - 1]; --j; }
+            v[j] = x;
+        }
+        return;
+    }
     if (n < (1u << 15)) {
         std::stable_sort(v, v + n, [](const KeyIdx& a, const KeyIdx& b) { return a.first < b.first; });
         return;
@@ -121,8 +133,8 @@ struct LeafOrderJob {
             for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = cen[3 * order[r.first] + a];
             for (size_t i = r.first + 1; i < r.second; ++i)
                 for (int a = 0; a < 3; ++a) {
-                    cmin[a] = std::fmin(cmin[a], cen[3 * order[i] + a]);
-                    cmax[a] = std::fmax(cmax[a], cen[3 * order[i] + a]);
+                    cmin[a] = fmin_(cmin[a], cen[3 * order[i] + a]);
+                    cmax[a] = fmax_(cmax[a], cen[3 * order[i] + a]);
                 }
             const float sx = cmax[0] - cmin[0], sy = cmax[1] - cmin[1], sz = cmax[2] - cmin[2];
             int axis;  // bvh.rs:71-77: strictly largest spread, else Z
@@ -134,7 +146,11 @@ struct LeafOrderJob {
                 keyed[i].first = total_key(cen[3 * order[r.first + i] + axis]);
                 keyed[i].second = order[r.first + i];
             }
-            stable_sort_by_key(keyed.data(), len, tmp);  // Vec::sort_by(total_cmp) is stable, bvh.rs:80-108
+            // Vec::sort_by(total_cmp) is stable, bvh.rs:80-108. A child that keeps its parent's axis is already in
+            // order (a stable sort of a sorted range is the identity): one linear check saves the sort.
+            bool sorted = true;
+            for (size_t i = 1; i < len && sorted; ++i) sorted = keyed[i - 1].first <= keyed[i].first;
+            if (!sorted) stable_sort_by_key(keyed.data(), len, tmp);
             for (size_t i = 0; i < len; ++i) order[r.first + i] = keyed[i].second;
             const size_t mid = r.first + len / 2;  // bvh.rs:111-120
             // the halves are independent: hand the left one to another thread while any are free
@@ -236,11 +252,53 @@ struct Builder {
             return leaf_code(lo, n);
         }
 
-        // binned SAH over the three axes
         float best_cost = FLT_MAX;
         int best_axis = -1, best_bin = -1;
         const float parent_area = std::max(bounds.half_area(), 1e-30f);
-        for (int axis = 0; axis < 3; ++axis) {
+
+        // small ranges (most of the nodes): exact sweep SAH over the sorted centroids instead of 32 bins
+        static const uint32_t SWEEP_MAX = 16;
+        uint32_t sweep_left = 0;  // > 0: the range has been reordered and the split is after this many prims
+        if (n <= SWEEP_MAX) {
+            uint8_t order[SWEEP_MAX], best_order[SWEEP_MAX];
+            float right_area[SWEEP_MAX];
+            for (int axis = 0; axis < 3; ++axis) {
+                if (!(cbounds.hi[axis] > cbounds.lo[axis])) continue;
+                for (uint32_t i = 0; i < n; ++i) order[i] = (uint8_t)i;
+                for (uint32_t i = 1; i < n; ++i) {  // insertion sort by centroid
+                    const uint8_t v = order[i];
+                    const float key = prims[lo + v].cen[axis];
+                    uint32_t j = i;
+                    while (j > 0 && prims[lo + order[j - 1]].cen[axis] > key) { order[j] = order[j - 1]; --j; }
+                    order[j] = v;
+                }
+                Box acc;
+                acc.reset();
+                for (uint32_t i = n - 1; i > 0; --i) {
+                    acc.grow(prims[lo + order[i]].box);
+                    right_area[i] = acc.half_area();
+                }
+                acc.reset();
+                for (uint32_t i = 1; i < n; ++i) {  // split: the first i prims go left
+                    acc.grow(prims[lo + order[i - 1]].box);
+                    const float cost = (acc.half_area() * (float)i + right_area[i] * (float)(n - i)) / parent_area;
+                    if (cost < best_cost) {
+                        best_cost = cost;
+                        best_axis = axis;
+                        sweep_left = i;
+                        std::memcpy(best_order, order, n);
+                    }
+                }
+            }
+            if (best_axis >= 0 && !(n <= leaf_max && (float)n <= node_cost + best_cost)) {
+                Prim tmp[SWEEP_MAX];
+                for (uint32_t i = 0; i < n; ++i) tmp[i] = prims[lo + best_order[i]];
+                for (uint32_t i = 0; i < n; ++i) prims[lo + i] = tmp[i];
+            }
+        }
+
+        // binned SAH over the three axes
+        for (int axis = 0; axis < 3 && n > SWEEP_MAX; ++axis) {
             const float cmin = cbounds.lo[axis], cmax = cbounds.hi[axis];
             if (!(cmax > cmin)) continue;
             const float k = (float)BINS * (1.0f - 1e-6f) / (cmax - cmin);
@@ -283,7 +341,9 @@ struct Builder {
         while ((1u << levels_needed) < n) ++levels_needed;
         const bool force_median = depth + levels_needed + 1 >= MAX_DEPTH;
         uint32_t mid;
-        if (force_median && best_axis >= 0) {
+        if (n <= SWEEP_MAX && best_axis >= 0) {
+            mid = force_median ? lo + n / 2 : lo + sweep_left;  // the range is already sorted along best_axis
+        } else if (force_median && best_axis >= 0) {
             Prim* first = prims.data() + lo;
             Prim* nth = first + n / 2;
             const int ax = best_axis;
@@ -402,8 +462,8 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
             b[3] = b[4] = b[5] = -INFINITY;
             for (uint32_t v = 0; v < m.n_vertices; ++v)
                 for (int a = 0; a < 3; ++a) {
-                    b[a] = std::fmin(b[a], m.pos[3 * v + a]);
-                    b[3 + a] = std::fmax(b[3 + a], m.pos[3 * v + a]);
+                    b[a] = fmin_(b[a], m.pos[3 * v + a]);
+                    b[3 + a] = fmax_(b[3 + a], m.pos[3 * v + a]);
                 }
             const size_t nt = m.idx.size() / 3;
             total_tris += nt;
@@ -418,8 +478,8 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                     for (int a = 0; a < 3; ++a) {
                         const float p0 = m.pos[3 * m.idx[3 * t] + a], p1 = m.pos[3 * m.idx[3 * t + 1] + a],
                                     p2 = m.pos[3 * m.idx[3 * t + 2] + a];
-                        tb[a] = std::fmin(p0, std::fmin(p1, p2));
-                        tb[3 + a] = std::fmax(p0, std::fmax(p1, p2));
+                        tb[a] = fmin_(p0, fmin_(p1, p2));
+                        tb[3 + a] = fmax_(p0, fmax_(p1, p2));
                     }
                     for (int a = 0; a < 3; ++a) {  // util/aabb.rs:62-83
                         const float dim = tb[3 + a] - tb[a];
