@@ -213,8 +213,19 @@ def run_ours(args):
     acc_t = target.as_torch()
     host_out = torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True).numpy()
 
+    peer_handles = []
+    if dist is not None and args.reduce == "peer":
+        from voidray_b200.distributed import gather_accum_handles, reduce_accum_peers
+        peer_handles = gather_accum_handles(target, 0)
+
     def reduce_():
-        if dist is not None:
+        if dist is None:
+            return
+        if args.reduce == "peer":
+            # the root sums the other ranks' accumulation buffers over NVLink peer memory inside its own kernel
+            with torch.cuda.stream(stream):
+                reduce_accum_peers(target, peer_handles, 0)
+        else:
             with torch.cuda.stream(stream):
                 dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
 
@@ -379,7 +390,9 @@ def run_ours(args):
         "mrays_per_s": mrays,
         "config": {"workload": name, "description": WORKLOADS[name], "width": w, "height": h, "spp_per_gpu": spp,
                    "total_samples": spp * world, "max_bounces": rs.max_bounces, "integrator": "parity (reference estimator)",
-                   "parallelism": f"sample-range x{world} + ncclReduce" if world > 1 else "1 GPU",
+                   "parallelism": (f"sample-range x{world} + " + ("peer-memory reduce kernel (CUDA IPC over NVLink)"
+                                                                  if args.reduce == "peer" else "ncclReduce"))
+                   if world > 1 else "1 GPU",
                    "triangles": info["n_triangles"], "bvh_nodes": info["n_bvh_nodes"],
                    "l2": "inputs larger than L2: each wavefront batch streams ~0.9 GB of path state plus "
                          f"{info['h2d_bytes'] / 1e6:.0f} MB of scene data through the 126 MB L2; no explicit flush"},
@@ -411,6 +424,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=5.0, help="--impl reference: CPU work per step")
     ap.add_argument("--paths", type=int, default=0, help="wavefront capacity (paths in flight); 0 = library default")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: sum the accumulation buffers with the library's peer-memory kernel (CUDA IPC + NVLink "
+                         "loads) or with ncclReduce through torch.distributed")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

@@ -206,6 +206,25 @@ int32_t vr_render_read_accum(vr_render* render, float* rgba);
  * issued by the caller on the context stream. */
 int32_t vr_render_accum_device_ptr(vr_render* render, void** device_ptr);
 
+/* ---- multi-GPU: peer-memory reduce (no counterpart in the reference, which is single-device) ----------
+ * One process per GPU. Every rank exports its accumulation buffer as a CUDA IPC handle (64 bytes, exchanged by
+ * the caller); the root maps the peers' buffers over NVLink and sums them with peer loads inside its own kernel,
+ * in list order (deterministic, unlike a ring / tree collective). The caller must order the calls: peers finish
+ * vr_render_accumulate (it is blocking) before the root reduces, and do not clear before the root is done. */
+#define VR_IPC_HANDLE_BYTES 64
+int32_t vr_render_export_accum(vr_render* render, uint8_t handle[VR_IPC_HANDLE_BYTES]);
+/* accum(root) += sum of peers (in place, on the device). */
+int32_t vr_render_reduce_peers(vr_render* render, const uint8_t* peer_handles, uint32_t n_peers);
+/* Fused reduce + PostProcessingPass::render: rgba_out = tonemap(scale * (accum(root) + sum of peers)) in ONE kernel,
+ * the root's accumulation buffer is left untouched. */
+int32_t vr_render_resolve_peers(vr_render* render, const uint8_t* peer_handles, uint32_t n_peers, float scale,
+                                float gamma, float exposure, int32_t tonemap, float* rgba_out);
+/* The same two operations on raw device pointers (peers living in this process, e.g. several renders or devices
+ * with peer access enabled). */
+int32_t vr_render_reduce_peer_ptrs(vr_render* render, void* const* peer_accum, uint32_t n_peers);
+int32_t vr_render_resolve_peer_ptrs(vr_render* render, void* const* peer_accum, uint32_t n_peers, float scale,
+                                    float gamma, float exposure, int32_t tonemap, float* rgba_out);
+
 /* PostProcessingPass::render(src, dst, PostProcessingData{scale, gamma, exposure, tonemap})
  * (render/post_process.rs:43-86, shaders/post_process.glsl, shaders/tonemapping.glsl) over the whole
  * W*H target (the reference dispatch is hard-wired to 1024x1024, post_process.rs:74).

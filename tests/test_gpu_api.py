@@ -188,3 +188,33 @@ def test_native_obj_loader_and_integer_textures(oracle, ctx):
     _lib.check(lib.vr_debug_texture_sample(h, 1, 5000, _lib.fptr(uv), _lib.fptr(b)))
     assert np.array_equal(a, b)
     lib.vr_scene_destroy(h)
+
+
+def test_peer_memory_reduce_and_fused_resolve(oracle, ctx):
+    # the multi-GPU reduce kernels on peers living in this process: three renders own disjoint sample ranges; the
+    # root sums the other two in list order (bit-exact against numpy in the same order) and the fused
+    # reduce + resolve equals resolve(sum)
+    w, h, spp = 160, 90, 12
+    scene, st, _ = scenes.config1_mushroom(w, h, spp)
+    accel = scene.build_acceleration(ctx)
+    parts = []
+    for rank in range(3):
+        off, cnt = shard_samples(spp, 3, rank)
+        t = RenderTarget(accel, (w, h), RenderSettings(total_samples=spp, max_bounces=8, sample_offset=off))
+        t.accumulate(cnt)
+        parts.append(t)
+    bufs = [t.read() for t in parts]
+    want = (bufs[0] + bufs[1]) + bufs[2]
+    for mode in (0, 1, 3):
+        fused = parts[0].resolve_peer_targets(parts[1:], 1.0, 2.2, 0.5, mode)
+        ref = oracle.resolve(want, 1.0, 2.2, 0.5, mode)
+        both_nan = np.isnan(fused) & np.isnan(ref)
+        assert np.all(np.isclose(fused, ref, rtol=1e-5, atol=1e-6) | both_nan)
+    assert np.array_equal(parts[0].read(), bufs[0])            # the fused kernel does not touch the accumulation buffer
+    parts[0].reduce_peer_targets(parts[1:])
+    assert np.array_equal(parts[0].read(), want)
+    full = RenderTarget(accel, (w, h), RenderSettings(total_samples=spp, max_bounces=8))
+    full.accumulate(spp)
+    assert np.abs(full.read()[..., :3] - want[..., :3]).max() <= 2e-6
+    handle = parts[1].export_accum_handle()
+    assert len(handle) == 64 and any(handle)

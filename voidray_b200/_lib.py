@@ -81,6 +81,11 @@ SIGNATURES = {
     "vr_render_read_accum": [_P, _FP],
     "vr_render_accum_device_ptr": [_P, C.POINTER(_P)],
     "vr_render_resolve": [_P, _F, _F, _F, _I32, _FP],
+    "vr_render_export_accum": [_P, C.POINTER(C.c_uint8)],
+    "vr_render_reduce_peers": [_P, C.POINTER(C.c_uint8), _U32],
+    "vr_render_resolve_peers": [_P, C.POINTER(C.c_uint8), _U32, _F, _F, _F, _I32, _FP],
+    "vr_render_reduce_peer_ptrs": [_P, C.POINTER(C.c_void_p), _U32],
+    "vr_render_resolve_peer_ptrs": [_P, C.POINTER(C.c_void_p), _U32, _F, _F, _F, _I32, _FP],
     "vr_debug_trace_primary": [_P, _U32, _UP, _UP, _FP],
     "vr_debug_trace_rays": [_P, _U64, _FP, _FP, _UP, _UP, _FP],
     "vr_debug_sample_radiance": [_P, _U64, _UP, _UP, _FP],

@@ -125,6 +125,8 @@ struct vr_render {
     unsigned long long segments_host = 0;
     std::vector<cudaEvent_t> events;  // pairs around trace launches, reused call to call
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // peer accumulation buffers opened through CUDA IPC: (handle bytes, mapped pointer)
+    std::vector<std::pair<std::string, void*>> ipc_peers;
     // gate scratch
     uint32_t* dbg_surface = nullptr;
     uint32_t* dbg_prim = nullptr;
@@ -675,6 +677,7 @@ int32_t vr_render_end(vr_render* r) {
     if (!r) return VR_OK;
     cudaSetDevice(r->scene->ctx->device);
     cudaStreamSynchronize(r->scene->ctx->stream);
+    for (auto& p : r->ipc_peers) cudaIpcCloseMemHandle(p.second);
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     if (r->ev_begin) cudaEventDestroy(r->ev_begin);
     if (r->ev_end) cudaEventDestroy(r->ev_end);
@@ -810,6 +813,97 @@ int32_t vr_render_resolve(vr_render* r, float scale, float gamma, float exposure
     VR_CUDA(cudaStreamSynchronize(st));
     VR_CUDA(cudaGetLastError());
     return VR_OK;
+}
+
+// ---- multi-GPU: peer-memory reduce ----------------------------------------------------------------
+
+int32_t vr_render_export_accum(vr_render* r, uint8_t handle[VR_IPC_HANDLE_BYTES]) {
+    if (!r || !handle) return fail(VR_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VR_IPC_HANDLE_BYTES, "IPC handle size");
+    VR_CUDA(cudaSetDevice(r->scene->ctx->device));
+    cudaIpcMemHandle_t h;
+    VR_CUDA(cudaIpcGetMemHandle(&h, r->accum));
+    std::memcpy(handle, &h, VR_IPC_HANDLE_BYTES);
+    return VR_OK;
+}
+
+static int32_t peer_reduce(vr_render* r, void* const* peer_accum, uint32_t n_peers, float scale, float gamma,
+                           float exposure, int32_t tonemap, float* rgba_out) {
+    if (n_peers > (uint32_t)MAX_PEERS) return fail(VR_ERR_INVALID, "too many peers (max 15)");
+    if (n_peers && !peer_accum) return fail(VR_ERR_INVALID, "null peer list");
+    cudaStream_t st = r->scene->ctx->stream;
+    PeerList peers;
+    peers.n = n_peers;
+    for (uint32_t k = 0; k < n_peers; ++k) {
+        if (!peer_accum[k]) return fail(VR_ERR_INVALID, "null peer pointer");
+        peers.ptr[k] = (const float4*)peer_accum[k];
+    }
+    for (uint32_t k = n_peers; k < (uint32_t)MAX_PEERS; ++k) peers.ptr[k] = nullptr;
+    if (tonemap < 0) {
+        launch_reduce_resolve_peers(r->accum, peers, r->accum, r->n_pixels, 1.0f, 1.0f, 1.0f, -1, st);
+        r->kernel_launches += 1;
+        VR_CUDA(cudaStreamSynchronize(st));
+    } else {
+        launch_reduce_resolve_peers(r->accum, peers, r->resolved, r->n_pixels, scale, std::pow(2.0f, exposure), 1.0f / gamma,
+                                    tonemap, st);
+        r->kernel_launches += 1;
+        VR_CUDA(cudaMemcpyAsync(rgba_out, r->resolved, 16ull * r->n_pixels, cudaMemcpyDeviceToHost, st));
+        VR_CUDA(cudaStreamSynchronize(st));
+    }
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+static int32_t open_peers(vr_render* r, const uint8_t* peer_handles, uint32_t n_peers, std::vector<void*>& out) {
+    if (n_peers && !peer_handles) return fail(VR_ERR_INVALID, "null peer handles");
+    VR_CUDA(cudaSetDevice(r->scene->ctx->device));
+    out.clear();
+    for (uint32_t k = 0; k < n_peers; ++k) {
+        const std::string key((const char*)peer_handles + (size_t)k * VR_IPC_HANDLE_BYTES, VR_IPC_HANDLE_BYTES);
+        void* p = nullptr;
+        for (auto& e : r->ipc_peers)
+            if (e.first == key) p = e.second;
+        if (!p) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, key.data(), VR_IPC_HANDLE_BYTES);
+            VR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            r->ipc_peers.emplace_back(key, p);
+        }
+        out.push_back(p);
+    }
+    return VR_OK;
+}
+
+int32_t vr_render_reduce_peers(vr_render* r, const uint8_t* peer_handles, uint32_t n_peers) {
+    if (!r) return fail(VR_ERR_INVALID, "null render");
+    std::vector<void*> ptrs;
+    const int32_t rc = open_peers(r, peer_handles, n_peers, ptrs);
+    if (rc) return rc;
+    return peer_reduce(r, ptrs.data(), n_peers, 1.0f, 1.0f, 0.0f, -1, nullptr);
+}
+
+int32_t vr_render_resolve_peers(vr_render* r, const uint8_t* peer_handles, uint32_t n_peers, float scale, float gamma,
+                                float exposure, int32_t tonemap, float* rgba_out) {
+    if (!r || !rgba_out) return fail(VR_ERR_INVALID, "null argument");
+    if (tonemap < 0 || tonemap > 4) return fail(VR_ERR_INVALID, "unknown tonemap");
+    std::vector<void*> ptrs;
+    const int32_t rc = open_peers(r, peer_handles, n_peers, ptrs);
+    if (rc) return rc;
+    return peer_reduce(r, ptrs.data(), n_peers, scale, gamma, exposure, tonemap, rgba_out);
+}
+
+int32_t vr_render_reduce_peer_ptrs(vr_render* r, void* const* peer_accum, uint32_t n_peers) {
+    if (!r) return fail(VR_ERR_INVALID, "null render");
+    VR_CUDA(cudaSetDevice(r->scene->ctx->device));
+    return peer_reduce(r, peer_accum, n_peers, 1.0f, 1.0f, 0.0f, -1, nullptr);
+}
+
+int32_t vr_render_resolve_peer_ptrs(vr_render* r, void* const* peer_accum, uint32_t n_peers, float scale, float gamma,
+                                    float exposure, int32_t tonemap, float* rgba_out) {
+    if (!r || !rgba_out) return fail(VR_ERR_INVALID, "null argument");
+    if (tonemap < 0 || tonemap > 4) return fail(VR_ERR_INVALID, "unknown tonemap");
+    VR_CUDA(cudaSetDevice(r->scene->ctx->device));
+    return peer_reduce(r, peer_accum, n_peers, scale, gamma, exposure, tonemap, rgba_out);
 }
 
 // ---- gates ----------------------------------------------------------------------------------------

@@ -867,32 +867,57 @@ __device__ __forceinline__ float uncharted_fit(float c) {
     return ((c * (A * c + C * B) + D * E) / (c * (A * c + B) + D * F)) - E / F;
 }
 
+__device__ __forceinline__ float4 resolve_pixel(float4 a, float scale, float exposure_mul, float inv_gamma, int32_t tonemap) {
+    const float ACES_IN[9] = {0.59719f, 0.076f, 0.0284f, 0.35458f, 0.90834f, 0.13383f, 0.04823f, 0.01566f, 0.83777f};
+    const float ACES_OUT[9] = {1.60475f, -0.10208f, -0.00327f, -0.53108f, 1.10813f, -0.07276f, -0.07367f, -0.00605f, 1.07602f};
+    f3 c = mk3(a.x * scale, a.y * scale, a.z * scale) * exposure_mul;
+    if (tonemap == 1) {
+        c = mat3_mul(ACES_IN, c);
+        c = mk3(aces_fit(c.x), aces_fit(c.y), aces_fit(c.z));
+        c = mat3_mul(ACES_OUT, c);
+    } else if (tonemap == 2) {
+        const float white = 2.0f;
+        const float luma = (c.x * 0.2126f + c.y * 0.7152f) + c.z * 0.0722f;
+        const float tm = luma * (1.0f + luma / (white * white)) / (1.0f + luma);
+        c = c * (tm / luma);
+    } else if (tonemap == 3) {
+        c = mk3(fmaxf(0.0f, c.x - 0.004f), fmaxf(0.0f, c.y - 0.004f), fmaxf(0.0f, c.z - 0.004f));
+        c = mk3(filmic_fit(c.x), filmic_fit(c.y), filmic_fit(c.z));
+    } else if (tonemap == 4) {
+        c = c * 2.0f;
+        c = mk3(uncharted_fit(c.x), uncharted_fit(c.y), uncharted_fit(c.z));
+        c = c / uncharted_fit(11.2f);
+    }
+    return make_float4(powf(c.x, inv_gamma), powf(c.y, inv_gamma), powf(c.z, inv_gamma), 1.0f);
+}
+
 __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accum, float4* __restrict__ out,
                                                  uint32_t n_pixels, float scale, float exposure_mul, float inv_gamma,
                                                  int32_t tonemap) {
-    const float ACES_IN[9] = {0.59719f, 0.076f, 0.0284f, 0.35458f, 0.90834f, 0.13383f, 0.04823f, 0.01566f, 0.83777f};
-    const float ACES_OUT[9] = {1.60475f, -0.10208f, -0.00327f, -0.53108f, 1.10813f, -0.07276f, -0.07367f, -0.00605f, 1.07602f};
+    for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += gridDim.x * blockDim.x)
+        out[px] = resolve_pixel(accum[px], scale, exposure_mul, inv_gamma, tonemap);
+}
+
+// Fused reduce + resolve over peer memory: every peer pointer is another GPU's accumulation buffer mapped into this
+// address space (CUDA IPC / peer access), so the loads below travel over NVLink and the sum never exists as a
+// separate buffer. All peer loads of a pixel are issued before the first add (independent 16-byte loads in flight).
+__global__ void __launch_bounds__(256) k_reduce_resolve_peers(const float4* own, PeerList peers, float4* out, uint32_t n_pixels,
+                                                              float scale, float exposure_mul, float inv_gamma, int32_t tonemap) {
     for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += gridDim.x * blockDim.x) {
-        const float4 a = accum[px];
-        f3 c = mk3(a.x * scale, a.y * scale, a.z * scale) * exposure_mul;
-        if (tonemap == 1) {
-            c = mat3_mul(ACES_IN, c);
-            c = mk3(aces_fit(c.x), aces_fit(c.y), aces_fit(c.z));
-            c = mat3_mul(ACES_OUT, c);
-        } else if (tonemap == 2) {
-            const float white = 2.0f;
-            const float luma = (c.x * 0.2126f + c.y * 0.7152f) + c.z * 0.0722f;
-            const float tm = luma * (1.0f + luma / (white * white)) / (1.0f + luma);
-            c = c * (tm / luma);
-        } else if (tonemap == 3) {
-            c = mk3(fmaxf(0.0f, c.x - 0.004f), fmaxf(0.0f, c.y - 0.004f), fmaxf(0.0f, c.z - 0.004f));
-            c = mk3(filmic_fit(c.x), filmic_fit(c.y), filmic_fit(c.z));
-        } else if (tonemap == 4) {
-            c = c * 2.0f;
-            c = mk3(uncharted_fit(c.x), uncharted_fit(c.y), uncharted_fit(c.z));
-            c = c / uncharted_fit(11.2f);
-        }
-        out[px] = make_float4(powf(c.x, inv_gamma), powf(c.y, inv_gamma), powf(c.z, inv_gamma), 1.0f);
+        float4 v[MAX_PEERS];
+#pragma unroll
+        for (int k = 0; k < MAX_PEERS; ++k)
+            if (k < (int)peers.n) v[k] = peers.ptr[k][px];
+        float4 a = own[px];
+#pragma unroll
+        for (int k = 0; k < MAX_PEERS; ++k)
+            if (k < (int)peers.n) {
+                a.x += v[k].x;
+                a.y += v[k].y;
+                a.z += v[k].z;
+                a.w += v[k].w;
+            }
+        out[px] = tonemap < 0 ? a : resolve_pixel(a, scale, exposure_mul, inv_gamma, tonemap);
     }
 }
 
@@ -1032,6 +1057,12 @@ void launch_expand_rgb(const float* rgb, float4* rgba, size_t n_texels, cudaStre
     if (n_texels == 0) return;
     const size_t grid = (n_texels + 255) / 256;
     k_expand_rgb<<<(unsigned)(grid > 148 * 16 ? 148 * 16 : grid), 256, 0, stream>>>(rgb, rgba, n_texels);
+}
+void launch_reduce_resolve_peers(const float4* own, PeerList peers, float4* out, uint32_t n_pixels, float scale,
+                                 float exposure_mul, float inv_gamma, int32_t tonemap, cudaStream_t stream) {
+    const uint32_t grid = (n_pixels + 255) / 256;
+    k_reduce_resolve_peers<<<grid > 148 * 8 ? 148 * 8 : grid, 256, 0, stream>>>(own, peers, out, n_pixels, scale,
+                                                                              exposure_mul, inv_gamma, tonemap);
 }
 void launch_trace_rays(const DeviceScene& sc, const float* origins, const float* dirs, uint64_t n, uint32_t* surface,
                        uint32_t* prim, float* t, cudaStream_t stream) {

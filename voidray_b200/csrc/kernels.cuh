@@ -60,6 +60,16 @@ void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint
 void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul,
                     float inv_gamma, int32_t tonemap, cudaStream_t stream);
 
+// Peer-memory reduce: sum = own + peers[0] + peers[1] + ... (that order) per pixel, read with peer loads over
+// NVLink. tonemap < 0: write the sum to `out` (may alias `own`); otherwise write the resolved pixel to `out`.
+static const int MAX_PEERS = 15;
+struct PeerList {
+    const float4* ptr[MAX_PEERS];
+    uint32_t n;
+};
+void launch_reduce_resolve_peers(const float4* own, PeerList peers, float4* out, uint32_t n_pixels, float scale,
+                                 float exposure_mul, float inv_gamma, int32_t tonemap, cudaStream_t stream);
+
 // RGB f32 (as uploaded) -> RGBA f32 texel records
 void launch_expand_rgb(const float* rgb, float4* rgba, size_t n_texels, cudaStream_t stream);
 

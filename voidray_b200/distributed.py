@@ -50,3 +50,33 @@ def reduce_accum(tensor, dst: int = 0, all_ranks: bool = False):
     else:
         dist.reduce(tensor, dst=dst, op=dist.ReduceOp.SUM)
     return tensor
+
+
+def gather_accum_handles(target, dst: int = 0):
+    """Exchange the CUDA IPC handles of every rank's accumulation buffer; returns the peers' handles (every rank
+    but `dst`, in rank order) on `dst` and [] elsewhere. Done once per RenderTarget."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return []
+    mine = torch.tensor(list(target.export_accum_handle()), dtype=torch.uint8,
+                        device=f"cuda:{target.scene.ctx.device}" if dist.get_backend() == "nccl" else "cpu")
+    out = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    if dist.get_rank() != dst:
+        return []
+    return [bytes(t.cpu().tolist()) for r, t in enumerate(out) if r != dst]
+
+
+def reduce_accum_peers(target, peer_handles, dst: int = 0):
+    """One reduce step over peer memory: all ranks have finished accumulating (barrier), the root sums the peers'
+    buffers into its own with NVLink peer loads, and nobody touches a buffer until it is done (barrier)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    dist.barrier()
+    if dist.get_rank() == dst:
+        target.reduce_peers(peer_handles)
+    dist.barrier()

@@ -249,6 +249,47 @@ class RenderTarget:
                                           fptr(out)))
         return out
 
+    # ---- multi-GPU: peer-memory reduce (include/voidray_cuda.h) ----
+    IPC_HANDLE_BYTES = 64
+
+    def export_accum_handle(self) -> bytes:
+        """CUDA IPC handle of the accumulation buffer, to be sent to the root rank."""
+        buf = (C.c_uint8 * self.IPC_HANDLE_BYTES)()
+        check(self._lib.vr_render_export_accum(self.handle, buf))
+        return bytes(buf)
+
+    @staticmethod
+    def _pack_handles(handles):
+        blob = b"".join(handles)
+        return (C.c_uint8 * len(blob)).from_buffer_copy(blob) if blob else None
+
+    def reduce_peers(self, handles) -> None:
+        """accum += the peers' accumulation buffers (other processes' GPUs, read over NVLink), in list order."""
+        check(self._lib.vr_render_reduce_peers(self.handle, self._pack_handles(handles), len(handles)))
+
+    def resolve_peers(self, handles, scale: float, gamma: float, exposure: float, tonemap: int,
+                      out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Fused reduce + tonemap: one kernel sums own + peers and resolves; accum is left untouched."""
+        if out is None:
+            out = np.empty((self.dimensions[1], self.dimensions[0], 4), F32)
+        check(self._lib.vr_render_resolve_peers(self.handle, self._pack_handles(handles), len(handles), float(scale),
+                                                float(gamma), float(exposure), int(tonemap), fptr(out)))
+        return out
+
+    def reduce_peer_targets(self, peers) -> None:
+        """The same for RenderTargets living in this process."""
+        ptrs = (C.c_void_p * max(1, len(peers)))(*[p.device_ptr() for p in peers])
+        check(self._lib.vr_render_reduce_peer_ptrs(self.handle, ptrs, len(peers)))
+
+    def resolve_peer_targets(self, peers, scale: float, gamma: float, exposure: float, tonemap: int,
+                             out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.dimensions[1], self.dimensions[0], 4), F32)
+        ptrs = (C.c_void_p * max(1, len(peers)))(*[p.device_ptr() for p in peers])
+        check(self._lib.vr_render_resolve_peer_ptrs(self.handle, ptrs, len(peers), float(scale), float(gamma),
+                                                    float(exposure), int(tonemap), fptr(out)))
+        return out
+
     # ---- gates ----
     def trace_primary(self, sample: int = 0):
         n = self.n_pixels
