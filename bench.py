@@ -409,8 +409,6 @@ def run_ours(args):
     if extra:
         line["other_scenes"] = extra
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        pass
 
 
 def main():

@@ -61,6 +61,14 @@ def test_primary_two_surfaces_and_materials_scene(oracle, ctx):
     check_primary(oracle, ctx, scene, st.render, 480, 270)
 
 
+@pytest.mark.parametrize("maker", [scenes.config2_mossy_ground, scenes.config3_materials, scenes.config5_combined])
+def test_primary_full_baseline_resolution(oracle, ctx, maker):
+    # the gate at BASELINE.json's own resolutions: 1920x1080 (configs 2, 3) and 3840x2160 (config 5)
+    scene, st, (w, h) = maker()
+    assert (w, h) in ((1920, 1080), (3840, 2160))
+    check_primary(oracle, ctx, scene, st.render, w, h)
+
+
 def test_primary_analytic_and_small_meshes(oracle, ctx):
     for fn in (scenes.example_cornell, scenes.example_spheres, scenes.example_material):
         scene, st, _ = fn()

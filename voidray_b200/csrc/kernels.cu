@@ -98,8 +98,8 @@ __device__ __forceinline__ void intersect_analytic(const AnalyticRec& a, int pri
     }
 }
 
-// Per-lane traversal state. The stack keeps its first SMEM_STACK entries in shared memory (one column per
-// thread, stride = blockDim.x, conflict-free) and spills deeper entries to local memory.
+// Per-lane traversal state. The SMEM_STACK-entry stack lives in shared memory (one column per thread,
+// stride = blockDim.x, conflict-free); the builder caps the BVH depth so it cannot overflow.
 struct Traversal {
     f3 o, d;
     // Slab tests on the quantised nodes (layout.h), never feeding a reported value:
