@@ -125,6 +125,11 @@ int32_t vr_scene_set_camera(vr_scene* scene, const float eye[3], const float dir
 int32_t vr_scene_set_camera_look_at(vr_scene* scene, const float eye[3], const float center[3],
                                     const float up[3], float fov);
 
+/* The arithmetic of Camera::look_at alone (no scene needed): direction = normalize(center - eye),
+ * up = normalize(up - up.dot(direction) * direction), in f32 with the reference's operation order. */
+int32_t vr_camera_look_at(const float eye[3], const float center[3], const float up[3], float direction_out[3],
+                          float up_out[3]);
+
 /* scene.environment = Environments::uniform(rgb) — voidray_common/src/environments.rs:9-11,19-33 */
 int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]);
 /* scene.environment = Environments::hdri(path) after image::open().to_rgb32f() — environments.rs:13-16,35-86 */

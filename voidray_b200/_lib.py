@@ -67,6 +67,7 @@ SIGNATURES = {
     "vr_scene_add_object": [_P, _U32, _U32, _UP],
     "vr_scene_set_camera": [_P, _FP, _FP, _FP, _F, _I32, _F, _FP],
     "vr_scene_set_camera_look_at": [_P, _FP, _FP, _FP, _F],
+    "vr_camera_look_at": [_FP, _FP, _FP, _FP, _FP],
     "vr_scene_set_environment_uniform": [_P, _FP],
     "vr_scene_set_environment_hdri_rgb32f": [_P, _FP, _U32, _U32],
     "vr_scene_clear_environment": [_P],

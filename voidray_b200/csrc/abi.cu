@@ -489,6 +489,13 @@ int32_t vr_scene_set_camera_look_at(vr_scene* scene, const float eye[3], const f
     return VR_OK;
 }
 
+int32_t vr_camera_look_at(const float eye[3], const float center[3], const float up[3], float direction_out[3],
+                          float up_out[3]) {
+    if (!eye || !center || !up || !direction_out || !up_out) return fail(VR_ERR_INVALID, "null camera vector");
+    camera_look_at(eye, center, up, direction_out, up_out);
+    return VR_OK;
+}
+
 int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]) {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!rgb) return fail(VR_ERR_INVALID, "null colour");
