@@ -394,6 +394,13 @@ public:
         const auto end = rendering_ ? std::chrono::steady_clock::now() : end_;
         return std::chrono::duration<double>(end - start_).count();
     }
+    // RendererStats.remaining (renderer.rs:75-77,95-98): elapsed / done * (total - done); negative = None
+    double remaining_time() const {
+        std::lock_guard<std::mutex> lock(mutex_);
+        if (!rendering_ || !started_ || samples_.first == 0) return -1.0;
+        const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count();
+        return elapsed / samples_.first * (samples_.second - samples_.first);
+    }
     // voidray_app/src/main.rs:68-90: scale = total / done (0 if not normal), then the tonemap pass
     std::vector<float> post_process() const {
         std::lock_guard<std::mutex> lock(mutex_);
