@@ -17,7 +17,7 @@ namespace vr {
 #define VR_TRACE_MIN_BLOCKS 8
 #endif
 #ifndef VR_REFILL_THRESHOLD
-#define VR_REFILL_THRESHOLD 16
+#define VR_REFILL_THRESHOLD 12
 #endif
 static constexpr int TRACE_THREADS = VR_TRACE_THREADS;
 static constexpr int SHADE_THREADS = 128;
@@ -407,13 +407,27 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
             const int live = __popc(m_node | m_leaf);
             if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
             const int n_node = __popc(m_node), n_leaf = __popc(m_leaf);
-            if (n_node >= n_leaf) {
-                if (at_node) trav_node(tr, nodes, sstack, TRACE_THREADS);
-                // when inner nodes clearly dominate, take a second step on one vote (the loop control is ~25
-                // instructions at full width, a third of a node step)
-                if (n_node >= 3 * n_leaf && have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS);
-            } else if (at_leaf) {
-                trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS);
+#ifndef VR_LEAF_VOTE_NUM
+#define VR_LEAF_VOTE_NUM 2
+#endif
+#ifndef VR_NODE_STEPS
+#define VR_NODE_STEPS 4
+#endif
+#ifndef VR_LEAF_STEPS
+#define VR_LEAF_STEPS 2
+#endif
+            // Vote: the leaf step runs once the lanes waiting at a leaf exceed 1/VR_LEAF_VOTE_NUM of the lanes at
+            // inner nodes; otherwise every lane that is (still) at an inner node takes VR_NODE_STEPS node steps on
+            // this one vote — the loop control costs ~25 full-width instructions, half a node step. Measured sweep
+            // in profiles/README.md.
+            if (n_node >= n_leaf * VR_LEAF_VOTE_NUM) {
+#pragma unroll
+                for (int step = 0; step < VR_NODE_STEPS; ++step)
+                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS);
+            } else {
+#pragma unroll
+                for (int step = 0; step < VR_LEAF_STEPS; ++step)
+                    if (have && tr.cur < 0) trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS);
             }
         }
     }
