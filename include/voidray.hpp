@@ -168,6 +168,16 @@ struct Surfaces {  // voidray_common/src/surfaces.rs:9-29
 };
 
 // ---- environments ---------------------------------------------------------------------------------
+// image::open(path).unwrap().to_rgb32f() (core/texture.rs:37, environments.rs:43) through the library's decoders;
+// throws where the reference panics.
+inline std::vector<float> load_image_rgb32f(const std::string& path, uint32_t* width, uint32_t* height) {
+    float* rgb = nullptr;
+    check(vr_image_load_rgb32f(path.c_str(), width, height, &rgb));
+    std::vector<float> out(rgb, rgb + (size_t)3 * *width * *height);
+    vr_image_free(rgb);
+    return out;
+}
+
 struct UniformEnvironment { Color color; };
 struct HDRIEnvironment { std::vector<float> rgb; uint32_t width, height; };
 struct NoEnvironment {};
@@ -175,6 +185,11 @@ typedef std::variant<NoEnvironment, UniformEnvironment, HDRIEnvironment> Environ
 struct Environments {  // voidray_common/src/environments.rs:9-17 (the image arrives decoded: to_rgb32f)
     static Environment uniform(Color background) { return UniformEnvironment{background}; }
     static Environment hdri(std::vector<float> rgb, uint32_t width, uint32_t height) { return HDRIEnvironment{std::move(rgb), width, height}; }
+    static Environment hdri(const std::string& path) {  // environments.rs:13-16,42-55
+        uint32_t w = 0, h = 0;
+        std::vector<float> rgb = load_image_rgb32f(path, &w, &h);
+        return HDRIEnvironment{std::move(rgb), w, h};
+    }
 };
 
 struct ImageTexture {
@@ -216,6 +231,11 @@ public:
     TextureHandle add_image_texture(std::vector<float> rgb, uint32_t width, uint32_t height, SampleType sample_type) {
         textures_.push_back(ImageTexture{std::move(rgb), width, height, sample_type});
         return TextureHandle{(uint32_t)textures_.size() - 1};
+    }
+    TextureHandle add_image_texture(const std::string& path, SampleType sample_type) {  // scene.rs:154-160
+        uint32_t w = 0, h = 0;
+        std::vector<float> rgb = load_image_rgb32f(path, &w, &h);
+        return add_image_texture(std::move(rgb), w, h, sample_type);
     }
     // Accelerable::build_acceleration, core/scene.rs:163-179
     std::shared_ptr<SceneAcceleration> build_acceleration(const Context& ctx) const;

@@ -68,6 +68,18 @@ int32_t vr_scene_add_texture_rgb8(vr_scene* scene, const uint8_t* pixels, uint32
 int32_t vr_scene_add_texture_rgb16(vr_scene* scene, const uint16_t* pixels, uint32_t w, uint32_t h, uint32_t channels,
                                    int32_t sample_type, uint32_t* texture);
 
+/* Scene::add_image_texture(path, sample_type) (scene.rs:154-160 -> ImageTexture::new, core/texture.rs:36-49):
+ * decodes the file in the library like `image::open(path).unwrap().to_rgb32f()` — PNG, baseline / progressive
+ * JPEG, TIFF (strips; none / LZW / Deflate / PackBits), Radiance HDR, scan-line OpenEXR (none / RLE / ZIPS / ZIP /
+ * PIZ), recognised by magic bytes. Where the reference panics (missing or undecodable file) this returns
+ * VR_ERR_INVALID with the reason in vr_last_error(). */
+int32_t vr_scene_add_image_texture_file(vr_scene* scene, const char* path, int32_t sample_type, uint32_t* texture);
+
+/* Host-only: the decoder behind the *_file calls. *rgb receives a malloc'ed w*h*3 f32 array (row 0 first), to be
+ * released with vr_image_free. Needs no CUDA device. */
+int32_t vr_image_load_rgb32f(const char* path, uint32_t* w, uint32_t* h, float** rgb);
+int32_t vr_image_free(float* rgb);
+
 /* Scene::add_mesh(Arc::new(Mesh::from_buffers(vertices, indices))) (scene.rs:128-135,
  * core/mesh.rs:76-116). positions 3*n_vertices, uvs 2*n_vertices, normals 3*n_vertices (uvs /
  * normals may be NULL = zeros, like Vertex::position, mesh.rs:26-32); indices: n_indices u32,
@@ -134,6 +146,9 @@ int32_t vr_camera_look_at(const float eye[3], const float center[3], const float
 int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]);
 /* scene.environment = Environments::hdri(path) after image::open().to_rgb32f() — environments.rs:13-16,35-86 */
 int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, uint32_t w, uint32_t h);
+/* scene.environment = Environments::hdri(path) with the file decoded in the library (environments.rs:42-55);
+ * formats as vr_scene_add_image_texture_file. */
+int32_t vr_scene_set_environment_hdri_file(vr_scene* scene, const char* path);
 /* scene.environment = None */
 int32_t vr_scene_clear_environment(vr_scene* scene);
 

@@ -1,5 +1,6 @@
 """-m gpu: behaviour of the C ABI / host mirror: call-order errors, accumulation semantics, batching
 invariance, cancel, the progressive driver, sample-range sharding on one device."""
+import os
 import threading
 import time
 
@@ -187,6 +188,50 @@ def test_native_obj_loader_and_integer_textures(oracle, ctx):
     _lib.check(lib.vr_debug_texture_sample(h, 0, 5000, _lib.fptr(uv), _lib.fptr(a)))
     _lib.check(lib.vr_debug_texture_sample(h, 1, 5000, _lib.fptr(uv), _lib.fptr(b)))
     assert np.array_equal(a, b)
+    lib.vr_scene_destroy(h)
+
+
+def test_image_file_entry_points(ctx, tmp_path):
+    # vr_scene_add_image_texture_file / vr_scene_set_environment_hdri_file (Scene::add_image_texture,
+    # Environments::hdri: decode inside the library) against the array entry points fed by the same decoder
+    import ctypes as C
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    from voidray_b200.assets import asset_path, load_image_native, synth_hdri
+    lib = _lib.load()
+    hdri_path = str(tmp_path / "env.exr")
+    assert cv2.imwrite(hdri_path, synth_hdri("indoor", 256, 128)[:, :, ::-1].astype(F32))
+    h = C.c_void_p()
+    _lib.check(lib.vr_scene_create(ctx.handle, C.byref(h)))
+    out = C.c_uint32()
+    names = ("mushroom_albedo.jpg", "wood_normal.tif", "uv_test.png")
+    for i, name in enumerate(names):
+        _lib.check(lib.vr_scene_add_image_texture_file(h, os.fsencode(asset_path(name)), 1, C.byref(out)))
+        assert out.value == 2 * i
+        img = load_image_native(asset_path(name))
+        _lib.check(lib.vr_scene_add_texture_rgb32f(h, _lib.fptr(img), img.shape[1], img.shape[0], 1, C.byref(out)))
+    assert lib.vr_scene_add_image_texture_file(h, b"/nonexistent.png", 1, C.byref(out)) == _lib.VR_ERR_INVALID
+    assert b"cannot open" in lib.vr_last_error()
+    assert lib.vr_scene_set_environment_hdri_file(h, os.fsencode(asset_path("cube.obj"))) == _lib.VR_ERR_INVALID
+    _lib.check(lib.vr_scene_set_environment_hdri_file(h, os.fsencode(hdri_path)))
+    _lib.check(lib.vr_scene_commit(h))
+    uv = np.random.default_rng(5).uniform(-1, 2, (4000, 2)).astype(F32)
+    for i in range(len(names)):
+        a, b = np.empty((4000, 3), F32), np.empty((4000, 3), F32)
+        _lib.check(lib.vr_debug_texture_sample(h, 2 * i, 4000, _lib.fptr(uv), _lib.fptr(a)))
+        _lib.check(lib.vr_debug_texture_sample(h, 2 * i + 1, 4000, _lib.fptr(uv), _lib.fptr(b)))
+        assert np.array_equal(a, b) and a.max() > 0.1
+    d = np.random.default_rng(6).normal(size=(4000, 3)).astype(F32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(F32)
+    e_file = np.empty((4000, 3), F32)
+    _lib.check(lib.vr_debug_environment_sample(h, 4000, _lib.fptr(d), _lib.fptr(e_file)))
+    env = load_image_native(hdri_path)
+    assert np.array_equal(env, synth_hdri("indoor", 256, 128).astype(F32))
+    _lib.check(lib.vr_scene_set_environment_hdri_rgb32f(h, _lib.fptr(env), 256, 128))
+    _lib.check(lib.vr_scene_commit(h))
+    e_arr = np.empty((4000, 3), F32)
+    _lib.check(lib.vr_debug_environment_sample(h, 4000, _lib.fptr(d), _lib.fptr(e_arr)))
+    assert np.array_equal(e_file, e_arr) and e_file.max() > 1.0
     lib.vr_scene_destroy(h)
 
 

@@ -1,0 +1,225 @@
+"""The library's own image decoders (csrc/image_io.cpp, `vr_image_load_rgb32f`) against PIL / OpenCV on the
+repository's texture files and on files written here in every supported encoding. They stand in for
+`image::open(path).to_rgb32f()` (core/texture.rs:37, environments.rs:43). Lossless formats must match bit for
+bit; JPEG is compared within the usual inter-decoder IDCT / colour rounding difference. Host-only: no GPU."""
+import os
+
+os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+
+import numpy as np
+import pytest
+
+from voidray_b200 import _lib, assets
+
+ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets")
+F32 = np.float32
+
+
+def _rng_image(h, w, c, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    hi = np.iinfo(dtype).max
+    # smooth + noise so every PNG filter / LZW path gets exercised
+    y, x = np.mgrid[0:h, 0:w]
+    base = ((np.sin(x / 7.0)[..., None] + np.cos(y / 5.0)[..., None] + 2.0) / 4.0 * hi)
+    img = base + rng.integers(0, hi // 8 + 1, size=(h, w, c))
+    return np.clip(img, 0, hi).astype(dtype)
+
+
+@pytest.mark.parametrize("name", ["test.png", "uv_test.png", "wood_albedo.tif", "wood_normal.tif"])
+def test_lossless_assets_match_pil(name):
+    path = os.path.join(ASSETS, name)
+    assert np.array_equal(assets.load_image_native(path), assets.load_image_rgb32f(path))
+
+
+@pytest.mark.parametrize("name", ["mossy_ground_albedo.jpg", "mushroom_albedo.jpg"])
+def test_jpeg_assets_match_libjpeg_within_rounding(name):
+    path = os.path.join(ASSETS, name)
+    a = assets.load_image_native(path)
+    b = assets.load_image_rgb32f(path)
+    assert a.shape == b.shape == (2048, 2048, 3)
+    d = np.abs(np.rint(a * 255.0) - np.rint(b * 255.0))
+    assert d.max() <= 3 and d.mean() < 0.01 and (d > 0).mean() < 0.01
+
+
+def test_png_variants(tmp_path):
+    from PIL import Image
+
+    rgb = _rng_image(37, 53, 3, np.uint8)
+    cases = {}
+    Image.fromarray(rgb).save(tmp_path / "rgb.png")
+    cases["rgb.png"] = rgb
+    rgba = np.dstack([rgb, _rng_image(37, 53, 1, np.uint8, 1)])
+    Image.fromarray(rgba).save(tmp_path / "rgba.png")
+    cases["rgba.png"] = rgb
+    grey = rgb[:, :, 0]
+    Image.fromarray(grey).save(tmp_path / "grey.png")
+    cases["grey.png"] = np.repeat(grey[:, :, None], 3, 2)
+    Image.fromarray(np.dstack([grey, rgba[:, :, 3]]), "LA").save(tmp_path / "la.png")
+    cases["la.png"] = np.repeat(grey[:, :, None], 3, 2)
+    pal = Image.fromarray(rgb).quantize(17)
+    pal.save(tmp_path / "pal.png", bits=8)
+    cases["pal.png"] = np.asarray(pal.convert("RGB"))
+    pal4 = Image.fromarray(rgb).quantize(13)
+    pal4.save(tmp_path / "pal4.png", bits=4)
+    cases["pal4.png"] = np.asarray(pal4.convert("RGB"))
+    one = Image.fromarray((grey > 128).astype(np.uint8) * 255).convert("1")
+    one.save(tmp_path / "bit.png")
+    cases["bit.png"] = np.repeat((np.asarray(one).astype(np.uint8) * 255)[:, :, None], 3, 2)
+    for name, want in cases.items():
+        got = assets.load_image_native(str(tmp_path / name))
+        assert np.array_equal(got, want.astype(F32) / F32(255.0)), name
+    # 16-bit grey
+    g16 = _rng_image(19, 23, 1, np.uint16)[:, :, 0]
+    Image.fromarray(g16).save(tmp_path / "g16.png")
+    got = assets.load_image_native(str(tmp_path / "g16.png"))
+    assert np.array_equal(got, np.repeat((g16.astype(F32) / F32(65535.0))[:, :, None], 3, 2))
+
+
+def test_png_16bit_rgb_and_interlaced(tmp_path):
+    import cv2
+
+    rgb16 = _rng_image(33, 41, 3, np.uint16)
+    assert cv2.imwrite(str(tmp_path / "rgb16.png"), rgb16[:, :, ::-1])
+    got = assets.load_image_native(str(tmp_path / "rgb16.png"))
+    assert np.array_equal(got, rgb16.astype(F32) / F32(65535.0))
+    # Adam7: hand-assembled with zlib (PIL / OpenCV cannot write interlaced files)
+    import struct
+    import zlib
+
+    rgb = _rng_image(21, 30, 3, np.uint8)
+    h, w, _ = rgb.shape
+    x0, y0, dx, dy = [0, 4, 0, 2, 0, 1, 0], [0, 0, 4, 0, 2, 0, 1], [8, 8, 4, 4, 2, 2, 1], [8, 8, 8, 4, 4, 2, 2]
+    raw = b""
+    for p in range(7):
+        sub = rgb[y0[p]::dy[p], x0[p]::dx[p]]
+        if sub.size == 0:
+            continue
+        for row in sub:
+            raw += b"\x00" + row.tobytes()
+
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body))
+
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 1)) + \
+        chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    (tmp_path / "adam7.png").write_bytes(png)
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "adam7.png").convert("RGB")), rgb)  # the file is valid
+    assert np.array_equal(assets.load_image_native(str(tmp_path / "adam7.png")), rgb.astype(F32) / F32(255.0))
+
+
+@pytest.mark.parametrize("compression", ["raw", "tiff_lzw", "tiff_adobe_deflate", "packbits"])
+def test_tiff_compressions(tmp_path, compression):
+    from PIL import Image
+
+    rgb = _rng_image(67, 91, 3, np.uint8)
+    path = str(tmp_path / f"{compression}.tif")
+    Image.fromarray(rgb).save(path, compression=compression)
+    assert np.array_equal(assets.load_image_native(path), rgb.astype(F32) / F32(255.0))
+    grey = rgb[:, :, 1]
+    Image.fromarray(grey).save(path, compression=compression)
+    assert np.array_equal(assets.load_image_native(path), np.repeat((grey.astype(F32) / F32(255.0))[:, :, None], 3, 2))
+
+
+def test_tiff_large_lzw_predictor_and_16bit(tmp_path):
+    import cv2
+    from PIL import Image
+
+    rgb = _rng_image(300, 400, 3, np.uint8)  # large enough for the LZW table to fill and reset many times
+    path = str(tmp_path / "big.tif")
+    Image.fromarray(rgb).save(path, compression="tiff_lzw", tiffinfo={317: 2})
+    im = Image.open(path)
+    assert im.tag_v2.get(317) == 2
+    assert np.array_equal(assets.load_image_native(path), rgb.astype(F32) / F32(255.0))
+    rgb16 = _rng_image(64, 80, 3, np.uint16)
+    p16 = str(tmp_path / "rgb16.tif")
+    assert cv2.imwrite(p16, rgb16[:, :, ::-1])  # OpenCV writes LZW + predictor for 16-bit TIFF
+    assert np.array_equal(assets.load_image_native(p16), rgb16.astype(F32) / F32(65535.0))
+
+
+@pytest.mark.parametrize("kwargs", [
+    dict(subsampling=0), dict(subsampling=1), dict(subsampling=2), dict(subsampling=0, progressive=True),
+    dict(subsampling=2, progressive=True), dict(subsampling=2, restart_marker_blocks=3), dict(grey=True),
+    dict(grey=True, progressive=True), dict(subsampling=0, quality=100), dict(subsampling=2, optimize=True),
+])
+def test_jpeg_variants(tmp_path, kwargs):
+    from PIL import Image
+
+    kwargs = dict(kwargs)
+    grey = kwargs.pop("grey", False)
+    # smooth content, like photographs: the decoders differ only in rounding
+    y, x = np.mgrid[0:75, 0:117]
+    img = np.stack([127 + 100 * np.sin(x / 9.0) * np.cos(y / 11.0), 127 + 90 * np.cos(x / 13.0 + y / 7.0),
+                    127 + 110 * np.sin((x + y) / 17.0)], axis=2).astype(np.uint8)
+    im = Image.fromarray(img[:, :, 0] if grey else img)
+    path = str(tmp_path / "t.jpg")
+    kwargs.setdefault("quality", 90)
+    im.save(path, **kwargs)
+    got = np.rint(assets.load_image_native(path) * 255.0)
+    want = np.asarray(Image.open(path).convert("RGB")).astype(np.float64)
+    d = np.abs(got - want)
+    assert got.shape == want.shape
+    # chroma upsampling filters differ slightly between libjpeg-turbo builds; rounding is at most a few levels
+    assert d.max() <= 4 and d.mean() < 0.5, (d.max(), d.mean())
+
+
+def test_radiance_hdr(tmp_path):
+    import cv2
+
+    rng = np.random.default_rng(3)
+    img = (rng.random((40, 64, 3)) ** 4 * 50.0).astype(F32)
+    img[5:9, 10:30] = 0.0
+    img[20:25] = F32(0.75)  # runs
+    path = str(tmp_path / "t.hdr")
+    assert cv2.imwrite(path, img[:, :, ::-1])
+    want = cv2.imread(path, cv2.IMREAD_UNCHANGED)[:, :, ::-1]
+    assert np.array_equal(assets.load_image_native(path), want)
+
+
+def _exr_flags():
+    import cv2
+
+    return cv2, {
+        "none": 0, "rle": 1, "zips": 2, "zip": 3, "piz": 4,
+    }
+
+
+@pytest.mark.parametrize("compression", ["none", "rle", "zips", "zip", "piz"])
+@pytest.mark.parametrize("half", [False, True])
+def test_openexr(tmp_path, compression, half):
+    cv2, flags = _exr_flags()
+    if not hasattr(cv2, "IMWRITE_EXR_COMPRESSION"):
+        pytest.skip("this OpenCV cannot choose the EXR compression")
+    img = assets.synth_hdri("studio", 96, 48)
+    rng = np.random.default_rng(5)
+    img = (img * (1.0 + 0.05 * rng.random(img.shape))).astype(F32)
+    path = str(tmp_path / f"{compression}_{half}.exr")
+    params = [cv2.IMWRITE_EXR_COMPRESSION, flags[compression], cv2.IMWRITE_EXR_TYPE,
+              cv2.IMWRITE_EXR_TYPE_HALF if half else cv2.IMWRITE_EXR_TYPE_FLOAT]
+    try:
+        ok = cv2.imwrite(path, img[:, :, ::-1], params)
+    except cv2.error as e:  # OpenCV built without the codec
+        pytest.skip(str(e))
+    assert ok
+    want = cv2.imread(path, cv2.IMREAD_UNCHANGED)[:, :, ::-1].astype(F32)
+    got = assets.load_image_native(path)
+    assert np.array_equal(got, want)
+    if not half:
+        assert np.array_equal(got, img)
+
+
+def test_errors_are_reported_not_fatal(tmp_path):
+    with pytest.raises(_lib.VoidrayError, match="cannot open"):
+        assets.load_image_native(str(tmp_path / "missing.png"))
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"not an image at all")
+    with pytest.raises(_lib.VoidrayError, match="unrecognised"):
+        assets.load_image_native(str(bad))
+    trunc = tmp_path / "trunc.png"
+    trunc.write_bytes(open(os.path.join(ASSETS, "uv_test.png"), "rb").read()[:900])
+    with pytest.raises(_lib.VoidrayError, match="png"):
+        assets.load_image_native(str(trunc))
+    tj = tmp_path / "trunc.jpg"
+    tj.write_bytes(open(os.path.join(ASSETS, "mushroom_albedo.jpg"), "rb").read()[:100000])
+    with pytest.raises(_lib.VoidrayError, match="jpeg"):
+        assets.load_image_native(str(tj))

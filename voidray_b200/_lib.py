@@ -61,6 +61,10 @@ SIGNATURES = {
     "vr_scene_add_mesh_from_obj_file": [_P, C.c_char_p, _UP, _UP, _UP],
     "vr_scene_add_texture_rgb8": [_P, C.POINTER(C.c_uint8), _U32, _U32, _U32, _I32, _UP],
     "vr_scene_add_texture_rgb16": [_P, C.POINTER(C.c_uint16), _U32, _U32, _U32, _I32, _UP],
+    "vr_scene_add_image_texture_file": [_P, C.c_char_p, _I32, _UP],
+    "vr_image_load_rgb32f": [C.c_char_p, _UP, _UP, C.POINTER(_FP)],
+    "vr_image_free": [_FP],
+    "vr_scene_set_environment_hdri_file": [_P, C.c_char_p],
     "vr_scene_add_sphere": [_P, _FP, _F, _UP],
     "vr_scene_add_ground_plane": [_P, _F, _UP],
     "vr_scene_add_material": [_P, C.POINTER(MaterialDescC), _UP],

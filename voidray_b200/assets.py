@@ -72,9 +72,28 @@ def load_obj(path: str):
     )
 
 
+def load_image_native(path: str) -> np.ndarray:
+    """`image::open(path).to_rgb32f()` through the library's own decoders (vr_image_load_rgb32f,
+    csrc/image_io.cpp): PNG, JPEG, TIFF, Radiance HDR, OpenEXR. Returns (h, w, 3) f32. Raises VoidrayError
+    where the reference would panic."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    w, h = C.c_uint32(), C.c_uint32()
+    ptr = C.POINTER(C.c_float)()
+    _lib.check(lib.vr_image_load_rgb32f(os.fsencode(path), C.byref(w), C.byref(h), C.byref(ptr)))
+    try:
+        return np.ctypeslib.as_array(ptr, shape=(h.value, w.value, 3)).copy()
+    finally:
+        lib.vr_image_free(ptr)
+
+
 def load_image_rgb32f(path: str) -> np.ndarray:
     """`image::open(path).to_rgb32f()`: 8-bit channels / 255, 16-bit / 65535, float passthrough,
-    alpha dropped, no sRGB decode. Returns (h, w, 3) f32."""
+    alpha dropped, no sRGB decode. Returns (h, w, 3) f32. Decodes with PIL / OpenCV: the independent
+    check of `load_image_native` (tests/test_image_io.py); the benchmark scene recipes feed its arrays to the library."""
     ext = os.path.splitext(path)[1].lower()
     if ext in (".exr", ".hdr", ".pfm"):
         os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")

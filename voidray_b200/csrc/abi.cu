@@ -5,6 +5,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "../../include/voidray_cuda.h"
+#include "image_io.h"
 #include "kernels.cuh"
 #include "layout.h"
 #include "scene_build.h"
@@ -355,6 +357,39 @@ int32_t vr_scene_add_texture_rgb16(vr_scene* scene, const uint16_t* pixels, uint
     return add_texture_int(scene, pixels, w, h, channels, sample_type, 65535.0f, texture);
 }
 
+int32_t vr_image_load_rgb32f(const char* path, uint32_t* w, uint32_t* h, float** rgb) {
+    if (!path || !w || !h || !rgb) return fail(VR_ERR_INVALID, "null argument");
+    *rgb = nullptr;
+    DecodedImage img;
+    std::string err;
+    if (!decode_image_file(path, img, err)) return fail(VR_ERR_INVALID, std::string(path) + ": " + err);
+    std::vector<float> f;
+    image_to_rgb32f(img, f);
+    float* out = (float*)std::malloc(f.size() * sizeof(float));
+    if (!out) return fail(VR_ERR_OOM, "host allocation failed");
+    std::memcpy(out, f.data(), f.size() * sizeof(float));
+    *w = img.w;
+    *h = img.h;
+    *rgb = out;
+    return VR_OK;
+}
+
+int32_t vr_image_free(float* rgb) {
+    std::free(rgb);
+    return VR_OK;
+}
+
+int32_t vr_scene_add_image_texture_file(vr_scene* scene, const char* path, int32_t sample_type, uint32_t* texture) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!path) return fail(VR_ERR_INVALID, "null path");
+    DecodedImage img;
+    std::string err;
+    if (!decode_image_file(path, img, err)) return fail(VR_ERR_INVALID, std::string(path) + ": " + err);
+    std::vector<float> f;
+    image_to_rgb32f(img, f);
+    return vr_scene_add_texture_rgb32f(scene, f.data(), img.w, img.h, sample_type, texture);
+}
+
 int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* uvs, const float* normals,
                           uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, uint32_t* surface) {
     if (check_scene(scene)) return VR_ERR_INVALID;
@@ -521,6 +556,17 @@ int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, 
     pin_host(scene, scene->host.env_image.rgb);
     scene->committed = false;
     return VR_OK;
+}
+
+int32_t vr_scene_set_environment_hdri_file(vr_scene* scene, const char* path) {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (!path) return fail(VR_ERR_INVALID, "null path");
+    DecodedImage img;
+    std::string err;
+    if (!decode_image_file(path, img, err)) return fail(VR_ERR_INVALID, std::string(path) + ": " + err);
+    std::vector<float> f;
+    image_to_rgb32f(img, f);
+    return vr_scene_set_environment_hdri_rgb32f(scene, f.data(), img.w, img.h);
 }
 
 int32_t vr_scene_clear_environment(vr_scene* scene) {

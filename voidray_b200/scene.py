@@ -271,9 +271,9 @@ class Environments:
 
     @staticmethod
     def hdri(path_or_image) -> HDRIEnvironment:
-        if isinstance(path_or_image, str):
-            from .assets import load_image_rgb32f
-            return HDRIEnvironment(load_image_rgb32f(path_or_image))
+        if isinstance(path_or_image, str):  # environments.rs:42-55, decoded by the library (image_io.cpp)
+            from .assets import load_image_native
+            return HDRIEnvironment(load_image_native(path_or_image))
         return HDRIEnvironment(np.ascontiguousarray(path_or_image, dtype=F32))
 
 
@@ -360,9 +360,9 @@ class Scene:
         return len(self.objects) - 1
 
     def add_image_texture(self, path_or_image, sample_type: SampleType) -> int:
-        if isinstance(path_or_image, str):
-            from .assets import load_image_rgb32f
-            image = load_image_rgb32f(path_or_image)
+        if isinstance(path_or_image, str):  # texture.rs:36-49, decoded by the library (image_io.cpp)
+            from .assets import load_image_native
+            image = load_image_native(path_or_image)
         else:
             image = np.ascontiguousarray(path_or_image, dtype=F32)
         assert image.ndim == 3 and image.shape[2] == 3
