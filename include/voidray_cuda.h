@@ -265,6 +265,9 @@ int32_t vr_debug_sample_radiance(vr_render* render, uint64_t n, const uint32_t* 
                                  float* out);
 /* Tie rank of every triangle of a mesh surface in the reference's in-order leaf sequence
  * (core/bvh.rs:48-130,171; core/mesh.rs:131). */
+/* Host-only: the in-order leaf sequence of the reference's median-split tree (core/bvh.rs:48-130) over n boxes
+ * (6 floats each: min xyz, max xyz) — the order the tie ranks are taken from. order[i] = item at position i. */
+int32_t vr_debug_reference_leaf_order(const float* boxes6, uint64_t n, uint32_t* order);
 int32_t vr_debug_tie_ranks(vr_scene* scene, uint32_t surface, uint32_t* out, uint32_t n);
 /* Device-side evaluations of texture / environment lookups and the samplers, for unit parity. */
 int32_t vr_debug_texture_sample(vr_scene* scene, uint32_t texture, uint64_t n, const float* uv, float* rgb);

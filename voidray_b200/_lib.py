@@ -65,6 +65,7 @@ SIGNATURES = {
     "vr_image_load_rgb32f": [C.c_char_p, _UP, _UP, C.POINTER(_FP)],
     "vr_image_free": [_FP],
     "vr_scene_set_environment_hdri_file": [_P, C.c_char_p],
+    "vr_debug_reference_leaf_order": [_FP, C.c_uint64, _UP],
     "vr_scene_add_sphere": [_P, _FP, _F, _UP],
     "vr_scene_add_ground_plane": [_P, _F, _UP],
     "vr_scene_add_material": [_P, C.POINTER(MaterialDescC), _UP],

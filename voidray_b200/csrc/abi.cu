@@ -212,13 +212,13 @@ int32_t upload_texture(vr_scene* scene, const HostTexture& t, void* stage, Textu
     return VR_OK;
 }
 
-template <typename T>
-int32_t upload_vector(vr_scene* scene, const std::vector<T>& v, const void** out) {
+template <typename V>
+int32_t upload_vector(vr_scene* scene, const V& v, const void** out) {
     void* d = nullptr;
-    VR_CUDA(scene->dev_mem.get(&d, v.size() * sizeof(T)));
-    if (!v.empty())
-        VR_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, scene->ctx->stream));
-    scene->h2d_bytes += v.size() * sizeof(T);
+    const size_t bytes = v.size() * sizeof(typename V::value_type);
+    VR_CUDA(scene->dev_mem.get(&d, bytes));
+    if (!v.empty()) VR_CUDA(cudaMemcpyAsync(d, v.data(), bytes, cudaMemcpyHostToDevice, scene->ctx->stream));
+    scene->h2d_bytes += bytes;
     *out = d;
     return VR_OK;
 }
@@ -1056,11 +1056,20 @@ int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel
     return VR_OK;
 }
 
+int32_t vr_debug_reference_leaf_order(const float* boxes6, uint64_t n, uint32_t* order) {
+    if ((!boxes6 || !order) && n) return fail(VR_ERR_INVALID, "null argument");
+    if (n >= (1ull << 32)) return fail(VR_ERR_INVALID, "too many items");
+    RawVector<uint32_t> o;
+    reference_leaf_order(boxes6, (size_t)n, o);
+    if (n) std::memcpy(order, o.data(), (size_t)n * sizeof(uint32_t));
+    return VR_OK;
+}
+
 int32_t vr_debug_tie_ranks(vr_scene* scene, uint32_t surface, uint32_t* out, uint32_t n) {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
     if (surface >= scene->flat.mesh_tie_rank.size()) return fail(VR_ERR_INVALID, "unknown surface");
-    const std::vector<uint32_t>& rank = scene->flat.mesh_tie_rank[surface];
+    const RawVector<uint32_t>& rank = scene->flat.mesh_tie_rank[surface];
     if (n != rank.size()) return fail(VR_ERR_INVALID, "n must equal the surface's triangle count");
     for (uint32_t i = 0; i < n; ++i) out[i] = scene->flat.surface_rank_base[surface] + rank[i];
     return VR_OK;

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -56,13 +57,12 @@ void camera_look_at(const float eye[3], const float center[3], const float up_in
 
 namespace {
 
-typedef std::pair<int32_t, uint32_t> KeyIdx;  // (total_cmp key of the centroid coordinate, item)
+inline size_t worker_count() { return std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32); }
 
 // fn(begin, end) over [0, n) in contiguous chunks, one per hardware thread (inline when n is small)
 template <typename Fn>
 void parallel_for(size_t n, Fn fn) {
-    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t T = n < 65536 ? 1 : std::min<size_t>(hw, 32);
+    const size_t T = n < 65536 ? 1 : worker_count();
     if (T == 1) {
         fn((size_t)0, n);
         return;
@@ -77,50 +77,146 @@ void parallel_for(size_t n, Fn fn) {
     for (std::thread& x : th) x.join();
 }
 
-// Stable sort by key: LSD radix sort (stable by construction) for large ranges, std::stable_sort otherwise.
-void stable_sort_by_key(KeyIdx* v, size_t n, std::vector<KeyIdx>& tmp) {
-    if (n <= 24) {  // most ranges of the recursion are tiny: stable insertion sort, no allocation
-        for (size_t i = 1; i < n; ++i) {
-            const KeyIdx x = v[i];
-            size_t j = i;
-            while (j > 0 && v[j - 1].first > x.first) { v[j] = v[j - 1]; --j; }
-            v[j] = x;
-        }
-        return;
+// fn(chunk index, begin, end): like parallel_for with the chunk number, for per-chunk partial results
+template <typename Fn>
+size_t parallel_chunks(size_t n, size_t T, Fn fn) {
+    T = std::max<size_t>(1, std::min(T, n));
+    const size_t chunk = (n + T - 1) / T;
+    std::vector<std::thread> th;
+    size_t used = 0;
+    for (size_t t = 0; t < T; ++t) {
+        const size_t b = t * chunk, e = std::min(n, b + chunk);
+        if (b >= e) break;
+        ++used;
+        if (T == 1) fn(t, b, e);
+        else th.emplace_back([=]() { fn(t, b, e); });
     }
-    if (n < (1u << 15)) {
-        std::stable_sort(v, v + n, [](const KeyIdx& a, const KeyIdx& b) { return a.first < b.first; });
-        return;
-    }
-    tmp.resize(n);
-    KeyIdx* src = v;
-    KeyIdx* dst = tmp.data();
-    for (int pass = 0; pass < 3; ++pass) {  // 11 + 11 + 10 bits of the sign-flipped key
+    for (std::thread& x : th) x.join();
+    return used;
+}
+
+// One item of the median-split recursion: its centroid travels with it, so every pass over a node streams.
+struct CenRec {
+    float c[3];
+    uint32_t idx;
+};
+inline uint32_t sort_key(const CenRec& r, int axis) { return (uint32_t)total_key(r.c[axis]) ^ 0x80000000u; }
+
+// Stable LSD radix sort (11 + 11 + 10 bits) of v[0, n) by the total_cmp key of c[axis]; tmp is scratch of the
+// same length. T > 1: every pass histograms and scatters T contiguous chunks in parallel — chunk t's items of a
+// digit go after chunk t-1's, so the result is the same stable order for any T.
+void radix_sort_records(CenRec* v, CenRec* tmp, size_t n, int axis, size_t T) {
+    T = std::max<size_t>(1, std::min<size_t>(T, n / 65536 + 1));
+    std::vector<size_t> hist(T * 2048);
+    CenRec* src = v;
+    CenRec* dst = tmp;
+    for (int pass = 0; pass < 3; ++pass) {
         const int shift = pass * 11;
         const uint32_t mask = pass == 2 ? 0x3FFu : 0x7FFu;
-        size_t count[2048] = {0};
-        for (size_t i = 0; i < n; ++i) count[(((uint32_t)src[i].first ^ 0x80000000u) >> shift) & mask]++;
+        std::fill(hist.begin(), hist.end(), (size_t)0);
+        const size_t used = parallel_chunks(n, T, [&](size_t t, size_t b, size_t e) {
+            size_t* h = &hist[t * 2048];
+            for (size_t i = b; i < e; ++i) h[(sort_key(src[i], axis) >> shift) & mask]++;
+        });
         size_t sum = 0;
-        for (uint32_t b = 0; b <= mask; ++b) {
-            const size_t c = count[b];
-            count[b] = sum;
-            sum += c;
-        }
-        for (size_t i = 0; i < n; ++i) dst[count[(((uint32_t)src[i].first ^ 0x80000000u) >> shift) & mask]++] = src[i];
+        for (uint32_t d = 0; d <= mask; ++d)
+            for (size_t t = 0; t < used; ++t) {
+                const size_t c = hist[t * 2048 + d];
+                hist[t * 2048 + d] = sum;
+                sum += c;
+            }
+        parallel_chunks(n, T, [&](size_t t, size_t b, size_t e) {
+            size_t* h = &hist[t * 2048];
+            for (size_t i = b; i < e; ++i) dst[h[(sort_key(src[i], axis) >> shift) & mask]++] = src[i];
+        });
         std::swap(src, dst);
     }
     // three passes: the result is in tmp
-    std::memcpy(v, tmp.data(), n * sizeof(KeyIdx));
+    parallel_chunks(n, T, [&](size_t, size_t b, size_t e) { std::memcpy(v + b, tmp + b, (e - b) * sizeof(CenRec)); });
+}
+
+inline void insertion_sort_records(CenRec* v, size_t n, int axis) {
+    for (size_t i = 1; i < n; ++i) {
+        const CenRec x = v[i];
+        const int32_t kx = total_key(x.c[axis]);
+        size_t j = i;
+        while (j > 0 && total_key(v[j - 1].c[axis]) > kx) { v[j] = v[j - 1]; --j; }
+        v[j] = x;
+    }
+}
+
+// Stable bottom-up merge sort with caller-provided scratch (std::stable_sort allocates on every call).
+void merge_sort_records(CenRec* v, CenRec* tmp, size_t n, int axis) {
+    const size_t RUN = 16;
+    for (size_t b = 0; b < n; b += RUN) insertion_sort_records(v + b, std::min(RUN, n - b), axis);
+    CenRec* src = v;
+    CenRec* dst = tmp;
+    for (size_t width = RUN; width < n; width *= 2) {
+        for (size_t b = 0; b < n; b += 2 * width) {
+            const size_t m = std::min(b + width, n), e = std::min(b + 2 * width, n);
+            size_t i = b, j = m, k = b;
+            while (i < m && j < e) dst[k++] = total_key(src[j].c[axis]) < total_key(src[i].c[axis]) ? src[j++] : src[i++];
+            while (i < m) dst[k++] = src[i++];
+            while (j < e) dst[k++] = src[j++];
+        }
+        std::swap(src, dst);
+    }
+    if (src != v) std::memcpy(v, src, n * sizeof(CenRec));
 }
 
 struct LeafOrderJob {
-    const std::vector<float>& cen;
-    std::vector<uint32_t>& order;
-    std::atomic<int> threads_left;
-    LeafOrderJob(const std::vector<float>& c, std::vector<uint32_t>& o, int t) : cen(c), order(o), threads_left(t) {}
+    CenRec* rec;
+    CenRec* tmp;  // scratch, indexed like rec: a node only uses its own range
+    std::atomic<int> threads_left{0};
+    LeafOrderJob(CenRec* r, CenRec* t) : rec(r), tmp(t) {}
+
+    // bvh.rs:58-108 on the range [lo, hi): pick the axis, stable-sort the range by it. T = threads for this node.
+    void sort_node(size_t lo, size_t hi, size_t T) {
+        CenRec* v = rec + lo;
+        const size_t len = hi - lo;
+        float cmin[3], cmax[3];
+        if (T > 1) {
+            std::vector<float> part(T * 6);
+            const size_t used = parallel_chunks(len, T, [&](size_t t, size_t b, size_t e) {
+                float mn[3], mx[3];
+                for (int a = 0; a < 3; ++a) mn[a] = mx[a] = v[b].c[a];
+                for (size_t i = b + 1; i < e; ++i)
+                    for (int a = 0; a < 3; ++a) {
+                        mn[a] = fmin_(mn[a], v[i].c[a]);
+                        mx[a] = fmax_(mx[a], v[i].c[a]);
+                    }
+                for (int a = 0; a < 3; ++a) { part[6 * t + a] = mn[a]; part[6 * t + 3 + a] = mx[a]; }
+            });
+            for (int a = 0; a < 3; ++a) { cmin[a] = part[a]; cmax[a] = part[3 + a]; }
+            for (size_t t = 1; t < used; ++t)
+                for (int a = 0; a < 3; ++a) {
+                    cmin[a] = fmin_(cmin[a], part[6 * t + a]);
+                    cmax[a] = fmax_(cmax[a], part[6 * t + 3 + a]);
+                }
+        } else {
+            for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = v[0].c[a];
+            for (size_t i = 1; i < len; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    cmin[a] = fmin_(cmin[a], v[i].c[a]);
+                    cmax[a] = fmax_(cmax[a], v[i].c[a]);
+                }
+        }
+        const float sx = cmax[0] - cmin[0], sy = cmax[1] - cmin[1], sz = cmax[2] - cmin[2];
+        int axis;  // bvh.rs:71-77: strictly largest spread, else Z
+        if (sx > sy && sx > sz) axis = 0;
+        else if (sy > sx && sy > sz) axis = 1;
+        else axis = 2;
+        // Vec::sort_by(total_cmp) is stable, bvh.rs:80-108. A child that keeps its parent's axis is already in
+        // order (a stable sort of a sorted range is the identity): one linear check saves the sort.
+        bool sorted = true;
+        for (size_t i = 1; i < len && sorted; ++i) sorted = total_key(v[i - 1].c[axis]) <= total_key(v[i].c[axis]);
+        if (sorted) return;
+        if (len <= 24) insertion_sort_records(v, len, axis);
+        else if (len < 4096) merge_sort_records(v, tmp + lo, len, axis);
+        else radix_sort_records(v, tmp + lo, len, axis, T);
+    }
 
     void run(size_t lo, size_t hi) {
-        std::vector<KeyIdx> keyed, tmp;
         std::vector<std::pair<size_t, size_t>> stack;
         std::vector<std::thread> spawned;
         stack.emplace_back(lo, hi);
@@ -129,29 +225,7 @@ struct LeafOrderJob {
             stack.pop_back();
             const size_t len = r.second - r.first;
             if (len < 2) continue;
-            float cmin[3], cmax[3];
-            for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = cen[3 * order[r.first] + a];
-            for (size_t i = r.first + 1; i < r.second; ++i)
-                for (int a = 0; a < 3; ++a) {
-                    cmin[a] = fmin_(cmin[a], cen[3 * order[i] + a]);
-                    cmax[a] = fmax_(cmax[a], cen[3 * order[i] + a]);
-                }
-            const float sx = cmax[0] - cmin[0], sy = cmax[1] - cmin[1], sz = cmax[2] - cmin[2];
-            int axis;  // bvh.rs:71-77: strictly largest spread, else Z
-            if (sx > sy && sx > sz) axis = 0;
-            else if (sy > sx && sy > sz) axis = 1;
-            else axis = 2;
-            keyed.resize(len);
-            for (size_t i = 0; i < len; ++i) {
-                keyed[i].first = total_key(cen[3 * order[r.first + i] + axis]);
-                keyed[i].second = order[r.first + i];
-            }
-            // Vec::sort_by(total_cmp) is stable, bvh.rs:80-108. A child that keeps its parent's axis is already in
-            // order (a stable sort of a sorted range is the identity): one linear check saves the sort.
-            bool sorted = true;
-            for (size_t i = 1; i < len && sorted; ++i) sorted = keyed[i - 1].first <= keyed[i].first;
-            if (!sorted) stable_sort_by_key(keyed.data(), len, tmp);
-            for (size_t i = 0; i < len; ++i) order[r.first + i] = keyed[i].second;
+            sort_node(r.first, r.second, 1);
             const size_t mid = r.first + len / 2;  // bvh.rs:111-120
             // the halves are independent: hand the left one to another thread while any are free
             if (len > 100000 && threads_left.fetch_sub(1) > 0) {
@@ -174,17 +248,54 @@ struct LeafOrderJob {
 // core/bvh.rs:48-130 restated on index ranges: a range of >= 2 items is stably sorted by the centroid
 // coordinate of the axis with the strictly largest centroid spread (else Z) and cut at len/2. The left
 // half precedes the right half, so after the recursion the array itself is the in-order leaf sequence.
-void reference_leaf_order(const std::vector<float>& boxes6, std::vector<uint32_t>& order) {
-    const size_t n = boxes6.size() / 6;
+// boxes6: n x (min xyz, max xyz).
+void reference_leaf_order(const float* boxes6, size_t n, RawVector<uint32_t>& order) {
     order.resize(n);
-    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
-    if (n < 2) return;
-    // centroid = (min + max) / 2.0 (util/aabb.rs:33-35)
-    std::vector<float> cen(3 * n);
-    for (size_t i = 0; i < n; ++i)
-        for (int a = 0; a < 3; ++a) cen[3 * i + a] = (boxes6[6 * i + a] + boxes6[6 * i + 3 + a]) / 2.0f;
-    LeafOrderJob job(cen, order, (int)std::max(1u, std::thread::hardware_concurrency()) - 1);
-    job.run(0, n);
+    if (n < 2) {
+        if (n) order[0] = 0;
+        return;
+    }
+    RawVector<CenRec> rec(n), tmp(n);
+    parallel_for(n, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            // centroid = (min + max) / 2.0 (util/aabb.rs:33-35)
+            for (int a = 0; a < 3; ++a) rec[i].c[a] = (boxes6[6 * i + a] + boxes6[6 * i + 3 + a]) / 2.0f;
+            rec[i].idx = (uint32_t)i;
+        }
+    });
+    LeafOrderJob job(rec.data(), tmp.data());
+    const size_t T = worker_count();
+    // the few nodes at the top are sorted one after the other with every thread; what is left below them are
+    // independent subtrees, one task each (a task hands halves to further threads while any are free)
+    size_t PAR_MIN = (size_t)1 << 20;
+    if (const char* e = std::getenv("VOIDRAY_PAR_MIN")) PAR_MIN = (size_t)std::max(2, atoi(e));  // test knob
+    std::vector<std::pair<size_t, size_t>> top, tasks;
+    top.emplace_back((size_t)0, n);
+    while (!top.empty()) {
+        const std::pair<size_t, size_t> r = top.back();
+        top.pop_back();
+        const size_t len = r.second - r.first;
+        if (len < PAR_MIN || T == 1) {
+            tasks.push_back(r);
+            continue;
+        }
+        job.sort_node(r.first, r.second, T);
+        const size_t mid = r.first + len / 2;
+        top.emplace_back(r.first, mid);
+        top.emplace_back(mid, r.second);
+    }
+    job.threads_left = (int)T - (int)tasks.size();
+    if (tasks.size() == 1) {
+        job.threads_left = (int)T - 1;
+        job.run(tasks[0].first, tasks[0].second);
+    } else {
+        std::vector<std::thread> th;
+        for (const std::pair<size_t, size_t>& r : tasks) th.emplace_back([&job, r]() { job.run(r.first, r.second); });
+        for (std::thread& t : th) t.join();
+    }
+    parallel_for(n, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) order[i] = rec[i].idx;
+    });
 }
 
 namespace {
@@ -217,8 +328,8 @@ struct Prim {
 };
 
 struct Builder {
-    std::vector<Prim>& prims;
-    std::vector<Quad>& nodes;
+    RawVector<Prim>& prims;
+    RawVector<Quad>& nodes;
     std::atomic<uint32_t> next_node{0};
     std::atomic<uint32_t> max_depth{0};
     std::atomic<int> threads_left{0};
@@ -227,7 +338,68 @@ struct Builder {
     uint32_t leaf_max = LEAF_MAX_TRIS;
     float node_cost = 1.0f;
 
-    Builder(std::vector<Prim>& p, std::vector<Quad>& n) : prims(p), nodes(n) {}
+    Builder(RawVector<Prim>& p, RawVector<Quad>& n) : prims(p), nodes(n) {}
+
+    struct Bins {
+        Box box[3][BINS];
+        uint32_t count[3][BINS];
+        void reset() {
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < BINS; ++b) { box[a][b].reset(); count[a][b] = 0; }
+        }
+        void merge(const Bins& o) {
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < BINS; ++b) { box[a][b].grow(o.box[a][b]); count[a][b] += o.count[a][b]; }
+        }
+    };
+
+    // Pieces a large node is cut into for its bounds / binning / partition passes. A function of the node size
+    // only, not of the machine, so the tree is the same wherever it is built.
+    static size_t par_chunks(size_t n) { return std::min<size_t>(std::max<size_t>(n >> 18, 1), 32); }
+
+    // In-place partition of v[0, n) by pred(piece, element) in `chunks` pieces: each piece is partitioned on its own thread, then the
+    // right-side elements left of the global split are swapped with the left-side elements right of it.
+    template <typename Pred>
+    static size_t parallel_partition(Prim* v, size_t n, size_t chunks, Pred pred) {
+        std::vector<size_t> cb(chunks, 0), cm(chunks, 0), ce(chunks, 0);
+        const size_t used = parallel_chunks(n, chunks, [&](size_t t, size_t b, size_t e) {
+            cb[t] = b;
+            ce[t] = e;
+            cm[t] = (size_t)(std::partition(v + b, v + e, [&pred, t](const Prim& p) { return pred(t, p); }) - v);
+        });
+        size_t mid = 0;
+        for (size_t t = 0; t < used; ++t) mid += cm[t] - cb[t];
+        struct Range {
+            size_t at, len;
+        };
+        std::vector<Range> wrong_left, wrong_right;  // right-side elements in [0, mid), left-side ones in [mid, n)
+        for (size_t t = 0; t < used; ++t) {
+            const size_t rb = cm[t], re = std::min(ce[t], mid);
+            if (rb < re) wrong_left.push_back(Range{rb, re - rb});
+            const size_t lb = std::max(cb[t], mid), le = cm[t];
+            if (lb < le) wrong_right.push_back(Range{lb, le - lb});
+        }
+        struct Swap {
+            size_t a, b, len;
+        };
+        std::vector<Swap> swaps;
+        size_t i = 0, j = 0;
+        const size_t PIECE = 1 << 16;
+        while (i < wrong_left.size() && j < wrong_right.size()) {
+            const size_t len = std::min(std::min(wrong_left[i].len, wrong_right[j].len), PIECE);
+            swaps.push_back(Swap{wrong_left[i].at, wrong_right[j].at, len});
+            wrong_left[i].at += len;
+            wrong_left[i].len -= len;
+            wrong_right[j].at += len;
+            wrong_right[j].len -= len;
+            if (!wrong_left[i].len) ++i;
+            if (!wrong_right[j].len) ++j;
+        }
+        parallel_chunks(swaps.size(), chunks, [&](size_t, size_t b, size_t e) {
+            for (size_t s = b; s < e; ++s) std::swap_ranges(v + swaps[s].a, v + swaps[s].a + swaps[s].len, v + swaps[s].b);
+        });
+        return mid;
+    }
 
     static int32_t leaf_code(uint32_t first, uint32_t count) { return ~(int32_t)((first << 3) | count); }
 
@@ -236,15 +408,38 @@ struct Builder {
         while (d > cur && !max_depth.compare_exchange_weak(cur, d)) {}
     }
 
-    // Builds the subtree over prims[lo, hi); returns its child code and box.
-    int32_t build(uint32_t lo, uint32_t hi, Box& out_box, uint32_t depth) {
+    // Builds the subtree over prims[lo, hi); returns its child code and box. known: the range's bounds and
+    // centroid bounds when the parent's partition pass has already gathered them.
+    int32_t build(uint32_t lo, uint32_t hi, Box& out_box, uint32_t depth, const Box* known = nullptr) {
         const uint32_t n = hi - lo;
         Box bounds, cbounds;
         bounds.reset();
         cbounds.reset();
-        for (uint32_t i = lo; i < hi; ++i) {
-            bounds.grow(prims[i].box);
-            cbounds.grow(prims[i].cen);
+        if (known) {
+            bounds = known[0];
+            cbounds = known[1];
+        } else if (par_chunks(n) > 1) {
+            std::vector<Box> part(2 * par_chunks(n));
+            const size_t used = parallel_chunks(n, par_chunks(n), [&](size_t t, size_t b, size_t e) {
+                Box bb, cb;
+                bb.reset();
+                cb.reset();
+                for (size_t i = lo + b; i < lo + e; ++i) {
+                    bb.grow(prims[i].box);
+                    cb.grow(prims[i].cen);
+                }
+                part[2 * t] = bb;
+                part[2 * t + 1] = cb;
+            });
+            for (size_t t = 0; t < used; ++t) {
+                bounds.grow(part[2 * t]);
+                cbounds.grow(part[2 * t + 1]);
+            }
+        } else {
+            for (uint32_t i = lo; i < hi; ++i) {
+                bounds.grow(prims[i].box);
+                cbounds.grow(prims[i].cen);
+            }
         }
         out_box = bounds;
         if (n == 1) {
@@ -297,35 +492,59 @@ struct Builder {
             }
         }
 
-        // binned SAH over the three axes
-        for (int axis = 0; axis < 3 && n > SWEEP_MAX; ++axis) {
-            const float cmin = cbounds.lo[axis], cmax = cbounds.hi[axis];
-            if (!(cmax > cmin)) continue;
-            const float k = (float)BINS * (1.0f - 1e-6f) / (cmax - cmin);
-            Box bin_box[BINS];
-            uint32_t bin_count[BINS];
-            for (int b = 0; b < BINS; ++b) { bin_box[b].reset(); bin_count[b] = 0; }
-            for (uint32_t i = lo; i < hi; ++i) {
-                int b = (int)((prims[i].cen[axis] - cmin) * k);
-                b = std::min(std::max(b, 0), BINS - 1);
-                bin_box[b].grow(prims[i].box);
-                bin_count[b]++;
+        // binned SAH over the three axes, one pass over the primitives (split over threads for a large node:
+        // the bins are merged with min / max / +, so the result does not depend on the chunking)
+        const size_t chunks = par_chunks(n);
+        if (n > SWEEP_MAX) {
+            float cmin[3], k[3];
+            bool valid[3];
+            for (int axis = 0; axis < 3; ++axis) {
+                cmin[axis] = cbounds.lo[axis];
+                valid[axis] = cbounds.hi[axis] > cbounds.lo[axis];
+                k[axis] = valid[axis] ? (float)BINS * (1.0f - 1e-6f) / (cbounds.hi[axis] - cbounds.lo[axis]) : 0.0f;
             }
-            float right_area[BINS];
-            Box acc;
-            acc.reset();
-            for (int b = BINS - 1; b > 0; --b) {
-                acc.grow(bin_box[b]);
-                right_area[b] = acc.half_area();
+            auto bin_range = [&](uint32_t b0, uint32_t e0, Bins& bins) {
+                bins.reset();
+                for (uint32_t i = b0; i < e0; ++i) {
+                    const Prim& p = prims[i];
+                    for (int axis = 0; axis < 3; ++axis) {
+                        if (!valid[axis]) continue;
+                        int b = (int)((p.cen[axis] - cmin[axis]) * k[axis]);
+                        b = std::min(std::max(b, 0), BINS - 1);
+                        bins.box[axis][b].grow(p.box);
+                        bins.count[axis][b]++;
+                    }
+                }
+            };
+            Bins bins;
+            if (chunks > 1) {
+                std::vector<Bins> part(chunks);
+                const size_t used = parallel_chunks(n, chunks, [&](size_t t, size_t b, size_t e) {
+                    bin_range(lo + (uint32_t)b, lo + (uint32_t)e, part[t]);
+                });
+                bins = part[0];
+                for (size_t t = 1; t < used; ++t) bins.merge(part[t]);
+            } else {
+                bin_range(lo, hi, bins);
             }
-            acc.reset();
-            uint32_t left_n = 0;
-            for (int b = 0; b < BINS - 1; ++b) {
-                acc.grow(bin_box[b]);
-                left_n += bin_count[b];
-                if (left_n == 0 || left_n == n) continue;
-                const float cost = (acc.half_area() * (float)left_n + right_area[b + 1] * (float)(n - left_n)) / parent_area;
-                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            for (int axis = 0; axis < 3; ++axis) {
+                if (!valid[axis]) continue;
+                float right_area[BINS];
+                Box acc;
+                acc.reset();
+                for (int b = BINS - 1; b > 0; --b) {
+                    acc.grow(bins.box[axis][b]);
+                    right_area[b] = acc.half_area();
+                }
+                acc.reset();
+                uint32_t left_n = 0;
+                for (int b = 0; b < BINS - 1; ++b) {
+                    acc.grow(bins.box[axis][b]);
+                    left_n += bins.count[axis][b];
+                    if (left_n == 0 || left_n == n) continue;
+                    const float cost = (acc.half_area() * (float)left_n + right_area[b + 1] * (float)(n - left_n)) / parent_area;
+                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+                }
             }
         }
 
@@ -341,6 +560,8 @@ struct Builder {
         while ((1u << levels_needed) < n) ++levels_needed;
         const bool force_median = depth + levels_needed + 1 >= MAX_DEPTH;
         uint32_t mid;
+        Box kids[4];  // left bounds, left centroid bounds, right bounds, right centroid bounds
+        bool have_kids = false;
         if (n <= SWEEP_MAX && best_axis >= 0) {
             mid = force_median ? lo + n / 2 : lo + sweep_left;  // the range is already sorted along best_axis
         } else if (force_median && best_axis >= 0) {
@@ -354,15 +575,40 @@ struct Builder {
         } else {
             const float cmin = cbounds.lo[best_axis], cmax = cbounds.hi[best_axis];
             const float k = (float)BINS * (1.0f - 1e-6f) / (cmax - cmin);
-            Prim* first = prims.data() + lo;
-            Prim* last = prims.data() + hi;
-            Prim* m = std::partition(first, last, [&](const Prim& p) {
+            auto goes_left = [&](const Prim& p) {
                 int b = (int)((p.cen[best_axis] - cmin) * k);
                 b = std::min(std::max(b, 0), BINS - 1);
                 return b <= best_bin;
-            });
-            mid = (uint32_t)(m - prims.data());
-            if (mid == lo || mid == hi) mid = lo + n / 2;
+            };
+            // the partition pass also gathers both sides' bounds (the predicate runs exactly once per element)
+            for (int i = 0; i < 4; ++i) kids[i].reset();
+            if (chunks > 1) {
+                std::vector<Box> part(4 * chunks);
+                for (Box& b : part) b.reset();
+                mid = lo + (uint32_t)parallel_partition(prims.data() + lo, n, chunks, [&](size_t t, const Prim& p) {
+                    const bool left = goes_left(p);
+                    Box* kb = &part[4 * t + (left ? 0 : 2)];
+                    kb[0].grow(p.box);
+                    kb[1].grow(p.cen);
+                    return left;
+                });
+                for (size_t t = 0; t < chunks; ++t)
+                    for (int i = 0; i < 4; ++i) kids[i].grow(part[4 * t + i]);
+            } else {
+                Prim* m = std::partition(prims.data() + lo, prims.data() + hi, [&](const Prim& p) {
+                    const bool left = goes_left(p);
+                    Box* kb = kids + (left ? 0 : 2);
+                    kb[0].grow(p.box);
+                    kb[1].grow(p.cen);
+                    return left;
+                });
+                mid = (uint32_t)(m - prims.data());
+            }
+            have_kids = true;
+            if (mid == lo || mid == hi) {
+                mid = lo + n / 2;
+                have_kids = false;
+            }
         }
 
         const uint32_t node = next_node.fetch_add(1);
@@ -371,16 +617,16 @@ struct Builder {
         bool spawned = false;
         if (n > 50000 && threads_left.fetch_sub(1) > 0) {
             spawned = true;
-            std::thread t([&]() { lcode = build(lo, mid, lbox, depth + 1); });
-            rcode = build(mid, hi, rbox, depth + 1);
+            std::thread t([&]() { lcode = build(lo, mid, lbox, depth + 1, have_kids ? kids : nullptr); });
+            rcode = build(mid, hi, rbox, depth + 1, have_kids ? kids + 2 : nullptr);
             t.join();
             threads_left.fetch_add(1);
         } else if (n > 50000) {
             threads_left.fetch_add(1);
         }
         if (!spawned) {
-            lcode = build(lo, mid, lbox, depth + 1);
-            rcode = build(mid, hi, rbox, depth + 1);
+            lcode = build(lo, mid, lbox, depth + 1, have_kids ? kids : nullptr);
+            rcode = build(mid, hi, rbox, depth + 1, have_kids ? kids + 2 : nullptr);
         }
         write_node(node, lcode, lbox, rcode, rbox);
         return (int32_t)node;
@@ -411,8 +657,23 @@ struct Builder {
 
 }  // namespace
 
+namespace {
+// VOIDRAY_TIMING=1 prints the host phases of a commit to stderr
+struct PhaseTimer {
+    bool on = std::getenv("VOIDRAY_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[voidray] flatten: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
 bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     out = FlatScene();
+    PhaseTimer timer;
     const size_t n_surfaces = in.surfaces.size();
     // scene.rs:183-184 resolves a hit's material through objects[surface index]
     if (in.objects.size() < n_surfaces) {
@@ -467,11 +728,11 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                 }
             const size_t nt = m.idx.size() / 3;
             total_tris += nt;
-            std::vector<uint32_t>& rank = out.mesh_tie_rank[s];
+            RawVector<uint32_t>& rank = out.mesh_tie_rank[s];
             rank.resize(nt);
             if (m.idx.size() > 4 * 3) {  // SMALL_MESH, mesh.rs:43,112
                 // per-triangle boxes, mesh.rs:193-205: vertex bounds, epsilon_expand(0.001)
-                std::vector<float> boxes(6 * nt);
+                RawVector<float> boxes(6 * nt);
                 parallel_for(nt, [&](size_t t_begin, size_t t_end) {
                 for (size_t t = t_begin; t < t_end; ++t) {
                     float* tb = &boxes[6 * t];
@@ -488,11 +749,13 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                     }
                 }
                 });
-                std::vector<uint32_t> order;
-                reference_leaf_order(boxes, order);
+                timer.lap("triangle boxes");
+                RawVector<uint32_t> order;
+                reference_leaf_order(boxes.data(), nt, order);
                 parallel_for(nt, [&](size_t b, size_t e) {
                     for (size_t i = b; i < e; ++i) rank[order[i]] = (uint32_t)i;
                 });
+                timer.lap("reference leaf order");
             } else {
                 // linear loop, first index wins a tie (mesh.rs:129-135)
                 for (size_t t = 0; t < nt; ++t) rank[t] = (uint32_t)(nt - 1 - t);
@@ -510,8 +773,8 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     if (total_tris >= (1u << 28)) { err = "too many triangles (limit 2^28)"; return false; }
 
     // ---- scene-level in-order sequence -> global rank base of every surface ----
-    std::vector<uint32_t> surface_order;
-    reference_leaf_order(surface_boxes, surface_order);
+    RawVector<uint32_t> surface_order;
+    reference_leaf_order(surface_boxes.data(), n_surfaces, surface_order);
     out.surface_rank_base.assign(n_surfaces, 0);
     {
         uint32_t base = 0;
@@ -540,11 +803,11 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     // ---- triangles ----
     const uint32_t n_tris = (uint32_t)total_tris;
     out.n_tris = n_tris;
-    std::vector<Prim> prims(n_tris);
+    RawVector<Prim> prims(n_tris);
     struct Src {
         uint32_t surface, prim;
     };
-    std::vector<Src> src(n_tris);
+    RawVector<Src> src(n_tris);
     {
         uint32_t g = 0;
         for (size_t s = 0; s < n_surfaces; ++s) {
@@ -568,8 +831,9 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         }
     }
 
+    timer.lap("primitive records");
     // ---- BVH ----
-    out.nodes.assign((size_t)std::max<uint32_t>(n_tris, 2) * NODE_QUADS, Quad{0, 0, 0, 0});
+    out.nodes.resize((size_t)std::max<uint32_t>(n_tris, 2) * NODE_QUADS);
     Builder builder(prims, out.nodes);
     {
         // quantisation grid = bounds of all triangles; a flat axis gets a token extent so the cell size is not 0
@@ -613,6 +877,7 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     }
     out.nodes.resize((size_t)builder.next_node.load() * NODE_QUADS);
     out.bvh_depth = builder.max_depth.load();
+    timer.lap("SAH build");
 
     // ---- packed records in BVH leaf order ----
     out.tri_isect.resize((size_t)n_tris * TRI_ISECT_QUADS);
@@ -648,6 +913,7 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         out.tri_prim[i] = sp.prim;
     }
     });
+    timer.lap("packed triangle records");
     return true;
 }
 

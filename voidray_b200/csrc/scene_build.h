@@ -3,12 +3,37 @@
 #pragma once
 #include <stdint.h>
 
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "layout.h"
 
 namespace vr {
+
+// std::vector whose resize() leaves trivially-constructible elements uninitialised: the large arrays of a commit
+// are first touched by the worker threads that fill them instead of being zeroed by one thread.
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        typedef DefaultInitAllocator<U> other;
+    };
+    DefaultInitAllocator() = default;
+    template <class U>
+    DefaultInitAllocator(const DefaultInitAllocator<U>&) {}
+    template <class U>
+    void construct(U* p) {
+        ::new ((void*)p) U;
+    }
+    template <class U, class... Args>
+    void construct(U* p, Args&&... args) {
+        ::new ((void*)p) U(std::forward<Args>(args)...);
+    }
+};
+template <class T>
+using RawVector = std::vector<T, DefaultInitAllocator<T>>;
 
 struct Quad {
     float x, y, z, w;
@@ -58,12 +83,12 @@ struct HostScene {
 };
 
 struct FlatScene {
-    std::vector<Quad> nodes;      // NODE_QUADS per node; node 0 is the root
-    std::vector<Quad> tri_isect;  // TRI_ISECT_QUADS per triangle, BVH leaf order
-    std::vector<Quad> tri_shade;  // TRI_SHADE_QUADS per triangle
-    std::vector<uint32_t> tri_surface, tri_prim;
+    RawVector<Quad> nodes;      // NODE_QUADS per node; node 0 is the root
+    RawVector<Quad> tri_isect;  // TRI_ISECT_QUADS per triangle, BVH leaf order
+    RawVector<Quad> tri_shade;  // TRI_SHADE_QUADS per triangle
+    RawVector<uint32_t> tri_surface, tri_prim;
     std::vector<AnalyticRec> analytics;
-    std::vector<std::vector<uint32_t>> mesh_tie_rank;  // per surface (empty for analytic): rank inside the mesh
+    std::vector<RawVector<uint32_t>> mesh_tie_rank;  // per surface (empty for analytic): rank inside the mesh
     std::vector<uint32_t> surface_rank_base;           // per surface: first global rank
     CameraRec camera;
     float grid_min[3] = {0, 0, 0}, grid_extent[3] = {1, 1, 1};  // node quantisation grid
@@ -73,7 +98,7 @@ struct FlatScene {
 
 // In-order leaf sequence of the reference's median-split tree (core/bvh.rs:48-130) over items with
 // the given boxes (6 floats each: min xyz, max xyz). order[i] = item at in-order position i.
-void reference_leaf_order(const std::vector<float>& boxes6, std::vector<uint32_t>& order);
+void reference_leaf_order(const float* boxes6, size_t n, RawVector<uint32_t>& order);
 
 // Camera::look_at, core/camera.rs:26-36
 void camera_look_at(const float eye[3], const float center[3], const float up_in[3], float direction[3],
