@@ -135,6 +135,22 @@ def test_tie_ranks_on_real_meshes(oracle, ctx):
         assert np.array_equal(scene.build_acceleration(ctx).tie_ranks(0), oracle.OracleScene(scene).global_tie_rank(0))
 
 
+def test_million_triangle_field(oracle, ctx):
+    # config 4's recipe at 16 x 15 copies = 1 067 520 triangles in ONE mesh: above the size where the commit sorts
+    # the top of the reference-order tree and bins / partitions the top of the SAH tree on several threads
+    scene, st, _ = scenes.config4_field(480, 270, 4, 8, nx=16, nz=15)
+    assert scene.n_triangles() == 1067520
+    osc = oracle.OracleScene(scene)
+    accel = scene.build_acceleration(ctx)
+    assert np.array_equal(accel.tie_ranks(0), osc.global_tie_rank(0))
+    check_primary(oracle, ctx, scene, st.render, 480, 270)
+    o, d = random_rays(100000, *scene_bounds(scene), seed=33)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d)
+    s, p, t = accel.trace_rays(o, d)
+    assert np.array_equal(s, s_ref) and np.array_equal(p, p_ref) and np.array_equal(t, t_ref)
+    assert 0.05 < (s_ref != MISS).mean()
+
+
 def test_degenerate_inputs(oracle, ctx):
     # empty scene, zero-area triangles, axis-parallel rays, rays inside flat boxes
     empty = Scene.empty()
