@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 
 namespace vr {
 namespace {
@@ -32,6 +34,21 @@ struct Reader {
         return (uint32_t)p[o + 3] << 24 | (uint32_t)p[o + 2] << 16 | (uint32_t)p[o + 1] << 8 | p[o];
     }
 };
+
+// Decoded size sanity: refuses headers whose pixel count cannot possibly come out of a file this small (a
+// corrupt or hostile header must not make the library allocate gigabytes). ratio = the codec's best case.
+bool plausible_size(uint64_t w, uint64_t h, uint64_t bytes_per_pixel, size_t file_size, uint64_t ratio, const char* fmt,
+                    std::string& err) {
+    if (w == 0 || h == 0 || w * h > (1ull << 30)) {
+        err = std::string(fmt) + ": image dimensions out of range";
+        return false;
+    }
+    if (w * h * bytes_per_pixel > (uint64_t)file_size * ratio + 65536) {
+        err = std::string(fmt) + ": header announces more pixels than the file can hold";
+        return false;
+    }
+    return true;
+}
 
 bool zlib_inflate(const uint8_t* src, size_t n_src, uint8_t* dst, size_t n_dst, size_t* produced, std::string& err) {
     z_stream zs;
@@ -180,6 +197,7 @@ bool decode_png(const uint8_t* data, size_t size, DecodedImage& out, std::string
             if (pw && ph) passes.push_back({X0[i], Y0[i], DX[i], DY[i], pw, ph});
         }
     }
+    if (!plausible_size(w, h, std::max<size_t>(1, bits_pp / 8), idat.size(), 1100, "png", err)) return false;
     size_t raw_size = 0;
     for (const Pass& p : passes) raw_size += (size_t)p.ph * (1 + ((size_t)p.pw * bits_pp + 7) / 8);
     std::vector<uint8_t> raw(raw_size);
@@ -507,6 +525,7 @@ struct JpegDecoder {
         const int nf = data[o + 5];
         if (width == 0 || height == 0) return fail("zero-sized frame (DNL is not supported)");
         if (nf != 1 && nf != 3) return fail("only 1- and 3-component images are supported");
+        if (!plausible_size((uint64_t)width, (uint64_t)height, (uint64_t)nf, size, 2048, "jpeg", err)) return false;
         if (len < (size_t)6 + 3 * nf) return fail("truncated SOF");
         comps.resize(nf);
         for (int i = 0; i < nf; ++i) {
@@ -1029,6 +1048,7 @@ bool decode_tiff(const uint8_t* data, size_t size, DecodedImage& out, std::strin
     rows_per_strip = std::min(rows_per_strip, h);
     if (rows_per_strip == 0) rows_per_strip = h;
     const size_t bps = depth / 8, row_bytes = (size_t)w * spp * bps;
+    if (!plausible_size(w, h, (uint64_t)spp * bps, size, 4096, "tiff", err)) return false;
     std::vector<uint8_t> pixels(row_bytes * h), strip;
     for (size_t s = 0; s < offsets.size(); ++s) {
         const size_t y0 = s * rows_per_strip;
@@ -1164,6 +1184,7 @@ bool decode_hdr(const uint8_t* data, size_t size, DecodedImage& out, std::string
         err = "hdr: unsupported orientation (need -Y h +X w)";
         return false;
     }
+    if (!plausible_size((uint64_t)w, (uint64_t)h, 4, size, 64, "hdr", err)) return false;
     std::vector<uint8_t> rgbe((size_t)4 * w);
     out.w = (uint32_t)w;
     out.h = (uint32_t)h;
@@ -1641,7 +1662,16 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
         case 4: lines_per_block = 32; break;
         default: err = "exr: unsupported compression " + std::to_string(compression) + " (none, RLE, ZIPS, ZIP and PIZ are)"; return false;
     }
+    if ((int64_t)x1 - x0 >= (1 << 30) || (int64_t)y1 - y0 >= (1 << 30)) {
+        err = "exr: image dimensions out of range";
+        return false;
+    }
     const int w = x1 - x0 + 1, h = y1 - y0 + 1;
+    {
+        uint64_t px_bytes = 0;
+        for (const ExrChannel& c : ch) px_bytes += (uint64_t)c.size();
+        if (!plausible_size((uint64_t)w, (uint64_t)h, px_bytes, size, 4096, "exr", err)) return false;
+    }
     // channel lookup: R, G, B (any layer-less name), else Y replicated
     int idx[3] = {-1, -1, -1};
     std::vector<size_t> ch_off(ch.size());
@@ -1756,7 +1786,24 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
 
 }  // namespace
 
+namespace {
+bool decode_dispatch(const uint8_t* data, size_t size, DecodedImage& out, std::string& err);
+}
+
 bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
+    try {
+        return decode_dispatch(data, size, out, err);
+    } catch (const std::bad_alloc&) {
+        err = "out of memory while decoding";
+    } catch (const std::length_error&) {
+        err = "image too large";
+    }
+    out = DecodedImage();
+    return false;
+}
+
+namespace {
+bool decode_dispatch(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
     out = DecodedImage();
     if (size >= 8 && !std::memcmp(data, "\x89PNG\r\n\x1a\n", 8)) return decode_png(data, size, out, err);
     if (size >= 4 && data[0] == 0xFF && data[1] == 0xD8) return decode_jpeg(data, size, out, err);
@@ -1766,6 +1813,7 @@ bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, st
     err = "unrecognised image format (PNG, JPEG, TIFF, Radiance HDR and OpenEXR are supported)";
     return false;
 }
+}  // namespace
 
 bool decode_image_file(const char* path, DecodedImage& out, std::string& err) {
     FILE* f = std::fopen(path, "rb");

@@ -639,11 +639,15 @@ struct Builder {
     // (lo > hi) becomes the inverted pair (32767, 0), which no ray enters.
     uint32_t quantize_pair(float lo, float hi, int axis) const {
         if (!(lo <= hi)) return (0x8000u | 32767u) | ((0x8000u | 0u) << 16);
-        long long ql = (long long)std::floor(((double)lo - grid_min[axis]) * grid_inv_cell[axis]) - 1;
-        long long qh = (long long)std::ceil(((double)hi - grid_min[axis]) * grid_inv_cell[axis]) + 1;
-        ql = std::min<long long>(std::max<long long>(ql, 0), 32767);
-        qh = std::min<long long>(std::max<long long>(qh, 0), 32767);
-        return (0x8000u | (uint32_t)ql) | ((0x8000u | (uint32_t)qh) << 16);
+        // clamped as doubles (infinite or NaN coordinates must not reach the integer conversion); a NaN cell
+        // index opens the box to the whole grid, the conservative side
+        double fl = std::floor(((double)lo - grid_min[axis]) * grid_inv_cell[axis]) - 1.0;
+        double fh = std::ceil(((double)hi - grid_min[axis]) * grid_inv_cell[axis]) + 1.0;
+        if (!(fl >= 0.0)) fl = 0.0;
+        if (fl > 32767.0) fl = 32767.0;
+        if (!(fh <= 32767.0)) fh = 32767.0;
+        if (fh < 0.0) fh = 0.0;
+        return (0x8000u | (uint32_t)fl) | ((0x8000u | (uint32_t)fh) << 16);
     }
 
     void write_node(uint32_t node, int32_t c0, const Box& b0, int32_t c1, const Box& b1) {
