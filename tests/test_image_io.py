@@ -211,6 +211,8 @@ def test_openexr(tmp_path, compression, half):
 def test_errors_are_reported_not_fatal(tmp_path):
     with pytest.raises(_lib.VoidrayError, match="cannot open"):
         assets.load_image_native(str(tmp_path / "missing.png"))
+    with pytest.raises(_lib.VoidrayError, match="not a regular file"):
+        assets.load_image_native(str(tmp_path))  # a directory
     bad = tmp_path / "bad.bin"
     bad.write_bytes(b"not an image at all")
     with pytest.raises(_lib.VoidrayError, match="unrecognised"):

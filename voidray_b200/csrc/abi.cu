@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <string>
@@ -123,7 +124,7 @@ struct vr_render {
     // statistics
     std::mutex stats_mutex;
     double seconds = 0.0, device_ms = 0.0, trace_ms = 0.0;
-    uint64_t trace_launches = 0, kernel_launches = 0;
+    std::atomic<uint64_t> trace_launches{0}, kernel_launches{0};  // bumped by the render thread, read by vr_render_stats
     unsigned long long segments_host = 0;
     std::vector<cudaEvent_t> events;  // pairs around trace launches, reused call to call
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -246,6 +247,21 @@ int32_t add_texture_int(vr_scene* scene, const T* pixels, uint32_t w, uint32_t h
     return vr_scene_add_texture_rgb32f(scene, rgb.data(), w, h, sample_type, texture);
 }
 
+// No exception leaves the library: every int32_t entry point is a function-try-block ending in VR_CATCH.
+int32_t translate_exception() {
+    try {
+        throw;
+    } catch (const std::bad_alloc&) {
+        return fail(VR_ERR_OOM, "host allocation failed");
+    } catch (const std::exception& e) {
+        return fail(VR_ERR_INVALID, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return fail(VR_ERR_INVALID, "internal error: unknown exception");
+    }
+}
+#define VR_CATCH \
+    catch (...) { return translate_exception(); }
+
 int32_t check_scene(vr_scene* s) {
     if (!s) return fail(VR_ERR_INVALID, "null scene");
     return VR_OK;
@@ -258,7 +274,7 @@ extern "C" {
 const char* vr_last_error(void) { return g_error.c_str(); }
 uint32_t vr_abi_version(void) { return 2; }
 
-int32_t vr_context_create(int32_t device, void* cuda_stream, vr_context** out) {
+int32_t vr_context_create(int32_t device, void* cuda_stream, vr_context** out) try {
     if (!out) return fail(VR_ERR_INVALID, "out is null");
     *out = nullptr;
     int count = 0;
@@ -289,17 +305,17 @@ int32_t vr_context_create(int32_t device, void* cuda_stream, vr_context** out) {
     query_launch_dims(&ctx->dims);
     *out = ctx;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_context_destroy(vr_context* ctx) {
+int32_t vr_context_destroy(vr_context* ctx) try {
     if (!ctx) return VR_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_create(vr_context* ctx, vr_scene** out) {
+int32_t vr_scene_create(vr_context* ctx, vr_scene** out) try {
     if (!ctx || !out) return fail(VR_ERR_INVALID, "null argument");
     vr_scene* s = new (std::nothrow) vr_scene();
     if (!s) return fail(VR_ERR_OOM, "host allocation failed");
@@ -315,9 +331,9 @@ int32_t vr_scene_create(vr_context* ctx, vr_scene** out) {
     c.focal_point[0] = c.focal_point[1] = c.focal_point[2] = 0.0f;
     *out = s;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_destroy(vr_scene* scene) {
+int32_t vr_scene_destroy(vr_scene* scene) try {
     if (!scene) return VR_OK;
     cudaSetDevice(scene->ctx->device);
     cudaStreamSynchronize(scene->ctx->stream);
@@ -325,10 +341,10 @@ int32_t vr_scene_destroy(vr_scene* scene) {
     for (const void* p : scene->pinned) cudaHostUnregister((void*)p);
     delete scene;
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t w, uint32_t h, int32_t sample_type,
-                                    uint32_t* texture) {
+                                    uint32_t* texture) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!rgb || w == 0 || h == 0) return fail(VR_ERR_INVALID, "empty texture");
     if ((uint64_t)w * h >= (1ull << 31)) return fail(VR_ERR_INVALID, "texture too large");
@@ -344,20 +360,20 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
     scene->committed = false;
     if (texture) *texture = (uint32_t)scene->host.textures.size() - 1;
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_scene_add_texture_rgb8(vr_scene* scene, const uint8_t* pixels, uint32_t w, uint32_t h, uint32_t channels,
-                                  int32_t sample_type, uint32_t* texture) {
+                                  int32_t sample_type, uint32_t* texture) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     return add_texture_int(scene, pixels, w, h, channels, sample_type, 255.0f, texture);
-}
+} VR_CATCH
 int32_t vr_scene_add_texture_rgb16(vr_scene* scene, const uint16_t* pixels, uint32_t w, uint32_t h, uint32_t channels,
-                                   int32_t sample_type, uint32_t* texture) {
+                                   int32_t sample_type, uint32_t* texture) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     return add_texture_int(scene, pixels, w, h, channels, sample_type, 65535.0f, texture);
-}
+} VR_CATCH
 
-int32_t vr_image_load_rgb32f(const char* path, uint32_t* w, uint32_t* h, float** rgb) {
+int32_t vr_image_load_rgb32f(const char* path, uint32_t* w, uint32_t* h, float** rgb) try {
     if (!path || !w || !h || !rgb) return fail(VR_ERR_INVALID, "null argument");
     *rgb = nullptr;
     DecodedImage img;
@@ -372,14 +388,14 @@ int32_t vr_image_load_rgb32f(const char* path, uint32_t* w, uint32_t* h, float**
     *h = img.h;
     *rgb = out;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_image_free(float* rgb) {
+int32_t vr_image_free(float* rgb) try {
     std::free(rgb);
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_add_image_texture_file(vr_scene* scene, const char* path, int32_t sample_type, uint32_t* texture) {
+int32_t vr_scene_add_image_texture_file(vr_scene* scene, const char* path, int32_t sample_type, uint32_t* texture) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!path) return fail(VR_ERR_INVALID, "null path");
     DecodedImage img;
@@ -388,10 +404,10 @@ int32_t vr_scene_add_image_texture_file(vr_scene* scene, const char* path, int32
     std::vector<float> f;
     image_to_rgb32f(img, f);
     return vr_scene_add_texture_rgb32f(scene, f.data(), img.w, img.h, sample_type, texture);
-}
+} VR_CATCH
 
 int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* uvs, const float* normals,
-                          uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, uint32_t* surface) {
+                          uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, uint32_t* surface) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if ((!positions && n_vertices) || (!indices && n_indices)) return fail(VR_ERR_INVALID, "null mesh buffers");
     const uint32_t n_idx = n_indices - n_indices % 3;  // chunks_exact(3), mesh.rs:79
@@ -413,10 +429,10 @@ int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* 
     scene->committed = false;
     if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_scene_add_mesh_from_obj_file(vr_scene* scene, const char* path, uint32_t* surface, uint32_t* n_vertices,
-                                        uint32_t* n_triangles) {
+                                        uint32_t* n_triangles) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!path) return fail(VR_ERR_INVALID, "null path");
     HostMesh m;
@@ -432,9 +448,9 @@ int32_t vr_scene_add_mesh_from_obj_file(vr_scene* scene, const char* path, uint3
     scene->committed = false;
     if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_add_sphere(vr_scene* scene, const float center[3], float radius, uint32_t* surface) {
+int32_t vr_scene_add_sphere(vr_scene* scene, const float center[3], float radius, uint32_t* surface) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!center) return fail(VR_ERR_INVALID, "null center");
     HostSurface sf;
@@ -445,9 +461,9 @@ int32_t vr_scene_add_sphere(vr_scene* scene, const float center[3], float radius
     scene->committed = false;
     if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_add_ground_plane(vr_scene* scene, float height, uint32_t* surface) {
+int32_t vr_scene_add_ground_plane(vr_scene* scene, float height, uint32_t* surface) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     HostSurface sf;
     sf.kind = 2;
@@ -456,9 +472,9 @@ int32_t vr_scene_add_ground_plane(vr_scene* scene, float height, uint32_t* surfa
     scene->committed = false;
     if (surface) *surface = (uint32_t)scene->host.surfaces.size() - 1;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_add_material(vr_scene* scene, const vr_material_desc* desc, uint32_t* material) {
+int32_t vr_scene_add_material(vr_scene* scene, const vr_material_desc* desc, uint32_t* material) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!desc) return fail(VR_ERR_INVALID, "null material desc");
     if (desc->kind < 0 || desc->kind > VR_MAT_MICROFACET) return fail(VR_ERR_INVALID, "unknown material kind");
@@ -482,9 +498,9 @@ int32_t vr_scene_add_material(vr_scene* scene, const vr_material_desc* desc, uin
     scene->committed = false;
     if (material) *material = (uint32_t)scene->host.materials.size() - 1;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_add_object(vr_scene* scene, uint32_t material, uint32_t surface, uint32_t* object) {
+int32_t vr_scene_add_object(vr_scene* scene, uint32_t material, uint32_t surface, uint32_t* object) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (material >= scene->host.materials.size()) return fail(VR_ERR_INVALID, "unknown material handle");
     if (surface >= scene->host.surfaces.size()) return fail(VR_ERR_INVALID, "unknown surface handle");
@@ -492,10 +508,10 @@ int32_t vr_scene_add_object(vr_scene* scene, uint32_t material, uint32_t surface
     scene->committed = false;
     if (object) *object = (uint32_t)scene->host.objects.size() - 1;
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_scene_set_camera(vr_scene* scene, const float eye[3], const float direction[3], const float up[3],
-                            float fov, int32_t has_dof, float aperture, const float focal_point[3]) {
+                            float fov, int32_t has_dof, float aperture, const float focal_point[3]) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!eye || !direction || !up) return fail(VR_ERR_INVALID, "null camera vector");
     if (has_dof && !focal_point) return fail(VR_ERR_INVALID, "has_dof needs a focal point");
@@ -509,10 +525,10 @@ int32_t vr_scene_set_camera(vr_scene* scene, const float eye[3], const float dir
     if (focal_point) std::memcpy(c.focal_point, focal_point, 12);
     scene->committed = false;
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_scene_set_camera_look_at(vr_scene* scene, const float eye[3], const float center[3], const float up[3],
-                                    float fov) {
+                                    float fov) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!eye || !center || !up) return fail(VR_ERR_INVALID, "null camera vector");
     HostCamera& c = scene->host.camera;
@@ -522,16 +538,16 @@ int32_t vr_scene_set_camera_look_at(vr_scene* scene, const float eye[3], const f
     c.has_dof = 0;
     scene->committed = false;
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_camera_look_at(const float eye[3], const float center[3], const float up[3], float direction_out[3],
-                          float up_out[3]) {
+                          float up_out[3]) try {
     if (!eye || !center || !up || !direction_out || !up_out) return fail(VR_ERR_INVALID, "null camera vector");
     camera_look_at(eye, center, up, direction_out, up_out);
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]) {
+int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!rgb) return fail(VR_ERR_INVALID, "null colour");
     scene->host.env_kind = 1;
@@ -540,9 +556,9 @@ int32_t vr_scene_set_environment_uniform(vr_scene* scene, const float rgb[3]) {
     scene->host.env_image = HostTexture();
     scene->committed = false;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, uint32_t w, uint32_t h) {
+int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, uint32_t w, uint32_t h) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!rgb || w == 0 || h == 0) return fail(VR_ERR_INVALID, "empty environment image");
     if ((uint64_t)w * h >= (1ull << 31)) return fail(VR_ERR_INVALID, "environment image too large");
@@ -556,9 +572,9 @@ int32_t vr_scene_set_environment_hdri_rgb32f(vr_scene* scene, const float* rgb, 
     pin_host(scene, scene->host.env_image.rgb);
     scene->committed = false;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_set_environment_hdri_file(vr_scene* scene, const char* path) {
+int32_t vr_scene_set_environment_hdri_file(vr_scene* scene, const char* path) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!path) return fail(VR_ERR_INVALID, "null path");
     DecodedImage img;
@@ -567,20 +583,21 @@ int32_t vr_scene_set_environment_hdri_file(vr_scene* scene, const char* path) {
     std::vector<float> f;
     image_to_rgb32f(img, f);
     return vr_scene_set_environment_hdri_rgb32f(scene, f.data(), img.w, img.h);
-}
+} VR_CATCH
 
-int32_t vr_scene_clear_environment(vr_scene* scene) {
+int32_t vr_scene_clear_environment(vr_scene* scene) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     scene->host.env_kind = 0;
     unpin_host(scene, scene->host.env_image.rgb);
     scene->host.env_image = HostTexture();
     scene->committed = false;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_commit(vr_scene* scene) {
+int32_t vr_scene_commit(vr_scene* scene) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     VR_CUDA(cudaSetDevice(scene->ctx->device));
+    scene->committed = false;  // a commit that fails half-way leaves no usable scene behind
     std::string err;
     const auto t_begin = std::chrono::steady_clock::now();
     if (!flatten_scene(scene->host, scene->flat, err)) return fail(VR_ERR_INVALID, err);
@@ -633,9 +650,9 @@ int32_t vr_scene_commit(vr_scene* scene) {
     scene->committed = true;
     scene->commit_serial++;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) {
+int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!out) return fail(VR_ERR_INVALID, "null argument");
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
@@ -649,10 +666,10 @@ int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) {
     out->flatten_ms = scene->flatten_ms;
     out->upload_ms = scene->upload_ms;
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const vr_render_settings* settings,
-                        vr_render** out) {
+                        vr_render** out) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!settings || !out) return fail(VR_ERR_INVALID, "null argument");
     if (!scene->committed) return fail(VR_ERR_INVALID, "vr_scene_commit must be called before vr_render_begin");
@@ -724,9 +741,9 @@ int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const 
     }
     *out = r;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_end(vr_render* r) {
+int32_t vr_render_end(vr_render* r) try {
     if (!r) return VR_OK;
     cudaSetDevice(r->scene->ctx->device);
     cudaStreamSynchronize(r->scene->ctx->stream);
@@ -737,9 +754,9 @@ int32_t vr_render_end(vr_render* r) {
     r->dev_mem.release();
     delete r;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_clear(vr_render* r) {
+int32_t vr_render_clear(vr_render* r) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
     cudaStream_t st = r->scene->ctx->stream;
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
@@ -754,9 +771,9 @@ int32_t vr_render_clear(vr_render* r) {
     r->segments_host = 0;
     r->cancel = 0;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_accumulate(vr_render* r, uint32_t samples) {
+int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
     if (!r->scene->committed) return fail(VR_ERR_INVALID, "scene was edited after commit");
     if (samples == 0) return VR_OK;
@@ -817,15 +834,15 @@ int32_t vr_render_accumulate(vr_render* r, uint32_t samples) {
         return fail(VR_ERR_CANCELLED, "accumulate cancelled");
     }
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_cancel(vr_render* r) {
+int32_t vr_render_cancel(vr_render* r) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
     r->cancel = 1;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_stats(vr_render* r, vr_stats* out) {
+int32_t vr_render_stats(vr_render* r, vr_stats* out) try {
     if (!r || !out) return fail(VR_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(r->stats_mutex);
     out->samples_done = r->samples_done;
@@ -838,24 +855,24 @@ int32_t vr_render_stats(vr_render* r, vr_stats* out) {
     out->trace_launches = r->trace_launches;
     out->kernel_launches = r->kernel_launches;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_read_accum(vr_render* r, float* rgba) {
+int32_t vr_render_read_accum(vr_render* r, float* rgba) try {
     if (!r || !rgba) return fail(VR_ERR_INVALID, "null argument");
     cudaStream_t st = r->scene->ctx->stream;
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
     VR_CUDA(cudaMemcpyAsync(rgba, r->accum, 16ull * r->n_pixels, cudaMemcpyDeviceToHost, st));
     VR_CUDA(cudaStreamSynchronize(st));
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_accum_device_ptr(vr_render* r, void** device_ptr) {
+int32_t vr_render_accum_device_ptr(vr_render* r, void** device_ptr) try {
     if (!r || !device_ptr) return fail(VR_ERR_INVALID, "null argument");
     *device_ptr = r->accum;
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_render_resolve(vr_render* r, float scale, float gamma, float exposure, int32_t tonemap, float* rgba_out) {
+int32_t vr_render_resolve(vr_render* r, float scale, float gamma, float exposure, int32_t tonemap, float* rgba_out) try {
     if (!r || !rgba_out) return fail(VR_ERR_INVALID, "null argument");
     if (tonemap < 0 || tonemap > 4) return fail(VR_ERR_INVALID, "unknown tonemap");
     cudaStream_t st = r->scene->ctx->stream;
@@ -866,11 +883,11 @@ int32_t vr_render_resolve(vr_render* r, float scale, float gamma, float exposure
     VR_CUDA(cudaStreamSynchronize(st));
     VR_CUDA(cudaGetLastError());
     return VR_OK;
-}
+} VR_CATCH
 
 // ---- multi-GPU: peer-memory reduce ----------------------------------------------------------------
 
-int32_t vr_render_export_accum(vr_render* r, uint8_t handle[VR_IPC_HANDLE_BYTES]) {
+int32_t vr_render_export_accum(vr_render* r, uint8_t handle[VR_IPC_HANDLE_BYTES]) try {
     if (!r || !handle) return fail(VR_ERR_INVALID, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == VR_IPC_HANDLE_BYTES, "IPC handle size");
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
@@ -878,7 +895,7 @@ int32_t vr_render_export_accum(vr_render* r, uint8_t handle[VR_IPC_HANDLE_BYTES]
     VR_CUDA(cudaIpcGetMemHandle(&h, r->accum));
     std::memcpy(handle, &h, VR_IPC_HANDLE_BYTES);
     return VR_OK;
-}
+} VR_CATCH
 
 static int32_t peer_reduce(vr_render* r, void* const* peer_accum, uint32_t n_peers, float scale, float gamma,
                            float exposure, int32_t tonemap, float* rgba_out) {
@@ -927,41 +944,41 @@ static int32_t open_peers(vr_render* r, const uint8_t* peer_handles, uint32_t n_
     return VR_OK;
 }
 
-int32_t vr_render_reduce_peers(vr_render* r, const uint8_t* peer_handles, uint32_t n_peers) {
+int32_t vr_render_reduce_peers(vr_render* r, const uint8_t* peer_handles, uint32_t n_peers) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
     std::vector<void*> ptrs;
     const int32_t rc = open_peers(r, peer_handles, n_peers, ptrs);
     if (rc) return rc;
     return peer_reduce(r, ptrs.data(), n_peers, 1.0f, 1.0f, 0.0f, -1, nullptr);
-}
+} VR_CATCH
 
 int32_t vr_render_resolve_peers(vr_render* r, const uint8_t* peer_handles, uint32_t n_peers, float scale, float gamma,
-                                float exposure, int32_t tonemap, float* rgba_out) {
+                                float exposure, int32_t tonemap, float* rgba_out) try {
     if (!r || !rgba_out) return fail(VR_ERR_INVALID, "null argument");
     if (tonemap < 0 || tonemap > 4) return fail(VR_ERR_INVALID, "unknown tonemap");
     std::vector<void*> ptrs;
     const int32_t rc = open_peers(r, peer_handles, n_peers, ptrs);
     if (rc) return rc;
     return peer_reduce(r, ptrs.data(), n_peers, scale, gamma, exposure, tonemap, rgba_out);
-}
+} VR_CATCH
 
-int32_t vr_render_reduce_peer_ptrs(vr_render* r, void* const* peer_accum, uint32_t n_peers) {
+int32_t vr_render_reduce_peer_ptrs(vr_render* r, void* const* peer_accum, uint32_t n_peers) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
     return peer_reduce(r, peer_accum, n_peers, 1.0f, 1.0f, 0.0f, -1, nullptr);
-}
+} VR_CATCH
 
 int32_t vr_render_resolve_peer_ptrs(vr_render* r, void* const* peer_accum, uint32_t n_peers, float scale, float gamma,
-                                    float exposure, int32_t tonemap, float* rgba_out) {
+                                    float exposure, int32_t tonemap, float* rgba_out) try {
     if (!r || !rgba_out) return fail(VR_ERR_INVALID, "null argument");
     if (tonemap < 0 || tonemap > 4) return fail(VR_ERR_INVALID, "unknown tonemap");
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
     return peer_reduce(r, peer_accum, n_peers, scale, gamma, exposure, tonemap, rgba_out);
-}
+} VR_CATCH
 
 // ---- gates ----------------------------------------------------------------------------------------
 
-int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface, uint32_t* prim, float* t) {
+int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface, uint32_t* prim, float* t) try {
     if (!r || !surface || !prim || !t) return fail(VR_ERR_INVALID, "null argument");
     vr_context* ctx = r->scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
@@ -983,10 +1000,10 @@ int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface,
     VR_CUDA(cudaStreamSynchronize(ctx->stream));
     VR_CUDA(cudaGetLastError());
     return VR_OK;
-}
+} VR_CATCH
 
 int32_t vr_debug_trace_rays(vr_scene* scene, uint64_t n, const float* origins, const float* directions,
-                            uint32_t* surface, uint32_t* prim, float* t) {
+                            uint32_t* surface, uint32_t* prim, float* t) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
     if (n == 0) return VR_OK;
@@ -1014,9 +1031,9 @@ int32_t vr_debug_trace_rays(vr_scene* scene, uint64_t n, const float* origins, c
     tmp.release();
     if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_trace_rays: ") + cudaGetErrorString(e));
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel, const uint32_t* sample, float* out) {
+int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel, const uint32_t* sample, float* out) try {
     if (!r || !pixel || !sample || !out) return fail(VR_ERR_INVALID, "null argument");
     vr_context* ctx = r->scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
@@ -1054,32 +1071,34 @@ int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel
     tmp.release();
     if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_sample_radiance: ") + cudaGetErrorString(e));
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_debug_reference_leaf_order(const float* boxes6, uint64_t n, uint32_t* order) {
+int32_t vr_debug_reference_leaf_order(const float* boxes6, uint64_t n, uint32_t* order) try {
     if ((!boxes6 || !order) && n) return fail(VR_ERR_INVALID, "null argument");
     if (n >= (1ull << 32)) return fail(VR_ERR_INVALID, "too many items");
     RawVector<uint32_t> o;
     reference_leaf_order(boxes6, (size_t)n, o);
     if (n) std::memcpy(order, o.data(), (size_t)n * sizeof(uint32_t));
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_debug_tie_ranks(vr_scene* scene, uint32_t surface, uint32_t* out, uint32_t n) {
+int32_t vr_debug_tie_ranks(vr_scene* scene, uint32_t surface, uint32_t* out, uint32_t n) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
     if (surface >= scene->flat.mesh_tie_rank.size()) return fail(VR_ERR_INVALID, "unknown surface");
     const RawVector<uint32_t>& rank = scene->flat.mesh_tie_rank[surface];
     if (n != rank.size()) return fail(VR_ERR_INVALID, "n must equal the surface's triangle count");
+    if (n && !out) return fail(VR_ERR_INVALID, "null argument");
     for (uint32_t i = 0; i < n; ++i) out[i] = scene->flat.surface_rank_base[surface] + rank[i];
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_debug_texture_sample(vr_scene* scene, uint32_t texture, uint64_t n, const float* uv, float* rgb) {
+int32_t vr_debug_texture_sample(vr_scene* scene, uint32_t texture, uint64_t n, const float* uv, float* rgb) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
     if (texture >= scene->dev_textures.size()) return fail(VR_ERR_INVALID, "unknown texture");
     if (n == 0) return VR_OK;
+    if (!uv || !rgb) return fail(VR_ERR_INVALID, "null argument");
     vr_context* ctx = scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
     DeviceBuffers tmp;
@@ -1096,12 +1115,13 @@ int32_t vr_debug_texture_sample(vr_scene* scene, uint32_t texture, uint64_t n, c
     tmp.release();
     if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_texture_sample: ") + cudaGetErrorString(e));
     return VR_OK;
-}
+} VR_CATCH
 
-int32_t vr_debug_environment_sample(vr_scene* scene, uint64_t n, const float* directions, float* rgb) {
+int32_t vr_debug_environment_sample(vr_scene* scene, uint64_t n, const float* directions, float* rgb) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
     if (n == 0) return VR_OK;
+    if (!directions || !rgb) return fail(VR_ERR_INVALID, "null argument");
     vr_context* ctx = scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
     DeviceBuffers tmp;
@@ -1118,7 +1138,7 @@ int32_t vr_debug_environment_sample(vr_scene* scene, uint64_t n, const float* di
     tmp.release();
     if (e != cudaSuccess) return fail(VR_ERR_CUDA, std::string("vr_debug_environment_sample: ") + cudaGetErrorString(e));
     return VR_OK;
-}
+} VR_CATCH
 
 static int32_t debug_draws(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, void* out,
                            int floats_per_item) {
@@ -1138,11 +1158,11 @@ static int32_t debug_draws(vr_context* ctx, uint64_t seed, uint32_t pixel, uint3
     return VR_OK;
 }
 
-int32_t vr_debug_rng_draws(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out) {
+int32_t vr_debug_rng_draws(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, uint32_t* out) try {
     return debug_draws(ctx, seed, pixel, sample, n, out, 1);
-}
-int32_t vr_debug_unit_sphere(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out) {
+} VR_CATCH
+int32_t vr_debug_unit_sphere(vr_context* ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out) try {
     return debug_draws(ctx, seed, pixel, sample, n, out, 3);
-}
+} VR_CATCH
 
 }  // extern "C"

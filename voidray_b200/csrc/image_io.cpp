@@ -1825,9 +1825,9 @@ bool decode_image_file(const char* path, DecodedImage& out, std::string& err) {
     std::fseek(f, 0, SEEK_END);
     const long n = std::ftell(f);
     std::fseek(f, 0, SEEK_SET);
-    if (n < 0) {
+    if (n < 0 || n > (1L << 40)) {  // a directory reports LONG_MAX
         std::fclose(f);
-        err = "cannot size file";
+        err = "not a regular file";
         return false;
     }
     buf.resize((size_t)n);
