@@ -1,0 +1,242 @@
+// scripts/bvh_stats.cpp — offline BVH quality meter (host only, not part of the library).
+// Flattens a scene with the library's own builder (csrc/scene_build.cpp) and walks the resulting quantised BVH2
+// on the CPU the way k_trace does (near child first, far child deferred, closest hit shrinks the interval),
+// for camera rays and three generations of diffuse bounce rays. Prints node visits and triangle tests per ray
+// and the tree's SAH cost, so that builder changes can be compared without a GPU.
+//
+//   g++ -O2 -std=c++17 -pthread -ffp-contract=off -Ivoidray_b200/csrc -x c++ voidray_b200/csrc/scene_build.cpp \
+//       scripts/bvh_stats.cpp -o /tmp/bvh_stats && /tmp/bvh_stats assets/mossy_ground.obj [copies_x copies_z]
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "scene_build.h"
+
+using namespace vr;
+
+struct Ray {
+    float o[3], d[3];
+};
+struct Hit {
+    float t;
+    int tri;
+};
+
+static uint32_t g_state = 12345u;
+static float rnd() {
+    g_state = g_state * 1664525u + 1013904223u;
+    return (float)(g_state >> 8) * (1.0f / 16777216.0f);
+}
+
+struct Tree {
+    const FlatScene& f;
+    float cell[3];
+    explicit Tree(const FlatScene& fs) : f(fs) {
+        for (int a = 0; a < 3; ++a) cell[a] = fs.grid_extent[a] / 32768.0f;
+    }
+    void child_box(size_t node, int c, float lo[3], float hi[3]) const {
+        const Quad* q = &f.nodes[node * NODE_QUADS];
+        uint32_t w[6];
+        const float src[6] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y};
+        std::memcpy(w, src, 24);
+        for (int a = 0; a < 3; ++a) {
+            const uint32_t p = w[3 * c + a];
+            lo[a] = f.grid_min[a] + (float)(p & 0x7FFF) * cell[a];
+            hi[a] = f.grid_min[a] + (float)((p >> 16) & 0x7FFF) * cell[a];
+        }
+    }
+    int child_code(size_t node, int c) const {
+        const Quad* q = &f.nodes[node * NODE_QUADS];
+        float v = c == 0 ? q[1].z : q[1].w;
+        int code;
+        std::memcpy(&code, &v, 4);
+        return code;
+    }
+    bool slab(const float lo[3], const float hi[3], const Ray& r, const float inv[3], float tmax, float& tn) const {
+        float t0 = 0.0f, t1 = tmax;
+        for (int a = 0; a < 3; ++a) {
+            float ta = (lo[a] - r.o[a]) * inv[a], tb = (hi[a] - r.o[a]) * inv[a];
+            if (ta > tb) std::swap(ta, tb);
+            if (ta > t0) t0 = ta;
+            if (tb < t1) t1 = tb;
+        }
+        tn = t0;
+        return t0 <= t1 * 1.0000005f;
+    }
+    bool tri_hit(int i, const Ray& r, float& t) const {
+        const Quad* q = &f.tri_isect[(size_t)i * TRI_ISECT_QUADS];
+        const float v0[3] = {q[0].x, q[0].y, q[0].z}, e1[3] = {q[1].x, q[1].y, q[1].z}, e2[3] = {q[2].x, q[2].y, q[2].z};
+        const float h[3] = {r.d[1] * e2[2] - r.d[2] * e2[1], r.d[2] * e2[0] - r.d[0] * e2[2], r.d[0] * e2[1] - r.d[1] * e2[0]};
+        const float a = e1[0] * h[0] + e1[1] * h[1] + e1[2] * h[2];
+        if (a > -1e-5f && a < 1e-5f) return false;
+        const float fi = 1.0f / a;
+        const float s[3] = {r.o[0] - v0[0], r.o[1] - v0[1], r.o[2] - v0[2]};
+        const float u = fi * (s[0] * h[0] + s[1] * h[1] + s[2] * h[2]);
+        if (u < 0.0f || u > 1.0f) return false;
+        const float qq[3] = {s[1] * e1[2] - s[2] * e1[1], s[2] * e1[0] - s[0] * e1[2], s[0] * e1[1] - s[1] * e1[0]};
+        const float v = fi * (r.d[0] * qq[0] + r.d[1] * qq[1] + r.d[2] * qq[2]);
+        if (v < 0.0f || u + v > 1.0f) return false;
+        t = fi * (e2[0] * qq[0] + e2[1] * qq[1] + e2[2] * qq[2]);
+        return t > 1e-5f;
+    }
+    Hit trace(const Ray& r, uint64_t& n_nodes, uint64_t& n_tris, uint32_t& max_sp) const {
+        Hit best{INFINITY, -1};
+        float inv[3];
+        for (int a = 0; a < 3; ++a) inv[a] = 1.0f / r.d[a];
+        int stack[64];
+        int sp = 0;
+        int cur = 0;
+        for (;;) {
+            if (cur >= 0) {
+                ++n_nodes;
+                float lo[3], hi[3], ta = 0, tb = 0;
+                child_box(cur, 0, lo, hi);
+                const bool ha = slab(lo, hi, r, inv, best.t, ta);
+                child_box(cur, 1, lo, hi);
+                const bool hb = slab(lo, hi, r, inv, best.t, tb);
+                const int ca = child_code(cur, 0), cb = child_code(cur, 1);
+                const bool b_first = hb && (!ha || tb < ta);
+                const int near_c = b_first ? cb : ca, far_c = b_first ? ca : cb;
+                if (ha && hb) {
+                    stack[sp++] = far_c;
+                    if ((uint32_t)sp > max_sp) max_sp = sp;
+                }
+                if (ha || hb) {
+                    cur = near_c;
+                    continue;
+                }
+            } else {
+                const uint32_t code = ~(uint32_t)cur;
+                const uint32_t first = code >> 3, count = code & 7;
+                for (uint32_t k = 0; k < count; ++k) {
+                    ++n_tris;
+                    float t;
+                    if (tri_hit((int)(first + k), r, t) && t < best.t) best = Hit{t, (int)(first + k)};
+                }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+        return best;
+    }
+    double sah_cost(float node_cost) const {
+        // sum over inner nodes of area(child) / area(root) * (node_cost or n_tris of a leaf child)
+        float lo[3], hi[3];
+        auto area = [&](const float* l, const float* h) {
+            const float dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2];
+            return dx < 0 || dy < 0 || dz < 0 ? 0.0 : (double)(dx * dy + dy * dz + dz * dx);
+        };
+        float rl[3] = {INFINITY, INFINITY, INFINITY}, rh[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < 2; ++c) {
+            child_box(0, c, lo, hi);
+            if (lo[0] > hi[0]) continue;
+            for (int a = 0; a < 3; ++a) { rl[a] = std::min(rl[a], lo[a]); rh[a] = std::max(rh[a], hi[a]); }
+        }
+        const double root = area(rl, rh);
+        double cost = node_cost;
+        std::vector<int> st{0};
+        while (!st.empty()) {
+            const int n = st.back();
+            st.pop_back();
+            for (int c = 0; c < 2; ++c) {
+                child_box(n, c, lo, hi);
+                const int code = child_code(n, c);
+                const double p = area(lo, hi) / root;
+                if (code >= 0) { cost += p * node_cost; st.push_back(code); }
+                else cost += p * (double)((~(uint32_t)code) & 7);
+            }
+        }
+        return cost;
+    }
+};
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    const int nx = argc > 2 ? atoi(argv[2]) : 1, nz = argc > 3 ? atoi(argv[3]) : 1;
+    HostMesh base;
+    std::string err;
+    if (!load_obj_file(argv[1], base, err)) { std::printf("%s\n", err.c_str()); return 1; }
+    HostScene sc;
+    HostMesh big;
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < nz; ++j) {
+            const float ang = 6.2831853f * (float)((i * 7919 + j * 104729) % 1000) / 1000.0f, c = cosf(ang), s = sinf(ang);
+            const float ox = 1.5f * (float)i, oz = 1.5f * (float)j;
+            const uint32_t v0 = (uint32_t)(big.pos.size() / 3);
+            for (uint32_t v = 0; v < base.n_vertices; ++v) {
+                const float x = base.pos[3 * v], y = base.pos[3 * v + 1], z = base.pos[3 * v + 2];
+                if (nx * nz == 1) { big.pos.push_back(x); big.pos.push_back(y); big.pos.push_back(z); }
+                else { big.pos.push_back(c * x + s * z + ox); big.pos.push_back(y); big.pos.push_back(-s * x + c * z + oz); }
+                big.uv.push_back(0); big.uv.push_back(0);
+                big.nrm.push_back(0); big.nrm.push_back(1); big.nrm.push_back(0);
+            }
+            for (uint32_t k : base.idx) big.idx.push_back(v0 + k);
+        }
+    big.n_vertices = (uint32_t)(big.pos.size() / 3);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t v = 0; v < big.n_vertices; ++v)
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], big.pos[3 * v + a]); hi[a] = std::max(hi[a], big.pos[3 * v + a]); }
+    sc.meshes.push_back(std::move(big));
+    HostSurface sf; sf.kind = 0; sf.mesh = 0; sc.surfaces.push_back(sf);
+    MaterialRec m{}; m.albedo_tex = -1; m.normal_tex = -1; sc.materials.push_back(m);
+    sc.objects.push_back(HostObject{0, 0});
+    const float ce[3] = {0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2])};
+    const float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+    const float eye[3] = {ce[0] + 0.2f * ext, ce[1] + 0.9f * ext, ce[2] - 1.6f * ext}, up[3] = {0, 1, 0};
+    std::memcpy(sc.camera.eye, eye, 12);
+    camera_look_at(eye, ce, up, sc.camera.direction, sc.camera.up);
+    sc.camera.fov = 0.6f; sc.camera.has_dof = 0;
+    FlatScene flat;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!flatten_scene(sc, flat, err)) { std::printf("%s\n", err.c_str()); return 1; }
+    const double build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    Tree tree(flat);
+    // camera rays on a 256 x 256 grid, then three generations of diffuse bounces (origin = hit point, direction = a
+    // random unit vector flipped into the hemisphere facing back along the ray)
+    std::vector<Ray> rays;
+    const float* dir = sc.camera.direction;
+    const float* cup = sc.camera.up;
+    const float right[3] = {dir[1] * cup[2] - dir[2] * cup[1], dir[2] * cup[0] - dir[0] * cup[2], dir[0] * cup[1] - dir[1] * cup[0]};
+    const float dd = 1.0f / std::tan(sc.camera.fov / 2.0f);
+    const int G = 256;
+    for (int y = 0; y < G; ++y)
+        for (int x = 0; x < G; ++x) {
+            const float px = ((float)x + 0.5f) / G * 2.0f - 1.0f, py = 1.0f - ((float)y + 0.5f) / G * 2.0f;
+            Ray r;
+            for (int a = 0; a < 3; ++a) { r.o[a] = eye[a]; r.d[a] = dd * dir[a] + px * right[a] + py * cup[a]; }
+            rays.push_back(r);
+        }
+    std::printf("%s x%d: %u triangles, %zu nodes, depth %u, build %.1f ms, SAH cost %.2f\n", argv[1], nx * nz, flat.n_tris,
+                flat.nodes.size() / NODE_QUADS, flat.bvh_depth, build_ms, tree.sah_cost(1.0f));
+    uint64_t all_nodes = 0, all_tris = 0, all_rays = 0;
+    for (int gen = 0; gen < 4 && !rays.empty(); ++gen) {
+        uint64_t n_nodes = 0, n_tris = 0, hits = 0;
+        uint32_t max_sp = 0;
+        std::vector<Ray> next;
+        for (const Ray& r : rays) {
+            const Hit h = tree.trace(r, n_nodes, n_tris, max_sp);
+            if (h.tri < 0) continue;
+            ++hits;
+            Ray b;
+            float v[3], len2;
+            do {
+                for (int a = 0; a < 3; ++a) v[a] = 2.0f * rnd() - 1.0f;
+                len2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+            } while (len2 > 1.0f || len2 < 1e-6f);
+            const float back = v[0] * r.d[0] + v[1] * r.d[1] + v[2] * r.d[2];
+            for (int a = 0; a < 3; ++a) { b.o[a] = r.o[a] + r.d[a] * h.t; b.d[a] = back > 0 ? -v[a] : v[a]; }
+            next.push_back(b);
+        }
+        std::printf("  generation %d: %zu rays, %.1f %% hit, %.2f nodes / ray, %.2f triangle tests / ray, max stack %u\n", gen,
+                    rays.size(), 100.0 * hits / rays.size(), (double)n_nodes / rays.size(), (double)n_tris / rays.size(), max_sp);
+        all_nodes += n_nodes; all_tris += n_tris; all_rays += rays.size();
+        rays.swap(next);
+    }
+    std::printf("  all: %.2f nodes / ray, %.2f triangle tests / ray, step estimate (nodes + 0.6 tris) %.2f\n", (double)all_nodes / all_rays,
+                (double)all_tris / all_rays, ((double)all_nodes + 0.6 * all_tris) / all_rays);
+    return 0;
+}

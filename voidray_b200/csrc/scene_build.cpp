@@ -228,13 +228,13 @@ struct LeafOrderJob {
             sort_node(r.first, r.second, 1);
             const size_t mid = r.first + len / 2;  // bvh.rs:111-120
             // the halves are independent: hand the left one to another thread while any are free
-            if (len > 100000 && threads_left.fetch_sub(1) > 0) {
+            if (len > 4096 && threads_left.fetch_sub(1) > 0) {
                 spawned.emplace_back([this, r, mid]() {
                     run(r.first, mid);
                     threads_left.fetch_add(1);
                 });
             } else {
-                if (len > 100000) threads_left.fetch_add(1);
+                if (len > 4096) threads_left.fetch_add(1);
                 stack.emplace_back(r.first, mid);
             }
             stack.emplace_back(mid, r.second);
@@ -615,13 +615,13 @@ struct Builder {
         Box lbox, rbox;
         int32_t lcode, rcode;
         bool spawned = false;
-        if (n > 50000 && threads_left.fetch_sub(1) > 0) {
+        if (n > 2048 && threads_left.fetch_sub(1) > 0) {
             spawned = true;
             std::thread t([&]() { lcode = build(lo, mid, lbox, depth + 1, have_kids ? kids : nullptr); });
             rcode = build(mid, hi, rbox, depth + 1, have_kids ? kids + 2 : nullptr);
             t.join();
             threads_left.fetch_add(1);
-        } else if (n > 50000) {
+        } else if (n > 2048) {
             threads_left.fetch_add(1);
         }
         if (!spawned) {
