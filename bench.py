@@ -310,16 +310,18 @@ def run_ours(args):
     roofline = None
     if ab is not None and stats_acc["trace_ms"] > 0:
         achieved = ab["bytes_per_segment"] * stats_acc["seg"] / (stats_acc["trace_ms"] * 1e-3) / 1e9
-        traffic = None
+        traffic, l2_level = None, None
         tp = os.path.join(ROOT, "profiles", "trace_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(name)
+            tj = json.load(open(tp))
+            traffic = tj.get(name)
+            l2_level = tj.get(name + "_l2")  # ncu: bytes L2 delivered to the L1s per launch, hit rates
         roofline = {"bound": "hbm", "kernel": "k_trace (closest hit)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_segment": ab["bytes_per_segment"], "n_box": ab["n_box"], "n_tri": ab["n_tri"],
                     "segments_per_launch": stats_acc["seg"] / max(1, stats_acc["trace_launches"]),
                     "avg_launch_ms": stats_acc["trace_ms"] / max(1, stats_acc["trace_launches"]),
-                    "trace_share_of_step": stats_acc["trace_ms"] / dev_ms}
+                    "trace_share_of_step": stats_acc["trace_ms"] / dev_ms, "l2_level": l2_level}
 
     cpu = None
     extra = {}

@@ -18,5 +18,15 @@ per = [r + w for r, w in zip(rd, wr)]
 out[wl] = sum(per) / len(per)
 out[wl + "_detail"] = {"launches": len(per), "dram_bytes_per_launch": per, "duration_s": dur,
                        "dram_gbs_per_launch": [b / t / 1e9 for b, t in zip(per, dur)], "source": os.path.basename(rep)}
+# the level the kernel actually works at when the tree is cache-resident: bytes L2 delivered to the L1s, hit rates
+try:
+    l2rd = col("l1tex__m_xbar2l1tex_read_bytes.sum")
+    l1hit, l2hit = col("l1tex__t_sector_hit_rate.pct"), col("lts__t_sector_hit_rate.pct")
+    out[wl + "_l2"] = {"l2_to_l1_read_bytes_per_launch": sum(l2rd) / len(l2rd),
+                       "l2_to_l1_read_gbs": sum(l2rd) / sum(dur) / 1e9,
+                       "l1_sector_hit_pct_per_launch": l1hit, "l2_sector_hit_pct_per_launch": l2hit,
+                       "source": os.path.basename(rep)}
+except ValueError:
+    pass
 json.dump(out, open(path, "w"), indent=1)
 print(wl, "avg DRAM bytes/launch %.1f MB" % (out[wl] / 1e6), "GB/s per launch", [round(x) for x in out[wl + "_detail"]["dram_gbs_per_launch"]])
