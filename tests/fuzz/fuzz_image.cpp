@@ -20,7 +20,8 @@ int main(int argc, char** argv) {
     size_t ok = 0, bad = 0;
     for (size_t c = 0; c < corpus.size(); ++c) {
         DecodedImage img; std::string err;
-        if (!decode_image_memory(corpus[c].data(), corpus[c].size(), img, err)) { printf("BASE FAIL %s: %s\n", names[c].c_str(), err.c_str()); return 1; }
+        std::string ext = names[c].substr(names[c].rfind('.') + 1);
+        if (!decode_image_memory(corpus[c].data(), corpus[c].size(), img, err, ext.c_str())) { printf("BASE FAIL %s: %s\n", names[c].c_str(), err.c_str()); return 1; }
         for (int it = 0; it < iters; ++it) {
             std::vector<uint8_t> m = corpus[c];
             int mode = rng() % 4;
@@ -31,7 +32,7 @@ int main(int argc, char** argv) {
             // exact-size heap copy so that ASan sees any over-read
             uint8_t* p = (uint8_t*)malloc(m.size() ? m.size() : 1); memcpy(p, m.data(), m.size());
             DecodedImage o; std::string er;
-            bool r = decode_image_memory(p, m.size(), o, er);
+            bool r = decode_image_memory(p, m.size(), o, er, (it & 1) ? ext.c_str() : nullptr);
             if (r) { ++ok; std::vector<float> f; image_to_rgb32f(o, f); } else ++bad;
             free(p);
         }

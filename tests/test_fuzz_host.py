@@ -53,6 +53,15 @@ def _corpus(tmp_path):
     Image.fromarray(rgb).save(d / "base.jpg", quality=90, subsampling=0)
     Image.fromarray(rgb).save(d / "sub.jpg", quality=90, subsampling=2, restart_marker_blocks=2)
     Image.fromarray(rgb).save(d / "prog.jpg", quality=90, subsampling=2, progressive=True)
+    Image.fromarray(rgb).save(d / "rgb.bmp")
+    Image.fromarray(rgb).quantize(16).save(d / "pal4.bmp", bits=4)
+    Image.fromarray(rgb).save(d / "raw.tga")
+    Image.fromarray(rgb).save(d / "rle.tga", compression="tga_rle")
+    Image.fromarray(rgb).quantize(40).save(d / "pal.tga", compression="tga_rle")
+    Image.fromarray(rgb).save(d / "p6.ppm")
+    Image.fromarray((rgb[:, :, 0] > 128).astype(np.uint8) * 255).convert("1").save(d / "p4.pbm")
+    (d / "p3.ppm").write_text("P3 4 2 255\n" + " ".join(str(int(v)) for v in rgb[:2, :4].reshape(-1)))
+    (d / "t.ff").write_bytes(b"farbfeld" + (5).to_bytes(4, "big") + (3).to_bytes(4, "big") + bytes(range(120)))
     f = (rgb.astype(np.float32) / 16.0) ** 2
     cv2.imwrite(str(d / "t.hdr"), f)
     if hasattr(cv2, "IMWRITE_EXR_COMPRESSION"):

@@ -208,6 +208,82 @@ def test_openexr(tmp_path, compression, half):
         assert np.array_equal(got, img)
 
 
+def test_bmp_tga_pnm_farbfeld(tmp_path):
+    import struct
+
+    from PIL import Image
+
+    rgb = _rng_image(29, 45, 3, np.uint8)  # odd width: BMP row padding, TGA / PBM bit packing
+    want = rgb.astype(F32) / F32(255.0)
+    grey = rgb[:, :, 1]
+    wantg = np.repeat((grey.astype(F32) / F32(255.0))[:, :, None], 3, 2)
+    im = Image.fromarray(rgb)
+    cases = []
+    im.save(tmp_path / "rgb24.bmp")
+    cases.append(("rgb24.bmp", want))
+    Image.fromarray(np.dstack([rgb, grey])).save(tmp_path / "rgba32.bmp")
+    cases.append(("rgba32.bmp", want))
+    pal = im.quantize(200)
+    pal.save(tmp_path / "pal8.bmp")
+    cases.append(("pal8.bmp", np.asarray(pal.convert("RGB")).astype(F32) / F32(255.0)))
+    pal16 = im.quantize(16)
+    pal16.save(tmp_path / "pal4.bmp", bits=4)
+    cases.append(("pal4.bmp", np.asarray(Image.open(tmp_path / "pal4.bmp").convert("RGB")).astype(F32) / F32(255.0)))
+    Image.fromarray(grey).save(tmp_path / "grey8.bmp")
+    cases.append(("grey8.bmp", wantg))
+    bit = Image.fromarray((grey > 128).astype(np.uint8) * 255).convert("1")
+    bit.save(tmp_path / "bit.bmp")
+    wantb = np.repeat((np.asarray(bit).astype(F32))[:, :, None], 3, 2)
+    cases.append(("bit.bmp", wantb))
+    for rle in (False, True):
+        tag = "rle" if rle else "raw"
+        im.save(tmp_path / f"rgb_{tag}.tga", compression="tga_rle" if rle else None)
+        cases.append((f"rgb_{tag}.tga", want))
+        Image.fromarray(np.dstack([rgb, grey])).save(tmp_path / f"rgba_{tag}.tga", compression="tga_rle" if rle else None)
+        cases.append((f"rgba_{tag}.tga", want))
+        Image.fromarray(grey).save(tmp_path / f"grey_{tag}.tga", compression="tga_rle" if rle else None)
+        cases.append((f"grey_{tag}.tga", wantg))
+        pal.save(tmp_path / f"pal_{tag}.tga", compression="tga_rle" if rle else None)
+        cases.append((f"pal_{tag}.tga", np.asarray(pal.convert("RGB")).astype(F32) / F32(255.0)))
+    im.save(tmp_path / "flip.tga", orientation=1)  # top-down rows
+    cases.append(("flip.tga", want))
+    im.save(tmp_path / "p6.ppm")
+    cases.append(("p6.ppm", want))
+    Image.fromarray(grey).save(tmp_path / "p5.pgm")
+    cases.append(("p5.pgm", wantg))
+    bit.save(tmp_path / "p4.pbm")
+    cases.append(("p4.pbm", wantb))
+    (tmp_path / "p3.ppm").write_text("P3\n# comment\n%d %d\n255\n" % (rgb.shape[1], rgb.shape[0]) +
+                                     "\n".join(" ".join(str(v) for v in row.reshape(-1)) for row in rgb) + "\n")
+    cases.append(("p3.ppm", want))
+    (tmp_path / "p2.pgm").write_text("P2 %d %d 255\n" % (grey.shape[1], grey.shape[0]) + " ".join(str(v) for v in grey.reshape(-1)))
+    cases.append(("p2.pgm", wantg))
+    (tmp_path / "p1.pbm").write_text("P1\n%d %d\n" % (grey.shape[1], grey.shape[0]) +
+                                     "\n".join("".join("1" if v <= 128 else "0" for v in row) for row in grey))
+    cases.append(("p1.pbm", wantb))
+    g16 = _rng_image(11, 13, 3, np.uint16)
+    (tmp_path / "p6_16.ppm").write_bytes(b"P6\n13 11\n65535\n" + g16.astype(">u2").tobytes())
+    cases.append(("p6_16.ppm", g16.astype(F32) / F32(65535.0)))
+    rgba16 = np.dstack([g16, g16[:, :, 0]])
+    (tmp_path / "t.ff").write_bytes(b"farbfeld" + struct.pack(">II", 13, 11) + rgba16.astype(">u2").tobytes())
+    cases.append(("t.ff", g16.astype(F32) / F32(65535.0)))
+    for name, w in cases:
+        got = assets.load_image_native(str(tmp_path / name))
+        assert got.shape == w.shape, name
+        assert np.array_equal(got, w), name
+    # 16-bit 5-5-5 BMP: channel expansion rounds (v * 255 / 31), PIL truncates: at most one level apart
+    v = (rgb >> 3).astype(np.uint16)
+    px = (v[:, :, 0] << 10) | (v[:, :, 1] << 5) | v[:, :, 2]
+    rows = b"".join(row.astype("<u2").tobytes() + b"\0" * ((4 - (2 * row.size) % 4) % 4) for row in px[::-1])
+    hdr = struct.pack("<2sIHHI", b"BM", 54 + len(rows), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, px.shape[1], px.shape[0], 1, 16, 0,
+                                                                                len(rows), 2835, 2835, 0, 0)
+    (tmp_path / "rgb555.bmp").write_bytes(hdr + rows)
+    got = np.rint(assets.load_image_native(str(tmp_path / "rgb555.bmp")) * 255.0)
+    assert np.array_equal(got, np.rint(v.astype(np.float64) * 255.0 / 31.0))
+    ref = np.asarray(Image.open(tmp_path / "rgb555.bmp").convert("RGB")).astype(np.float64)
+    assert np.abs(got - ref).max() <= 1
+
+
 def test_errors_are_reported_not_fatal(tmp_path):
     with pytest.raises(_lib.VoidrayError, match="cannot open"):
         assets.load_image_native(str(tmp_path / "missing.png"))

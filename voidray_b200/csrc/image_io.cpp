@@ -9,6 +9,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1787,12 +1788,12 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
 }  // namespace
 
 namespace {
-bool decode_dispatch(const uint8_t* data, size_t size, DecodedImage& out, std::string& err);
+bool decode_dispatch(const uint8_t* data, size_t size, const char* ext, DecodedImage& out, std::string& err);
 }
 
-bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
+bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, std::string& err, const char* ext) {
     try {
-        return decode_dispatch(data, size, out, err);
+        return decode_dispatch(data, size, ext, out, err);
     } catch (const std::bad_alloc&) {
         err = "out of memory while decoding";
     } catch (const std::length_error&) {
@@ -1803,14 +1804,365 @@ bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, st
 }
 
 namespace {
-bool decode_dispatch(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
+// ===================================================================================== BMP
+// bits of a channel mask scaled to 8 bits with rounding (v * 255 / (2^n - 1))
+uint8_t scale_bits(uint32_t v, int bits) {
+    if (bits <= 0) return 0;
+    if (bits >= 8) return (uint8_t)(v >> (bits - 8));
+    const uint32_t maxv = (1u << bits) - 1;
+    return (uint8_t)((v * 255u + maxv / 2) / maxv);
+}
+
+bool decode_bmp(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
+    Reader r{data, size, false};
+    if (size < 26) {
+        err = "bmp: truncated header";
+        return false;
+    }
+    const uint32_t data_off = r.u32le(10), hdr = r.u32le(14);
+    int64_t w, h;
+    uint32_t bpp, compression = 0, colours = 0;
+    if (hdr == 12) {
+        w = (int16_t)(data[18] | data[19] << 8);
+        h = (int16_t)(data[20] | data[21] << 8);
+        bpp = data[24] | data[25] << 8;
+    } else if (hdr >= 40 && r.has(14, hdr)) {
+        w = (int32_t)r.u32le(18);
+        h = (int32_t)r.u32le(22);
+        bpp = data[28] | data[29] << 8;
+        compression = r.u32le(30);
+        colours = r.u32le(46);
+    } else {
+        err = "bmp: unsupported header";
+        return false;
+    }
+    const bool top_down = h < 0;
+    if (top_down) h = -h;
+    if (w <= 0 || h <= 0 || !(bpp == 1 || bpp == 4 || bpp == 8 || bpp == 16 || bpp == 24 || bpp == 32)) {
+        err = "bmp: bad dimensions or bit depth";
+        return false;
+    }
+    if (compression != 0 && compression != 3 && compression != 6) {
+        err = "bmp: RLE / embedded JPEG / PNG compression is not supported";
+        return false;
+    }
+    uint32_t mask[3] = {0, 0, 0};
+    if (compression == 3 || compression == 6) {
+        if (bpp != 16 && bpp != 32) {
+            err = "bmp: bit fields need 16 or 32 bits per pixel";
+            return false;
+        }
+        if (!r.has(54, 12)) {
+            err = "bmp: truncated bit masks";
+            return false;
+        }
+        for (int c = 0; c < 3; ++c) mask[c] = r.u32le(54 + 4 * (size_t)c);  // right after a 40-byte header, inside a larger one
+    } else if (bpp == 16) {
+        mask[0] = 0x7C00;
+        mask[1] = 0x03E0;
+        mask[2] = 0x001F;
+    } else if (bpp == 32) {
+        mask[0] = 0x00FF0000;
+        mask[1] = 0x0000FF00;
+        mask[2] = 0x000000FF;
+    }
+    int shift[3] = {0, 0, 0}, bits[3] = {0, 0, 0};
+    for (int c = 0; c < 3; ++c)
+        if (mask[c]) {
+            while (!((mask[c] >> shift[c]) & 1)) ++shift[c];
+            while (shift[c] + bits[c] < 32 && ((mask[c] >> (shift[c] + bits[c])) & 1)) ++bits[c];
+        }
+    const size_t row_bytes = (((size_t)w * bpp + 31) / 32) * 4;
+    if (!plausible_size((uint64_t)w, (uint64_t)h, 1, size, 8, "bmp", err)) return false;
+    if (!r.has(data_off, row_bytes * (size_t)h)) {
+        err = "bmp: pixel data outside the file";
+        return false;
+    }
+    std::vector<uint8_t> palette;
+    if (bpp <= 8) {
+        const size_t entry = hdr == 12 ? 3 : 4, n = colours ? colours : (1u << bpp);
+        const size_t at = 14 + (size_t)hdr;
+        if (n > 256 || !r.has(at, n * entry)) {
+            err = "bmp: bad palette";
+            return false;
+        }
+        palette.resize(3 * 256, 0);
+        for (size_t i = 0; i < n; ++i)
+            for (int c = 0; c < 3; ++c) palette[3 * i + c] = data[at + i * entry + (2 - c)];
+    }
+    out.w = (uint32_t)w;
+    out.h = (uint32_t)h;
+    out.bits = 8;
+    out.format = "bmp";
+    out.u8.resize((size_t)3 * w * h);
+    for (int64_t y = 0; y < h; ++y) {
+        const uint8_t* row = data + data_off + row_bytes * (size_t)(top_down ? y : h - 1 - y);
+        uint8_t* o = &out.u8[(size_t)3 * w * y];
+        for (int64_t x = 0; x < w; ++x, o += 3) {
+            if (bpp <= 8) {
+                const size_t bit = (size_t)x * bpp;
+                const uint32_t idx = (row[bit >> 3] >> (8 - bpp - (bit & 7))) & ((1u << bpp) - 1);
+                for (int c = 0; c < 3; ++c) o[c] = palette[3 * idx + c];
+            } else if (bpp == 24) {
+                o[0] = row[3 * x + 2];
+                o[1] = row[3 * x + 1];
+                o[2] = row[3 * x];
+            } else {
+                const uint32_t px = bpp == 16 ? (uint32_t)(row[2 * x] | row[2 * x + 1] << 8) : r.u32le((size_t)(row - data) + 4 * (size_t)x);
+                for (int c = 0; c < 3; ++c) o[c] = scale_bits((px & mask[c]) >> shift[c], bits[c]);
+            }
+        }
+    }
+    return true;
+}
+
+// ===================================================================================== TGA
+bool tga_header_plausible(const uint8_t* d, size_t size) {
+    if (size < 18) return false;
+    const int cmap = d[1], type = d[2], bpp = d[16];
+    const bool type_ok = type == 1 || type == 2 || type == 3 || type == 9 || type == 10 || type == 11;
+    return cmap <= 1 && type_ok && (bpp == 8 || bpp == 15 || bpp == 16 || bpp == 24 || bpp == 32) && (d[12] | d[13] << 8) > 0 &&
+           (d[14] | d[15] << 8) > 0;
+}
+
+bool decode_tga(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
+    if (!tga_header_plausible(data, size)) {
+        err = "tga: bad header";
+        return false;
+    }
+    const int id_len = data[0], cmap_type = data[1], type = data[2] & 7, rle = data[2] & 8;
+    const uint32_t cmap_first = data[3] | data[4] << 8, cmap_len = data[5] | data[6] << 8, cmap_bits = data[7];
+    const uint32_t w = data[12] | data[13] << 8, h = data[14] | data[15] << 8, bpp = data[16], desc = data[17];
+    const size_t pb = (bpp + 7) / 8;
+    size_t pos = 18 + (size_t)id_len;
+    auto to_rgb = [](const uint8_t* p, uint32_t bits, uint8_t* o) {
+        if (bits == 8) {
+            o[0] = o[1] = o[2] = p[0];
+        } else if (bits == 15 || bits == 16) {
+            const uint32_t v = p[0] | p[1] << 8;
+            o[0] = scale_bits((v >> 10) & 31, 5);
+            o[1] = scale_bits((v >> 5) & 31, 5);
+            o[2] = scale_bits(v & 31, 5);
+        } else {
+            o[0] = p[2];
+            o[1] = p[1];
+            o[2] = p[0];
+        }
+    };
+    std::vector<uint8_t> cmap;
+    if (cmap_type == 1) {
+        const size_t eb = (cmap_bits + 7) / 8;
+        if (!(cmap_bits == 15 || cmap_bits == 16 || cmap_bits == 24 || cmap_bits == 32) || pos + cmap_len * eb > size) {
+            err = "tga: bad colour map";
+            return false;
+        }
+        cmap.resize((size_t)3 * cmap_len);
+        for (uint32_t i = 0; i < cmap_len; ++i) to_rgb(data + pos + i * eb, cmap_bits, &cmap[3 * i]);
+        pos += cmap_len * eb;
+    }
+    if (type == 1 && (cmap_type != 1 || bpp != 8)) {
+        err = "tga: colour-mapped image without an 8-bit index / colour map";
+        return false;
+    }
+    if (type == 3 && bpp != 8 && bpp != 16) {
+        err = "tga: unsupported grey depth";
+        return false;
+    }
+    if (!plausible_size(w, h, pb, size, 128, "tga", err)) return false;
+    std::vector<uint8_t> px((size_t)w * h * pb);
+    if (!rle) {
+        if (pos + px.size() > size) {
+            err = "tga: truncated pixel data";
+            return false;
+        }
+        std::memcpy(px.data(), data + pos, px.size());
+    } else {
+        size_t o = 0;
+        while (o < px.size()) {
+            if (pos >= size) {
+                err = "tga: truncated RLE data";
+                return false;
+            }
+            const uint8_t hd = data[pos++];
+            const size_t count = (size_t)(hd & 127) + 1;
+            if (o + count * pb > px.size()) {
+                err = "tga: RLE packet past the image";
+                return false;
+            }
+            if (hd & 128) {
+                if (pos + pb > size) {
+                    err = "tga: truncated RLE data";
+                    return false;
+                }
+                for (size_t i = 0; i < count; ++i, o += pb) std::memcpy(&px[o], data + pos, pb);
+                pos += pb;
+            } else {
+                if (pos + count * pb > size) {
+                    err = "tga: truncated RLE data";
+                    return false;
+                }
+                std::memcpy(&px[o], data + pos, count * pb);
+                pos += count * pb;
+                o += count * pb;
+            }
+        }
+    }
+    out.w = w;
+    out.h = h;
+    out.bits = 8;
+    out.format = "tga";
+    out.u8.resize((size_t)3 * w * h);
+    const bool top_down = desc & 0x20, right_left = desc & 0x10;
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const uint32_t sy = top_down ? y : h - 1 - y, sx = right_left ? w - 1 - x : x;
+            const uint8_t* p = &px[((size_t)sy * w + sx) * pb];
+            uint8_t* o = &out.u8[3 * ((size_t)y * w + x)];
+            if (type == 1) {
+                const uint32_t idx = p[0];
+                if (idx < cmap_first || idx - cmap_first >= cmap_len) {
+                    err = "tga: colour index out of range";
+                    return false;
+                }
+                std::memcpy(o, &cmap[3 * (size_t)(idx - cmap_first)], 3);
+            } else if (type == 3) {
+                o[0] = o[1] = o[2] = p[0];  // 16-bit grey = grey + alpha
+            } else {
+                to_rgb(p, bpp, o);
+            }
+        }
+    return true;
+}
+
+// ===================================================================================== PNM (P1..P6), farbfeld
+bool decode_pnm(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
+    const int kind = data[1] - '0';
+    size_t pos = 2;
+    auto token = [&](uint32_t& v) -> bool {
+        for (;;) {  // whitespace and comments
+            while (pos < size && (data[pos] == ' ' || data[pos] == '\t' || data[pos] == '\r' || data[pos] == '\n')) ++pos;
+            if (pos < size && data[pos] == '#') {
+                while (pos < size && data[pos] != '\n') ++pos;
+                continue;
+            }
+            break;
+        }
+        if (pos >= size || data[pos] < '0' || data[pos] > '9') return false;
+        uint64_t x = 0;
+        while (pos < size && data[pos] >= '0' && data[pos] <= '9') {
+            x = x * 10 + (uint64_t)(data[pos++] - '0');
+            if (x > 0xFFFFFFFFull) return false;
+        }
+        v = (uint32_t)x;
+        return true;
+    };
+    uint32_t w = 0, h = 0, maxv = 1;
+    if (!token(w) || !token(h) || ((kind != 1 && kind != 4) && !token(maxv)) || maxv == 0 || maxv > 65535) {
+        err = "pnm: bad header";
+        return false;
+    }
+    const bool ascii = kind <= 3, bitmap = kind == 1 || kind == 4;
+    const int ch = (kind == 3 || kind == 6) ? 3 : 1;
+    const bool wide = maxv > 255;
+    if (!plausible_size(w, h, 1, size, bitmap ? 8 : 1, "pnm", err)) return false;
+    if (!ascii) ++pos;  // the single whitespace byte after the header
+    out.w = w;
+    out.h = h;
+    out.format = "pnm";
+    out.bits = wide ? 16 : 8;
+    if (wide) out.u16.resize((size_t)3 * w * h);
+    else out.u8.resize((size_t)3 * w * h);
+    // samples are stored as they are, like image 0.24's decoder (maxval only chooses between 8 and 16 bits)
+    auto put = [&](size_t px, int c, uint32_t v) {
+        if (wide) out.u16[3 * px + c] = (uint16_t)v;
+        else out.u8[3 * px + c] = (uint8_t)v;
+        if (ch == 1) {
+            if (wide) out.u16[3 * px + 1] = out.u16[3 * px + 2] = (uint16_t)v;
+            else out.u8[3 * px + 1] = out.u8[3 * px + 2] = (uint8_t)v;
+        }
+    };
+    const size_t n_px = (size_t)w * h;
+    if (ascii) {
+        for (size_t px = 0; px < n_px; ++px)
+            for (int c = 0; c < ch; ++c) {
+                uint32_t v;
+                if (bitmap) {  // digits need no separators in P1
+                    while (pos < size && data[pos] != '0' && data[pos] != '1') {
+                        if (data[pos] == '#') while (pos < size && data[pos] != '\n') ++pos;
+                        else ++pos;
+                    }
+                    if (pos >= size) {
+                        err = "pnm: truncated data";
+                        return false;
+                    }
+                    v = data[pos++] == '1' ? 0u : 255u;
+                } else if (!token(v) || v > maxv) {
+                    err = "pnm: bad sample";
+                    return false;
+                }
+                put(px, c, v);
+            }
+        return true;
+    }
+    if (bitmap) {
+        const size_t row_bytes = ((size_t)w + 7) / 8;
+        if (pos + row_bytes * h > size) {
+            err = "pnm: truncated data";
+            return false;
+        }
+        for (uint32_t y = 0; y < h; ++y)
+            for (uint32_t x = 0; x < w; ++x) put((size_t)y * w + x, 0, (data[pos + row_bytes * y + (x >> 3)] >> (7 - (x & 7))) & 1 ? 0u : 255u);
+        return true;
+    }
+    const size_t sb = wide ? 2 : 1;
+    if (pos + n_px * ch * sb > size) {
+        err = "pnm: truncated data";
+        return false;
+    }
+    for (size_t px = 0; px < n_px; ++px)
+        for (int c = 0; c < ch; ++c) {
+            const uint8_t* p = data + pos + (px * ch + c) * sb;
+            put(px, c, wide ? (uint32_t)(p[0] << 8 | p[1]) : p[0]);
+        }
+    return true;
+}
+
+bool decode_farbfeld(const uint8_t* data, size_t size, DecodedImage& out, std::string& err) {
+    Reader r{data, size, true};
+    if (size < 16) {
+        err = "farbfeld: truncated header";
+        return false;
+    }
+    const uint32_t w = r.u32(8), h = r.u32(12);
+    if (!plausible_size(w, h, 8, size, 1, "farbfeld", err)) return false;
+    if ((uint64_t)w * h * 8 + 16 > size) {
+        err = "farbfeld: truncated data";
+        return false;
+    }
+    out.w = w;
+    out.h = h;
+    out.bits = 16;
+    out.format = "farbfeld";
+    out.u16.resize((size_t)3 * w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i)
+        for (int c = 0; c < 3; ++c) out.u16[3 * i + c] = r.u16(16 + 8 * i + 2 * (size_t)c);
+    return true;
+}
+
+bool decode_dispatch(const uint8_t* data, size_t size, const char* ext, DecodedImage& out, std::string& err) {
     out = DecodedImage();
     if (size >= 8 && !std::memcmp(data, "\x89PNG\r\n\x1a\n", 8)) return decode_png(data, size, out, err);
     if (size >= 4 && data[0] == 0xFF && data[1] == 0xD8) return decode_jpeg(data, size, out, err);
     if (size >= 8 && ((data[0] == 'I' && data[1] == 'I') || (data[0] == 'M' && data[1] == 'M'))) return decode_tiff(data, size, out, err);
     if (size >= 10 && (!std::memcmp(data, "#?RADIANCE", 10) || !std::memcmp(data, "#?RGBE", 6))) return decode_hdr(data, size, out, err);
     if (size >= 4 && data[0] == 0x76 && data[1] == 0x2F && data[2] == 0x31 && data[3] == 0x01) return decode_exr(data, size, out, err);
-    err = "unrecognised image format (PNG, JPEG, TIFF, Radiance HDR and OpenEXR are supported)";
+    if (size >= 2 && data[0] == 'B' && data[1] == 'M') return decode_bmp(data, size, out, err);
+    if (size >= 3 && data[0] == 'P' && data[1] >= '1' && data[1] <= '6' && (data[2] == ' ' || data[2] == '\n' || data[2] == '\r' || data[2] == '\t' || data[2] == '#'))
+        return decode_pnm(data, size, out, err);
+    if (size >= 8 && !std::memcmp(data, "farbfeld", 8)) return decode_farbfeld(data, size, out, err);
+    // TGA has no signature: the file extension decides (as in image::open), else a plausible header
+    if ((ext && !std::strcmp(ext, "tga")) || (!ext && tga_header_plausible(data, size))) return decode_tga(data, size, out, err);
+    err = "unrecognised image format (PNG, JPEG, TIFF, BMP, TGA, PNM, farbfeld, Radiance HDR and OpenEXR are supported)";
     return false;
 }
 }  // namespace
@@ -1837,7 +2189,10 @@ bool decode_image_file(const char* path, DecodedImage& out, std::string& err) {
         err = "short read";
         return false;
     }
-    return decode_image_memory(buf.data(), buf.size(), out, err);
+    std::string ext;
+    if (const char* dot = std::strrchr(path, '.'))
+        for (const char* c = dot + 1; *c; ++c) ext.push_back((char)std::tolower((unsigned char)*c));
+    return decode_image_memory(buf.data(), buf.size(), out, err, ext.c_str());
 }
 
 void image_to_rgb32f(const DecodedImage& img, std::vector<float>& rgb) {

@@ -17,13 +17,15 @@ struct DecodedImage {
     std::vector<uint8_t> u8;     // 3*w*h when bits == 8
     std::vector<uint16_t> u16;   // 3*w*h when bits == 16
     std::vector<float> f32;      // 3*w*h when bits == 32
-    const char* format = "";     // "png", "jpeg", "tiff", "hdr", "exr"
+    const char* format = "";     // "png", "jpeg", "tiff", "bmp", "tga", "pnm", "farbfeld", "hdr", "exr"
 };
 
-// Decodes PNG, baseline/progressive JPEG, TIFF (strips; none / LZW / Deflate / PackBits), Radiance HDR,
-// and scan-line OpenEXR (none / RLE / ZIPS / ZIP / PIZ), recognised by their magic bytes.
+// Decodes PNG, baseline/progressive JPEG, TIFF (strips; none / LZW / Deflate / PackBits), BMP (uncompressed, bit
+// fields), TGA (colour-mapped / true-colour / grey, RLE), PNM (P1..P6), farbfeld, Radiance HDR and scan-line OpenEXR
+// (none / RLE / ZIPS / ZIP / PIZ), recognised by their magic bytes (TGA: by extension).
 bool decode_image_file(const char* path, DecodedImage& out, std::string& err);
-bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, std::string& err);
+// ext: lower-case file extension when known (TGA has no signature); nullptr = guess from the bytes alone.
+bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, std::string& err, const char* ext = nullptr);
 
 // to_rgb32f: row-major, top row first, 3 floats per pixel.
 void image_to_rgb32f(const DecodedImage& img, std::vector<float>& rgb);
