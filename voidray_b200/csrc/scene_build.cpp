@@ -756,8 +756,8 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                 timer.lap("triangle boxes");
                 RawVector<uint32_t> order;
                 reference_leaf_order(boxes.data(), nt, order);
-                parallel_for(nt, [&](size_t b, size_t e) {
-                    for (size_t i = b; i < e; ++i) rank[order[i]] = (uint32_t)i;
+                parallel_for(nt, [&](size_t i_begin, size_t i_end) {
+                    for (size_t i = i_begin; i < i_end; ++i) rank[order[i]] = (uint32_t)i;
                 });
                 timer.lap("reference leaf order");
             } else {
