@@ -94,6 +94,18 @@ int32_t vr_scene_add_mesh(vr_scene* scene, const float* positions, const float* 
 int32_t vr_scene_add_mesh_from_obj_file(vr_scene* scene, const char* path, uint32_t* surface, uint32_t* n_vertices,
                                         uint32_t* n_triangles);
 
+/* Host-only: the loader behind vr_scene_add_mesh_from_obj_file (needs no CUDA device). The arrays are malloc'ed:
+ * positions 3*n_vertices, uvs 2*n_vertices, normals 3*n_vertices, indices n_indices; release with vr_obj_free. */
+typedef struct vr_obj_mesh {
+    uint32_t n_vertices, n_indices;
+    float* positions;
+    float* uvs;
+    float* normals;
+    uint32_t* indices;
+} vr_obj_mesh;
+int32_t vr_obj_load(const char* path, vr_obj_mesh* out);
+int32_t vr_obj_free(vr_obj_mesh* mesh);
+
 /* Scene::add_analytic_surface(Surfaces::sphere(center, radius)) — voidray_common/src/surfaces.rs:18-20,31-80 */
 int32_t vr_scene_add_sphere(vr_scene* scene, const float center[3], float radius, uint32_t* surface);
 /* Scene::add_analytic_surface(Surfaces::ground_plane(height)) — surfaces.rs:22-24,82-114 */

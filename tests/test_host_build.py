@@ -87,3 +87,44 @@ def test_leaf_order_parallel_top_equals_serial(mode):
     serial = _native_order(boxes, par_min=10**9)
     assert np.array_equal(_native_order(boxes, par_min=1 << 16), serial)
     assert sorted(serial.tolist()) == list(range(400000))
+
+
+# ---- the native OBJ loader (vr_obj_load = the loader behind vr_scene_add_mesh_from_obj_file) ----------------------
+from voidray_b200 import assets  # noqa: E402
+
+ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets")
+
+
+@pytest.mark.parametrize("name", ["cube.obj", "mushroom.obj", "fancy_monkey.obj", "mossy_ground.obj", "material_testing_stand.obj"])
+def test_native_obj_loader_matches_python_loader(name):
+    # obj-rs 0.7.0 `load_obj::<TexturedVertex, u32>`: one vertex per distinct v/vt/vn triple in first-seen order
+    a = assets.load_obj_native(os.path.join(ASSETS, name))
+    b = assets.load_obj(os.path.join(ASSETS, name))
+    assert np.array_equal(a.indices, b.indices)
+    assert np.array_equal(a.positions, b.positions) and np.array_equal(a.uvs, b.uvs) and np.array_equal(a.normals, b.normals)
+
+
+def test_native_obj_loader_edge_cases(tmp_path):
+    def load(text):
+        p = tmp_path / "t.obj"
+        p.write_text(text)
+        return assets.load_obj_native(str(p))
+
+    base = "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nvn 0 0 1\n"
+    m = load(base + "f 1/1/1 2/2/1 3/3/1\n")
+    assert m.indices.tolist() == [0, 1, 2] and m.positions.shape == (3, 3)
+    # negative (relative) indices, a very long comment line, CRLF line ends, other statements ignored
+    m2 = load("# " + "x" * 5000 + "\r\nmtllib a.mtl\r\no thing\r\n" + base.replace("\n", "\r\n") +
+              "usemtl m\r\ns off\r\nf -3/-3/-1 -2/-2/-1 -1/-1/-1\r\n")
+    assert np.array_equal(m2.positions, m.positions) and np.array_equal(m2.uvs, m.uvs) and m2.indices.tolist() == [0, 1, 2]
+    # shared corners are deduplicated, distinct triples are not
+    m3 = load(base + "f 1/1/1 2/2/1 3/3/1\nf 1/1/1 3/3/1 2/1/1\n")
+    assert m3.indices.tolist() == [0, 1, 2, 0, 2, 3] and m3.positions.shape == (4, 3)
+    for bad, why in [(base + "f 1/1/1 2/2/1 3/3/1 1/2/1\n", "triangulated"), (base + "f 1 2 3\n", "position/texture/normal"),
+                     (base + "f 1/1/1 2/2/1 9/3/1\n", "missing position"), ("f 1/1/1 1/1/1 1/1/1\n", "missing position"),
+                     (base + "f 1/1/1 2/2/1\n", "triangulated"), (base + "f 1/7/1 2/2/1 3/3/1\n", "missing texture"),
+                     (base + "v 1 2\n", "malformed v")]:
+        with pytest.raises(_lib.VoidrayError, match=why):
+            load(bad)
+    with pytest.raises(_lib.VoidrayError, match="cannot open"):
+        assets.load_obj_native(str(tmp_path / "missing.obj"))

@@ -27,6 +27,11 @@ class MaterialDescC(C.Structure):
                 ("emittance", C.c_float), ("transparent", C.c_int32)]
 
 
+class ObjMeshC(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint32), ("n_indices", C.c_uint32), ("positions", C.POINTER(C.c_float)),
+                ("uvs", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_uint32))]
+
+
 class RenderSettingsC(C.Structure):
     _fields_ = [("total_samples", C.c_uint32), ("max_bounces", C.c_uint32), ("firefly_clamp", C.c_float),
                 ("render_mode", C.c_int32), ("pixel_mapping", C.c_int32), ("integrator", C.c_int32),
@@ -66,6 +71,8 @@ SIGNATURES = {
     "vr_image_free": [_FP],
     "vr_scene_set_environment_hdri_file": [_P, C.c_char_p],
     "vr_debug_reference_leaf_order": [_FP, C.c_uint64, _UP],
+    "vr_obj_load": [C.c_char_p, C.POINTER(ObjMeshC)],
+    "vr_obj_free": [C.POINTER(ObjMeshC)],
     "vr_scene_add_sphere": [_P, _FP, _F, _UP],
     "vr_scene_add_ground_plane": [_P, _F, _UP],
     "vr_scene_add_material": [_P, C.POINTER(MaterialDescC), _UP],

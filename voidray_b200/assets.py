@@ -72,6 +72,27 @@ def load_obj(path: str):
     )
 
 
+def load_obj_native(path: str) -> MeshData:
+    """`Mesh::from_file` (core/mesh.rs:46-74) through the library's own OBJ loader (vr_obj_load,
+    csrc/scene_build.cpp) — the loader `Scene.add_mesh_from_file` uses at commit. Raises VoidrayError where the
+    reference would panic."""
+    import ctypes as C
+
+    from . import _lib
+    from .scene import MeshData
+
+    lib = _lib.load()
+    m = _lib.ObjMeshC()
+    _lib.check(lib.vr_obj_load(os.fsencode(path), C.byref(m)))
+    try:
+        nv, ni = m.n_vertices, m.n_indices
+        arr = lambda p, n, t: np.ctypeslib.as_array(p, shape=(n,)).astype(t, copy=True) if n else np.zeros(0, t)  # noqa: E731
+        return MeshData(positions=arr(m.positions, 3 * nv, F32).reshape(-1, 3), uvs=arr(m.uvs, 2 * nv, F32).reshape(-1, 2),
+                        normals=arr(m.normals, 3 * nv, F32).reshape(-1, 3), indices=arr(m.indices, ni, np.uint32))
+    finally:
+        lib.vr_obj_free(C.byref(m))
+
+
 def load_image_native(path: str) -> np.ndarray:
     """`image::open(path).to_rgb32f()` through the library's own decoders (vr_image_load_rgb32f,
     csrc/image_io.cpp): PNG, JPEG, TIFF, Radiance HDR, OpenEXR. Returns (h, w, 3) f32. Raises VoidrayError

@@ -450,6 +450,40 @@ int32_t vr_scene_add_mesh_from_obj_file(vr_scene* scene, const char* path, uint3
     return VR_OK;
 } VR_CATCH
 
+int32_t vr_obj_load(const char* path, vr_obj_mesh* out) try {
+    if (!path || !out) return fail(VR_ERR_INVALID, "null argument");
+    std::memset(out, 0, sizeof *out);
+    HostMesh m;
+    std::string err;
+    if (!load_obj_file(path, m, err)) return fail(VR_ERR_INVALID, std::string(path) + ": " + err);
+    auto dup = [](const void* src, size_t bytes) -> void* {
+        void* p = std::malloc(bytes ? bytes : 1);
+        if (p && bytes) std::memcpy(p, src, bytes);
+        return p;
+    };
+    out->n_vertices = m.n_vertices;
+    out->n_indices = (uint32_t)m.idx.size();
+    out->positions = (float*)dup(m.pos.data(), m.pos.size() * sizeof(float));
+    out->uvs = (float*)dup(m.uv.data(), m.uv.size() * sizeof(float));
+    out->normals = (float*)dup(m.nrm.data(), m.nrm.size() * sizeof(float));
+    out->indices = (uint32_t*)dup(m.idx.data(), m.idx.size() * sizeof(uint32_t));
+    if (!out->positions || !out->uvs || !out->normals || !out->indices) {
+        vr_obj_free(out);
+        return fail(VR_ERR_OOM, "host allocation failed");
+    }
+    return VR_OK;
+} VR_CATCH
+
+int32_t vr_obj_free(vr_obj_mesh* mesh) try {
+    if (!mesh) return VR_OK;
+    std::free(mesh->positions);
+    std::free(mesh->uvs);
+    std::free(mesh->normals);
+    std::free(mesh->indices);
+    std::memset(mesh, 0, sizeof *mesh);
+    return VR_OK;
+} VR_CATCH
+
 int32_t vr_scene_add_sphere(vr_scene* scene, const float center[3], float radius, uint32_t* surface) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!center) return fail(VR_ERR_INVALID, "null center");

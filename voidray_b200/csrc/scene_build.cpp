@@ -983,10 +983,22 @@ bool load_obj_file(const char* path, HostMesh& out, std::string& err) {
     std::unordered_map<Key, uint32_t, KeyHash> seen;
     std::vector<Key> order;
     out = HostMesh();
-    char line[1024];
+    // the whole file in memory, one NUL-terminated line at a time (lines of any length)
+    std::vector<char> text;
+    {
+        char buf[65536];
+        size_t got;
+        while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.insert(text.end(), buf, buf + got);
+        text.push_back('\n');
+        text.push_back(0);
+    }
     bool ok = true;
-    while (ok && std::fgets(line, sizeof line, f)) {
-        char* s = line;
+    for (size_t line_begin = 0; ok && line_begin + 1 < text.size();) {
+        size_t line_end = line_begin;
+        while (text[line_end] != '\n' && text[line_end] != 0) ++line_end;
+        text[line_end] = 0;
+        char* s = text.data() + line_begin;
+        line_begin = line_end + 1;
         while (*s == ' ' || *s == '\t') ++s;
         if (s[0] == 'v' && (s[1] == ' ' || s[1] == '\t')) {
             float x = 0, y = 0, z = 0;
@@ -1043,9 +1055,9 @@ bool load_obj_file(const char* path, HostMesh& out, std::string& err) {
     out.nrm.resize(3 * order.size());
     for (size_t i = 0; i < order.size(); ++i) {
         const Key& k = order[i];
-        if ((size_t)k.p * 3 + 2 >= pos.size() + 0 && (size_t)k.p * 3 + 2 > pos.size() - 1) { err = "face refers to a missing position"; return false; }
-        if ((size_t)k.t * 2 + 1 > tex.size() - 1 || tex.empty()) { err = "face refers to a missing texture coordinate"; return false; }
-        if ((size_t)k.n * 3 + 2 > nrm.size() - 1 || nrm.empty()) { err = "face refers to a missing normal"; return false; }
+        if ((uint64_t)k.p >= pos.size() / 3) { err = "face refers to a missing position"; return false; }
+        if ((uint64_t)k.t >= tex.size() / 2) { err = "face refers to a missing texture coordinate"; return false; }
+        if ((uint64_t)k.n >= nrm.size() / 3) { err = "face refers to a missing normal"; return false; }
         for (int a = 0; a < 3; ++a) out.pos[3 * i + a] = pos[3 * k.p + a];
         for (int a = 0; a < 2; ++a) out.uv[2 * i + a] = tex[2 * k.t + a];
         for (int a = 0; a < 3; ++a) out.nrm[3 * i + a] = nrm[3 * k.n + a];
