@@ -128,3 +128,16 @@ def test_native_obj_loader_edge_cases(tmp_path):
             load(bad)
     with pytest.raises(_lib.VoidrayError, match="cannot open"):
         assets.load_obj_native(str(tmp_path / "missing.obj"))
+
+
+def test_bvh_quality_meter_builds_and_runs(tmp_path):
+    # scripts/bvh_stats.cpp: the offline meter behind the builder numbers in profiles/README.md
+    import subprocess
+    root = os.path.dirname(ASSETS)
+    exe = str(tmp_path / "bvh_stats")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-I", os.path.join(root, "voidray_b200", "csrc"),
+                        "-x", "c++", os.path.join(root, "voidray_b200", "csrc", "scene_build.cpp"),
+                        os.path.join(root, "scripts", "bvh_stats.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([exe, os.path.join(ASSETS, "fancy_monkey.obj")], capture_output=True, text=True, timeout=300).stdout
+    assert "3936 triangles" in out and "nodes / ray" in out and "SAH cost" in out
