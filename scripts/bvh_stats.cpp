@@ -180,6 +180,7 @@ int main(int argc, char** argv) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t v = 0; v < big.n_vertices; ++v)
         for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], big.pos[3 * v + a]); hi[a] = std::max(hi[a], big.pos[3 * v + a]); }
+    const float lo_all[3] = {lo[0], lo[1], lo[2]}, hi_all[3] = {hi[0], hi[1], hi[2]};
     sc.meshes.push_back(std::move(big));
     HostSurface sf; sf.kind = 0; sf.mesh = 0; sc.surfaces.push_back(sf);
     MaterialRec m{}; m.albedo_tex = -1; m.normal_tex = -1; sc.materials.push_back(m);
@@ -235,6 +236,27 @@ int main(int argc, char** argv) {
                     rays.size(), 100.0 * hits / rays.size(), (double)n_nodes / rays.size(), (double)n_tris / rays.size(), max_sp);
         all_nodes += n_nodes; all_tris += n_tris; all_rays += rays.size();
         rays.swap(next);
+    }
+    // the tree only culls: on a sample of the last generation's parents, the walk must find exactly the hit a loop
+    // over every triangle finds
+    {
+        uint64_t dummy_n = 0, dummy_t = 0, mismatches = 0, checked = 0;
+        uint32_t dummy_sp = 0;
+        g_state = 777u;
+        for (int k = 0; k < 3000; ++k) {
+            Ray r;
+            for (int a = 0; a < 3; ++a) { r.o[a] = lo_all[a] + rnd() * (hi_all[a] - lo_all[a]); r.d[a] = 2.0f * rnd() - 1.0f; }
+            const Hit h = tree.trace(r, dummy_n, dummy_t, dummy_sp);
+            Hit b{INFINITY, -1};
+            for (uint32_t i = 0; i < flat.n_tris; ++i) {
+                float t;
+                if (tree.tri_hit((int)i, r, t) && t < b.t) b = Hit{t, (int)i};
+            }
+            ++checked;
+            if (h.t != b.t) ++mismatches;
+        }
+        std::printf("  brute-force check: %llu of %llu random rays differ\n", (unsigned long long)mismatches, (unsigned long long)checked);
+        if (mismatches) return 1;
     }
     std::printf("  all: %.2f nodes / ray, %.2f triangle tests / ray, step estimate (nodes + 0.6 tris) %.2f\n", (double)all_nodes / all_rays,
                 (double)all_tris / all_rays, ((double)all_nodes + 0.6 * all_tris) / all_rays);

@@ -141,3 +141,4 @@ def test_bvh_quality_meter_builds_and_runs(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     out = subprocess.run([exe, os.path.join(ASSETS, "fancy_monkey.obj")], capture_output=True, text=True, timeout=300).stdout
     assert "3936 triangles" in out and "nodes / ray" in out and "SAH cost" in out
+    assert "brute-force check: 0 of 3000 random rays differ" in out  # the quantised tree never culls a real hit
