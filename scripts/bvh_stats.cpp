@@ -4,8 +4,9 @@
 // for camera rays and three generations of diffuse bounce rays. Prints node visits and triangle tests per ray
 // and the tree's SAH cost, so that builder changes can be compared without a GPU.
 //
-//   g++ -O2 -std=c++17 -pthread -ffp-contract=off -Ivoidray_b200/csrc -x c++ voidray_b200/csrc/scene_build.cpp \
-//       scripts/bvh_stats.cpp -o /tmp/bvh_stats && /tmp/bvh_stats assets/mossy_ground.obj [copies_x copies_z]
+//   g++ -O2 -std=c++17 -pthread -ffp-contract=off -Ivoidray_b200/csrc -x c++ voidray_b200/csrc/scene_build.cpp
+//       scripts/bvh_stats.cpp -o /tmp/bvh_stats   (one command line)
+//   /tmp/bvh_stats assets/mossy_ground.obj [copies_x copies_z]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -195,6 +196,19 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!flatten_scene(sc, flat, err)) { std::printf("%s\n", err.c_str()); return 1; }
     const double build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    {
+        // FNV-1a of what the device receives: the same scene must flatten to the same bytes on every run
+        auto fnv = [](const void* ptr, size_t n, uint64_t d) {
+            const unsigned char* b = (const unsigned char*)ptr;
+            for (size_t i = 0; i < n; ++i) d = (d ^ b[i]) * 1099511628211ull;
+            return d;
+        };
+        uint64_t d = 1469598103934665603ull;
+        d = fnv(flat.nodes.data(), flat.nodes.size() * sizeof(Quad), d);
+        d = fnv(flat.tri_isect.data(), flat.tri_isect.size() * sizeof(Quad), d);
+        d = fnv(flat.tri_shade.data(), flat.tri_shade.size() * sizeof(Quad), d);
+        std::printf("flatten digest %016llx\n", (unsigned long long)d);
+    }
     Tree tree(flat);
     // camera rays on a 256 x 256 grid, then three generations of diffuse bounces (origin = hit point, direction = a
     // random unit vector flipped into the hemisphere facing back along the ray)

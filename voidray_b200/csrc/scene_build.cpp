@@ -338,7 +338,45 @@ struct Builder {
     uint32_t leaf_max = LEAF_MAX_TRIS;
     float node_cost = 1.0f;
 
-    Builder(RawVector<Prim>& p, RawVector<Quad>& n) : prims(p), nodes(n) {}
+    RawVector<uint32_t> subtree_nodes;  // per node: inner nodes in its subtree, itself included (for the renumbering)
+    Builder(RawVector<Prim>& p, RawVector<Quad>& n) : prims(p), nodes(n) { subtree_nodes.resize(n.size() / NODE_QUADS); }
+
+    // Copies the subtree rooted at old node `from` into `dst` in depth-first pre-order starting at index `to`
+    // (parent, left subtree, right subtree): the new index of a right child is known from the left subtree's size,
+    // so large subtrees are renumbered on other threads.
+    void renumber(uint32_t from, uint32_t to, RawVector<Quad>& dst) {
+        struct Item {
+            uint32_t from, to;
+        };
+        std::vector<Item> todo;
+        std::vector<std::thread> spawned;
+        todo.push_back(Item{from, to});
+        while (!todo.empty()) {
+            const Item it = todo.back();
+            todo.pop_back();
+            const Quad* src = &nodes[(size_t)it.from * NODE_QUADS];
+            Quad* out = &dst[(size_t)it.to * NODE_QUADS];
+            int32_t c0, c1;
+            std::memcpy(&c0, &src[1].z, 4);
+            std::memcpy(&c1, &src[1].w, 4);
+            const uint32_t left_to = it.to + 1, right_to = it.to + 1 + (c0 >= 0 ? subtree_nodes[c0] : 0u);
+            out[0] = src[0];
+            out[1] = Quad{src[1].x, src[1].y, c0 >= 0 ? bits_f(left_to) : src[1].z, c1 >= 0 ? bits_f(right_to) : src[1].w};
+            if (c1 >= 0) {
+                if (subtree_nodes[c1] > 65536 && threads_left.fetch_sub(1) > 0) {
+                    spawned.emplace_back([this, c1, right_to, &dst]() {
+                        renumber((uint32_t)c1, right_to, dst);
+                        threads_left.fetch_add(1);
+                    });
+                } else {
+                    if (subtree_nodes[c1] > 65536) threads_left.fetch_add(1);
+                    todo.push_back(Item{(uint32_t)c1, right_to});
+                }
+            }
+            if (c0 >= 0) todo.push_back(Item{(uint32_t)c0, left_to});
+        }
+        for (std::thread& t : spawned) t.join();
+    }
 
     struct Bins {
         Box box[3][BINS];
@@ -629,6 +667,7 @@ struct Builder {
             rcode = build(mid, hi, rbox, depth + 1, have_kids ? kids + 2 : nullptr);
         }
         write_node(node, lcode, lbox, rcode, rbox);
+        subtree_nodes[node] = 1u + (lcode >= 0 ? subtree_nodes[lcode] : 0u) + (rcode >= 0 ? subtree_nodes[rcode] : 0u);
         return (int32_t)node;
     }
 
@@ -875,8 +914,17 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         if (code < 0) {
             builder.write_node(0, code, root_box, Builder::leaf_code(0, 0), empty);
         } else {
-            // copy the subtree root into slot 0 (children indices are absolute, so this is a plain copy)
-            for (int q = 0; q < NODE_QUADS; ++q) out.nodes[q] = out.nodes[(size_t)code * NODE_QUADS + q];
+            // Subtrees built on other threads take their node numbers in whatever order the threads run. Renumber in
+            // depth-first pre-order (parent, left subtree, right subtree — what a single thread produces): the layout
+            // the kernel sees is then the same on every run and machine, and a parent sits next to its left child.
+            const size_t n_nodes = builder.next_node.load();
+            RawVector<Quad> ordered(n_nodes * NODE_QUADS);
+            const uint32_t next = 1u + builder.subtree_nodes[code];
+            builder.renumber((uint32_t)code, 1u, ordered);
+            // node 0 is the root: a copy of node 1 (children indices are absolute, so this is a plain copy)
+            for (int q = 0; q < NODE_QUADS; ++q) ordered[q] = ordered[NODE_QUADS + q];
+            out.nodes.swap(ordered);
+            builder.next_node = next;
         }
     }
     out.nodes.resize((size_t)builder.next_node.load() * NODE_QUADS);
