@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
+#include <system_error>
 #include <thread>
 #include <unordered_map>
 
@@ -59,6 +60,17 @@ namespace {
 
 inline size_t worker_count() { return std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32); }
 
+// std::thread creation can fail (thread limits of a container): the caller then does the work itself
+template <typename F>
+bool try_spawn(std::vector<std::thread>& pool, F&& f) {
+    try {
+        pool.emplace_back(std::forward<F>(f));
+        return true;
+    } catch (const std::system_error&) {
+        return false;
+    }
+}
+
 // fn(begin, end) over [0, n) in contiguous chunks, one per hardware thread (inline when n is small)
 template <typename Fn>
 void parallel_for(size_t n, Fn fn) {
@@ -72,7 +84,7 @@ void parallel_for(size_t n, Fn fn) {
     for (size_t t = 0; t < T; ++t) {
         const size_t b = t * chunk, e = std::min(n, b + chunk);
         if (b >= e) break;
-        th.emplace_back([=]() { fn(b, e); });
+        if (!try_spawn(th, [=]() { fn(b, e); })) fn(b, e);
     }
     for (std::thread& x : th) x.join();
 }
@@ -89,7 +101,7 @@ size_t parallel_chunks(size_t n, size_t T, Fn fn) {
         if (b >= e) break;
         ++used;
         if (T == 1) fn(t, b, e);
-        else th.emplace_back([=]() { fn(t, b, e); });
+        else if (!try_spawn(th, [=]() { fn(t, b, e); })) fn(t, b, e);
     }
     for (std::thread& x : th) x.join();
     return used;
@@ -228,15 +240,16 @@ struct LeafOrderJob {
             sort_node(r.first, r.second, 1);
             const size_t mid = r.first + len / 2;  // bvh.rs:111-120
             // the halves are independent: hand the left one to another thread while any are free
-            if (len > 4096 && threads_left.fetch_sub(1) > 0) {
-                spawned.emplace_back([this, r, mid]() {
-                    run(r.first, mid);
-                    threads_left.fetch_add(1);
-                });
-            } else {
-                if (len > 4096) threads_left.fetch_add(1);
-                stack.emplace_back(r.first, mid);
+            bool handed_over = false;
+            if (len > 4096) {
+                if (threads_left.fetch_sub(1) > 0)
+                    handed_over = try_spawn(spawned, [this, r, mid]() {
+                        run(r.first, mid);
+                        threads_left.fetch_add(1);
+                    });
+                if (!handed_over) threads_left.fetch_add(1);
             }
+            if (!handed_over) stack.emplace_back(r.first, mid);
             stack.emplace_back(mid, r.second);
         }
         for (std::thread& t : spawned) t.join();
@@ -290,7 +303,8 @@ void reference_leaf_order(const float* boxes6, size_t n, RawVector<uint32_t>& or
         job.run(tasks[0].first, tasks[0].second);
     } else {
         std::vector<std::thread> th;
-        for (const std::pair<size_t, size_t>& r : tasks) th.emplace_back([&job, r]() { job.run(r.first, r.second); });
+        for (const std::pair<size_t, size_t>& r : tasks)
+            if (!try_spawn(th, [&job, r]() { job.run(r.first, r.second); })) job.run(r.first, r.second);
         for (std::thread& t : th) t.join();
     }
     parallel_for(n, [&](size_t b, size_t e) {
@@ -363,15 +377,16 @@ struct Builder {
             out[0] = src[0];
             out[1] = Quad{src[1].x, src[1].y, c0 >= 0 ? bits_f(left_to) : src[1].z, c1 >= 0 ? bits_f(right_to) : src[1].w};
             if (c1 >= 0) {
-                if (subtree_nodes[c1] > 65536 && threads_left.fetch_sub(1) > 0) {
-                    spawned.emplace_back([this, c1, right_to, &dst]() {
-                        renumber((uint32_t)c1, right_to, dst);
-                        threads_left.fetch_add(1);
-                    });
-                } else {
-                    if (subtree_nodes[c1] > 65536) threads_left.fetch_add(1);
-                    todo.push_back(Item{(uint32_t)c1, right_to});
+                bool handed_over = false;
+                if (subtree_nodes[c1] > 65536) {
+                    if (threads_left.fetch_sub(1) > 0)
+                        handed_over = try_spawn(spawned, [this, c1, right_to, &dst]() {
+                            renumber((uint32_t)c1, right_to, dst);
+                            threads_left.fetch_add(1);
+                        });
+                    if (!handed_over) threads_left.fetch_add(1);
                 }
+                if (!handed_over) todo.push_back(Item{(uint32_t)c1, right_to});
             }
             if (c0 >= 0) todo.push_back(Item{(uint32_t)c0, left_to});
         }
@@ -653,13 +668,15 @@ struct Builder {
         Box lbox, rbox;
         int32_t lcode, rcode;
         bool spawned = false;
-        if (n > 2048 && threads_left.fetch_sub(1) > 0) {
-            spawned = true;
-            std::thread t([&]() { lcode = build(lo, mid, lbox, depth + 1, have_kids ? kids : nullptr); });
-            rcode = build(mid, hi, rbox, depth + 1, have_kids ? kids + 2 : nullptr);
-            t.join();
-            threads_left.fetch_add(1);
-        } else if (n > 2048) {
+        if (n > 2048) {
+            if (threads_left.fetch_sub(1) > 0) {
+                std::vector<std::thread> left_thread;
+                spawned = try_spawn(left_thread, [&]() { lcode = build(lo, mid, lbox, depth + 1, have_kids ? kids : nullptr); });
+                if (spawned) {
+                    rcode = build(mid, hi, rbox, depth + 1, have_kids ? kids + 2 : nullptr);
+                    left_thread[0].join();
+                }
+            }
             threads_left.fetch_add(1);
         }
         if (!spawned) {
