@@ -65,7 +65,7 @@ def _corpus(tmp_path):
     f = (rgb.astype(np.float32) / 16.0) ** 2
     cv2.imwrite(str(d / "t.hdr"), f)
     if hasattr(cv2, "IMWRITE_EXR_COMPRESSION"):
-        for name, flag in (("none", 0), ("rle", 1), ("zips", 2), ("zip", 3), ("piz", 4)):
+        for name, flag in (("none", 0), ("rle", 1), ("zips", 2), ("zip", 3), ("piz", 4), ("pxr24", 5), ("b44", 6), ("b44a", 7)):
             for half in (0, 1):
                 cv2.imwrite(str(d / f"{name}_{half}.exr"), f, [cv2.IMWRITE_EXR_COMPRESSION, flag, cv2.IMWRITE_EXR_TYPE,
                                                                cv2.IMWRITE_EXR_TYPE_HALF if half else cv2.IMWRITE_EXR_TYPE_FLOAT])

@@ -180,17 +180,17 @@ def _exr_flags():
     import cv2
 
     return cv2, {
-        "none": 0, "rle": 1, "zips": 2, "zip": 3, "piz": 4,
+        "none": 0, "rle": 1, "zips": 2, "zip": 3, "piz": 4, "pxr24": 5, "b44": 6, "b44a": 7,
     }
 
 
-@pytest.mark.parametrize("compression", ["none", "rle", "zips", "zip", "piz"])
+@pytest.mark.parametrize("compression", ["none", "rle", "zips", "zip", "piz", "pxr24", "b44", "b44a"])
 @pytest.mark.parametrize("half", [False, True])
 def test_openexr(tmp_path, compression, half):
     cv2, flags = _exr_flags()
     if not hasattr(cv2, "IMWRITE_EXR_COMPRESSION"):
         pytest.skip("this OpenCV cannot choose the EXR compression")
-    img = assets.synth_hdri("studio", 96, 48)
+    img = assets.synth_hdri("studio", 98, 50)  # not multiples of 4: partial B44 blocks
     rng = np.random.default_rng(5)
     img = (img * (1.0 + 0.05 * rng.random(img.shape))).astype(F32)
     path = str(tmp_path / f"{compression}_{half}.exr")
@@ -204,7 +204,7 @@ def test_openexr(tmp_path, compression, half):
     want = cv2.imread(path, cv2.IMREAD_UNCHANGED)[:, :, ::-1].astype(F32)
     got = assets.load_image_native(path)
     assert np.array_equal(got, want)
-    if not half:
+    if not half and compression != "pxr24":  # PXR24 keeps 24 bits of a float; B44 only packs half channels
         assert np.array_equal(got, img)
 
 

@@ -1661,7 +1661,9 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
         case 0: case 1: case 2: lines_per_block = 1; break;
         case 3: lines_per_block = 16; break;
         case 4: lines_per_block = 32; break;
-        default: err = "exr: unsupported compression " + std::to_string(compression) + " (none, RLE, ZIPS, ZIP and PIZ are)"; return false;
+        case 5: lines_per_block = 16; break;
+        case 6: case 7: lines_per_block = 32; break;
+        default: err = "exr: unsupported compression " + std::to_string(compression) + " (none, RLE, ZIPS, ZIP, PIZ, PXR24, B44 and B44A are)"; return false;
     }
     if ((int64_t)x1 - x0 >= (1 << 30) || (int64_t)y1 - y0 >= (1 << 30)) {
         err = "exr: image dimensions out of range";
@@ -1721,7 +1723,123 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
         const size_t expect = line_bytes * rows;
         const uint8_t* src = data + off + 8;
         raw.resize(expect);
-        if (csize == expect || compression == 0) {  // stored
+        if (compression == 6 || compression == 7) {
+            // B44 / B44A: half channels in 4x4 blocks of 14 bytes (3 bytes for a flat block), other channels raw;
+            // the block holds one channel after the other
+            if (csize == expect) {
+                std::memcpy(raw.data(), src, expect);  // stored uncompressed
+            } else {
+                const uint8_t* in = src;
+                const uint8_t* const in_end = src + csize;
+                for (size_t ci = 0; ci < ch.size(); ++ci) {
+                    const ExrChannel& c = ch[ci];
+                    if (c.type != 1) {
+                        const size_t nb = (size_t)w * 4;
+                        for (int y = 0; y < rows; ++y) {
+                            if (in + nb > in_end) {
+                                err = "exr: short B44 block";
+                                return false;
+                            }
+                            std::memcpy(raw.data() + (size_t)y * line_bytes + ch_off[ci], in, nb);
+                            in += nb;
+                        }
+                        continue;
+                    }
+                    for (int y = 0; y < rows; y += 4)
+                        for (int x = 0; x < w; x += 4) {
+                            uint16_t v[16];
+                            if (in + 3 > in_end) {
+                                err = "exr: short B44 block";
+                                return false;
+                            }
+                            if (in[2] == 0xfc) {
+                                uint16_t t = (uint16_t)(in[0] << 8 | in[1]);
+                                t = (t & 0x8000) ? (uint16_t)(t & 0x7fff) : (uint16_t)~t;
+                                for (int i = 0; i < 16; ++i) v[i] = t;
+                                in += 3;
+                            } else {
+                                if (in + 14 > in_end) {
+                                    err = "exr: short B44 block";
+                                    return false;
+                                }
+                                const uint8_t* b = in;
+                                const uint32_t shift = b[2] >> 2;
+                                if (shift > 15) {  // 16-bit values: a larger shift only occurs in corrupt data
+                                    err = "exr: corrupt B44 block";
+                                    return false;
+                                }
+                                const uint32_t bias = 0x20u << shift;
+                                uint32_t t[16];
+                                t[0] = (uint32_t)b[0] << 8 | b[1];
+                                t[4] = t[0] + (((((uint32_t)b[2] << 4) | (b[3] >> 4)) & 0x3f) << shift) - bias;
+                                t[8] = t[4] + (((((uint32_t)b[3] << 2) | (b[4] >> 6)) & 0x3f) << shift) - bias;
+                                t[12] = t[8] + (((uint32_t)b[4] & 0x3f) << shift) - bias;
+                                t[1] = t[0] + (((uint32_t)b[5] >> 2) << shift) - bias;
+                                t[5] = t[4] + (((((uint32_t)b[5] << 4) | (b[6] >> 4)) & 0x3f) << shift) - bias;
+                                t[9] = t[8] + (((((uint32_t)b[6] << 2) | (b[7] >> 6)) & 0x3f) << shift) - bias;
+                                t[13] = t[12] + (((uint32_t)b[7] & 0x3f) << shift) - bias;
+                                t[2] = t[1] + (((uint32_t)b[8] >> 2) << shift) - bias;
+                                t[6] = t[5] + (((((uint32_t)b[8] << 4) | (b[9] >> 4)) & 0x3f) << shift) - bias;
+                                t[10] = t[9] + (((((uint32_t)b[9] << 2) | (b[10] >> 6)) & 0x3f) << shift) - bias;
+                                t[14] = t[13] + (((uint32_t)b[10] & 0x3f) << shift) - bias;
+                                t[3] = t[2] + (((uint32_t)b[11] >> 2) << shift) - bias;
+                                t[7] = t[6] + (((((uint32_t)b[11] << 4) | (b[12] >> 4)) & 0x3f) << shift) - bias;
+                                t[11] = t[10] + (((((uint32_t)b[12] << 2) | (b[13] >> 6)) & 0x3f) << shift) - bias;
+                                t[15] = t[14] + (((uint32_t)b[13] & 0x3f) << shift) - bias;
+                                for (int i = 0; i < 16; ++i) {
+                                    const uint16_t u = (uint16_t)t[i];
+                                    v[i] = (u & 0x8000) ? (uint16_t)(u & 0x7fff) : (uint16_t)~u;
+                                }
+                                in += 14;
+                            }
+                            for (int dy = 0; dy < 4 && y + dy < rows; ++dy)
+                                for (int dx = 0; dx < 4 && x + dx < w; ++dx) {
+                                    uint8_t* o = raw.data() + (size_t)(y + dy) * line_bytes + ch_off[ci] + 2 * (size_t)(x + dx);
+                                    o[0] = (uint8_t)v[4 * dy + dx];
+                                    o[1] = (uint8_t)(v[4 * dy + dx] >> 8);
+                                }
+                        }
+                }
+            }
+        } else if (compression == 5) {
+            // PXR24: deflate over per-channel byte planes of differences; floats keep their top 24 bits
+            size_t planes = 0;
+            for (const ExrChannel& c : ch) planes += (size_t)w * (c.type == 1 ? 2 : (c.type == 2 ? 3 : 4));
+            scratch.resize(planes * rows);
+            size_t produced = 0;
+            if (!zlib_inflate(src, csize, scratch.data(), scratch.size(), &produced, err)) return false;
+            if (produced != scratch.size()) {
+                err = "exr: short PXR24 block";
+                return false;
+            }
+            const uint8_t* in = scratch.data();
+            uint8_t* o = raw.data();
+            for (int y = 0; y < rows; ++y)
+                for (const ExrChannel& c : ch) {
+                    const int nb = c.type == 1 ? 2 : (c.type == 2 ? 3 : 4);
+                    const uint8_t* p[4] = {in, in + w, in + 2 * (size_t)w, in + 3 * (size_t)w};
+                    in += (size_t)nb * w;
+                    uint32_t pixel = 0;
+                    for (int x = 0; x < w; ++x) {
+                        uint32_t diff;
+                        if (c.type == 1) diff = (uint32_t)p[0][x] << 8 | p[1][x];
+                        else if (c.type == 2) diff = (uint32_t)p[0][x] << 24 | (uint32_t)p[1][x] << 16 | (uint32_t)p[2][x] << 8;
+                        else diff = (uint32_t)p[0][x] << 24 | (uint32_t)p[1][x] << 16 | (uint32_t)p[2][x] << 8 | p[3][x];
+                        pixel += diff;
+                        if (c.type == 1) {
+                            o[0] = (uint8_t)pixel;
+                            o[1] = (uint8_t)(pixel >> 8);
+                            o += 2;
+                        } else {
+                            o[0] = (uint8_t)pixel;
+                            o[1] = (uint8_t)(pixel >> 8);
+                            o[2] = (uint8_t)(pixel >> 16);
+                            o[3] = (uint8_t)(pixel >> 24);
+                            o += 4;
+                        }
+                    }
+                }
+        } else if (csize == expect || compression == 0) {  // stored
             if (csize < expect) {
                 err = "exr: short block";
                 return false;
