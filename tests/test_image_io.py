@@ -284,6 +284,67 @@ def test_bmp_tga_pnm_farbfeld(tmp_path):
     assert np.abs(got - ref).max() <= 1
 
 
+def _write_tiled_exr(path, img, tile, compression, half):
+    """A minimal single-part tiled OpenEXR writer (ONE_LEVEL; compression 0 = none or 3 = ZIP), enough to exercise the
+    decoder's tile path; the files it writes are checked with OpenCV's (OpenEXR's) reader first."""
+    import struct
+    import zlib
+
+    h, w, _ = img.shape
+    tw, th = tile
+    dt = np.float16 if half else np.float32
+
+    def attr(name, typ, body):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(body)) + body
+
+    chlist = b"".join(n.encode() + b"\0" + struct.pack("<iBBBBii", 1 if half else 2, 0, 0, 0, 0, 1, 1) for n in "BGR") + b"\0"
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    header = struct.pack("<II", 20000630, 2 | 0x200)
+    header += attr("channels", "chlist", chlist) + attr("compression", "compression", bytes([compression]))
+    header += attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0")
+    header += attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + attr("screenWindowCenter", "v2f", struct.pack("<ff", 0, 0))
+    header += attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + attr("tiles", "tiledesc", struct.pack("<IIB", tw, th, 0))
+    header += b"\0"
+    nx, ny = (w + tw - 1) // tw, (h + th - 1) // th
+    chunks = []
+    for ty in range(ny):
+        for tx in range(nx):
+            t = img[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw]
+            raw = b"".join(t[y, :, c].astype(dt).tobytes() for y in range(t.shape[0]) for c in (2, 1, 0))  # B, G, R per line
+            data = raw
+            if compression == 3:
+                a = np.frombuffer(raw, np.uint8)
+                r = np.concatenate([a[0::2], a[1::2]]).astype(np.int32)
+                d = r.copy()
+                d[1:] = (r[1:] - r[:-1] + 128 + 256) & 255
+                z = zlib.compress(d.astype(np.uint8).tobytes())
+                data = z if len(z) < len(raw) else raw
+            chunks.append(struct.pack("<iiiii", tx, ty, 0, 0, len(data)) + data)
+    table_at = len(header)
+    offs, at = [], table_at + 8 * len(chunks)
+    for c in chunks:
+        offs.append(at)
+        at += len(c)
+    with open(path, "wb") as f:
+        f.write(header + b"".join(struct.pack("<Q", o) for o in offs) + b"".join(chunks))
+
+
+@pytest.mark.parametrize("compression", [0, 3])
+@pytest.mark.parametrize("half", [False, True])
+def test_openexr_tiled(tmp_path, compression, half):
+    import cv2
+
+    img = assets.synth_hdri("indoor", 83, 37).astype(F32)  # neither dimension a multiple of the tile size
+    img = (img * (1.0 + 0.05 * np.random.default_rng(9).random(img.shape))).astype(F32)
+    path = str(tmp_path / "tiled.exr")
+    _write_tiled_exr(path, img, (32, 16), compression, half)
+    ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert ref is not None, "OpenEXR rejects the test file"
+    want = ref[:, :, 2::-1].astype(F32)
+    assert np.array_equal(want, img.astype(np.float16).astype(F32) if half else img)
+    assert np.array_equal(assets.load_image_native(path), want)
+
+
 def test_errors_are_reported_not_fatal(tmp_path):
     with pytest.raises(_lib.VoidrayError, match="cannot open"):
         assets.load_image_native(str(tmp_path / "missing.png"))

@@ -1591,10 +1591,12 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
         return false;
     }
     const uint32_t version = r.u32le(4);
-    if ((version & 0xFF) != 2 || (version & 0x200) || (version & 0x800) || (version & 0x1000)) {
-        err = "exr: only single-part scan-line files are supported (no tiles, deep data or multi-part)";
+    if ((version & 0xFF) != 2 || (version & 0x800) || (version & 0x1000)) {
+        err = "exr: only single-part flat images are supported (no deep data or multi-part files)";
         return false;
     }
+    const bool tiled = (version & 0x200) != 0;
+    uint32_t tile_w = 0, tile_h = 0;
     size_t pos = 8;
     std::vector<ExrChannel> ch;
     int compression = -1, x0 = 0, y0 = 0, x1 = -1, y1 = -1;
@@ -1642,6 +1644,9 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
                 }
                 ch.push_back(c);
             }
+        } else if (name == "tiles" && alen >= 9) {
+            tile_w = r.u32le(pos);
+            tile_h = r.u32le(pos + 4);  // byte 8: level mode | rounding mode << 4; level 0 is read whatever the mode
         } else if (name == "compression" && alen >= 1) {
             compression = data[pos];
         } else if (name == "dataWindow" && alen >= 16) {
@@ -1678,10 +1683,7 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
     // channel lookup: R, G, B (any layer-less name), else Y replicated
     int idx[3] = {-1, -1, -1};
     std::vector<size_t> ch_off(ch.size());
-    size_t line_bytes = 0;
     for (size_t c = 0; c < ch.size(); ++c) {
-        ch_off[c] = line_bytes;
-        line_bytes += (size_t)w * ch[c].size();
         if (ch[c].name == "R") idx[0] = (int)c;
         if (ch[c].name == "G") idx[1] = (int)c;
         if (ch[c].name == "B") idx[2] = (int)c;
@@ -1696,7 +1698,13 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
         }
         idx[0] = idx[1] = idx[2] = y;
     }
-    const int n_blocks = (h + lines_per_block - 1) / lines_per_block;
+    if (tiled && (tile_w == 0 || tile_h == 0 || tile_w > (1u << 20) || tile_h > (1u << 20))) {
+        err = "exr: tiled file without a usable tile description";
+        return false;
+    }
+    // scan-line files: blocks of whole lines; tiled files: the tiles of level 0 (they lead the offset table)
+    const int tiles_x = tiled ? (int)((w + (int64_t)tile_w - 1) / tile_w) : 1;
+    const int n_blocks = tiled ? tiles_x * (int)((h + (int64_t)tile_h - 1) / tile_h) : (h + lines_per_block - 1) / lines_per_block;
     if (!r.has(pos, (size_t)8 * n_blocks)) {
         err = "exr: truncated offset table";
         return false;
@@ -1709,19 +1717,44 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
     std::vector<uint8_t> raw, scratch;
     for (int b = 0; b < n_blocks; ++b) {
         const uint64_t off = r.u64le(pos + (size_t)8 * b);
-        if (!r.has((size_t)off, 8)) {
+        const size_t head = tiled ? 20 : 8;
+        if (off > size || !r.has((size_t)off, head)) {
             err = "exr: block outside the file";
             return false;
         }
-        const int by = (int)r.u32le((size_t)off) - y0;
-        const uint32_t csize = r.u32le((size_t)off + 4);
-        if (by < 0 || by >= h || !r.has((size_t)off + 8, csize)) {
+        int bx = 0, by, bw = w, rows;
+        if (tiled) {
+            const uint32_t tx = r.u32le((size_t)off), ty = r.u32le((size_t)off + 4);
+            if (r.u32le((size_t)off + 8) != 0 || r.u32le((size_t)off + 12) != 0 || tx >= (uint32_t)tiles_x ||
+                (uint64_t)ty * tile_h >= (uint64_t)h) {
+                err = "exr: corrupt tile header";
+                return false;
+            }
+            bx = (int)(tx * tile_w);
+            by = (int)(ty * tile_h);
+            bw = std::min((int)tile_w, w - bx);
+            rows = std::min((int)tile_h, h - by);
+        } else {
+            by = (int)r.u32le((size_t)off) - y0;
+            if (by < 0 || by >= h) {
+                err = "exr: corrupt block header";
+                return false;
+            }
+            rows = std::min(lines_per_block, h - by);
+        }
+        const uint32_t csize = r.u32le((size_t)off + head - 4);
+        if (!r.has((size_t)off + head, csize)) {
             err = "exr: corrupt block header";
             return false;
         }
-        const int rows = std::min(lines_per_block, h - by);
+        // layout of this block's lines: one channel after the other, bw samples each
+        size_t line_bytes = 0;
+        for (size_t c = 0; c < ch.size(); ++c) {
+            ch_off[c] = line_bytes;
+            line_bytes += (size_t)bw * ch[c].size();
+        }
         const size_t expect = line_bytes * rows;
-        const uint8_t* src = data + off + 8;
+        const uint8_t* src = data + off + head;
         raw.resize(expect);
         if (compression == 6 || compression == 7) {
             // B44 / B44A: half channels in 4x4 blocks of 14 bytes (3 bytes for a flat block), other channels raw;
@@ -1734,7 +1767,7 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
                 for (size_t ci = 0; ci < ch.size(); ++ci) {
                     const ExrChannel& c = ch[ci];
                     if (c.type != 1) {
-                        const size_t nb = (size_t)w * 4;
+                        const size_t nb = (size_t)bw * 4;
                         for (int y = 0; y < rows; ++y) {
                             if (in + nb > in_end) {
                                 err = "exr: short B44 block";
@@ -1746,7 +1779,7 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
                         continue;
                     }
                     for (int y = 0; y < rows; y += 4)
-                        for (int x = 0; x < w; x += 4) {
+                        for (int x = 0; x < bw; x += 4) {
                             uint16_t v[16];
                             if (in + 3 > in_end) {
                                 err = "exr: short B44 block";
@@ -1793,7 +1826,7 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
                                 in += 14;
                             }
                             for (int dy = 0; dy < 4 && y + dy < rows; ++dy)
-                                for (int dx = 0; dx < 4 && x + dx < w; ++dx) {
+                                for (int dx = 0; dx < 4 && x + dx < bw; ++dx) {
                                     uint8_t* o = raw.data() + (size_t)(y + dy) * line_bytes + ch_off[ci] + 2 * (size_t)(x + dx);
                                     o[0] = (uint8_t)v[4 * dy + dx];
                                     o[1] = (uint8_t)(v[4 * dy + dx] >> 8);
@@ -1804,7 +1837,7 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
         } else if (compression == 5) {
             // PXR24: deflate over per-channel byte planes of differences; floats keep their top 24 bits
             size_t planes = 0;
-            for (const ExrChannel& c : ch) planes += (size_t)w * (c.type == 1 ? 2 : (c.type == 2 ? 3 : 4));
+            for (const ExrChannel& c : ch) planes += (size_t)bw * (c.type == 1 ? 2 : (c.type == 2 ? 3 : 4));
             scratch.resize(planes * rows);
             size_t produced = 0;
             if (!zlib_inflate(src, csize, scratch.data(), scratch.size(), &produced, err)) return false;
@@ -1817,10 +1850,10 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
             for (int y = 0; y < rows; ++y)
                 for (const ExrChannel& c : ch) {
                     const int nb = c.type == 1 ? 2 : (c.type == 2 ? 3 : 4);
-                    const uint8_t* p[4] = {in, in + w, in + 2 * (size_t)w, in + 3 * (size_t)w};
-                    in += (size_t)nb * w;
+                    const uint8_t* p[4] = {in, in + bw, in + 2 * (size_t)bw, in + 3 * (size_t)bw};
+                    in += (size_t)nb * bw;
                     uint32_t pixel = 0;
-                    for (int x = 0; x < w; ++x) {
+                    for (int x = 0; x < bw; ++x) {
                         uint32_t diff;
                         if (c.type == 1) diff = (uint32_t)p[0][x] << 8 | p[1][x];
                         else if (c.type == 2) diff = (uint32_t)p[0][x] << 24 | (uint32_t)p[1][x] << 16 | (uint32_t)p[2][x] << 8;
@@ -1882,14 +1915,14 @@ bool decode_exr(const uint8_t* data, size_t size, DecodedImage& out, std::string
             }
             exr_unpredict(raw, scratch);
         } else {
-            if (!exr_piz_block(src, csize, raw.data(), expect, ch, w, rows, err)) return false;
+            if (!exr_piz_block(src, csize, raw.data(), expect, ch, bw, rows, err)) return false;
         }
         for (int y = 0; y < rows; ++y)
             for (int c = 0; c < 3; ++c) {
                 const ExrChannel& cc = ch[idx[c]];
                 const uint8_t* s = raw.data() + (size_t)y * line_bytes + ch_off[idx[c]];
-                float* o = &out.f32[3 * ((size_t)(by + y) * w) + c];
-                for (int x = 0; x < w; ++x, o += 3) {
+                float* o = &out.f32[3 * ((size_t)(by + y) * w + bx) + c];
+                for (int x = 0; x < bw; ++x, o += 3) {
                     if (cc.type == 1) {
                         *o = half_to_float((uint16_t)(s[2 * x] | s[2 * x + 1] << 8));
                     } else {
