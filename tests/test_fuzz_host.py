@@ -69,7 +69,9 @@ def _corpus(tmp_path):
             for half in (0, 1):
                 cv2.imwrite(str(d / f"{name}_{half}.exr"), f, [cv2.IMWRITE_EXR_COMPRESSION, flag, cv2.IMWRITE_EXR_TYPE,
                                                                cv2.IMWRITE_EXR_TYPE_HALF if half else cv2.IMWRITE_EXR_TYPE_FLOAT])
-    from test_image_io import _write_tiled_exr
+    from test_image_io import _write_tiled_exr, _write_tiled_tiff
+    _write_tiled_tiff(str(d / "tiled8.tif"), rgb, (32, 16), True, True)
+    _write_tiled_tiff(str(d / "tiled16.tif"), rgb.astype(np.uint16) * 257, (16, 16), False, True, big_endian=True)
     for comp in (0, 3):
         _write_tiled_exr(str(d / f"tiled_{comp}.exr"), f[:21, :30], (16, 8), comp, half=bool(comp))
     return str(d)

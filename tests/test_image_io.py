@@ -284,6 +284,92 @@ def test_bmp_tga_pnm_farbfeld(tmp_path):
     assert np.abs(got - ref).max() <= 1
 
 
+def _write_tiled_tiff(path, img, tile, deflate, predictor, big_endian=False):
+    """A minimal tiled TIFF writer (chunky RGB, 8 or 16 bit, none / Deflate, optional horizontal differencing); PIL
+    (libtiff) reads the files it writes, which is checked before the library's decoder is."""
+    import struct
+    import zlib
+
+    h, w, spp = img.shape
+    tw, tl = tile
+    bps = img.dtype.itemsize
+    e = ">" if big_endian else "<"
+    nx, ny = (w + tw - 1) // tw, (h + tl - 1) // tl
+    blobs = []
+    for ty in range(ny):
+        for tx in range(nx):
+            t = np.zeros((tl, tw, spp), img.dtype)
+            part = img[ty * tl:(ty + 1) * tl, tx * tw:(tx + 1) * tw]
+            t[:part.shape[0], :part.shape[1]] = part
+            if predictor:
+                d = t.copy()
+                d[:, 1:] = t[:, 1:] - t[:, :-1]  # wraps modulo 2^bits
+                t = d
+            raw = t.astype(t.dtype.newbyteorder(e)).tobytes()
+            blobs.append(zlib.compress(raw) if deflate else raw)
+    entries = []  # (tag, type, count, values)
+    def add(tag, typ, vals):
+        entries.append((tag, typ, vals))
+    add(256, 4, [w]); add(257, 4, [h]); add(258, 3, [8 * bps] * spp); add(259, 3, [8 if deflate else 1]); add(262, 3, [2])
+    add(277, 3, [spp]); add(284, 3, [1]); add(317, 3, [2 if predictor else 1]); add(322, 4, [tw]); add(323, 4, [tl])
+    add(324, 4, None); add(325, 4, [len(b) for b in blobs])
+    entries.sort(key=lambda t: t[0])
+    ifd_at = 8
+    ifd_size = 2 + 12 * len(entries) + 4
+    extra_at = ifd_at + ifd_size
+    # first pass: sizes of out-of-line arrays
+    def size_of(typ, n):
+        return n * (2 if typ == 3 else 4)
+    extra = b""
+    placed = {}
+    data_at = None
+    for tag, typ, vals in entries:
+        n = len(blobs) if vals is None else len(vals)
+        if size_of(typ, n) > 4:
+            placed[tag] = extra_at + len(extra)
+            extra += b"\0" * size_of(typ, n)
+    data_at = extra_at + len(extra)
+    offs, at = [], data_at
+    for b in blobs:
+        offs.append(at)
+        at += len(b)
+    out = (b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, ifd_at) + struct.pack(e + "H", len(entries))
+    extra = bytearray(extra)
+    for tag, typ, vals in entries:
+        if vals is None:
+            vals = offs
+        n = len(vals)
+        body = b"".join(struct.pack(e + ("H" if typ == 3 else "I"), v) for v in vals)
+        if len(body) > 4:
+            o = placed[tag] - extra_at
+            extra[o:o + len(body)] = body
+            out += struct.pack(e + "HHII", tag, typ, n, placed[tag])
+        else:
+            out += struct.pack(e + "HHI", tag, typ, n) + body.ljust(4, b"\0")
+    out += struct.pack(e + "I", 0) + bytes(extra) + b"".join(blobs)
+    with open(path, "wb") as f:
+        f.write(out)
+
+
+@pytest.mark.parametrize("dtype,deflate,predictor,big", [(np.uint8, False, False, False), (np.uint8, True, True, False),
+                                                         (np.uint16, True, True, False), (np.uint16, True, True, True),
+                                                         (np.uint16, False, False, True)])
+def test_tiff_tiled(tmp_path, dtype, deflate, predictor, big):
+    from PIL import Image
+
+    img = _rng_image(70, 101, 3, dtype)  # edge tiles are partial in both directions
+    path = str(tmp_path / "tiled.tif")
+    _write_tiled_tiff(path, img, (32, 16), deflate, predictor, big)
+    scale = F32(255.0) if dtype == np.uint8 else F32(65535.0)
+    if dtype == np.uint8:  # PIL has no 16-bit RGB mode; libtiff still validates the 8-bit files
+        assert np.array_equal(np.asarray(Image.open(path).convert("RGB")), img)
+    else:
+        import cv2
+        ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        assert ref is not None and np.array_equal(ref[:, :, ::-1], img)
+    assert np.array_equal(assets.load_image_native(path), img.astype(F32) / scale)
+
+
 def _write_tiled_exr(path, img, tile, compression, half):
     """A minimal single-part tiled OpenEXR writer (ONE_LEVEL; compression 0 = none or 3 = ZIP), enough to exercise the
     decoder's tile path; the files it writes are checked with OpenCV's (OpenEXR's) reader first."""

@@ -984,7 +984,7 @@ bool decode_tiff(const uint8_t* data, size_t size, DecodedImage& out, std::strin
         return false;
     }
     uint32_t w = 0, h = 0, compression = 1, photometric = 2, spp = 1, rows_per_strip = 0xFFFFFFFFu, planar = 1,
-             predictor = 1, sample_format = 1;
+             predictor = 1, sample_format = 1, tile_w = 0, tile_l = 0;
     std::vector<uint32_t> bits, offsets, counts, colormap;
     bool tiled = false;
     auto read_array = [&](size_t e, std::vector<uint32_t>& v) -> bool {
@@ -1017,12 +1017,18 @@ bool decode_tiff(const uint8_t* data, size_t size, DecodedImage& out, std::strin
             case 279: if (!read_array(e, counts)) { err = "tiff: bad StripByteCounts"; return false; } break;
             case 320: if (!read_array(e, colormap)) { err = "tiff: bad ColorMap"; return false; } break;
             case 339: if (read_array(e, v) && !v.empty()) sample_format = v[0]; break;
-            case 322: case 323: case 324: case 325: tiled = true; break;
+            case 322: case 323:
+                if (!read_array(e, v) || v.empty()) { err = "tiff: bad tile size"; return false; }
+                (tag == 322 ? tile_w : tile_l) = v[0];
+                tiled = true;
+                break;
+            case 324: if (!read_array(e, offsets)) { err = "tiff: bad TileOffsets"; return false; } tiled = true; break;
+            case 325: if (!read_array(e, counts)) { err = "tiff: bad TileByteCounts"; return false; } tiled = true; break;
             default: break;
         }
     }
-    if (tiled) {
-        err = "tiff: tiled files are not supported";
+    if (tiled && (tile_w == 0 || tile_l == 0 || tile_w > (1u << 20) || tile_l > (1u << 20))) {
+        err = "tiff: tiled file without a usable tile size";
         return false;
     }
     if (bits.empty()) bits.push_back(1);
@@ -1035,7 +1041,7 @@ bool decode_tiff(const uint8_t* data, size_t size, DecodedImage& out, std::strin
     const bool is_float = sample_format == 3;
     if (w == 0 || h == 0 || spp == 0 || spp > 8 || planar != 1 || offsets.empty() || offsets.size() != counts.size() ||
         (!((depth == 8 || depth == 16) && sample_format == 1) && !(depth == 32 && is_float))) {
-        err = "tiff: unsupported layout (need chunky 8/16-bit integer or 32-bit float samples in strips)";
+        err = "tiff: unsupported layout (need chunky 8/16-bit integer or 32-bit float samples)";
         return false;
     }
     if (photometric > 3 || (photometric == 3 && (depth != 8 || colormap.size() < 768)) || (photometric == 2 && spp < 3)) {
@@ -1051,53 +1057,96 @@ bool decode_tiff(const uint8_t* data, size_t size, DecodedImage& out, std::strin
     const size_t bps = depth / 8, row_bytes = (size_t)w * spp * bps;
     if (!plausible_size(w, h, (uint64_t)spp * bps, size, 4096, "tiff", err)) return false;
     std::vector<uint8_t> pixels(row_bytes * h), strip;
-    for (size_t s = 0; s < offsets.size(); ++s) {
-        const size_t y0 = s * rows_per_strip;
-        if (y0 >= h) break;
-        const size_t rows = std::min<size_t>(rows_per_strip, h - y0), expect = rows * row_bytes;
-        if (!r.has(offsets[s], counts[s])) {
-            err = "tiff: strip outside the file";
-            return false;
-        }
-        const uint8_t* src = data + offsets[s];
-        uint8_t* dst = pixels.data() + y0 * row_bytes;
+    auto decompress = [&](const uint8_t* src, size_t n_src, uint8_t* dst, size_t expect) -> bool {
         switch (compression) {
             case 1:
-                if (counts[s] < expect) {
+                if (n_src < expect) {
                     err = "tiff: short strip";
                     return false;
                 }
                 std::memcpy(dst, src, expect);
-                break;
+                return true;
             case 5:
-                if (!tiff_lzw(src, counts[s], strip, expect, err)) return false;
+                if (!tiff_lzw(src, n_src, strip, expect, err)) return false;
                 if (strip.size() < expect) {
                     err = "tiff: short LZW strip";
                     return false;
                 }
                 std::memcpy(dst, strip.data(), expect);
-                break;
+                return true;
             case 8:
             case 32946: {
                 size_t produced = 0;
-                if (!zlib_inflate(src, counts[s], dst, expect, &produced, err)) return false;
+                if (!zlib_inflate(src, n_src, dst, expect, &produced, err)) return false;
                 if (produced < expect) {
                     err = "tiff: short Deflate strip";
                     return false;
                 }
-                break;
+                return true;
             }
             case 32773:
-                if (!tiff_packbits(src, counts[s], strip, expect) || strip.size() < expect) {
+                if (!tiff_packbits(src, n_src, strip, expect) || strip.size() < expect) {
                     err = "tiff: corrupt PackBits strip";
                     return false;
                 }
                 std::memcpy(dst, strip.data(), expect);
-                break;
+                return true;
             default: err = "tiff: unsupported compression scheme " + std::to_string(compression); return false;
         }
+    };
+    // horizontal differencing (predictor 2) runs along each row of a strip or tile, on samples in file byte order
+    auto unpredict = [&](uint8_t* buf, size_t rows, size_t samples_per_row) {
+        if (predictor != 2) return;
+        for (size_t y = 0; y < rows; ++y) {
+            uint8_t* row = buf + y * samples_per_row * bps;
+            if (depth == 8) {
+                for (size_t i = spp; i < samples_per_row; ++i) row[i] = (uint8_t)(row[i] + row[i - spp]);
+            } else {
+                const int hi_at = r.big ? 0 : 1, lo_at = 1 - hi_at;
+                for (size_t i = spp; i < samples_per_row; ++i) {
+                    const uint32_t prev = (uint32_t)row[2 * (i - spp) + hi_at] << 8 | row[2 * (i - spp) + lo_at];
+                    const uint32_t cur = ((uint32_t)row[2 * i + hi_at] << 8 | row[2 * i + lo_at]) + prev;
+                    row[2 * i + hi_at] = (uint8_t)(cur >> 8);
+                    row[2 * i + lo_at] = (uint8_t)cur;
+                }
+            }
+        }
+    };
+    if (!tiled) {
+        for (size_t s = 0; s < offsets.size(); ++s) {
+            const size_t y0 = s * rows_per_strip;
+            if (y0 >= h) break;
+            const size_t rows = std::min<size_t>(rows_per_strip, h - y0), expect = rows * row_bytes;
+            if (!r.has(offsets[s], counts[s])) {
+                err = "tiff: strip outside the file";
+                return false;
+            }
+            uint8_t* dst = pixels.data() + y0 * row_bytes;
+            if (!decompress(data + offsets[s], counts[s], dst, expect)) return false;
+            unpredict(dst, rows, (size_t)w * spp);
+        }
+    } else {
+        const size_t tiles_x = ((size_t)w + tile_w - 1) / tile_w, tiles_y = ((size_t)h + tile_l - 1) / tile_l;
+        const size_t tile_row_bytes = (size_t)tile_w * spp * bps, tile_bytes = tile_row_bytes * tile_l;
+        if (offsets.size() < tiles_x * tiles_y || tile_bytes > ((size_t)1 << 31)) {
+            err = "tiff: tile table does not cover the image";
+            return false;
+        }
+        std::vector<uint8_t> tile(tile_bytes);
+        for (size_t t = 0; t < tiles_x * tiles_y; ++t) {
+            if (!r.has(offsets[t], counts[t])) {
+                err = "tiff: tile outside the file";
+                return false;
+            }
+            if (!decompress(data + offsets[t], counts[t], tile.data(), tile_bytes)) return false;  // edge tiles are padded to full size
+            unpredict(tile.data(), tile_l, (size_t)tile_w * spp);
+            const size_t x0 = (t % tiles_x) * tile_w, y0 = (t / tiles_x) * tile_l;
+            const size_t cw = std::min<size_t>(tile_w, w - x0), chh = std::min<size_t>(tile_l, h - y0);
+            for (size_t y = 0; y < chh; ++y)
+                std::memcpy(pixels.data() + (y0 + y) * row_bytes + x0 * spp * bps, tile.data() + y * tile_row_bytes, cw * spp * bps);
+        }
     }
-    // samples to host order, horizontal differencing undone
+    // samples to host order
     out.w = w;
     out.h = h;
     out.format = "tiff";
@@ -1105,11 +1154,6 @@ bool decode_tiff(const uint8_t* data, size_t size, DecodedImage& out, std::strin
     const size_t n_px = (size_t)w * h;
     auto channel_of = [&](int c) -> int { return photometric == 2 ? c : 0; };
     if (depth == 8) {
-        if (predictor == 2)
-            for (size_t y = 0; y < h; ++y) {
-                uint8_t* row = pixels.data() + y * row_bytes;
-                for (size_t i = spp; i < (size_t)w * spp; ++i) row[i] = (uint8_t)(row[i] + row[i - spp]);
-            }
         out.u8.resize(3 * n_px);
         for (size_t i = 0; i < n_px; ++i)
             for (int c = 0; c < 3; ++c) {
@@ -1123,11 +1167,6 @@ bool decode_tiff(const uint8_t* data, size_t size, DecodedImage& out, std::strin
         std::vector<uint16_t> s16((size_t)w * h * spp);
         for (size_t i = 0; i < s16.size(); ++i)
             s16[i] = r.big ? (uint16_t)(pixels[2 * i] << 8 | pixels[2 * i + 1]) : (uint16_t)(pixels[2 * i + 1] << 8 | pixels[2 * i]);
-        if (predictor == 2)
-            for (size_t y = 0; y < h; ++y) {
-                uint16_t* row = s16.data() + y * (size_t)w * spp;
-                for (size_t i = spp; i < (size_t)w * spp; ++i) row[i] = (uint16_t)(row[i] + row[i - spp]);
-            }
         out.u16.resize(3 * n_px);
         for (size_t i = 0; i < n_px; ++i)
             for (int c = 0; c < 3; ++c) {

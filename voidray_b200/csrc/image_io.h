@@ -20,7 +20,7 @@ struct DecodedImage {
     const char* format = "";     // "png", "jpeg", "tiff", "bmp", "tga", "pnm", "farbfeld", "hdr", "exr"
 };
 
-// Decodes PNG, baseline/progressive JPEG, TIFF (strips; none / LZW / Deflate / PackBits), BMP (uncompressed, bit
+// Decodes PNG, baseline/progressive JPEG, TIFF (strips and tiles; none / LZW / Deflate / PackBits), BMP (uncompressed, bit
 // fields), TGA (colour-mapped / true-colour / grey, RLE), PNM (P1..P6), farbfeld, Radiance HDR and scan-line / tiled OpenEXR
 // (none / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A), recognised by their magic bytes (TGA: by extension).
 bool decode_image_file(const char* path, DecodedImage& out, std::string& err);
