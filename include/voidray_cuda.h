@@ -280,6 +280,12 @@ int32_t vr_debug_sample_radiance(vr_render* render, uint64_t n, const uint32_t* 
 /* Host-only: the in-order leaf sequence of the reference's median-split tree (core/bvh.rs:48-130) over n boxes
  * (6 floats each: min xyz, max xyz) — the order the tie ranks are taken from. order[i] = item at position i. */
 int32_t vr_debug_reference_leaf_order(const float* boxes6, uint64_t n, uint32_t* order);
+/* Host-only: flattens one mesh the way vr_scene_commit does (reference-order tie ranks + SAH BVH2 + packed records,
+ * csrc/scene_build.cpp) and returns the FNV-1a digest of the bytes the device would receive (nodes, intersection
+ * records, shading records), so the shipped builder is pinned without a GPU. uvs / normals may be NULL (zeros). */
+int32_t vr_debug_flatten_mesh_digest(const float* positions, const float* uvs, const float* normals, uint32_t n_vertices,
+                                     const uint32_t* indices, uint32_t n_indices, uint64_t* digest, uint32_t* n_nodes,
+                                     uint32_t* bvh_depth, double* flatten_ms);
 int32_t vr_debug_tie_ranks(vr_scene* scene, uint32_t surface, uint32_t* out, uint32_t n);
 /* Device-side evaluations of texture / environment lookups and the samplers, for unit parity. */
 int32_t vr_debug_texture_sample(vr_scene* scene, uint32_t texture, uint64_t n, const float* uv, float* rgb);

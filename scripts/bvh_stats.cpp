@@ -7,6 +7,7 @@
 //   g++ -O2 -std=c++17 -pthread -ffp-contract=off -Ivoidray_b200/csrc -x c++ voidray_b200/csrc/scene_build.cpp
 //       scripts/bvh_stats.cpp -o /tmp/bvh_stats   (one command line)
 //   /tmp/bvh_stats assets/mossy_ground.obj [copies_x copies_z]
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -196,6 +197,18 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!flatten_scene(sc, flat, err)) { std::printf("%s\n", err.c_str()); return 1; }
     const double build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (const char* e = std::getenv("BVH_STATS_REPEAT")) {
+        // warm repeat timing (a commit is repeated every bench step): minimum and median of N more flattens
+        std::vector<double> ms;
+        for (int k = 0, n = atoi(e); k < n; ++k) {
+            FlatScene again;
+            const auto r0 = std::chrono::steady_clock::now();
+            if (!flatten_scene(sc, again, err)) return 1;
+            ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - r0).count());
+        }
+        std::sort(ms.begin(), ms.end());
+        if (!ms.empty()) std::printf("flatten x%zu: min %.3f ms, median %.3f ms\n", ms.size(), ms[0], ms[ms.size() / 2]);
+    }
     {
         // FNV-1a of what the device receives: the same scene must flatten to the same bytes on every run
         auto fnv = [](const void* ptr, size_t n, uint64_t d) {

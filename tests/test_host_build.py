@@ -150,3 +150,31 @@ def test_bvh_quality_meter_builds_and_runs(tmp_path):
     runs = [subprocess.run([exe, os.path.join(ASSETS, "mossy_ground.obj")], capture_output=True, text=True, timeout=300).stdout
             for _ in range(2)]
     assert digest(runs[0]) == digest(runs[1]) == "8301c250a458b25e"
+
+
+def _library_digest(name):
+    m = assets.load_obj_native(os.path.join(ASSETS, name))
+    lib = _lib.load()
+    n = len(m.positions)
+    pos = np.ascontiguousarray(m.positions, F32)
+    uv = np.zeros((n, 2), F32)  # the same filler attributes scripts/bvh_stats.cpp uses
+    nrm = np.tile(np.array([0, 1, 0], F32), (n, 1))
+    idx = np.ascontiguousarray(m.indices, np.uint32).ravel()
+    digest, nodes, depth, ms = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0), C.c_double(0)
+    _lib.check(lib.vr_debug_flatten_mesh_digest(_lib.fptr(pos), _lib.fptr(uv), _lib.fptr(nrm), n,
+                                                idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.size, C.byref(digest),
+                                                C.byref(nodes), C.byref(depth), C.byref(ms)))
+    return f"{digest.value:016x}", nodes.value, depth.value
+
+
+@pytest.mark.parametrize("name,want,nodes", [("fancy_monkey.obj", "cbf0e27fea44afdd", None), ("mushroom.obj", "88b409cb71cbab75", 2530),
+                                             ("mossy_ground.obj", "8301c250a458b25e", 8382),
+                                             ("material_testing_stand.obj", "66408269f0926fcd", 19306)])
+def test_shipped_builder_digest(name, want, nodes):
+    # The flatten inside libvoidray_cuda.so itself (host-only gate): the bytes the device receives are those of the
+    # builder the GPU numbers in profiles/ were measured with, whatever the thread timing (three runs).
+    runs = [_library_digest(name) for _ in range(3)]
+    assert runs[0] == runs[1] == runs[2]
+    assert runs[0][0] == want
+    assert nodes is None or runs[0][1] == nodes
+    assert runs[0][2] <= 32  # the traversal stack depth

@@ -71,6 +71,8 @@ SIGNATURES = {
     "vr_image_free": [_FP],
     "vr_scene_set_environment_hdri_file": [_P, C.c_char_p],
     "vr_debug_reference_leaf_order": [_FP, C.c_uint64, _UP],
+    "vr_debug_flatten_mesh_digest": [_FP, _FP, _FP, C.c_uint32, _UP, C.c_uint32, C.POINTER(C.c_uint64), _UP, _UP,
+                                     C.POINTER(C.c_double)],
     "vr_obj_load": [C.c_char_p, C.POINTER(ObjMeshC)],
     "vr_obj_free": [C.POINTER(ObjMeshC)],
     "vr_scene_add_sphere": [_P, _FP, _F, _UP],

@@ -1116,6 +1116,59 @@ int32_t vr_debug_reference_leaf_order(const float* boxes6, uint64_t n, uint32_t*
     return VR_OK;
 } VR_CATCH
 
+int32_t vr_debug_flatten_mesh_digest(const float* positions, const float* uvs, const float* normals, uint32_t n_vertices,
+                                     const uint32_t* indices, uint32_t n_indices, uint64_t* digest, uint32_t* n_nodes,
+                                     uint32_t* bvh_depth, double* flatten_ms) try {
+    if (!positions || !indices || !digest) return fail(VR_ERR_INVALID, "null argument");
+    HostScene sc;
+    HostMesh m;
+    m.n_vertices = n_vertices;
+    m.pos.assign(positions, positions + 3ull * n_vertices);
+    if (uvs) m.uv.assign(uvs, uvs + 2ull * n_vertices);
+    else m.uv.assign(2ull * n_vertices, 0.0f);
+    if (normals) m.nrm.assign(normals, normals + 3ull * n_vertices);
+    else m.nrm.assign(3ull * n_vertices, 0.0f);
+    const uint32_t n_idx = n_indices - n_indices % 3;
+    for (uint32_t i = 0; i < n_idx; ++i)
+        if (indices[i] >= n_vertices) return fail(VR_ERR_INVALID, "mesh index out of range");
+    m.idx.assign(indices, indices + n_idx);
+    sc.meshes.push_back(std::move(m));
+    HostSurface sf;
+    sf.kind = 0;
+    sf.mesh = 0;
+    sc.surfaces.push_back(sf);
+    MaterialRec mat{};
+    mat.albedo_tex = -1;
+    mat.normal_tex = -1;
+    sc.materials.push_back(mat);
+    sc.objects.push_back(HostObject{0, 0});
+    const float eye[3] = {0.0f, 0.0f, -1.0f}, dir[3] = {0.0f, 0.0f, 1.0f}, up[3] = {0.0f, 1.0f, 0.0f};
+    std::memcpy(sc.camera.eye, eye, 12);
+    std::memcpy(sc.camera.direction, dir, 12);
+    std::memcpy(sc.camera.up, up, 12);
+    sc.camera.fov = 0.6f;
+    sc.camera.has_dof = 0;
+    FlatScene flat;
+    std::string err;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!flatten_scene(sc, flat, err)) return fail(VR_ERR_INVALID, err);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    auto fnv = [](const void* ptr, size_t n, uint64_t d) {  // FNV-1a
+        const unsigned char* b = (const unsigned char*)ptr;
+        for (size_t i = 0; i < n; ++i) d = (d ^ b[i]) * 1099511628211ull;
+        return d;
+    };
+    uint64_t d = 1469598103934665603ull;
+    d = fnv(flat.nodes.data(), flat.nodes.size() * sizeof(Quad), d);
+    d = fnv(flat.tri_isect.data(), flat.tri_isect.size() * sizeof(Quad), d);
+    d = fnv(flat.tri_shade.data(), flat.tri_shade.size() * sizeof(Quad), d);
+    *digest = d;
+    if (n_nodes) *n_nodes = (uint32_t)(flat.nodes.size() / NODE_QUADS);
+    if (bvh_depth) *bvh_depth = flat.bvh_depth;
+    if (flatten_ms) *flatten_ms = ms;
+    return VR_OK;
+} VR_CATCH
+
 int32_t vr_debug_tie_ranks(vr_scene* scene, uint32_t surface, uint32_t* out, uint32_t n) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");

@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
+#include <emmintrin.h>
+#include <exception>
 #include <system_error>
 #include <thread>
 #include <unordered_map>
@@ -335,11 +337,52 @@ struct Box {
     }
 };
 
+// One primitive of the build: 32 bytes, two 16-byte halves (min | id, max | 0) that the passes below read with one
+// SSE load each. The centroid 0.5 * (min + max) is recomputed where it is needed instead of being carried along.
 struct Prim {
-    Box box;
-    float cen[3];
+    float lo[3];
     uint32_t id;
+    float hi[3];
+    uint32_t pad;
+    float cen(int a) const { return 0.5f * (lo[a] + hi[a]); }
 };
+static_assert(sizeof(Prim) == 32, "Prim is two 16-byte halves");
+
+// Box in SSE registers (lanes x, y, z; lane 3 carries whatever the loads brought along and is never read).
+// _mm_min_ps(p, lo) == (p < lo ? p : lo) == std::min(lo, p) and _mm_max_ps(p, hi) == std::max(hi, p) operand for
+// operand, so the bounds are bit-identical to the scalar Box above, signed zeros and NaNs included.
+struct SBox {
+    __m128 lo, hi;
+    void reset() {
+        lo = _mm_set1_ps(FLT_MAX);
+        hi = _mm_set1_ps(-FLT_MAX);
+    }
+    void grow(__m128 plo, __m128 phi) {
+        lo = _mm_min_ps(plo, lo);
+        hi = _mm_max_ps(phi, hi);
+    }
+    void grow(__m128 point) { grow(point, point); }
+    void grow(const SBox& b) { grow(b.lo, b.hi); }
+    void grow(const Prim& p) { grow(_mm_loadu_ps(p.lo), _mm_loadu_ps(p.hi)); }
+    void grow(const Box& b) {
+        grow(_mm_setr_ps(b.lo[0], b.lo[1], b.lo[2], 0.0f), _mm_setr_ps(b.hi[0], b.hi[1], b.hi[2], 0.0f));
+    }
+    Box box() const {
+        float l[4], h[4];
+        _mm_storeu_ps(l, lo);
+        _mm_storeu_ps(h, hi);
+        Box b;
+        for (int a = 0; a < 3; ++a) { b.lo[a] = l[a]; b.hi[a] = h[a]; }
+        return b;
+    }
+    float half_area() const { return box().half_area(); }
+};
+// centroid of a primitive in lanes x, y, z (lane 3 = 0: the id bits are masked out before the arithmetic, a small
+// integer read as a float is a denormal)
+inline __m128 prim_centroid(const Prim& p) {
+    const __m128 mask = _mm_castsi128_ps(_mm_setr_epi32(-1, -1, -1, 0));
+    return _mm_mul_ps(_mm_set1_ps(0.5f), _mm_add_ps(_mm_and_ps(_mm_loadu_ps(p.lo), mask), _mm_loadu_ps(p.hi)));
+}
 
 struct Builder {
     RawVector<Prim>& prims;
@@ -394,7 +437,7 @@ struct Builder {
     }
 
     struct Bins {
-        Box box[3][BINS];
+        SBox box[3][BINS];
         uint32_t count[3][BINS];
         void reset() {
             for (int a = 0; a < 3; ++a)
@@ -474,25 +517,30 @@ struct Builder {
         } else if (par_chunks(n) > 1) {
             std::vector<Box> part(2 * par_chunks(n));
             const size_t used = parallel_chunks(n, par_chunks(n), [&](size_t t, size_t b, size_t e) {
-                Box bb, cb;
+                SBox bb, cb;
                 bb.reset();
                 cb.reset();
                 for (size_t i = lo + b; i < lo + e; ++i) {
-                    bb.grow(prims[i].box);
-                    cb.grow(prims[i].cen);
+                    bb.grow(prims[i]);
+                    cb.grow(prim_centroid(prims[i]));
                 }
-                part[2 * t] = bb;
-                part[2 * t + 1] = cb;
+                part[2 * t] = bb.box();
+                part[2 * t + 1] = cb.box();
             });
             for (size_t t = 0; t < used; ++t) {
                 bounds.grow(part[2 * t]);
                 cbounds.grow(part[2 * t + 1]);
             }
         } else {
+            SBox bb, cb;
+            bb.reset();
+            cb.reset();
             for (uint32_t i = lo; i < hi; ++i) {
-                bounds.grow(prims[i].box);
-                cbounds.grow(prims[i].cen);
+                bb.grow(prims[i]);
+                cb.grow(prim_centroid(prims[i]));
             }
+            bounds = bb.box();
+            cbounds = cb.box();
         }
         out_box = bounds;
         if (n == 1) {
@@ -512,23 +560,27 @@ struct Builder {
             float right_area[SWEEP_MAX];
             for (int axis = 0; axis < 3; ++axis) {
                 if (!(cbounds.hi[axis] > cbounds.lo[axis])) continue;
-                for (uint32_t i = 0; i < n; ++i) order[i] = (uint8_t)i;
+                float cen[SWEEP_MAX];
+                for (uint32_t i = 0; i < n; ++i) {
+                    order[i] = (uint8_t)i;
+                    cen[i] = prims[lo + i].cen(axis);
+                }
                 for (uint32_t i = 1; i < n; ++i) {  // insertion sort by centroid
                     const uint8_t v = order[i];
-                    const float key = prims[lo + v].cen[axis];
+                    const float key = cen[v];
                     uint32_t j = i;
-                    while (j > 0 && prims[lo + order[j - 1]].cen[axis] > key) { order[j] = order[j - 1]; --j; }
+                    while (j > 0 && cen[order[j - 1]] > key) { order[j] = order[j - 1]; --j; }
                     order[j] = v;
                 }
-                Box acc;
+                SBox acc;
                 acc.reset();
                 for (uint32_t i = n - 1; i > 0; --i) {
-                    acc.grow(prims[lo + order[i]].box);
+                    acc.grow(prims[lo + order[i]]);
                     right_area[i] = acc.half_area();
                 }
                 acc.reset();
                 for (uint32_t i = 1; i < n; ++i) {  // split: the first i prims go left
-                    acc.grow(prims[lo + order[i - 1]].box);
+                    acc.grow(prims[lo + order[i - 1]]);
                     const float cost = (acc.half_area() * (float)i + right_area[i] * (float)(n - i)) / parent_area;
                     if (cost < best_cost) {
                         best_cost = cost;
@@ -556,15 +608,20 @@ struct Builder {
                 valid[axis] = cbounds.hi[axis] > cbounds.lo[axis];
                 k[axis] = valid[axis] ? (float)BINS * (1.0f - 1e-6f) / (cbounds.hi[axis] - cbounds.lo[axis]) : 0.0f;
             }
+            // all three bin indices of a primitive at once: (int)((centroid - cmin) * k) per lane (cvttps2dq truncates
+            // like the scalar conversion and gives INT_MIN out of range, which the clamp sends to bin 0 either way);
+            // a flat axis (k = 0) lands in bin 0 and is skipped by the sweep below
+            const __m128 cmin4 = _mm_setr_ps(cmin[0], cmin[1], cmin[2], 0.0f), k4 = _mm_setr_ps(k[0], k[1], k[2], 0.0f);
             auto bin_range = [&](uint32_t b0, uint32_t e0, Bins& bins) {
                 bins.reset();
                 for (uint32_t i = b0; i < e0; ++i) {
                     const Prim& p = prims[i];
+                    const __m128 plo = _mm_loadu_ps(p.lo), phi = _mm_loadu_ps(p.hi);
+                    alignas(16) int bi[4];
+                    _mm_store_si128((__m128i*)bi, _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(prim_centroid(p), cmin4), k4)));
                     for (int axis = 0; axis < 3; ++axis) {
-                        if (!valid[axis]) continue;
-                        int b = (int)((p.cen[axis] - cmin[axis]) * k[axis]);
-                        b = std::min(std::max(b, 0), BINS - 1);
-                        bins.box[axis][b].grow(p.box);
+                        const int b = std::min(std::max(bi[axis], 0), BINS - 1);
+                        bins.box[axis][b].grow(plo, phi);
                         bins.count[axis][b]++;
                     }
                 }
@@ -583,7 +640,7 @@ struct Builder {
             for (int axis = 0; axis < 3; ++axis) {
                 if (!valid[axis]) continue;
                 float right_area[BINS];
-                Box acc;
+                SBox acc;
                 acc.reset();
                 for (int b = BINS - 1; b > 0; --b) {
                     acc.grow(bins.box[axis][b]);
@@ -621,7 +678,7 @@ struct Builder {
             Prim* first = prims.data() + lo;
             Prim* nth = first + n / 2;
             const int ax = best_axis;
-            std::nth_element(first, nth, prims.data() + hi, [ax](const Prim& a, const Prim& b) { return a.cen[ax] < b.cen[ax]; });
+            std::nth_element(first, nth, prims.data() + hi, [ax](const Prim& a, const Prim& b) { return a.cen(ax) < b.cen(ax); });
             mid = lo + n / 2;
         } else if (best_axis < 0) {
             mid = lo + n / 2;  // identical centroids: split by position
@@ -629,32 +686,35 @@ struct Builder {
             const float cmin = cbounds.lo[best_axis], cmax = cbounds.hi[best_axis];
             const float k = (float)BINS * (1.0f - 1e-6f) / (cmax - cmin);
             auto goes_left = [&](const Prim& p) {
-                int b = (int)((p.cen[best_axis] - cmin) * k);
+                int b = (int)((p.cen(best_axis) - cmin) * k);
                 b = std::min(std::max(b, 0), BINS - 1);
                 return b <= best_bin;
             };
             // the partition pass also gathers both sides' bounds (the predicate runs exactly once per element)
             for (int i = 0; i < 4; ++i) kids[i].reset();
             if (chunks > 1) {
-                std::vector<Box> part(4 * chunks);
-                for (Box& b : part) b.reset();
+                std::vector<SBox> part(4 * chunks);
+                for (SBox& b : part) b.reset();
                 mid = lo + (uint32_t)parallel_partition(prims.data() + lo, n, chunks, [&](size_t t, const Prim& p) {
                     const bool left = goes_left(p);
-                    Box* kb = &part[4 * t + (left ? 0 : 2)];
-                    kb[0].grow(p.box);
-                    kb[1].grow(p.cen);
+                    SBox* kb = &part[4 * t + (left ? 0 : 2)];
+                    kb[0].grow(p);
+                    kb[1].grow(prim_centroid(p));
                     return left;
                 });
                 for (size_t t = 0; t < chunks; ++t)
-                    for (int i = 0; i < 4; ++i) kids[i].grow(part[4 * t + i]);
+                    for (int i = 0; i < 4; ++i) kids[i].grow(part[4 * t + i].box());
             } else {
+                SBox sk[4];
+                for (int i = 0; i < 4; ++i) sk[i].reset();
                 Prim* m = std::partition(prims.data() + lo, prims.data() + hi, [&](const Prim& p) {
                     const bool left = goes_left(p);
-                    Box* kb = kids + (left ? 0 : 2);
-                    kb[0].grow(p.box);
-                    kb[1].grow(p.cen);
+                    SBox* kb = sk + (left ? 0 : 2);
+                    kb[0].grow(p);
+                    kb[1].grow(prim_centroid(p));
                     return left;
                 });
+                for (int i = 0; i < 4; ++i) kids[i] = sk[i].box();
                 mid = (uint32_t)(m - prims.data());
             }
             have_kids = true;
@@ -769,7 +829,7 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         r.focal_length = c.has_dof ? dot(sub(ld3(c.focal_point), eye), dir) : 0.0f;
     }
 
-    // ---- per-surface bounds (scene.rs:72-79) and per-mesh tie ranks ----
+    // ---- per-surface bounds (scene.rs:72-79) ----
     std::vector<float> surface_boxes(6 * n_surfaces);
     out.mesh_tie_rank.resize(n_surfaces);
     uint64_t total_tris = 0;
@@ -786,8 +846,30 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                     b[a] = fmin_(b[a], m.pos[3 * v + a]);
                     b[3 + a] = fmax_(b[3 + a], m.pos[3 * v + a]);
                 }
+            total_tris += m.idx.size() / 3;
+        } else if (sf.kind == 1) {  // surfaces.rs:36-43
+            for (int a = 0; a < 3; ++a) {
+                b[a] = sf.center[a] - sf.radius_or_height;
+                b[3 + a] = sf.center[a] + sf.radius_or_height;
+            }
+        } else {  // surfaces.rs:107-114
+            b[0] = -INFINITY; b[1] = sf.radius_or_height - 0.0001f; b[2] = -INFINITY;
+            b[3] = INFINITY; b[4] = sf.radius_or_height + 0.0001f; b[5] = INFINITY;
+        }
+    }
+    timer.lap("surface bounds");
+    if (total_tris >= (1u << 28)) { err = "too many triangles (limit 2^28)"; return false; }
+
+    // ---- per-mesh tie ranks: the reference tree's in-order leaf sequence (mesh.rs:112-141) ----
+    // Only the packed triangle records at the end read them, so they are computed on a second thread while this
+    // one builds the BVH (the two share nothing; both fan out further on their own).
+    auto tie_ranks = [&in, &out, n_surfaces]() {
+        PhaseTimer rank_timer;
+        for (size_t s = 0; s < n_surfaces; ++s) {
+            const HostSurface& sf = in.surfaces[s];
+            if (sf.kind != 0) continue;
+            const HostMesh& m = in.meshes[sf.mesh];
             const size_t nt = m.idx.size() / 3;
-            total_tris += nt;
             RawVector<uint32_t>& rank = out.mesh_tie_rank[s];
             rank.resize(nt);
             if (m.idx.size() > 4 * 3) {  // SMALL_MESH, mesh.rs:43,112
@@ -809,28 +891,34 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                     }
                 }
                 });
-                timer.lap("triangle boxes");
+                rank_timer.lap("(2nd thread) triangle boxes");
                 RawVector<uint32_t> order;
                 reference_leaf_order(boxes.data(), nt, order);
                 parallel_for(nt, [&](size_t i_begin, size_t i_end) {
                     for (size_t i = i_begin; i < i_end; ++i) rank[order[i]] = (uint32_t)i;
                 });
-                timer.lap("reference leaf order");
+                rank_timer.lap("(2nd thread) ref. leaf order");
             } else {
                 // linear loop, first index wins a tie (mesh.rs:129-135)
                 for (size_t t = 0; t < nt; ++t) rank[t] = (uint32_t)(nt - 1 - t);
             }
-        } else if (sf.kind == 1) {  // surfaces.rs:36-43
-            for (int a = 0; a < 3; ++a) {
-                b[a] = sf.center[a] - sf.radius_or_height;
-                b[3 + a] = sf.center[a] + sf.radius_or_height;
-            }
-        } else {  // surfaces.rs:107-114
-            b[0] = -INFINITY; b[1] = sf.radius_or_height - 0.0001f; b[2] = -INFINITY;
-            b[3] = INFINITY; b[4] = sf.radius_or_height + 0.0001f; b[5] = INFINITY;
         }
-    }
-    if (total_tris >= (1u << 28)) { err = "too many triangles (limit 2^28)"; return false; }
+    };
+    std::vector<std::thread> rank_thread;
+    std::exception_ptr rank_error;  // an exception of the second thread (bad_alloc) is rethrown on this one
+    auto tie_ranks_guarded = [&tie_ranks, &rank_error]() {
+        try {
+            tie_ranks();
+        } catch (...) {
+            rank_error = std::current_exception();
+        }
+    };
+    if (total_tris < 1024 || std::thread::hardware_concurrency() < 2 || !try_spawn(rank_thread, tie_ranks_guarded)) tie_ranks();
+    struct Joiner {  // joined before the records are packed, and on every early return
+        std::vector<std::thread>& t;
+        void join() { for (std::thread& x : t) if (x.joinable()) x.join(); }
+        ~Joiner() { join(); }
+    } rank_join{rank_thread};
 
     // ---- scene-level in-order sequence -> global rank base of every surface ----
     RawVector<uint32_t> surface_order;
@@ -880,10 +968,12 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
                 for (size_t t = t_begin; t < t_end; ++t) {
                     const uint32_t gi = g0 + (uint32_t)t;
                     Prim& p = prims[gi];
-                    p.box.reset();
-                    for (int k = 0; k < 3; ++k) p.box.grow(&m.pos[3 * m.idx[3 * t + k]]);
-                    for (int a = 0; a < 3; ++a) p.cen[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
+                    Box b;
+                    b.reset();
+                    for (int k = 0; k < 3; ++k) b.grow(&m.pos[3 * m.idx[3 * t + k]]);
+                    for (int a = 0; a < 3; ++a) { p.lo[a] = b.lo[a]; p.hi[a] = b.hi[a]; }
                     p.id = gi;
+                    p.pad = 0;
                     src[gi] = Src{(uint32_t)s, (uint32_t)t};
                 }
             });
@@ -899,7 +989,10 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         // quantisation grid = bounds of all triangles; a flat axis gets a token extent so the cell size is not 0
         Box scene_box;
         scene_box.reset();
-        for (uint32_t i = 0; i < n_tris; ++i) scene_box.grow(prims[i].box);
+        for (uint32_t i = 0; i < n_tris; ++i) {
+            scene_box.grow(prims[i].lo);
+            scene_box.grow(prims[i].hi);
+        }
         float max_extent = 0.0f;
         for (int a = 0; a < 3; ++a) max_extent = std::max(max_extent, n_tris ? scene_box.hi[a] - scene_box.lo[a] : 0.0f);
         if (!(max_extent > 0.0f)) max_extent = 1.0f;
@@ -948,6 +1041,9 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     out.bvh_depth = builder.max_depth.load();
     timer.lap("SAH build");
 
+    rank_join.join();
+    if (rank_error) std::rethrow_exception(rank_error);
+    timer.lap("wait for the tie ranks");
     // ---- packed records in BVH leaf order ----
     out.tri_isect.resize((size_t)n_tris * TRI_ISECT_QUADS);
     out.tri_shade.resize((size_t)n_tris * TRI_SHADE_QUADS);
