@@ -1,0 +1,27 @@
+#!/bin/bash
+# Builds experiment variants of libvoidray_cuda.so into gpurun_variants/ (travels to the GPU box with the snapshot;
+# scripts/perf_variants.sh then runs scripts/perf_check.sh on the default build and on each of them through
+# VOIDRAY_CUDA_LIB). Each variant is one set of -D flags applied to every translation unit.
+#   bash scripts/build_variants.sh                # all variants below
+#   bash scripts/build_variants.sh stack16        # only the named ones
+set -e
+cd "$(dirname "$0")/.."
+declare -A FLAGS=(
+  [stack16]="-DVR_SMEM_STACK=16"
+  [stack12]="-DVR_SMEM_STACK=12"
+  [tri48]="-DVR_TRI48"
+  [stack16_tri48]="-DVR_SMEM_STACK=16 -DVR_TRI48"
+)
+names=("$@")
+[ ${#names[@]} -eq 0 ] && names=("${!FLAGS[@]}")
+mkdir -p gpurun_variants
+for name in "${names[@]}"; do
+  flags="${FLAGS[$name]}"
+  [ -z "$flags" ] && { echo "unknown variant $name"; exit 2; }
+  obj="build/variants/$name"
+  mkdir -p "$obj"
+  echo "== $name: $flags"
+  make -C voidray_b200/csrc -s -j4 OBJDIR="$PWD/$obj" OUT="$PWD/gpurun_variants/$name.so" EXTRA="$flags" 2>&1 |
+    grep -A2 "k_traceENS" | grep -E "registers|stack frame" || true
+done
+ls -la gpurun_variants/

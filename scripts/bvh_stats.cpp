@@ -156,6 +156,165 @@ struct Tree {
     }
 };
 
+
+// ---- L1 model (BVH_STATS_CACHE=<KB>): how the node order decides what an SM's L1 holds -----------------------------
+// 1024 rays in flight (32 warps x 32 lanes) take one traversal step each per round, a finished ray is replaced by the
+// next one of the list; every node visit touches one 32-byte sector, every triangle test two. The cache is a fully
+// associative LRU over 128-byte lines with per-sector valid bits (a line is allocated on its first sector).
+// Node orders for the L1 model. perm[new index] = old index; node 0 (a copy of the root, node 1) stays.
+static void reorder_nodes(FlatScene& f, const std::vector<uint32_t>& perm) {
+    const size_t n = f.nodes.size() / NODE_QUADS;
+    std::vector<uint32_t> where(n);
+    for (size_t i = 0; i < n; ++i) where[perm[i]] = (uint32_t)i;
+    RawVector<Quad> out(f.nodes.size());
+    for (size_t i = 0; i < n; ++i) {
+        Quad a = f.nodes[(size_t)perm[i] * NODE_QUADS], b = f.nodes[(size_t)perm[i] * NODE_QUADS + 1];
+        int32_t c0, c1;
+        std::memcpy(&c0, &b.z, 4);
+        std::memcpy(&c1, &b.w, 4);
+        if (c0 >= 0) { c0 = (int32_t)where[c0]; std::memcpy(&b.z, &c0, 4); }
+        if (c1 >= 0) { c1 = (int32_t)where[c1]; std::memcpy(&b.w, &c1, 4); }
+        out[i * NODE_QUADS] = a;
+        out[i * NODE_QUADS + 1] = b;
+    }
+    f.nodes.swap(out);
+}
+// area: nodes sorted by the surface area of their own box (the chance that a random ray visits them), largest first;
+// bfs<k>: the top k levels breadth-first, the subtrees below them depth-first as before
+static std::vector<uint32_t> node_order(const FlatScene& f, const std::string& kind) {
+    const size_t n = f.nodes.size() / NODE_QUADS;
+    Tree tree(f);
+    std::vector<uint32_t> perm;
+    perm.push_back(0);
+    if (n < 2) return perm;
+    std::vector<double> area(n, 0.0);
+    std::vector<uint32_t> depth(n, 0);
+    {
+        // node 1 is the root (node 0 its copy); area of a node = area of the union of its two child boxes
+        std::vector<uint32_t> st{1};
+        depth[1] = 0;
+        while (!st.empty()) {
+            const uint32_t i = st.back();
+            st.pop_back();
+            float lo[3], hi[3], l2[3], h2[3];
+            tree.child_box(i, 0, lo, hi);
+            tree.child_box(i, 1, l2, h2);
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], l2[a]); hi[a] = std::max(hi[a], h2[a]); }
+            const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+            area[i] = dx * dy + dy * dz + dz * dx;
+            for (int c = 0; c < 2; ++c) {
+                const int code = tree.child_code(i, c);
+                if (code >= 0) { depth[code] = depth[i] + 1; st.push_back((uint32_t)code); }
+            }
+        }
+    }
+    std::vector<uint32_t> rest;
+    for (uint32_t i = 1; i < n; ++i) rest.push_back(i);
+    if (kind == "area") {
+        std::stable_sort(rest.begin(), rest.end(), [&](uint32_t a, uint32_t b) { return area[a] > area[b]; });
+    } else if (kind.rfind("bfs", 0) == 0) {
+        const uint32_t k = (uint32_t)atoi(kind.c_str() + 3);
+        std::stable_sort(rest.begin(), rest.end(), [&](uint32_t a, uint32_t b) {
+            const uint32_t da = std::min(depth[a], k), db = std::min(depth[b], k);
+            return da < db;  // levels < k breadth-first (stable: left to right), everything deeper keeps the DFS order
+        });
+    }
+    perm.insert(perm.end(), rest.begin(), rest.end());
+    return perm;
+}
+
+struct Walker {
+    const Tree* tree;
+    Ray r;
+    float inv[3];
+    Hit best;
+    int stack[64];
+    int sp, cur, leaf_k;
+    bool done;
+    void start(const Tree* t, const Ray& ray) {
+        tree = t; r = ray; best = Hit{INFINITY, -1}; sp = 0; cur = 0; leaf_k = 0; done = false;
+        for (int a = 0; a < 3; ++a) inv[a] = 1.0f / r.d[a];
+    }
+    // one step; returns the byte address touched (nodes from 0, triangle records from 1 << 40) and its length
+    void step(uint64_t& addr, uint32_t& len) {
+        if (cur >= 0) {
+            addr = (uint64_t)cur * 32; len = 32;
+            float lo[3], hi[3], ta = 0, tb = 0;
+            tree->child_box(cur, 0, lo, hi);
+            const bool ha = tree->slab(lo, hi, r, inv, best.t, ta);
+            tree->child_box(cur, 1, lo, hi);
+            const bool hb = tree->slab(lo, hi, r, inv, best.t, tb);
+            const int ca = tree->child_code(cur, 0), cb = tree->child_code(cur, 1);
+            const bool b_first = hb && (!ha || tb < ta);
+            const int near_c = b_first ? cb : ca, far_c = b_first ? ca : cb;
+            if (ha && hb) stack[sp++] = far_c;
+            if (ha || hb) { cur = near_c; leaf_k = 0; return; }
+        } else {
+            const uint32_t code = ~(uint32_t)cur;
+            const uint32_t first = code >> 3, count = code & 7;
+            if ((uint32_t)leaf_k < count) {
+                addr = ((uint64_t)1 << 40) + (uint64_t)(first + leaf_k) * 64; len = 64;
+                float t;
+                if (tree->tri_hit((int)(first + leaf_k), r, t) && t < best.t) best = Hit{t, (int)(first + leaf_k)};
+                if ((uint32_t)++leaf_k < count) return;
+            } else { addr = 0; len = 0; }
+        }
+        if (sp == 0) { done = true; return; }
+        cur = stack[--sp]; leaf_k = 0;
+    }
+};
+
+struct SectorCache {
+    struct Line { uint64_t tag; uint32_t valid; uint64_t stamp; };
+    std::vector<Line> lines;
+    std::vector<std::pair<uint64_t, uint32_t>> index;  // open-addressing map tag -> slot (slot + 1, 0 = empty)
+    uint64_t clock = 0, hits = 0, misses = 0;
+    explicit SectorCache(size_t kb) : lines(kb * 1024 / 128, Line{~0ull, 0, 0}) {}
+    void touch(uint64_t addr, uint32_t len) {
+        for (uint64_t a = addr & ~31ull; a < addr + len; a += 32) {
+            const uint64_t tag = a >> 7;
+            const uint32_t bit = 1u << ((a >> 5) & 3);
+            ++clock;
+            Line* found = nullptr;
+            Line* lru = &lines[0];
+            for (Line& l : lines) {  // small (a few hundred lines): a linear scan is fine for an offline meter
+                if (l.tag == tag) { found = &l; break; }
+                if (l.stamp < lru->stamp) lru = &l;
+            }
+            if (found) {
+                found->stamp = clock;
+                if (found->valid & bit) ++hits; else { ++misses; found->valid |= bit; }
+            } else {
+                ++misses;
+                *lru = Line{tag, bit, clock};
+            }
+        }
+    }
+};
+
+static void cache_model(const Tree& tree, const std::vector<Ray>& rays, size_t kb, const char* what) {
+    SectorCache cache(kb);
+    const size_t IN_FLIGHT = 1024;
+    std::vector<Walker> w(std::min(IN_FLIGHT, rays.size()));
+    size_t next = 0;
+    for (Walker& x : w) x.start(&tree, rays[next++]);
+    size_t live = w.size();
+    while (live) {
+        for (Walker& x : w) {
+            if (x.done) continue;
+            uint64_t addr = 0; uint32_t len = 0;
+            x.step(addr, len);
+            if (len) cache.touch(addr, len);
+            if (x.done) {
+                if (next < rays.size()) x.start(&tree, rays[next++]);
+                else --live;
+            }
+        }
+    }
+    std::printf("  L1 model %zu KB, %s: %.1f %% sector hit rate (%llu sector accesses)\n", kb, what,
+                100.0 * cache.hits / std::max<uint64_t>(1, cache.hits + cache.misses), (unsigned long long)(cache.hits + cache.misses));
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     const int nx = argc > 2 ? atoi(argv[2]) : 1, nz = argc > 3 ? atoi(argv[3]) : 1;
@@ -222,6 +381,7 @@ int main(int argc, char** argv) {
         d = fnv(flat.tri_shade.data(), flat.tri_shade.size() * sizeof(Quad), d);
         std::printf("flatten digest %016llx\n", (unsigned long long)d);
     }
+    if (const char* e = std::getenv("BVH_STATS_ORDER")) reorder_nodes(flat, node_order(flat, e));  // experiment: see node_order
     Tree tree(flat);
     // camera rays on a 256 x 256 grid, then three generations of diffuse bounces (origin = hit point, direction = a
     // random unit vector flipped into the hemisphere facing back along the ray)
@@ -262,6 +422,9 @@ int main(int argc, char** argv) {
         std::printf("  generation %d: %zu rays, %.1f %% hit, %.2f nodes / ray, %.2f triangle tests / ray, max stack %u\n", gen,
                     rays.size(), 100.0 * hits / rays.size(), (double)n_nodes / rays.size(), (double)n_tris / rays.size(), max_sp);
         all_nodes += n_nodes; all_tris += n_tris; all_rays += rays.size();
+        if (const char* e = std::getenv("BVH_STATS_CACHE")) {
+            if (gen <= 1) cache_model(tree, rays, (size_t)atoi(e), gen == 0 ? "camera rays" : "first-bounce rays");
+        }
         rays.swap(next);
     }
     // the tree only culls: on a sample of the last generation's parents, the walk must find exactly the hit a loop
@@ -284,6 +447,17 @@ int main(int argc, char** argv) {
         }
         std::printf("  brute-force check: %llu of %llu random rays differ\n", (unsigned long long)mismatches, (unsigned long long)checked);
         if (mismatches) return 1;
+    }
+    if (const char* e = std::getenv("BVH_STATS_CACHE")) {
+        // deep-bounce stand-in: random origins inside the scene box, random directions
+        std::vector<Ray> random_rays;
+        g_state = 4242u;
+        for (int k = 0; k < 30000; ++k) {
+            Ray r;
+            for (int a = 0; a < 3; ++a) { r.o[a] = lo_all[a] + rnd() * (hi_all[a] - lo_all[a]); r.d[a] = 2.0f * rnd() - 1.0f; }
+            random_rays.push_back(r);
+        }
+        cache_model(tree, random_rays, (size_t)atoi(e), "random rays");
     }
     std::printf("  all: %.2f nodes / ray, %.2f triangle tests / ray, step estimate (nodes + 0.6 tris) %.2f\n", (double)all_nodes / all_rays,
                 (double)all_tris / all_rays, ((double)all_nodes + 0.6 * all_tris) / all_rays);

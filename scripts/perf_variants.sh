@@ -1,6 +1,13 @@
 #!/bin/bash
-# perf_check.sh for the default build and every library under gpurun_variants/
+# On the GPU box: scripts/perf_check.sh for the default build and every library under gpurun_variants/
+# (built here by scripts/build_variants.sh). PARITY=1 first runs the closest-hit and radiance gates on each variant,
+# so that a variant that is faster but wrong is seen as such.
+#   gpurun --timeout 900 -- 'PARITY=1 bash scripts/perf_variants.sh > gpurun_out/variants.log 2>&1'
 for lib in default gpurun_variants/*.so; do
   if [ "$lib" = default ]; then unset VOIDRAY_CUDA_LIB; else export VOIDRAY_CUDA_LIB=$PWD/$lib; fi
-  echo "== $lib"; bash scripts/perf_check.sh
+  echo "== $lib"
+  if [ -n "$PARITY" ] && [ "$lib" != default ]; then
+    python -m pytest tests/test_gpu_closest_hit.py tests/test_gpu_radiance.py -x -q -m gpu 2>&1 | tail -2
+  fi
+  bash scripts/perf_check.sh
 done

@@ -21,7 +21,16 @@ namespace vr {
 #endif
 static constexpr int TRACE_THREADS = VR_TRACE_THREADS;
 static constexpr int SHADE_THREADS = 128;
-static constexpr int SMEM_STACK = 32;  // per-thread traversal stack, all in shared memory; the builder caps the BVH depth at 32
+// Per-thread traversal stack: VR_SMEM_STACK entries in shared memory; the builder caps the BVH depth at STACK_DEPTH.
+// Experiment -DVR_SMEM_STACK=16: half the shared memory per block (more of the SM's 256 KB left to the L1; the L1
+// model of scripts/bvh_stats.cpp gives 64 -> 128 KB about 8 points of sector hit rate on bounce rays), entries past
+// the shared part go to a per-thread local array (the deepest stack seen on the BASELINE scenes is 13).
+#ifndef VR_SMEM_STACK
+#define VR_SMEM_STACK 32
+#endif
+static constexpr int STACK_DEPTH = 32;
+static constexpr int SMEM_STACK = VR_SMEM_STACK;
+static_assert(SMEM_STACK >= 1 && SMEM_STACK <= STACK_DEPTH, "VR_SMEM_STACK");
 static constexpr float T_MIN = 0.00001f;  // core/scene.rs:183
 static constexpr int SENTINEL = 0x7FFFFFFF;
 
@@ -39,10 +48,16 @@ struct HitResult {
 
 __device__ __forceinline__ void intersect_triangle(const float4* __restrict__ tri_isect, int tri, f3 o, f3 d,
                                                    HitResult& best, uint32_t& best_rank) {
+#ifdef VR_TRI48
+    const float4 q0 = ldg4(tri_isect + TRI_ISECT_QUADS * tri);  // 48-byte records: only 16-byte aligned
+    const f3 v0 = xyz(q0), e1 = xyz(ldg4(tri_isect + TRI_ISECT_QUADS * tri + 1)),
+             e2 = xyz(ldg4(tri_isect + TRI_ISECT_QUADS * tri + 2));
+#else
     const float8 r0 = ldg8(tri_isect + TRI_ISECT_QUADS * tri);      // v0 | e1
     const float8 r1 = ldg8(tri_isect + TRI_ISECT_QUADS * tri + 2);  // e2 | -
     const float4 q0 = r0.lo;
     const f3 v0 = xyz(r0.lo), e1 = xyz(r0.hi), e2 = xyz(r1.lo);
+#endif
     // core/mesh.rs:153-175, same operation order
     const f3 h = cross(d, e2);
     const float a = dot(e1, h);
@@ -113,6 +128,17 @@ struct Traversal {
     uint32_t best_rank;
     int cur, sp;
 };
+// VR_SMEM_STACK < 32: entries SMEM_STACK.. of the stack live in a per-thread local array that is passed alongside
+// the shared part (kept out of Traversal: a dynamically indexed member would drag the whole struct into local memory)
+#if VR_SMEM_STACK < 32
+#define VR_SPILL_PARAM , int* __restrict__ spill
+#define VR_SPILL_ARG , spill
+#define VR_SPILL_DECL int spill[STACK_DEPTH - SMEM_STACK];
+#else
+#define VR_SPILL_PARAM
+#define VR_SPILL_ARG
+#define VR_SPILL_DECL
+#endif
 
 __device__ __forceinline__ void trav_axis(float o, float d, float gmin, float extent, float& a, float& bn, float& bf,
                                           uint32_t& sel) {
@@ -143,10 +169,14 @@ __device__ __forceinline__ void trav_begin(Traversal& tr, const DeviceScene& sc,
 
 // The stack lives entirely in shared memory (one column per thread, stride = blockDim.x: conflict-free).
 // Push and pop are written so that they compile to predicated STS / LDS instead of branches.
-__device__ __forceinline__ int trav_pop(Traversal& tr, const int* sstack, int sstride) {
+__device__ __forceinline__ int trav_pop(Traversal& tr, const int* sstack, int sstride VR_SPILL_PARAM) {
     const bool empty = tr.sp == 0;
     tr.sp -= empty ? 0 : 1;
+#if VR_SMEM_STACK < 32
+    const int v = tr.sp < SMEM_STACK ? sstack[tr.sp * sstride] : spill[tr.sp - SMEM_STACK];
+#else
     const int v = sstack[tr.sp * sstride];
+#endif
     return empty ? SENTINEL : v;
 }
 
@@ -158,7 +188,7 @@ __device__ __forceinline__ float plane_t(uint32_t pair, uint32_t sel, float a, f
 }
 
 // One inner node: two slab tests from a single 32-byte record, near child first, far child pushed.
-__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride) {
+__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride VR_SPILL_PARAM) {
     const float8 n = ldg8(nodes + 2 * tr.cur);
     const uint32_t w0 = __float_as_uint(n.lo.x), w1 = __float_as_uint(n.lo.y), w2 = __float_as_uint(n.lo.z),
                    w3 = __float_as_uint(n.lo.w), w4 = __float_as_uint(n.hi.x), w5 = __float_as_uint(n.hi.y);
@@ -181,22 +211,29 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
     const int near_c = b_first ? cb : ca;
     const int far_c = b_first ? ca : cb;
     const bool both = hit_a && hit_b, any = hit_a || hit_b;
+#if VR_SMEM_STACK < 32
+    if (both) {
+        if (tr.sp < SMEM_STACK) sstack[tr.sp * sstride] = far_c;
+        else spill[tr.sp - SMEM_STACK] = far_c;
+    }
+#else
     if (both) sstack[tr.sp * sstride] = far_c;
+#endif
     tr.sp += both ? 1 : 0;
     int next = near_c;
-    if (!any) next = trav_pop(tr, sstack, sstride);
+    if (!any) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
     tr.cur = next;
 }
 
 // One triangle of the current leaf; the leaf code counts down so that lanes with short leaves do not idle
 // through a neighbour's longer one.
 __device__ __forceinline__ void trav_leaf_step(Traversal& tr, const float4* __restrict__ tri_isect, int* sstack,
-                                               int sstride) {
+                                               int sstride VR_SPILL_PARAM) {
     const int code = ~tr.cur;
     const int first = code >> 3, count = code & 7;
     if (count > 0) intersect_triangle(tri_isect, first, tr.o, tr.d, tr.best, tr.best_rank);
     int next = ~(((first + 1) << 3) | (count - 1));
-    if (count <= 1) next = trav_pop(tr, sstack, sstride);
+    if (count <= 1) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
     tr.cur = next;
 }
 
@@ -209,12 +246,13 @@ __device__ __forceinline__ HitResult trav_finish(Traversal& tr, const DeviceScen
 // One ray, start to finish (gate kernels).
 __device__ __forceinline__ HitResult closest_hit(const DeviceScene& sc, f3 o, f3 d, int* sstack, int sstride) {
     Traversal tr;
+    VR_SPILL_DECL
     trav_begin(tr, sc, o, d);
     const float4* __restrict__ nodes = (const float4*)sc.nodes;
     const float4* __restrict__ tri_isect = (const float4*)sc.tri_isect;
     while (tr.cur != SENTINEL) {
-        if (is_inner(tr.cur)) trav_node(tr, nodes, sstack, sstride);
-        else trav_leaf_step(tr, tri_isect, sstack, sstride);
+        if (is_inner(tr.cur)) trav_node(tr, nodes, sstack, sstride VR_SPILL_ARG);
+        else trav_leaf_step(tr, tri_isect, sstack, sstride VR_SPILL_ARG);
     }
     return trav_finish(tr, sc);
 }
@@ -366,6 +404,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
     const unsigned lt_mask = (1u << lane) - 1u;
 
     Traversal tr;
+    VR_SPILL_DECL
     tr.cur = SENTINEL;
     bool have = false;
     bool exhausted = false;  // warp-uniform: the queue has no more rays
@@ -423,11 +462,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
             if (n_node >= n_leaf * VR_LEAF_VOTE_NUM) {
 #pragma unroll
                 for (int step = 0; step < VR_NODE_STEPS; ++step)
-                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS);
+                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG);
             } else {
 #pragma unroll
                 for (int step = 0; step < VR_LEAF_STEPS; ++step)
-                    if (have && tr.cur < 0) trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS);
+                    if (have && tr.cur < 0) trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS VR_SPILL_ARG);
             }
         }
     }

@@ -22,7 +22,13 @@ static const int LEAF_MAX_TRIS = 4;
 //   q1 = (e1.xyz, 0)
 //   q2 = (e2.xyz, 0)
 //   q3 = padding to the 32-byte alignment the 256-bit loads need
+// Experiment -DVR_TRI48 (every translation unit): 48-byte records, q3 dropped, three 128-bit loads; the L1 model of
+// scripts/bvh_stats.cpp gives it 2-3 points of sector hit rate. Not the shipped layout.
+#ifdef VR_TRI48
+static const int TRI_ISECT_QUADS = 3;
+#else
 static const int TRI_ISECT_QUADS = 4;
+#endif
 
 // Shading record, 80 B = 5 x float4, fetched once per closest hit.
 //   q0 = (n0.xyz, uv0.x)   q1 = (n1.xyz, uv0.y)   q2 = (n2.xyz, uv1.x)

@@ -1061,7 +1061,7 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         qi[0] = Quad{p0.x, p0.y, p0.z, bits_f(rank)};
         qi[1] = Quad{e1.x, e1.y, e1.z, 0.0f};
         qi[2] = Quad{e2.x, e2.y, e2.z, 0.0f};
-        qi[3] = Quad{0.0f, 0.0f, 0.0f, 0.0f};
+        if (TRI_ISECT_QUADS > 3) qi[3] = Quad{0.0f, 0.0f, 0.0f, 0.0f};
         // geometric normal, mesh.rs:80-84
         const V3 ng = normalize(cross(sub(p2, p1), sub(p0, p1)));
         const V3 n0 = ld3(&m.nrm[3 * i0]), n1 = ld3(&m.nrm[3 * i1]), n2 = ld3(&m.nrm[3 * i2]);
