@@ -11,6 +11,8 @@ declare -A FLAGS=(
   [stack12]="-DVR_SMEM_STACK=12"
   [tri48]="-DVR_TRI48"
   [stack16_tri48]="-DVR_SMEM_STACK=16 -DVR_TRI48"
+  [tex8]="-DVR_TEX8"
+  [stack16_tri48_tex8]="-DVR_SMEM_STACK=16 -DVR_TRI48 -DVR_TEX8"
 )
 names=("$@")
 [ ${#names[@]} -eq 0 ] && names=("${!FLAGS[@]}")

@@ -25,3 +25,12 @@ def test_header_compiles_as_c99_and_host_calls_work(tmp_path):
     assert m, r.stdout
     assert (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (C.sizeof(_lib.RenderSettingsC), C.sizeof(_lib.StatsC),
                                                                    C.sizeof(_lib.MaterialDescC))
+
+
+def test_unorm8_conversion_of_the_tex8_experiment_is_exact(tmp_path):
+    exe = str(tmp_path / "unorm8_exact")
+    r = subprocess.run(["gcc", "-O1", "-ffp-contract=off", os.path.join(ROOT, "tests", "c", "unorm8_exact.c"), "-lm", "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "0 of 256 values differ" in r.stdout, r.stdout

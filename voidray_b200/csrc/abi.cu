@@ -201,6 +201,19 @@ void unpin_host(vr_scene* scene, const std::vector<float>& v) {
 int32_t upload_texture(vr_scene* scene, const HostTexture& t, void* stage, TextureRec* rec) {
     const size_t n = (size_t)t.w * t.h;
     void* d = nullptr;
+#ifdef VR_TEX8
+    if (!t.rgba8.empty()) {  // 8-bit source: 4 B/texel over the bus and in HBM, widened per tap in the kernel
+        VR_CUDA(scene->dev_mem.get(&d, 4 * n));
+        VR_CUDA(cudaMemcpyAsync(d, t.rgba8.data(), 4 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
+        scene->h2d_bytes += 4 * n;
+        rec->texels = d;
+        rec->width = t.w;
+        rec->height = t.h;
+        rec->sample_type = t.sample_type;
+        rec->pad = 1;
+        return VR_OK;
+    }
+#endif
     VR_CUDA(scene->dev_mem.get(&d, 16 * n));
     VR_CUDA(cudaMemcpyAsync(stage, t.rgb.data(), 12 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
     launch_expand_rgb((const float*)stage, (float4*)d, n, scene->ctx->stream);
@@ -235,6 +248,28 @@ int32_t ensure_env_tables(vr_scene* scene) {
     VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));  // the host vectors go out of scope
     return VR_OK;
 }
+
+#ifdef VR_TEX8
+// Experiment: a texture whose every value is exactly v / 255 (an 8-bit source through to_rgb32f) also keeps its
+// RGBA8 form; the kernel's conversion reproduces the same floats, so the lookups do not change by a bit.
+void pack_rgba8(HostTexture& t) {
+    const size_t n = (size_t)t.w * t.h;
+    std::vector<uint8_t> out(4 * n);
+    for (size_t i = 0; i < n; ++i) {
+        for (int c = 0; c < 3; ++c) {
+            const float f = t.rgb[3 * i + c];
+            const float scaled = f * 255.0f;
+            if (!(scaled >= 0.0f && scaled <= 255.0f)) return;
+            const int v = (int)(scaled + 0.5f);
+            const float back = (float)v / 255.0f;
+            if (std::memcmp(&back, &f, 4) != 0) return;  // bit for bit (-0.0 is not an 8-bit value)
+            out[4 * i + c] = (uint8_t)v;
+        }
+        out[4 * i + 3] = 0;
+    }
+    t.rgba8.swap(out);
+}
+#endif
 
 template <typename T>
 int32_t add_texture_int(vr_scene* scene, const T* pixels, uint32_t w, uint32_t h, uint32_t channels,
@@ -354,9 +389,21 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
     t.h = h;
     t.sample_type = sample_type;
     t.rgb.assign(rgb, rgb + (size_t)3 * w * h);
+#ifdef VR_TEX8
+    pack_rgba8(t);
+#endif
     scene->host.textures.push_back(std::move(t));
     cudaSetDevice(scene->ctx->device);
     pin_host(scene, scene->host.textures.back().rgb);
+#ifdef VR_TEX8
+    {
+        const std::vector<uint8_t>& p8 = scene->host.textures.back().rgba8;
+        if (!p8.empty() && cudaHostRegister((void*)p8.data(), p8.size(), cudaHostRegisterDefault) == cudaSuccess)
+            scene->pinned.push_back(p8.data());
+        else
+            cudaGetLastError();
+    }
+#endif
     scene->committed = false;
     if (texture) *texture = (uint32_t)scene->host.textures.size() - 1;
     return VR_OK;

@@ -260,8 +260,23 @@ __device__ __forceinline__ HitResult closest_hit(const DeviceScene& sc, f3 o, f3
 // ------------------------------------------------------------------------------------------------
 // Textures and environment (core/texture.rs:52-98, voidray_common/src/environments.rs:57-86)
 // ------------------------------------------------------------------------------------------------
+#ifdef VR_TEX8
+// (float)v / 255.0f, correctly rounded, without the division: one Newton step on v * (1 / 255) recovers the exact
+// quotient for every v in 0..255 (checked exhaustively on the host: tests/c/unorm8_exact.c)
+__device__ __forceinline__ float unorm8(uint32_t v) {
+    const float x = (float)v, r = 1.0f / 255.0f;
+    const float q = x * r;
+    return __fmaf_rn(__fmaf_rn(-q, 255.0f, x), r, q);
+}
+#endif
 __device__ __forceinline__ f3 texel(const TextureRec& tex, uint32_t idx, uint32_t len) {
     if (idx >= len) idx -= len;  // `% len`: idx < 2*len always
+#ifdef VR_TEX8
+    if (tex.pad == 1) {
+        const uchar4 v = __ldg((const uchar4*)tex.texels + idx);
+        return mk3(unorm8(v.x), unorm8(v.y), unorm8(v.z));
+    }
+#endif
     return xyz(ldg4((const float4*)tex.texels + idx));
 }
 __device__ __forceinline__ f3 bilinear_sample(const TextureRec& tex, float x, float y) {

@@ -49,7 +49,7 @@ struct TextureRec {  // texels are RGBA f32 (w unused) so one tap is one 16-byte
     const void* texels;  // float4*
     uint32_t width, height;
     int32_t sample_type;
-    uint32_t pad;
+    uint32_t pad;  // experiment -DVR_TEX8: 1 = texels are RGBA8 (4 B), converted on the device with the exact v / 255
 };
 
 struct AnalyticRec {  // 32 B; tested linearly after the triangle BVH (scenes have a handful)

@@ -54,6 +54,9 @@ struct HostSurface {
 
 struct HostTexture {
     std::vector<float> rgb;  // 3*w*h
+#ifdef VR_TEX8
+    std::vector<uint8_t> rgba8;  // experiment: 4*w*h when every float is exactly v / 255 (an 8-bit source), else empty
+#endif
     uint32_t w = 0, h = 0;
     int32_t sample_type = 0;
 };
