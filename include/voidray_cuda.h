@@ -70,7 +70,7 @@ int32_t vr_scene_add_texture_rgb16(vr_scene* scene, const uint16_t* pixels, uint
 
 /* Scene::add_image_texture(path, sample_type) (scene.rs:154-160 -> ImageTexture::new, core/texture.rs:36-49):
  * decodes the file in the library like `image::open(path).unwrap().to_rgb32f()` — PNG, baseline / progressive
- * JPEG, TIFF (strips and tiles; none / LZW / Deflate / PackBits), BMP, TGA, PNM, farbfeld, Radiance HDR, scan-line / tiled OpenEXR
+ * JPEG, TIFF (strips and tiles; none / LZW / Deflate / PackBits), BMP, GIF, ICO, DDS (DXT1/3/5), TGA, PNM, farbfeld, Radiance HDR, scan-line / tiled OpenEXR
  * (none / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A), recognised by magic bytes (TGA by its extension). Where the
  * reference panics (missing or undecodable file) this returns VR_ERR_INVALID with the reason in vr_last_error(). */
 int32_t vr_scene_add_image_texture_file(vr_scene* scene, const char* path, int32_t sample_type, uint32_t* texture);

@@ -69,7 +69,16 @@ def _corpus(tmp_path):
             for half in (0, 1):
                 cv2.imwrite(str(d / f"{name}_{half}.exr"), f, [cv2.IMWRITE_EXR_COMPRESSION, flag, cv2.IMWRITE_EXR_TYPE,
                                                                cv2.IMWRITE_EXR_TYPE_HALF if half else cv2.IMWRITE_EXR_TYPE_FLOAT])
-    from test_image_io import _write_tiled_exr, _write_tiled_tiff
+    Image.fromarray(rgb).quantize(40).save(d / "a.gif")
+    Image.fromarray(rgb).quantize(6).save(d / "b.gif", interlace=True)
+    icon = Image.fromarray(np.dstack([rgb[:32, :32], np.full((32, 32), 255, np.uint8)]))
+    icon.save(d / "p.ico", sizes=[(32, 32)])
+    icon.save(d / "q.ico", sizes=[(16, 16), (32, 32)], bitmap_format="bmp")
+    for fmt in ("DXT1", "DXT5"):
+        Image.fromarray(np.dstack([rgb, rgb[:, :, 0]])).save(d / f"{fmt}.dds", pixel_format=fmt)
+    from test_image_io import _rle8_bmp, _write_tiled_exr, _write_tiled_tiff
+    pal_img = Image.fromarray(rgb).quantize(32)
+    (d / "rle8.bmp").write_bytes(_rle8_bmp(np.asarray(pal_img), np.asarray(pal_img.getpalette()[:96], np.uint8).reshape(-1, 3), 2))
     _write_tiled_tiff(str(d / "tiled8.tif"), rgb, (32, 16), True, True)
     _write_tiled_tiff(str(d / "tiled16.tif"), rgb.astype(np.uint16) * 257, (16, 16), False, True, big_endian=True)
     for comp in (0, 3):

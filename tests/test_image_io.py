@@ -431,6 +431,89 @@ def test_openexr_tiled(tmp_path, compression, half):
     assert np.array_equal(assets.load_image_native(path), want)
 
 
+def _rle8_bmp(idx, palette, absolute_every=0):
+    """A BMP with BI_RLE8 pixel data, written by hand (Pillow reads RLE BMPs but does not write them)."""
+    import struct
+    h, w = idx.shape
+    body = bytearray()
+    for y in range(h - 1, -1, -1):  # bottom-up
+        row, x = idx[y], 0
+        while x < w:
+            if absolute_every and (x // 7) % absolute_every == 0 and w - x >= 3:
+                n = min(5, w - x)  # absolute run of n >= 3 literal indices, padded to 16 bits
+                body += bytes([0, n]) + bytes(int(v) for v in row[x:x + n]) + (b"\0" if n & 1 else b"")
+                x += n
+                continue
+            n = 1
+            while x + n < w and n < 255 and row[x + n] == row[x]:
+                n += 1
+            body += bytes([n, int(row[x])])
+            x += n
+        body += b"\0\0"
+    body += b"\0\1"
+    pal = b"".join(bytes([int(c[2]), int(c[1]), int(c[0]), 0]) for c in palette)
+    off = 14 + 40 + len(pal)
+    return (b"BM" + struct.pack("<IHHI", off + len(body), 0, 0, off) +
+            struct.pack("<IiiHHIIiiII", 40, w, h, 1, 8, 1, len(body), 2835, 2835, len(palette), 0) + pal + bytes(body))
+
+
+def test_gif_ico_dds_and_rle_bmp(tmp_path):
+    # the rest of the `image` crate's default decoder set (image 0.24.3: gif, ico, dds / dxt; bmp with RLE)
+    from PIL import Image
+
+    y, x = np.mgrid[0:61, 0:83]
+    rgb = np.stack([(np.sin(x / 7.0) + 1) * 120, (np.cos(y / 5.0) + 1) * 120, (x + y) % 256], -1).astype(np.uint8)
+    pil = lambda p: np.asarray(Image.open(p).convert("RGB"), F32) / F32(255.0)  # noqa: E731
+    # GIF: 8-bit and 3-bit code sizes, interlaced rows, a transparent index (keeps its palette colour), > 4096 codes
+    Image.fromarray(rgb).quantize(200).save(tmp_path / "a.gif")
+    Image.fromarray(rgb).quantize(200).save(tmp_path / "b.gif", interlace=True)
+    Image.fromarray(rgb).quantize(200).save(tmp_path / "c.gif", transparency=3)
+    Image.fromarray(rgb).quantize(5).save(tmp_path / "d.gif")
+    Image.fromarray(np.repeat(np.repeat(rgb, 9, 0), 7, 1)).quantize(256).save(tmp_path / "e.gif")
+    for n in "abcde":
+        assert np.array_equal(assets.load_image_native(str(tmp_path / f"{n}.gif")), pil(tmp_path / f"{n}.gif")), n
+    # ICO: PNG payload, BMP payload (XOR + AND bitmaps), several entries (the largest wins)
+    icon = Image.fromarray(np.dstack([rgb[:48, :48], np.full((48, 48), 255, np.uint8)]))
+    icon.save(tmp_path / "p.ico", sizes=[(48, 48)])
+    icon.save(tmp_path / "q.ico", sizes=[(48, 48)], bitmap_format="bmp")
+    icon.save(tmp_path / "r.ico", sizes=[(16, 16), (48, 48), (32, 32)], bitmap_format="bmp")
+    for n in "pqr":
+        got = assets.load_image_native(str(tmp_path / f"{n}.ico"))
+        assert got.shape == (48, 48, 3) and np.array_equal(got, pil(tmp_path / f"{n}.ico")), n
+    # DDS: DXT1 / DXT3 / DXT5 colour blocks; decoders differ in how they widen 5:6:5 and round the interpolants
+    for fmt in ("DXT1", "DXT3", "DXT5"):
+        Image.fromarray(np.dstack([rgb[:58, :79], np.full((58, 79), 255, np.uint8)])).save(tmp_path / f"{fmt}.dds", pixel_format=fmt)
+        got = assets.load_image_native(str(tmp_path / f"{fmt}.dds"))
+        d = np.abs(np.rint(got * 255.0) - np.rint(pil(tmp_path / f"{fmt}.dds") * 255.0))
+        assert got.shape == (58, 79, 3) and d.max() <= 2, fmt
+    # a hand-made DXT1 block pair: endpoints 0xFFFF / 0x0000 (4-colour mode) and the 3-colour + black mode
+    import struct
+    hdr = bytearray(128)
+    hdr[0:4] = b"DDS "
+    struct.pack_into("<III", hdr, 4, 124, 0x1007, 4)
+    struct.pack_into("<I", hdr, 16, 8)
+    struct.pack_into("<II4s", hdr, 76, 32, 4, b"DXT1")
+    blocks = struct.pack("<HHI", 0xFFFF, 0x0000, 0xE4E4E4E4) + struct.pack("<HHI", 0x0000, 0xFFFF, 0xE4E4E4E4)
+    (tmp_path / "hand.dds").write_bytes(bytes(hdr) + blocks)
+    got = np.rint(assets.load_image_native(str(tmp_path / "hand.dds")) * 255.0)
+    assert got[0, :4, 0].tolist() == [255, 0, 170, 85] and got[0, 4:, 0].tolist() == [0, 255, 128, 0]
+    # BMP RLE8: encoded runs only, then with absolute runs mixed in
+    pal_img = Image.fromarray(rgb).quantize(64)
+    idx = np.asarray(pal_img)
+    palette = np.asarray(pal_img.getpalette()[:64 * 3], np.uint8).reshape(-1, 3)
+    for k, every in enumerate((0, 2)):
+        path = tmp_path / f"rle{k}.bmp"
+        path.write_bytes(_rle8_bmp(idx, palette, every))
+        want = palette[idx].astype(F32) / F32(255.0)
+        assert np.array_equal(pil(path), want)  # the file is a valid RLE8 BMP
+        assert np.array_equal(assets.load_image_native(str(path)), want)
+    for name, why in [("a.gif", "gif"), ("q.ico", "ico|bmp"), ("DXT5.dds", "dds")]:
+        cut = tmp_path / ("cut_" + name)
+        cut.write_bytes((tmp_path / name).read_bytes()[:150])
+        with pytest.raises(_lib.VoidrayError, match=why):
+            assets.load_image_native(str(cut))
+
+
 def test_errors_are_reported_not_fatal(tmp_path):
     with pytest.raises(_lib.VoidrayError, match="cannot open"):
         assets.load_image_native(str(tmp_path / "missing.png"))

@@ -17,12 +17,13 @@ struct DecodedImage {
     std::vector<uint8_t> u8;     // 3*w*h when bits == 8
     std::vector<uint16_t> u16;   // 3*w*h when bits == 16
     std::vector<float> f32;      // 3*w*h when bits == 32
-    const char* format = "";     // "png", "jpeg", "tiff", "bmp", "tga", "pnm", "farbfeld", "hdr", "exr"
+    const char* format = "";     // "png", "jpeg", "tiff", "bmp", "gif", "ico", "dds", "tga", "pnm", "farbfeld", "hdr", "exr"
 };
 
 // Decodes PNG, baseline/progressive JPEG, TIFF (strips and tiles; none / LZW / Deflate / PackBits), BMP (uncompressed, bit
-// fields), TGA (colour-mapped / true-colour / grey, RLE), PNM (P1..P6), farbfeld, Radiance HDR and scan-line / tiled OpenEXR
-// (none / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A), recognised by their magic bytes (TGA: by extension).
+// fields, RLE4 / RLE8), GIF (first frame), ICO / CUR, DDS (DXT1 / DXT3 / DXT5), TGA (colour-mapped / true-colour / grey, RLE),
+// PNM (P1..P6), farbfeld, Radiance HDR and scan-line / tiled OpenEXR (none / RLE / ZIPS / ZIP / PIZ / PXR24 / B44 / B44A),
+// recognised by their magic bytes (TGA, ICO: by extension or a plausible header).
 bool decode_image_file(const char* path, DecodedImage& out, std::string& err);
 // ext: lower-case file extension when known (TGA has no signature); nullptr = guess from the bytes alone.
 bool decode_image_memory(const uint8_t* data, size_t size, DecodedImage& out, std::string& err, const char* ext = nullptr);
