@@ -150,6 +150,12 @@ def test_bvh_quality_meter_builds_and_runs(tmp_path):
     runs = [subprocess.run([exe, os.path.join(ASSETS, "mossy_ground.obj")], capture_output=True, text=True, timeout=300).stdout
             for _ in range(2)]
     assert digest(runs[0]) == digest(runs[1]) == "8301c250a458b25e"
+    # the opt-in insertion-based optimiser (VOIDRAY_BVH_OPT) re-hangs subtrees: still no real hit culled, depth within
+    # the traversal stack, and a different tree than the default one
+    opt = subprocess.run([exe, os.path.join(ASSETS, "fancy_monkey.obj")], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, VOIDRAY_BVH_OPT="2")).stdout
+    assert "brute-force check: 0 of 3000 random rays differ" in opt and digest(opt) != "cbf0e27fea44afdd"
+    assert int(re.search(r"depth (\d+)", opt).group(1)) <= 32
 
 
 def _library_digest(name):

@@ -775,6 +775,250 @@ struct Builder {
     }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Optional post-pass (VOIDRAY_BVH_OPT=<passes>, default off): insertion-based tree optimisation
+// (Bittner, Hapala, Havran, "Fast insertion-based optimization of bounding volume hierarchies", 2013) on the
+// finished, quantised tree. A subtree is cut out (its parent is replaced by its sibling) and re-inserted where the
+// summed area of the inner nodes grows least, found by branch and bound from the root. All boxes are the 15-bit grid
+// boxes of layout.h, so unions are exact and every node stays the union of its leaves: the tree remains conservative
+// for the same reason the input was. Leaves (triangle ranges) are never changed, only where they hang.
+// ------------------------------------------------------------------------------------------------
+struct QBox {
+    uint16_t lo[3], hi[3];
+    void grow(const QBox& b) {
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
+    }
+    bool operator==(const QBox& b) const { return !std::memcmp(this, &b, sizeof *this); }
+};
+
+struct TreeOptimizer {
+    struct Item {
+        QBox box;
+        int32_t parent, child[2];  // child[0] < 0: a leaf, leaf_code holds its code
+        int32_t leaf_code;
+        uint32_t height;           // 0 for a leaf
+    };
+    std::vector<Item> items;
+    double cell[3];
+    int32_t root = -1;
+
+    double area(const QBox& b) const {
+        const double dx = (double)(b.hi[0] - b.lo[0]) * cell[0], dy = (double)(b.hi[1] - b.lo[1]) * cell[1],
+                     dz = (double)(b.hi[2] - b.lo[2]) * cell[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    static QBox child_qbox(const Quad* q, int c) {
+        uint32_t w[6];
+        const float src[6] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y};
+        std::memcpy(w, src, 24);
+        QBox b;
+        for (int a = 0; a < 3; ++a) {
+            b.lo[a] = (uint16_t)(w[3 * c + a] & 0x7FFF);
+            b.hi[a] = (uint16_t)((w[3 * c + a] >> 16) & 0x7FFF);
+        }
+        return b;
+    }
+    static bool empty_box(const QBox& b) { return b.lo[0] > b.hi[0] || b.lo[1] > b.hi[1] || b.lo[2] > b.hi[2]; }
+
+    // flat nodes -> items (iterative; node 1 is the root, node 0 its copy)
+    bool load(const FlatScene& f) {
+        for (int a = 0; a < 3; ++a) cell[a] = (double)f.grid_extent[a] / 32768.0;
+        const size_t n_nodes = f.nodes.size() / NODE_QUADS;
+        if (n_nodes < 2) return false;
+        items.reserve(2 * n_nodes + 1);
+        struct Todo {
+            int32_t node, item;
+        };
+        std::vector<Todo> todo;
+        items.push_back(Item{});
+        items[0].parent = -1;
+        root = 0;
+        todo.push_back(Todo{1, 0});
+        while (!todo.empty()) {
+            const Todo t = todo.back();
+            todo.pop_back();
+            const Quad* q = &f.nodes[(size_t)t.node * NODE_QUADS];
+            int32_t code[2];
+            std::memcpy(&code[0], &q[1].z, 4);
+            std::memcpy(&code[1], &q[1].w, 4);
+            for (int c = 0; c < 2; ++c) {
+                const int32_t id = (int32_t)items.size();
+                items.push_back(Item{});
+                Item& it = items[id];
+                it.box = child_qbox(q, c);
+                if (empty_box(it.box)) return false;  // a one-leaf tree carries an empty second child: nothing to optimise
+                it.parent = t.item;
+                it.leaf_code = code[c];
+                it.child[0] = it.child[1] = -1;
+                it.height = 0;
+                items[t.item].child[c] = id;
+                if (code[c] >= 0) todo.push_back(Todo{code[c], id});
+            }
+        }
+        refit_all();
+        return true;
+    }
+    bool is_leaf(int32_t i) const { return items[i].child[0] < 0; }
+    void refit_all() {
+        // children always have larger ids than their parents after load(); afterwards refit() keeps boxes current
+        for (int32_t i = (int32_t)items.size() - 1; i >= 0; --i) {
+            if (is_leaf(i)) continue;
+            Item& it = items[i];
+            it.box = items[it.child[0]].box;
+            it.box.grow(items[it.child[1]].box);
+            it.height = 1 + std::max(items[it.child[0]].height, items[it.child[1]].height);
+        }
+    }
+    void refit(int32_t i) {  // from inner node i upwards until nothing changes
+        while (i >= 0) {
+            Item& it = items[i];
+            QBox b = items[it.child[0]].box;
+            b.grow(items[it.child[1]].box);
+            const uint32_t h = 1 + std::max(items[it.child[0]].height, items[it.child[1]].height);
+            if (b == it.box && h == it.height) break;
+            it.box = b;
+            it.height = h;
+            i = it.parent;
+        }
+    }
+    uint32_t depth_of(int32_t i) const {  // the root has depth 1 (as in Builder::build)
+        uint32_t d = 1;
+        for (int32_t p = items[i].parent; p >= 0; p = items[p].parent) ++d;
+        return d;
+    }
+    double inner_area_sum() const {
+        double s = 0.0;
+        for (size_t i = 0; i < items.size(); ++i)
+            if (!is_leaf((int32_t)i)) s += area(items[i].box);
+        return s;
+    }
+
+    // Cuts n out and re-inserts it at the cheapest position. Returns true if the tree changed.
+    bool reinsert(int32_t n) {
+        const int32_t p = items[n].parent;
+        if (p < 0) return false;
+        const int32_t g = items[p].parent;
+        if (g < 0) return false;  // children of the root stay (the root node itself is not re-created)
+        const int32_t s = items[p].child[0] == n ? items[p].child[1] : items[p].child[0];
+        // remove: s takes p's place under g
+        items[g].child[items[g].child[0] == p ? 0 : 1] = s;
+        items[s].parent = g;
+        refit(g);
+        // branch and bound for the best sibling x: cost = area(x + n) + sum over x's ancestors of their growth
+        const QBox nb = items[n].box;
+        const double n_area = area(nb);
+        const uint32_t n_height = items[n].height;
+        std::vector<Cand>& heap = heap_;
+        heap.clear();
+        heap.push_back(Cand{0.0, root, 1});
+        double best_cost = 1e300;
+        int32_t best = -1;
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end());
+            const Cand c = heap.back();
+            heap.pop_back();
+            if (c.induced + n_area >= best_cost) break;  // nothing left in the queue can do better
+            QBox u = items[c.item].box;
+            u.grow(nb);
+            const double direct = area(u);
+            // the new parent sits at c.depth, n below it: the deepest leaf of n lands at c.depth + 1 + n_height
+            const bool fits = c.depth + 1 + std::max(n_height, items[c.item].height) <= Builder::MAX_DEPTH;
+            if (fits && c.item != root && c.induced + direct < best_cost) {
+                best_cost = c.induced + direct;
+                best = c.item;
+            }
+            if (!is_leaf(c.item)) {
+                const double child_induced = c.induced + direct - area(items[c.item].box);
+                if (child_induced + n_area < best_cost) {
+                    for (int k = 0; k < 2; ++k) {
+                        heap.push_back(Cand{child_induced, items[c.item].child[k], c.depth + 1});
+                        std::push_heap(heap.begin(), heap.end());
+                    }
+                }
+            }
+        }
+        if (best < 0) best = s;  // cannot happen (s itself is a candidate), kept as a guard
+        // insert: p becomes the parent of {best, n} where best was
+        const int32_t bp = items[best].parent;
+        items[bp].child[items[bp].child[0] == best ? 0 : 1] = p;
+        items[p].parent = bp;
+        items[p].child[0] = best;
+        items[p].child[1] = n;
+        items[best].parent = p;
+        items[n].parent = p;
+        items[p].box = items[best].box;
+        items[p].box.grow(nb);
+        items[p].height = 1 + std::max(items[best].height, n_height);
+        refit(bp);
+        return best != s;
+    }
+    struct Cand {
+        double induced;
+        int32_t item;
+        uint32_t depth;
+        bool operator<(const Cand& o) const { return induced > o.induced; }  // min-heap on the induced cost
+    };
+    std::vector<Cand> heap_;
+
+    // `passes` sweeps over every item in order of decreasing area (large nodes first: they are visited most)
+    void run(int passes) {
+        std::vector<int32_t> order;
+        for (int pass = 0; pass < passes; ++pass) {
+            order.clear();
+            for (int32_t i = 1; i < (int32_t)items.size(); ++i) order.push_back(i);
+            std::vector<double> key(items.size());
+            for (size_t i = 0; i < items.size(); ++i) key[i] = area(items[i].box);
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] > key[b]; });
+            size_t changed = 0;
+            for (int32_t i : order) changed += reinsert(i) ? 1 : 0;
+            if (!changed) break;
+        }
+    }
+
+    // items -> flat nodes in depth-first pre-order (node 0 = copy of the root, node 1 = the root)
+    void store(FlatScene& f, uint32_t* depth_out) const {
+        size_t n_inner = 0;
+        for (size_t i = 0; i < items.size(); ++i) n_inner += is_leaf((int32_t)i) ? 0 : 1;
+        RawVector<Quad> out((n_inner + 1) * NODE_QUADS);
+        auto pair = [](const QBox& b, int a) { return (0x8000u | b.lo[a]) | ((0x8000u | (uint32_t)b.hi[a]) << 16); };
+        struct Todo {
+            int32_t item;
+            uint32_t node, depth;
+        };
+        std::vector<Todo> todo;
+        std::vector<uint32_t> inner_count(items.size(), 0);  // inner nodes in each subtree, for the pre-order numbers
+        for (int32_t i = (int32_t)items.size() - 1; i >= 0; --i) {
+            // parents no longer precede children after re-insertions: count by walking up instead
+            if (!is_leaf(i))
+                for (int32_t a = i; a >= 0; a = items[a].parent) inner_count[a]++;
+        }
+        uint32_t max_depth = 0;
+        todo.push_back(Todo{root, 1, 1});
+        while (!todo.empty()) {
+            const Todo t = todo.back();
+            todo.pop_back();
+            const Item& it = items[t.item];
+            const int32_t c0 = it.child[0], c1 = it.child[1];
+            const uint32_t left_node = t.node + 1, right_node = t.node + 1 + (is_leaf(c0) ? 0u : inner_count[c0]);
+            const uint32_t code0 = is_leaf(c0) ? (uint32_t)items[c0].leaf_code : left_node;
+            const uint32_t code1 = is_leaf(c1) ? (uint32_t)items[c1].leaf_code : right_node;
+            const QBox &b0 = items[c0].box, &b1 = items[c1].box;
+            Quad* q = &out[(size_t)t.node * NODE_QUADS];
+            q[0] = Quad{bits_f(pair(b0, 0)), bits_f(pair(b0, 1)), bits_f(pair(b0, 2)), bits_f(pair(b1, 0))};
+            q[1] = Quad{bits_f(pair(b1, 1)), bits_f(pair(b1, 2)), bits_f(code0), bits_f(code1)};
+            for (int c = 0; c < 2; ++c) {
+                const int32_t ch = it.child[c];
+                if (is_leaf(ch)) max_depth = std::max(max_depth, t.depth + 1);
+                else todo.push_back(Todo{ch, c == 0 ? left_node : right_node, t.depth + 1});
+            }
+        }
+        for (int k = 0; k < NODE_QUADS; ++k) out[k] = out[NODE_QUADS + k];
+        f.nodes.swap(out);
+        *depth_out = max_depth;
+    }
+};
+
 }  // namespace
 
 namespace {
@@ -1040,6 +1284,18 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     out.nodes.resize((size_t)builder.next_node.load() * NODE_QUADS);
     out.bvh_depth = builder.max_depth.load();
     timer.lap("SAH build");
+    if (const char* e = std::getenv("VOIDRAY_BVH_OPT")) {  // experiment, default off (see TreeOptimizer)
+        TreeOptimizer opt;
+        if (atoi(e) > 0 && opt.load(out)) {
+            const double before = opt.inner_area_sum();
+            opt.run(atoi(e));
+            uint32_t depth = 0;
+            opt.store(out, &depth);
+            out.bvh_depth = depth;
+            if (timer.on) std::fprintf(stderr, "[voidray] flatten: inner-node area %.4g -> %.4g\n", before, opt.inner_area_sum());
+            timer.lap("insertion-based optimisation");
+        }
+    }
 
     rank_join.join();
     if (rank_error) std::rethrow_exception(rank_error);
