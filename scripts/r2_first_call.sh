@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU call of the next session, one gpurun (~12 min of box time):
+#   bash scripts/build_variants.sh                      # here, before the call (the .so files travel with the snapshot)
+#   gpurun --timeout 1500 -- 'bash scripts/r2_first_call.sh > gpurun_out/r2_first.log 2>&1'
+# 1. the GPU gates on the default build (the commit path changed on the host since the last GPU run: same bytes, pinned
+#    by digests on CPU, but this is the first time the device sees them again)
+# 2. bench.py on all five configs (refreshes BASELINE.md §5: the host commit is 1.3-2x faster, e2e moves)
+# 3. every experiment variant: closest-hit + radiance gates, then the three-regime perf check
+# 4. launch list of the default build for profiles/
+mkdir -p gpurun_out
+echo "=== gates"; python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+echo "=== bench, all configs"; bash scripts/bench_all.sh r2
+echo "=== variants"; PARITY=1 bash scripts/perf_variants.sh
+echo "=== launch list"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_config2_r2.csv \
+    python bench.py --workload config2_mossy_ground --spp 16 --steps 1 --warmup 3 --no-cpu --no-extra > gpurun_out/launches_config2_r2.log 2>&1
+tail -1 gpurun_out/launches_config2_r2.log | cut -c1-300
