@@ -13,6 +13,11 @@ declare -A FLAGS=(
   [stack16_tri48]="-DVR_SMEM_STACK=16 -DVR_TRI48"
   [tex8]="-DVR_TEX8"
   [stack16_tri48_tex8]="-DVR_SMEM_STACK=16 -DVR_TRI48 -DVR_TEX8"
+  [bvh4]="-DVR_BVH4 -DVR_NODE_STEPS=2"
+  [bvh4_steps3]="-DVR_BVH4 -DVR_NODE_STEPS=3"
+  [bvh4_steps1]="-DVR_BVH4 -DVR_NODE_STEPS=1"
+  [bvh4_stack16]="-DVR_BVH4 -DVR_NODE_STEPS=2 -DVR_SMEM_STACK=16"
+  [bvh4_stack16_tex8]="-DVR_BVH4 -DVR_NODE_STEPS=2 -DVR_SMEM_STACK=16 -DVR_TEX8"
 )
 names=("$@")
 [ ${#names[@]} -eq 0 ] && names=("${!FLAGS[@]}")

@@ -223,6 +223,147 @@ static std::vector<uint32_t> node_order(const FlatScene& f, const std::string& k
     return perm;
 }
 
+// ---- kernel-exact walks: the slab arithmetic of k_trace (PRMT-decoded plane, one FMA per plane, per-axis error
+// bounds, best-t culling, rank tie rule) restated op for op, over the shipped BVH2 records and over the 4-wide nodes of
+// collapse_bvh4 (experiment -DVR_BVH4). Both must report the brute-force closest hit bit for bit; the step counts are
+// what the two traversals cost.
+struct KHit {
+    float t;
+    int tri;
+    uint32_t rank;
+};
+struct KernelWalk {
+    const FlatScene& f;
+    const RawVector<Quad>& wide;
+    float a[3], bn[3], bf[3], o[3], d[3];
+    bool pos[3];
+    KHit best;
+    KernelWalk(const FlatScene& fs, const RawVector<Quad>& w) : f(fs), wide(w) {}
+    static uint32_t bits(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
+    static float plane(uint32_t half, float a_, float b_) {
+        const uint32_t u = 0x3F000000u | ((half & 0xFFFFu) << 8);
+        float x; std::memcpy(&x, &u, 4);
+        return std::fmaf(x, a_, b_);
+    }
+    void begin(const Ray& r) {
+        for (int k = 0; k < 3; ++k) {
+            o[k] = r.o[k]; d[k] = r.d[k];
+            const float tiny = 1e-20f;
+            const float id = 1.0f / (std::fabs(d[k]) > tiny ? d[k] : std::copysign(tiny, d[k]));
+            a[k] = f.grid_extent[k] * id;
+            const float g = (f.grid_min[k] - o[k]) * id;
+            const float b = g - a[k];
+            const float err = 2.4e-7f * (std::fabs(g) + std::fabs(a[k])) + 1e-30f;
+            bn[k] = b - err; bf[k] = b + err; pos[k] = id >= 0.0f;
+        }
+        best = KHit{INFINITY, -1, 0};
+    }
+    bool slab(const uint32_t w[3], float& tn) const {
+        float n = 0.0f, fr = best.t;
+        float nn[3], ff[3];
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+            nn[k] = plane(pos[k] ? lo : hi, a[k], bn[k]);
+            ff[k] = plane(pos[k] ? hi : lo, a[k], bf[k]);
+        }
+        n = std::fmax(std::fmax(nn[0], nn[1]), std::fmax(nn[2], 0.0f));
+        fr = std::fmin(std::fmin(ff[0], ff[1]), std::fmin(ff[2], best.t));
+        tn = n;
+        return n <= fr * 1.0000005f;
+    }
+    void leaf(int code_neg, uint64_t& n_tris) {
+        const uint32_t code = ~(uint32_t)code_neg;
+        const uint32_t first = code >> 3, count = code & 7;
+        for (uint32_t k = 0; k < count; ++k) {
+            ++n_tris;
+            const int i = (int)(first + k);
+            const Quad* q = &f.tri_isect[(size_t)i * TRI_ISECT_QUADS];
+            const float v0[3] = {q[0].x, q[0].y, q[0].z}, e1[3] = {q[1].x, q[1].y, q[1].z}, e2[3] = {q[2].x, q[2].y, q[2].z};
+            const float h[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+            const float det = e1[0] * h[0] + e1[1] * h[1] + e1[2] * h[2];
+            if (det > -1e-5f && det < 1e-5f) continue;
+            const float fi = 1.0f / det;
+            const float s[3] = {o[0] - v0[0], o[1] - v0[1], o[2] - v0[2]};
+            const float u = fi * (s[0] * h[0] + s[1] * h[1] + s[2] * h[2]);
+            if (u < 0.0f || u > 1.0f) continue;
+            const float qq[3] = {s[1] * e1[2] - s[2] * e1[1], s[2] * e1[0] - s[0] * e1[2], s[0] * e1[1] - s[1] * e1[0]};
+            const float v = fi * (d[0] * qq[0] + d[1] * qq[1] + d[2] * qq[2]);
+            if (v < 0.0f || u + v > 1.0f) continue;
+            const float t = fi * (e2[0] * qq[0] + e2[1] * qq[1] + e2[2] * qq[2]);
+            if (!(t > 1e-5f)) continue;
+            const uint32_t rank = bits(q[0].w);
+            if (t < best.t || (t == best.t && rank > best.rank)) best = KHit{t, i, rank};
+        }
+    }
+    // k_trace over the BVH2 records (trav_node / trav_leaf_step of kernels.cu)
+    KHit trace2(const Ray& r, uint64_t& n_nodes, uint64_t& n_tris, uint32_t& max_sp) {
+        begin(r);
+        int stack[128], sp = 0, cur = f.n_tris ? 0 : 0x7FFFFFFF;
+        while (cur != 0x7FFFFFFF) {
+            if (cur >= 0) {
+                ++n_nodes;
+                const Quad* q = &f.nodes[(size_t)cur * NODE_QUADS];
+                const uint32_t w[8] = {bits(q[0].x), bits(q[0].y), bits(q[0].z), bits(q[0].w), bits(q[1].x), bits(q[1].y), bits(q[1].z), bits(q[1].w)};
+                float ta, tb;
+                const bool ha = slab(w, ta), hb = slab(w + 3, tb);
+                const int ca = (int)w[6], cb = (int)w[7];
+                const bool b_first = hb && (!ha || tb < ta);
+                const int near_c = b_first ? cb : ca, far_c = b_first ? ca : cb;
+                if (ha && hb) { stack[sp++] = far_c; max_sp = std::max(max_sp, (uint32_t)sp); }
+                cur = (ha || hb) ? near_c : (sp ? stack[--sp] : 0x7FFFFFFF);
+            } else {
+                leaf(cur, n_tris);
+                cur = sp ? stack[--sp] : 0x7FFFFFFF;
+            }
+        }
+        return best;
+    }
+    // the -DVR_BVH4 trav_node: four slab tests per 64-byte node, hits sorted by entry distance, nearest first
+    KHit trace4(const Ray& r, uint64_t& n_nodes, uint64_t& n_tris, uint32_t& max_sp) {
+        begin(r);
+        int stack[WIDE_STACK_LIMIT + 4], sp = 0, cur = f.n_tris ? 0 : 0x7FFFFFFF;
+        while (cur != 0x7FFFFFFF) {
+            if (cur >= 0) {
+                ++n_nodes;
+                const Quad* q = &wide[(size_t)cur * WIDE_NODE_QUADS];
+                float key[4];
+                int code[4];
+                int h = 0;
+                for (int p = 0; p < 2; ++p) {
+                    const Quad* r2 = q + 2 * p;
+                    const uint32_t w[8] = {bits(r2[0].x), bits(r2[0].y), bits(r2[0].z), bits(r2[0].w), bits(r2[1].x), bits(r2[1].y), bits(r2[1].z), bits(r2[1].w)};
+                    for (int c = 0; c < 2; ++c) {
+                        float tn;
+                        const bool hit = slab(w + 3 * c, tn);
+                        key[2 * p + c] = hit ? tn : INFINITY;
+                        code[2 * p + c] = (int)w[6 + c];
+                        h += hit ? 1 : 0;
+                    }
+                }
+                auto cswap = [&](int i, int j) {
+                    if (key[j] < key[i]) { std::swap(key[i], key[j]); std::swap(code[i], code[j]); }
+                };
+                cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+                if (h > 3) stack[sp++] = code[3];
+                if (h > 2) stack[sp++] = code[2];
+                if (h > 1) stack[sp++] = code[1];
+                max_sp = std::max(max_sp, (uint32_t)sp);
+                cur = h > 0 ? code[0] : (sp ? stack[--sp] : 0x7FFFFFFF);
+            } else {
+                leaf(cur, n_tris);
+                cur = sp ? stack[--sp] : 0x7FFFFFFF;
+            }
+        }
+        return best;
+    }
+    KHit brute(const Ray& r) {
+        begin(r);
+        uint64_t n = 0;
+        for (uint32_t i = 0; i < f.n_tris; ++i) leaf(~(int)((i << 3) | 1u), n);
+        return best;
+    }
+};
+
 struct Walker {
     const Tree* tree;
     Ray r;
@@ -401,6 +542,7 @@ int main(int argc, char** argv) {
     std::printf("%s x%d: %u triangles, %zu nodes, depth %u, build %.1f ms, SAH cost %.2f\n", argv[1], nx * nz, flat.n_tris,
                 flat.nodes.size() / NODE_QUADS, flat.bvh_depth, build_ms, tree.sah_cost(1.0f));
     uint64_t all_nodes = 0, all_tris = 0, all_rays = 0;
+    std::vector<std::vector<Ray>> gen_rays;
     for (int gen = 0; gen < 4 && !rays.empty(); ++gen) {
         uint64_t n_nodes = 0, n_tris = 0, hits = 0;
         uint32_t max_sp = 0;
@@ -422,6 +564,7 @@ int main(int argc, char** argv) {
         std::printf("  generation %d: %zu rays, %.1f %% hit, %.2f nodes / ray, %.2f triangle tests / ray, max stack %u\n", gen,
                     rays.size(), 100.0 * hits / rays.size(), (double)n_nodes / rays.size(), (double)n_tris / rays.size(), max_sp);
         all_nodes += n_nodes; all_tris += n_tris; all_rays += rays.size();
+        gen_rays.push_back(rays);
         if (const char* e = std::getenv("BVH_STATS_CACHE")) {
             if (gen <= 1) cache_model(tree, rays, (size_t)atoi(e), gen == 0 ? "camera rays" : "first-bounce rays");
         }
@@ -459,6 +602,57 @@ int main(int argc, char** argv) {
         }
         cache_model(tree, random_rays, (size_t)atoi(e), "random rays");
     }
+#ifndef VR_BVH4
+    if (std::getenv("BVH_STATS_WIDE")) {
+        // the 4-wide collapse (experiment -DVR_BVH4) next to the shipped BVH2, both walked with the kernel's own slab
+        // arithmetic: identical hits, and what each costs in node fetches
+        RawVector<Quad> wide;
+        uint32_t wide_depth = 0, stack_bound = 0;
+        const auto c0 = std::chrono::steady_clock::now();
+        // BVH_STATS_WIDE=<n> with n > 1 collapses under a stack limit of n instead of the kernel's (checks that the
+        // collapse narrows nodes to keep deep paths within the limit)
+        const uint32_t limit = atoi(std::getenv("BVH_STATS_WIDE")) > 1 ? (uint32_t)atoi(std::getenv("BVH_STATS_WIDE")) : (uint32_t)WIDE_STACK_LIMIT;
+        collapse_bvh4(flat.nodes, flat.grid_extent, flat.bvh_depth, limit, wide, &wide_depth, &stack_bound);
+        if (stack_bound > std::max(limit, flat.bvh_depth)) { std::printf("stack bound %u exceeds the limit %u\n", stack_bound, limit); return 1; }
+        const double collapse_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
+        size_t slots = 0;
+        for (size_t i = 0; i < wide.size() / WIDE_NODE_QUADS; ++i)
+            for (int p = 0; p < 2; ++p) {
+                const Quad* q = &wide[i * WIDE_NODE_QUADS + 2 * p];
+                slots += (KernelWalk::bits(q[1].z) != 0xFFFFFFFFu) + (KernelWalk::bits(q[1].w) != 0xFFFFFFFFu);
+            }
+        std::printf("  4-wide collapse: %zu nodes (%.2f children / node), depth %u, stack bound %u, %.2f ms\n", wide.size() / WIDE_NODE_QUADS,
+                    (double)slots / std::max<size_t>(1, wide.size() / WIDE_NODE_QUADS), wide_depth, stack_bound, collapse_ms);
+        KernelWalk kw(flat, wide);
+        uint64_t differ = 0;
+        for (size_t gen = 0; gen < gen_rays.size(); ++gen) {
+            uint64_t n2 = 0, t2 = 0, n4 = 0, t4 = 0;
+            uint32_t sp2 = 0, sp4 = 0;
+            for (const Ray& r : gen_rays[gen]) {
+                const KHit a = kw.trace2(r, n2, t2, sp2);
+                const KHit b = kw.trace4(r, n4, t4, sp4);
+                if (a.tri != b.tri || std::memcmp(&a.t, &b.t, 4) != 0) ++differ;
+            }
+            const double nr = (double)std::max<size_t>(1, gen_rays[gen].size());
+            std::printf("  generation %zu, kernel walk: BVH2 %.2f nodes + %.2f tris (stack %u) | BVH4 %.2f nodes + %.2f tris (stack %u)\n", gen,
+                        n2 / nr, t2 / nr, sp2, n4 / nr, t4 / nr, sp4);
+        }
+        g_state = 777u;
+        uint64_t brute_differ = 0;
+        for (int k = 0; k < 3000; ++k) {
+            Ray r;
+            for (int a = 0; a < 3; ++a) { r.o[a] = lo_all[a] + rnd() * (hi_all[a] - lo_all[a]); r.d[a] = 2.0f * rnd() - 1.0f; }
+            if (k % 7 == 0) r.d[k % 3] = 0.0f;  // axis-parallel rays
+            uint64_t n = 0, t = 0;
+            uint32_t sp = 0;
+            const KHit a = kw.trace2(r, n, t, sp), b = kw.trace4(r, n, t, sp), c = kw.brute(r);
+            if (a.tri != c.tri || std::memcmp(&a.t, &c.t, 4) != 0 || b.tri != c.tri || std::memcmp(&b.t, &c.t, 4) != 0) ++brute_differ;
+        }
+        std::printf("  kernel walks: %llu BVH2 / BVH4 differences, %llu of 3000 random rays differ from brute force\n",
+                    (unsigned long long)differ, (unsigned long long)brute_differ);
+        if (differ || brute_differ) return 1;
+    }
+#endif
     std::printf("  all: %.2f nodes / ray, %.2f triangle tests / ray, step estimate (nodes + 0.6 tris) %.2f\n", (double)all_nodes / all_rays,
                 (double)all_tris / all_rays, ((double)all_nodes + 0.6 * all_tris) / all_rays);
     return 0;

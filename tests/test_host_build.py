@@ -156,6 +156,15 @@ def test_bvh_quality_meter_builds_and_runs(tmp_path):
                          env=dict(os.environ, VOIDRAY_BVH_OPT="2")).stdout
     assert "brute-force check: 0 of 3000 random rays differ" in opt and digest(opt) != "cbf0e27fea44afdd"
     assert int(re.search(r"depth (\d+)", opt).group(1)) <= 32
+    # experiment -DVR_BVH4: the 4-wide collapse of the same tree, walked with the kernel's own slab arithmetic next to
+    # the BVH2 — same closest hits bit for bit (also against brute force), about half the node fetches, stack bounded
+    wide = subprocess.run([exe, os.path.join(ASSETS, "fancy_monkey.obj")], capture_output=True, text=True, timeout=300,
+                          env=dict(os.environ, BVH_STATS_WIDE="1")).stdout
+    assert "kernel walks: 0 BVH2 / BVH4 differences, 0 of 3000 random rays differ from brute force" in wide
+    m = re.search(r"4-wide collapse: (\d+) nodes \(([\d.]+) children / node\), depth (\d+), stack bound (\d+)", wide)
+    assert m and int(m.group(4)) <= 64 and float(m.group(2)) > 2.5
+    g = re.search(r"generation 1, kernel walk: BVH2 ([\d.]+) nodes .* BVH4 ([\d.]+) nodes", wide)
+    assert float(g.group(2)) < 0.6 * float(g.group(1))
 
 
 def _library_digest(name):

@@ -738,7 +738,7 @@ int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) try {
     if (!out) return fail(VR_ERR_INVALID, "null argument");
     if (!scene->committed) return fail(VR_ERR_INVALID, "scene not committed");
     out->n_triangles = scene->flat.n_tris;
-    out->n_bvh_nodes = (uint32_t)(scene->flat.nodes.size() / NODE_QUADS);
+    out->n_bvh_nodes = (uint32_t)(scene->flat.nodes.size() / DEVICE_NODE_QUADS);
     out->bvh_depth = scene->flat.bvh_depth;
     out->n_analytic_surfaces = (uint32_t)scene->flat.analytics.size();
     out->n_textures = (uint32_t)scene->host.textures.size();
@@ -1210,7 +1210,7 @@ int32_t vr_debug_flatten_mesh_digest(const float* positions, const float* uvs, c
     d = fnv(flat.tri_isect.data(), flat.tri_isect.size() * sizeof(Quad), d);
     d = fnv(flat.tri_shade.data(), flat.tri_shade.size() * sizeof(Quad), d);
     *digest = d;
-    if (n_nodes) *n_nodes = (uint32_t)(flat.nodes.size() / NODE_QUADS);
+    if (n_nodes) *n_nodes = (uint32_t)(flat.nodes.size() / DEVICE_NODE_QUADS);
     if (bvh_depth) *bvh_depth = flat.bvh_depth;
     if (flatten_ms) *flatten_ms = ms;
     return VR_OK;

@@ -28,7 +28,18 @@ static constexpr int SHADE_THREADS = 128;
 #ifndef VR_SMEM_STACK
 #define VR_SMEM_STACK 32
 #endif
+// Experiment -DVR_BVH4 (layout.h): 4-wide nodes park up to three children per step, so the stack is
+// WIDE_STACK_LIMIT deep — the host collapse keeps every path within it — and the part beyond the shared-memory
+// entries always exists as a local tail (the deepest stack seen on the BASELINE scenes is 13).
+#ifdef VR_BVH4
+static constexpr int STACK_DEPTH = WIDE_STACK_LIMIT;
+#define VR_HAS_SPILL 1
+#else
 static constexpr int STACK_DEPTH = 32;
+#if VR_SMEM_STACK < 32
+#define VR_HAS_SPILL 1
+#endif
+#endif
 static constexpr int SMEM_STACK = VR_SMEM_STACK;
 static_assert(SMEM_STACK >= 1 && SMEM_STACK <= STACK_DEPTH, "VR_SMEM_STACK");
 static constexpr float T_MIN = 0.00001f;  // core/scene.rs:183
@@ -130,7 +141,7 @@ struct Traversal {
 };
 // VR_SMEM_STACK < 32: entries SMEM_STACK.. of the stack live in a per-thread local array that is passed alongside
 // the shared part (kept out of Traversal: a dynamically indexed member would drag the whole struct into local memory)
-#if VR_SMEM_STACK < 32
+#ifdef VR_HAS_SPILL
 #define VR_SPILL_PARAM , int* __restrict__ spill
 #define VR_SPILL_ARG , spill
 #define VR_SPILL_DECL int spill[STACK_DEPTH - SMEM_STACK];
@@ -172,7 +183,7 @@ __device__ __forceinline__ void trav_begin(Traversal& tr, const DeviceScene& sc,
 __device__ __forceinline__ int trav_pop(Traversal& tr, const int* sstack, int sstride VR_SPILL_PARAM) {
     const bool empty = tr.sp == 0;
     tr.sp -= empty ? 0 : 1;
-#if VR_SMEM_STACK < 32
+#ifdef VR_HAS_SPILL
     const int v = tr.sp < SMEM_STACK ? sstack[tr.sp * sstride] : spill[tr.sp - SMEM_STACK];
 #else
     const int v = sstack[tr.sp * sstride];
@@ -187,6 +198,57 @@ __device__ __forceinline__ float plane_t(uint32_t pair, uint32_t sel, float a, f
     return __fmaf_rn(__uint_as_float(__byte_perm(pair, 0x3F000000u, sel)), a, b);
 }
 
+#ifdef VR_BVH4
+// One slab test on the three packed words of a child; same arithmetic as the BVH2 step below.
+__device__ __forceinline__ float wide_child(const Traversal& tr, uint32_t wx, uint32_t wy, uint32_t wz) {
+    const uint32_t fx = tr.selx ^ 0x0220u, fy = tr.sely ^ 0x0220u, fz = tr.selz ^ 0x0220u;
+    const float tn = fmaxf(fmaxf(plane_t(wx, tr.selx, tr.ax, tr.bnx), plane_t(wy, tr.sely, tr.ay, tr.bny)),
+                           fmaxf(plane_t(wz, tr.selz, tr.az, tr.bnz), 0.0f));
+    const float tf = fminf(fminf(plane_t(wx, fx, tr.ax, tr.bfx), plane_t(wy, fy, tr.ay, tr.bfy)),
+                           fminf(plane_t(wz, fz, tr.az, tr.bfz), tr.best.t));
+    return tn <= tf * 1.0000005f ? tn : INFINITY;  // the sort key: entry distance, +inf for a miss
+}
+__device__ __forceinline__ void wide_cswap(float& ka, int& ca, float& kb, int& cb) {
+    const bool s = kb < ka;
+    const float k0 = s ? kb : ka, k1 = s ? ka : kb;
+    const int c0 = s ? cb : ca, c1 = s ? ca : cb;
+    ka = k0;
+    kb = k1;
+    ca = c0;
+    cb = c1;
+}
+__device__ __forceinline__ void wide_push(Traversal& tr, int* sstack, int sstride, int* __restrict__ spill, bool pred, int v) {
+    if (pred) {
+        if (tr.sp < SMEM_STACK) sstack[tr.sp * sstride] = v;
+        else spill[tr.sp - SMEM_STACK] = v;
+    }
+    tr.sp += pred ? 1 : 0;
+}
+// One 4-wide node: two 256-bit loads, four slab tests, children that are hit sorted by entry distance (a 5-comparator
+// network, branch-free); the nearest is next, the others are parked farthest first. scripts/bvh_stats.cpp walks the
+// same node array with the same arithmetic on the CPU: half the node fetches of the BVH2 for the same triangle tests.
+__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride VR_SPILL_PARAM) {
+    const float8 p0 = ldg8(nodes + WIDE_NODE_QUADS * tr.cur);
+    const float8 p1 = ldg8(nodes + WIDE_NODE_QUADS * tr.cur + 2);
+    float k0 = wide_child(tr, __float_as_uint(p0.lo.x), __float_as_uint(p0.lo.y), __float_as_uint(p0.lo.z));
+    float k1 = wide_child(tr, __float_as_uint(p0.lo.w), __float_as_uint(p0.hi.x), __float_as_uint(p0.hi.y));
+    float k2 = wide_child(tr, __float_as_uint(p1.lo.x), __float_as_uint(p1.lo.y), __float_as_uint(p1.lo.z));
+    float k3 = wide_child(tr, __float_as_uint(p1.lo.w), __float_as_uint(p1.hi.x), __float_as_uint(p1.hi.y));
+    int c0 = __float_as_int(p0.hi.z), c1 = __float_as_int(p0.hi.w), c2 = __float_as_int(p1.hi.z), c3 = __float_as_int(p1.hi.w);
+    const int hits = (k0 < INFINITY ? 1 : 0) + (k1 < INFINITY ? 1 : 0) + (k2 < INFINITY ? 1 : 0) + (k3 < INFINITY ? 1 : 0);
+    wide_cswap(k0, c0, k1, c1);
+    wide_cswap(k2, c2, k3, c3);
+    wide_cswap(k0, c0, k2, c2);
+    wide_cswap(k1, c1, k3, c3);
+    wide_cswap(k1, c1, k2, c2);
+    wide_push(tr, sstack, sstride, spill, hits > 3, c3);
+    wide_push(tr, sstack, sstride, spill, hits > 2, c2);
+    wide_push(tr, sstack, sstride, spill, hits > 1, c1);
+    int next = c0;
+    if (hits == 0) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
+    tr.cur = next;
+}
+#else
 // One inner node: two slab tests from a single 32-byte record, near child first, far child pushed.
 __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride VR_SPILL_PARAM) {
     const float8 n = ldg8(nodes + 2 * tr.cur);
@@ -211,7 +273,7 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
     const int near_c = b_first ? cb : ca;
     const int far_c = b_first ? ca : cb;
     const bool both = hit_a && hit_b, any = hit_a || hit_b;
-#if VR_SMEM_STACK < 32
+#ifdef VR_HAS_SPILL
     if (both) {
         if (tr.sp < SMEM_STACK) sstack[tr.sp * sstride] = far_c;
         else spill[tr.sp - SMEM_STACK] = far_c;
@@ -224,6 +286,8 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
     if (!any) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
     tr.cur = next;
 }
+
+#endif  // VR_BVH4
 
 // One triangle of the current leaf; the leaf code counts down so that lanes with short leaves do not idle
 // through a neighbour's longer one.

@@ -14,6 +14,16 @@ namespace vr {
 //   t = f * (extent * id) + ((grid_min - o) * id - extent * id),
 // with the near / far plane picked by the ray's sign (PRMT selector) instead of min / max.
 static const int NODE_QUADS = 2;
+// Experiment -DVR_BVH4 (every translation unit): 4-wide nodes, 64 B = two records of the format above back to back
+// (children 0, 1 | children 2, 3), child codes index wide nodes; an unused child is an inverted box with an empty
+// leaf code. The traversal parks up to three children per node, so its stack is WIDE_STACK_LIMIT entries deep.
+static const int WIDE_NODE_QUADS = 4;
+static const int WIDE_STACK_LIMIT = 64;
+#ifdef VR_BVH4
+static const int DEVICE_NODE_QUADS = WIDE_NODE_QUADS;
+#else
+static const int DEVICE_NODE_QUADS = NODE_QUADS;
+#endif
 static const int LEAF_MAX_TRIS = 4;
 
 // Intersection record, 64 B = 4 x float4 = two 256-bit loads (pre-subtracted edges: e1 = v1 - v0,

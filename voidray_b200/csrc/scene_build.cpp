@@ -1021,6 +1021,129 @@ struct TreeOptimizer {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// 4-wide nodes (experiment -DVR_BVH4; this pass is always compiled so that the CPU walk of scripts/bvh_stats.cpp
+// and the host tests can run it next to the shipped BVH2).
+// A wide node is 64 B = two records of the BVH2 format (layout.h): up to four children, each with the quantised box
+// its BVH2 parent already stored for it, so the wide tree culls with exactly the boxes of the BVH2 and stays
+// conservative for the same reason. Built by the usual greedy collapse: start from a node's two children and, while
+// a slot is free, replace the inner child with the largest surface area by its own two children. Nodes are numbered
+// in depth-first pre-order, node 0 is the root. A ray that enters a wide node parks at most (children - 1) entries
+// on the traversal stack; the collapse keeps the worst case over any root-to-leaf path within stack_limit by
+// leaving nodes narrower where a deep BVH2 path would not fit (never happens on the BASELINE scenes).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct WideSlot {
+    uint32_t w[3];   // quantised (lo | hi << 16) pairs, x y z
+    int32_t code;    // BVH2 child code: >= 0 inner BVH2 node, < 0 leaf
+    uint32_t depth;  // BVH2 depth of the child (root = 0)
+};
+struct WideCollapse {
+    const RawVector<Quad>& src;
+    RawVector<Quad>& dst;
+    double cell[3];
+    uint32_t bvh2_depth, stack_limit;
+    uint32_t wide_depth = 0, max_stack = 0;
+    static const uint32_t EMPTY_PAIR = (0x8000u | 32767u) | ((0x8000u | 0u) << 16);
+
+    static uint32_t f_bits(float f) {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        return u;
+    }
+    static bool is_empty(const WideSlot& s) { return s.code < 0 && ((~(uint32_t)s.code) & 7u) == 0; }
+    double area(const WideSlot& s) const {
+        double e[3];
+        for (int a = 0; a < 3; ++a) {
+            const int lo = (int)(s.w[a] & 0x7FFFu), hi = (int)((s.w[a] >> 16) & 0x7FFFu);
+            e[a] = hi > lo ? (double)(hi - lo) * cell[a] : 0.0;
+        }
+        return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+    }
+    // the (non-empty) children of BVH2 node `node` appended to slots[n..]
+    int children(uint32_t node, uint32_t depth, WideSlot* slots, int n) const {
+        const Quad* q = &src[(size_t)node * 2];
+        const uint32_t w[8] = {f_bits(q[0].x), f_bits(q[0].y), f_bits(q[0].z), f_bits(q[0].w),
+                               f_bits(q[1].x), f_bits(q[1].y), f_bits(q[1].z), f_bits(q[1].w)};
+        for (int c = 0; c < 2; ++c) {
+            WideSlot s{{w[3 * c], w[3 * c + 1], w[3 * c + 2]}, (int32_t)w[6 + c], depth + 1};
+            if (!is_empty(s)) slots[n++] = s;
+        }
+        return n;
+    }
+    // Emits the wide node that replaces BVH2 node `node`; `used` = stack entries that may be occupied on arrival.
+    uint32_t emit(uint32_t node, uint32_t depth, uint32_t used, uint32_t level) {
+        WideSlot slots[5];
+        int n = children(node, depth, slots, 0);
+        // widest node the remaining stack allows if every level below degrades to two children (one entry each)
+        const uint32_t below = bvh2_depth > depth + 1 ? bvh2_depth - depth - 1 : 0;
+        int width = 4;
+        while (width > 2 && used + (uint32_t)(width - 1) + below > stack_limit) --width;
+        while (n < width) {
+            int pick = -1;
+            double best = -1.0;
+            for (int i = 0; i < n; ++i)
+                if (slots[i].code >= 0) {
+                    const double a = area(slots[i]);
+                    if (a > best) {
+                        best = a;
+                        pick = i;
+                    }
+                }
+            if (pick < 0) break;
+            const WideSlot parent = slots[pick];
+            WideSlot kids[2];
+            const int nk = children((uint32_t)parent.code, parent.depth, kids, 0);
+            // the first child takes the parent's place, the second goes to the end
+            if (nk == 0) {
+                slots[pick] = slots[--n];
+                continue;
+            }
+            slots[pick] = kids[0];
+            if (nk == 2) slots[n++] = kids[1];
+        }
+        const uint32_t index = (uint32_t)(dst.size() / WIDE_NODE_QUADS);
+        dst.resize(dst.size() + WIDE_NODE_QUADS);
+        wide_depth = std::max(wide_depth, level + 1);
+        const uint32_t parked = n > 0 ? (uint32_t)(n - 1) : 0u;
+        max_stack = std::max(max_stack, used + parked);
+        uint32_t words[4][4];  // per slot: x y z code
+        for (int i = 0; i < 4; ++i) {
+            if (i < n) {
+                uint32_t code = (uint32_t)slots[i].code;
+                if (slots[i].code >= 0) code = emit((uint32_t)slots[i].code, slots[i].depth, used + parked, level + 1);
+                words[i][0] = slots[i].w[0];
+                words[i][1] = slots[i].w[1];
+                words[i][2] = slots[i].w[2];
+                words[i][3] = code;
+            } else {
+                words[i][0] = words[i][1] = words[i][2] = EMPTY_PAIR;
+                words[i][3] = 0xFFFFFFFFu;  // leaf code of an empty range
+            }
+        }
+        Quad* q = &dst[(size_t)index * WIDE_NODE_QUADS];
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t* a = words[2 * p];
+            const uint32_t* b = words[2 * p + 1];
+            q[2 * p] = Quad{bits_f(a[0]), bits_f(a[1]), bits_f(a[2]), bits_f(b[0])};
+            q[2 * p + 1] = Quad{bits_f(b[1]), bits_f(b[2]), bits_f(a[3]), bits_f(b[3])};
+        }
+        return index;
+    }
+};
+}  // namespace
+
+void collapse_bvh4(const RawVector<Quad>& nodes2, const float grid_extent[3], uint32_t bvh2_depth, uint32_t stack_limit,
+                   RawVector<Quad>& wide, uint32_t* wide_depth, uint32_t* max_stack) {
+    wide.clear();
+    wide.reserve(nodes2.size());
+    WideCollapse c{nodes2, wide, {}, bvh2_depth, stack_limit};
+    for (int a = 0; a < 3; ++a) c.cell[a] = (double)grid_extent[a] / 32768.0;
+    c.emit(0, 0, 0, 0);
+    if (wide_depth) *wide_depth = c.wide_depth;
+    if (max_stack) *max_stack = c.max_stack;
+}
+
 namespace {
 // VOIDRAY_TIMING=1 prints the host phases of a commit to stderr
 struct PhaseTimer {
@@ -1296,6 +1419,22 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
             timer.lap("insertion-based optimisation");
         }
     }
+
+#ifdef VR_BVH4
+    {
+        RawVector<Quad> wide;
+        uint32_t wide_depth = 0, max_stack = 0;
+        collapse_bvh4(out.nodes, out.grid_extent, out.bvh_depth, WIDE_STACK_LIMIT, wide, &wide_depth, &max_stack);
+        if (max_stack > (uint32_t)WIDE_STACK_LIMIT) {
+            err = "4-wide BVH too deep for the traversal stack";
+            return false;
+        }
+        out.nodes.swap(wide);
+        if (timer.on) std::fprintf(stderr, "[voidray] flatten: %zu wide nodes, depth %u, stack bound %u\n",
+                                   out.nodes.size() / WIDE_NODE_QUADS, wide_depth, max_stack);
+        timer.lap("4-wide collapse");
+    }
+#endif
 
     rank_join.join();
     if (rank_error) std::rethrow_exception(rank_error);

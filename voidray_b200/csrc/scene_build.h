@@ -109,6 +109,11 @@ void camera_look_at(const float eye[3], const float center[3], const float up_in
 
 bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err);
 
+// Collapses a finished BVH2 node array (layout.h, node 0 = root) into 4-wide nodes of WIDE_NODE_QUADS quads each
+// (experiment -DVR_BVH4, see scene_build.cpp). max_stack = the most entries a traversal can park on its stack.
+void collapse_bvh4(const RawVector<Quad>& nodes2, const float grid_extent[3], uint32_t bvh2_depth, uint32_t stack_limit,
+                   RawVector<Quad>& wide, uint32_t* wide_depth, uint32_t* max_stack);
+
 // Wavefront OBJ with obj-rs 0.7.0 `load_obj::<TexturedVertex, u32>` semantics (core/mesh.rs:46-74).
 bool load_obj_file(const char* path, HostMesh& out, std::string& err);
 
