@@ -1,0 +1,102 @@
+"""The closest-hit traversal source of the CUDA kernels (voidray_b200/csrc/traversal.cuh) compiled for the CPU
+(tests/c/trav_host.cpp + tests/c/host_shim.h) and compared with the oracle bit for bit: the k_trace_rays gate of
+tests/test_gpu_closest_hit.py without a GPU. Run for the shipped layout and for the experiment variants, whose
+kernels have not seen a GPU yet (-DVR_BVH4, -DVR_TRI48, -DVR_SMEM_STACK=n)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from voidray_b200.assets import asset_path, load_obj
+from voidray_b200.scene import Environments, Materials, Scene, Surfaces
+
+from util import F32, MISS, random_rays, scene_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VARIANTS = {
+    "default": [],
+    "bvh4": ["-DVR_BVH4"],
+    "bvh4_stack4": ["-DVR_BVH4", "-DVR_SMEM_STACK=4"],  # nearly every push and pop goes through the local tail
+    "stack8": ["-DVR_SMEM_STACK=8"],
+    "tri48": ["-DVR_TRI48"],
+}
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    built = {}
+
+    def get(variant):
+        if variant not in built:
+            exe = str(tmp_path_factory.mktemp("trav") / f"trav_host_{variant}")
+            csrc = os.path.join(ROOT, "voidray_b200", "csrc")
+            r = subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-ffp-contract=off", "-DVR_HOST_SHIM",
+                                *VARIANTS[variant], "-I", os.path.join(ROOT, "tests", "c"), "-I", csrc, "-x", "c++",
+                                os.path.join(csrc, "scene_build.cpp"), os.path.join(ROOT, "tests", "c", "trav_host.cpp"),
+                                "-o", exe], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-3000:]
+            built[variant] = exe
+        return built[variant]
+    return get
+
+
+def run_harness(exe, tmp_path, origins, dirs, surfaces):
+    rays = np.concatenate([origins, dirs], axis=1).astype(F32)
+    rp, op = str(tmp_path / "rays.bin"), str(tmp_path / "out.bin")
+    rays.tofile(rp)
+    r = subprocess.run([exe, rp, op, *surfaces], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    out = np.fromfile(op, dtype=np.dtype([("surface", "<u4"), ("prim", "<u4"), ("t", "<f4")]))
+    assert len(out) == len(rays)
+    return out, r.stdout
+
+
+def mixed_rays(scene, n, seed):
+    lo, hi = scene_bounds(scene)
+    o, d = random_rays(n, lo, hi, seed)
+    # a share of axis-parallel and exactly diagonal directions (zero components, equal slab distances)
+    rng = np.random.default_rng(seed + 1)
+    k = n // 8
+    d[:k, rng.integers(0, 3, k)] = 0.0
+    d[k:2 * k] = np.sign(d[k:2 * k]) + (d[k:2 * k] == 0)
+    return o, d
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("name,n", [("cube.obj", 20000), ("mushroom.obj", 40000), ("mossy_ground.obj", 30000)])
+def test_kernel_traversal_source_matches_oracle(oracle, harness, tmp_path, variant, name, n):
+    scene = Scene.empty()
+    scene.add_object(scene.add_material(Materials.lambertian((0.5, 0.5, 0.5))), scene.add_mesh(load_obj(asset_path(name))))
+    scene.environment = Environments.uniform((0.5, 0.5, 0.5))
+    o, d = mixed_rays(scene, n, 11)
+    s_ref, p_ref, t_ref, _ = oracle.OracleScene(scene).trace_rays(o, d)
+    out, log = run_harness(harness(variant), tmp_path, o, d, ["obj", asset_path(name)])
+    assert (s_ref != MISS).mean() > 0.1
+    assert np.array_equal(out["surface"], s_ref) and np.array_equal(out["prim"], p_ref)
+    assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))  # bit-equal distances, inf on a miss
+    if variant.startswith("bvh4"):
+        assert "of 4 quads" in log
+
+
+@pytest.mark.parametrize("variant", ["default", "bvh4", "bvh4_stack4"])
+def test_kernel_traversal_source_two_meshes_and_analytic_surfaces(oracle, harness, tmp_path, variant):
+    # two meshes, a sphere inside the scene and a ground plane: surface handles, the analytic pass after the BVH and
+    # the tie ranks across surfaces
+    scene = Scene.empty()
+    mat = scene.add_material(Materials.lambertian((0.5, 0.5, 0.5)))
+    scene.add_object(mat, scene.add_mesh(load_obj(asset_path("mushroom.obj"))))
+    scene.add_object(mat, scene.add_analytic_surface(Surfaces.sphere((0.5, 1.0, 0.25), 0.75)))
+    scene.add_object(mat, scene.add_mesh(load_obj(asset_path("fancy_monkey.obj"))))
+    scene.add_object(mat, scene.add_analytic_surface(Surfaces.ground_plane(-0.125)))
+    scene.environment = Environments.uniform((0.5, 0.5, 0.5))
+    o, d = mixed_rays(scene, 30000, 5)
+    s_ref, p_ref, t_ref, _ = oracle.OracleScene(scene).trace_rays(o, d)
+    out, _ = run_harness(harness(variant), tmp_path, o, d,
+                         ["obj", asset_path("mushroom.obj"), "sphere", "0.5", "1.0", "0.25", "0.75",
+                          "obj", asset_path("fancy_monkey.obj"), "plane", "-0.125"])
+    assert len(set(s_ref.tolist())) >= 4
+    assert np.array_equal(out["surface"], s_ref)
+    tri = p_ref != MISS
+    assert np.array_equal(out["prim"][tri], p_ref[tri])
+    assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))

@@ -6,7 +6,11 @@
 // barycentrics, normals and scatter directions bit-identical to a CPU evaluation of the same
 // expressions; FMA is used only where written explicitly (__fmaf_rn).
 #pragma once
+#ifdef VR_HOST_SHIM  // tests only: this source compiled for the CPU (tests/c/host_shim.h, tests/c/trav_host.cpp)
+#include "host_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace vr {
@@ -46,10 +50,15 @@ struct __align__(32) float8 {
 };
 __device__ __forceinline__ float8 ldg8(const float4* p) {
     float8 r;
+#ifdef VR_HOST_SHIM
+    r.lo = p[0];
+    r.hi = p[1];
+#else
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
                    "=f"(r.hi.w)
                  : "l"(p));
+#endif
     return r;
 }
 
