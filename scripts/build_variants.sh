@@ -16,6 +16,7 @@ declare -A FLAGS=(
   [bvh4]="-DVR_BVH4 -DVR_NODE_STEPS=2"
   [bvh4_steps3]="-DVR_BVH4 -DVR_NODE_STEPS=3"
   [bvh4_steps1]="-DVR_BVH4 -DVR_NODE_STEPS=1"
+  [bvh4_nosort]="-DVR_BVH4 -DVR_BVH4_NOSORT -DVR_NODE_STEPS=2"
   [bvh4_stack16]="-DVR_BVH4 -DVR_NODE_STEPS=2 -DVR_SMEM_STACK=16"
   [bvh4_stack16_tex8]="-DVR_BVH4 -DVR_NODE_STEPS=2 -DVR_SMEM_STACK=16 -DVR_TEX8"
 )

@@ -319,9 +319,19 @@ struct KernelWalk {
         return best;
     }
     // the -DVR_BVH4 trav_node: four slab tests per 64-byte node, hits sorted by entry distance, nearest first
+    int sort_mode = 0;
+    bool cull_on_pop = false;  // experiment: park the entry distance with the child and drop it at pop time if the closest hit got nearer
     KHit trace4(const Ray& r, uint64_t& n_nodes, uint64_t& n_tris, uint32_t& max_sp) {
         begin(r);
         int stack[WIDE_STACK_LIMIT + 4], sp = 0, cur = f.n_tris ? 0 : 0x7FFFFFFF;
+        float kstack[WIDE_STACK_LIMIT + 4];
+        auto pop = [&]() {
+            while (sp) {
+                --sp;
+                if (!cull_on_pop || kstack[sp] <= best.t * 1.0000005f) return stack[sp];
+            }
+            return 0x7FFFFFFF;
+        };
         while (cur != 0x7FFFFFFF) {
             if (cur >= 0) {
                 ++n_nodes;
@@ -343,15 +353,25 @@ struct KernelWalk {
                 auto cswap = [&](int i, int j) {
                     if (key[j] < key[i]) { std::swap(key[i], key[j]); std::swap(code[i], code[j]); }
                 };
-                cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
-                if (h > 3) stack[sp++] = code[3];
-                if (h > 2) stack[sp++] = code[2];
-                if (h > 1) stack[sp++] = code[1];
+                if (sort_mode == 0) {  // the kernel's 5-comparator network
+                    cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+                } else {  // experiment: only the nearest child is found, the others keep their slot order (misses last)
+                    int m = 0;
+                    for (int i = 1; i < 4; ++i) if (key[i] < key[m]) m = i;
+                    std::swap(key[0], key[m]); std::swap(code[0], code[m]);
+                    // stable partition of slots 1..3: hits first
+                    for (int pass = 0; pass < 2; ++pass)
+                        for (int i = 1; i < 3; ++i)
+                            if (!(key[i] < INFINITY) && key[i + 1] < INFINITY) { std::swap(key[i], key[i + 1]); std::swap(code[i], code[i + 1]); }
+                }
+                if (h > 3) { kstack[sp] = key[3]; stack[sp++] = code[3]; }
+                if (h > 2) { kstack[sp] = key[2]; stack[sp++] = code[2]; }
+                if (h > 1) { kstack[sp] = key[1]; stack[sp++] = code[1]; }
                 max_sp = std::max(max_sp, (uint32_t)sp);
-                cur = h > 0 ? code[0] : (sp ? stack[--sp] : 0x7FFFFFFF);
+                cur = h > 0 ? code[0] : pop();
             } else {
                 leaf(cur, n_tris);
-                cur = sp ? stack[--sp] : 0x7FFFFFFF;
+                cur = pop();
             }
         }
         return best;
@@ -633,9 +653,19 @@ int main(int argc, char** argv) {
                 const KHit b = kw.trace4(r, n4, t4, sp4);
                 if (a.tri != b.tri || std::memcmp(&a.t, &b.t, 4) != 0) ++differ;
             }
+            uint64_t n4c = 0, t4c = 0;
+            if (std::getenv("BVH_STATS_NOSORT")) kw.sort_mode = 1; else kw.cull_on_pop = true;
+            for (const Ray& r : gen_rays[gen]) {
+                const KHit a = kw.trace2(r, n2, t2, sp2);
+                const KHit b = kw.trace4(r, n4c, t4c, sp4);
+                if (a.tri != b.tri || std::memcmp(&a.t, &b.t, 4) != 0) ++differ;
+            }
+            kw.cull_on_pop = false;
+            kw.sort_mode = 0;
+            n2 /= 2; t2 /= 2;
             const double nr = (double)std::max<size_t>(1, gen_rays[gen].size());
-            std::printf("  generation %zu, kernel walk: BVH2 %.2f nodes + %.2f tris (stack %u) | BVH4 %.2f nodes + %.2f tris (stack %u)\n", gen,
-                        n2 / nr, t2 / nr, sp2, n4 / nr, t4 / nr, sp4);
+            std::printf("  generation %zu, kernel walk: BVH2 %.2f nodes + %.2f tris (stack %u) | BVH4 %.2f nodes + %.2f tris (stack %u) | "
+                        "BVH4 + cull on pop %.2f nodes + %.2f tris\n", gen, n2 / nr, t2 / nr, sp2, n4 / nr, t4 / nr, sp4, n4c / nr, t4c / nr);
         }
         g_state = 777u;
         uint64_t brute_differ = 0;

@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "default": [],
     "bvh4": ["-DVR_BVH4"],
-    "bvh4_stack4": ["-DVR_BVH4", "-DVR_SMEM_STACK=4"],  # nearly every push and pop goes through the local tail
+    "bvh4_stack4": ["-DVR_BVH4", "-DVR_SMEM_STACK=4"],  # most pushes and pops go through the local tail
+    "bvh4_nosort": ["-DVR_BVH4", "-DVR_BVH4_NOSORT"],
     "stack8": ["-DVR_SMEM_STACK=8"],
     "tri48": ["-DVR_TRI48"],
 }
@@ -79,7 +80,7 @@ def test_kernel_traversal_source_matches_oracle(oracle, harness, tmp_path, varia
         assert "of 4 quads" in log
 
 
-@pytest.mark.parametrize("variant", ["default", "bvh4", "bvh4_stack4"])
+@pytest.mark.parametrize("variant", ["default", "bvh4", "bvh4_stack4", "bvh4_nosort"])
 def test_kernel_traversal_source_two_meshes_and_analytic_surfaces(oracle, harness, tmp_path, variant):
     # two meshes, a sphere inside the scene and a ground plane: surface handles, the analytic pass after the BVH and
     # the tie ranks across surfaces

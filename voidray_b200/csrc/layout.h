@@ -16,9 +16,10 @@ namespace vr {
 static const int NODE_QUADS = 2;
 // Experiment -DVR_BVH4 (every translation unit): 4-wide nodes, 64 B = two records of the format above back to back
 // (children 0, 1 | children 2, 3), child codes index wide nodes; an unused child is an inverted box with an empty
-// leaf code. The traversal parks up to three children per node, so its stack is WIDE_STACK_LIMIT entries deep.
+// leaf code. The traversal parks up to three children per node; the collapse leaves nodes narrower where a path could
+// otherwise park more than WIDE_STACK_LIMIT entries (= the kernel's stack, the same 32 as for the BVH2).
 static const int WIDE_NODE_QUADS = 4;
-static const int WIDE_STACK_LIMIT = 64;
+static const int WIDE_STACK_LIMIT = 32;
 #ifdef VR_BVH4
 static const int DEVICE_NODE_QUADS = WIDE_NODE_QUADS;
 #else

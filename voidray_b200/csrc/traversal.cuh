@@ -16,17 +16,14 @@ namespace vr {
 #ifndef VR_SMEM_STACK
 #define VR_SMEM_STACK 32
 #endif
-// Experiment -DVR_BVH4 (layout.h): 4-wide nodes park up to three children per step, so the stack is
-// WIDE_STACK_LIMIT deep — the host collapse keeps every path within it — and the part beyond the shared-memory
-// entries always exists as a local tail (the deepest stack seen on the BASELINE scenes is 13).
-#ifdef VR_BVH4
-static constexpr int STACK_DEPTH = WIDE_STACK_LIMIT;
-#define VR_HAS_SPILL 1
-#else
+// Experiment -DVR_BVH4 (layout.h): 4-wide nodes park up to three children per step; the host collapse narrows nodes
+// where needed so that no path can park more than WIDE_STACK_LIMIT = 32 entries, the same stack as the BVH2.
 static constexpr int STACK_DEPTH = 32;
+#ifdef VR_BVH4
+static_assert(WIDE_STACK_LIMIT == STACK_DEPTH, "the collapse must bound the stack the kernel has");
+#endif
 #if VR_SMEM_STACK < 32
 #define VR_HAS_SPILL 1
-#endif
 #endif
 static constexpr int SMEM_STACK = VR_SMEM_STACK;
 static_assert(SMEM_STACK >= 1 && SMEM_STACK <= STACK_DEPTH, "VR_SMEM_STACK");
@@ -205,11 +202,15 @@ __device__ __forceinline__ void wide_cswap(float& ka, int& ca, float& kb, int& c
     ca = c0;
     cb = c1;
 }
-__device__ __forceinline__ void wide_push(Traversal& tr, int* sstack, int sstride, int* __restrict__ spill, bool pred, int v) {
+__device__ __forceinline__ void wide_push(Traversal& tr, int* sstack, int sstride VR_SPILL_PARAM, bool pred, int v) {
+#ifdef VR_HAS_SPILL
     if (pred) {
         if (tr.sp < SMEM_STACK) sstack[tr.sp * sstride] = v;
         else spill[tr.sp - SMEM_STACK] = v;
     }
+#else
+    if (pred) sstack[tr.sp * sstride] = v;
+#endif
     tr.sp += pred ? 1 : 0;
 }
 // One 4-wide node: two 256-bit loads, four slab tests, children that are hit sorted by entry distance (a 5-comparator
@@ -224,14 +225,25 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
     float k3 = wide_child(tr, __float_as_uint(p1.lo.w), __float_as_uint(p1.hi.x), __float_as_uint(p1.hi.y));
     int c0 = __float_as_int(p0.hi.z), c1 = __float_as_int(p0.hi.w), c2 = __float_as_int(p1.hi.z), c3 = __float_as_int(p1.hi.w);
     const int hits = (k0 < INFINITY ? 1 : 0) + (k1 < INFINITY ? 1 : 0) + (k2 < INFINITY ? 1 : 0) + (k3 < INFINITY ? 1 : 0);
+#ifdef VR_BVH4_NOSORT
+    // Experiment: only the nearest child is found (three compare-selects instead of five), the other hits are parked
+    // in slot order. The CPU walk gives +1 % node fetches and triangle tests for it (BVH_STATS_NOSORT=1).
+    wide_cswap(k0, c0, k1, c1);
+    wide_cswap(k0, c0, k2, c2);
+    wide_cswap(k0, c0, k3, c3);
+    wide_push(tr, sstack, sstride VR_SPILL_ARG, k3 < INFINITY, c3);
+    wide_push(tr, sstack, sstride VR_SPILL_ARG, k2 < INFINITY, c2);
+    wide_push(tr, sstack, sstride VR_SPILL_ARG, k1 < INFINITY, c1);
+#else
     wide_cswap(k0, c0, k1, c1);
     wide_cswap(k2, c2, k3, c3);
     wide_cswap(k0, c0, k2, c2);
     wide_cswap(k1, c1, k3, c3);
     wide_cswap(k1, c1, k2, c2);
-    wide_push(tr, sstack, sstride, spill, hits > 3, c3);
-    wide_push(tr, sstack, sstride, spill, hits > 2, c2);
-    wide_push(tr, sstack, sstride, spill, hits > 1, c1);
+    wide_push(tr, sstack, sstride VR_SPILL_ARG, hits > 3, c3);
+    wide_push(tr, sstack, sstride VR_SPILL_ARG, hits > 2, c2);
+    wide_push(tr, sstack, sstride VR_SPILL_ARG, hits > 1, c1);
+#endif
     int next = c0;
     if (hits == 0) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
     tr.cur = next;
