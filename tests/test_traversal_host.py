@@ -101,3 +101,57 @@ def test_kernel_traversal_source_two_meshes_and_analytic_surfaces(oracle, harnes
     tri = p_ref != MISS
     assert np.array_equal(out["prim"][tri], p_ref[tri])
     assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))
+
+
+def _write_obj(path, positions, faces):
+    with open(path, "w") as f:
+        for p in positions:
+            f.write(f"v {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
+        f.write("vt 0 0\nvn 0 0 1\n")
+        for a, b, c in faces:
+            f.write(f"f {a + 1}/1/1 {b + 1}/1/1 {c + 1}/1/1\n")
+
+
+@pytest.mark.parametrize("variant", ["default", "bvh4", "bvh4_nosort", "tri48"])
+def test_kernel_traversal_source_tie_rule_and_surface_starts(oracle, harness, tmp_path, variant):
+    # (1) three coincident layers of an 8 x 8 quad grid (shared edges and vertices, every hit distance tied three to
+    # eighteen ways): the winner is the reference's right-most leaf (bvh.rs:171), whatever order the traversal takes;
+    # rays through vertices, edge mid-points and interiors, axis-parallel
+    n = 8
+    xs = np.arange(n + 1, dtype=F32) * F32(0.25) - F32(1.0)
+    grid = np.array([[x, y, 2.0] for y in xs for x in xs], F32)
+    quads = []
+    for j in range(n):
+        for i in range(n):
+            a, b, c, d = j * (n + 1) + i, j * (n + 1) + i + 1, (j + 1) * (n + 1) + i + 1, (j + 1) * (n + 1) + i
+            quads += [(a, b, c), (a, c, d)]
+    pos = np.concatenate([grid, grid, grid])
+    faces = [(a + k * len(grid), b + k * len(grid), c + k * len(grid)) for k in range(3) for a, b, c in quads]
+    obj = str(tmp_path / "layers.obj")
+    _write_obj(obj, pos, faces)
+    scene = Scene.empty()
+    scene.add_object(scene.add_material(Materials.lambertian((0.5, 0.5, 0.5))), scene.add_mesh(load_obj(obj)))
+    scene.environment = Environments.uniform((0.5, 0.5, 0.5))
+    pts = np.arange(4 * n + 1, dtype=F32) * F32(0.0625) - F32(1.0)  # vertices, edge mid-points, quarter points
+    o = np.array([[x, y, 0.0] for y in pts for x in pts], F32)
+    d = np.tile(np.array([0, 0, 1], F32), (len(o), 1))
+    s_ref, p_ref, t_ref, _ = oracle.OracleScene(scene).trace_rays(o, d)
+    out, _ = run_harness(harness(variant), tmp_path, o, d, ["obj", obj])
+    assert (s_ref != MISS).mean() > 0.9 and len(set(p_ref.tolist())) > 100
+    assert np.array_equal(out["prim"], p_ref) and np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))
+    # (2) rays that start on a surface (every scattered ray does) must not re-hit it below t = 1e-5
+    name = "mushroom.obj"
+    scene = Scene.empty()
+    scene.add_object(scene.add_material(Materials.lambertian((0.5, 0.5, 0.5))), scene.add_mesh(load_obj(asset_path(name))))
+    scene.environment = Environments.uniform((0.5, 0.5, 0.5))
+    osc = oracle.OracleScene(scene)
+    o, d = random_rays(30000, *scene_bounds(scene), seed=21)
+    s0, _, t0, _ = osc.trace_rays(o, d)
+    hit = s0 != MISS
+    dn = d / np.linalg.norm(d, axis=1, keepdims=True)
+    o2 = (o[hit] + dn[hit] * t0[hit, None]).astype(F32)
+    d2 = np.random.default_rng(5).normal(size=o2.shape).astype(F32)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o2, d2)
+    out, _ = run_harness(harness(variant), tmp_path, o2, d2, ["obj", asset_path(name)])
+    assert np.array_equal(out["surface"], s_ref) and np.array_equal(out["prim"], p_ref)
+    assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))
