@@ -3,7 +3,10 @@
 # (built here by scripts/build_variants.sh). PARITY=1 first runs the closest-hit and radiance gates on each variant,
 # so that a variant that is faster but wrong is seen as such.
 #   gpurun --timeout 900 -- 'PARITY=1 bash scripts/perf_variants.sh > gpurun_out/variants.log 2>&1'
-for lib in default gpurun_variants/*.so; do
+#   VARIANTS="bvh4 bvh4_steps1" ... restricts the run to the named variants (default: every library built)
+libs="default"
+if [ -n "$VARIANTS" ]; then for v in $VARIANTS; do libs="$libs gpurun_variants/$v.so"; done; else libs="default $(ls gpurun_variants/*.so)"; fi
+for lib in $libs; do
   if [ "$lib" = default ]; then unset VOIDRAY_CUDA_LIB; else export VOIDRAY_CUDA_LIB=$PWD/$lib; fi
   echo "== $lib"
   if [ -n "$PARITY" ] && [ "$lib" != default ]; then
