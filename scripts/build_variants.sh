@@ -13,6 +13,12 @@ declare -A FLAGS=(
   [stack16_tri48]="-DVR_SMEM_STACK=16 -DVR_TRI48"
   [tex8]="-DVR_TEX8"
   [stack16_tri48_tex8]="-DVR_SMEM_STACK=16 -DVR_TRI48 -DVR_TEX8"
+  [chunk]="-DVR_TRACE_CHUNK -DVR_LEAF_COMPACT"
+  [chunk_r16]="-DVR_TRACE_CHUNK -DVR_LEAF_COMPACT -DVR_REFILL_THRESHOLD=16"
+  [chunk_r20]="-DVR_TRACE_CHUNK -DVR_LEAF_COMPACT -DVR_REFILL_THRESHOLD=20"
+  [chunk_r24]="-DVR_TRACE_CHUNK -DVR_LEAF_COMPACT -DVR_REFILL_THRESHOLD=24"
+  [chunk_r20_b7]="-DVR_TRACE_CHUNK -DVR_LEAF_COMPACT -DVR_REFILL_THRESHOLD=20 -DVR_TRACE_MIN_BLOCKS=7"
+  [bvh4_chunk_r20_b7]="-DVR_BVH4 -DVR_NODE_STEPS=2 -DVR_TRACE_CHUNK -DVR_LEAF_COMPACT -DVR_REFILL_THRESHOLD=20 -DVR_TRACE_MIN_BLOCKS=7"
   [bvh4]="-DVR_BVH4 -DVR_NODE_STEPS=2"
   [bvh4_steps3]="-DVR_BVH4 -DVR_NODE_STEPS=3"
   [bvh4_steps1]="-DVR_BVH4 -DVR_NODE_STEPS=1"

@@ -193,7 +193,71 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
     bool exhausted = false;  // warp-uniform: the queue has no more rays
     uint32_t slot = 0;
 
+#ifdef VR_TRACE_CHUNK
+    // Experiment -DVR_TRACE_CHUNK: a refill of the default kernel is three dependent long-latency operations
+    // (atomicAdd on the cursor -> queue entry -> ray), during which the whole warp waits; that is why the refill
+    // threshold that measured best is as low as 12 lanes, and why a warp runs with about 22 live lanes on average
+    // (profiles/README.md). Here a warp claims the queue in chunks of 32 entries and keeps two of them in registers
+    // (one entry per lane, read with one coalesced load): the entries of the chunk after the current one are loaded
+    // and the chunk after that is claimed when the current one is opened, so both results are long there when they
+    // are needed; the rays of a freshly opened chunk are prefetched into L2. A refill then costs the ray loads only.
+    constexpr uint32_t NO_ENTRY = 0xFFFFFFFFu;
+    uint32_t cur_entry, nxt_entry, claim = 0u, cur_used = 0u;  // claim (lane 0): first index of the chunk after nxt
+    {
+        uint32_t base = 0u;
+        if (lane == 0u) base = atomicAdd(cursor, 64u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const uint32_t i0 = base + lane, i1 = base + 32u + lane;
+        cur_entry = i0 < n ? (queue ? queue[i0] : i0) : NO_ENTRY;
+        nxt_entry = i1 < n ? (queue ? queue[i1] : i1) : NO_ENTRY;
+        if (lane == 0u) claim = base + 64u < n ? atomicAdd(cursor, 32u) : n;
+        if (cur_entry != NO_ENTRY) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_o + cur_entry));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_d + cur_entry));
+        }
+    }
+#endif
+
     while (true) {
+#ifdef VR_TRACE_CHUNK
+        if (!exhausted) {
+            unsigned need = __ballot_sync(0xFFFFFFFFu, !have);
+            while (need) {  // at most two rounds: the rest of the current chunk, then the head of the next one
+                const uint32_t avail = 32u - cur_used;
+                const uint32_t r = (uint32_t)__popc(need & lt_mask);
+                const bool take = !have && r < avail;
+                const uint32_t e = __shfl_sync(0xFFFFFFFFu, cur_entry, (int)((cur_used + r) & 31u));
+                if (take && e != NO_ENTRY) {
+                    slot = e;
+                    const float4 ro = wf.ray_o[slot];
+                    const float4 rd = wf.ray_d[slot];
+                    trav_begin(tr, sc, xyz(ro), xyz(rd));
+                    have = true;
+                }
+                // entries are valid up to the end of the queue and a warp's chunks ascend: one missing entry means
+                // that nothing is left for this warp
+                if (__any_sync(0xFFFFFFFFu, take && e == NO_ENTRY)) {
+                    exhausted = true;
+                    break;
+                }
+                const uint32_t wanted = (uint32_t)__popc(need);
+                cur_used += wanted < avail ? wanted : avail;
+                if (cur_used < 32u) break;  // every lane is served
+                // open the next chunk
+                cur_entry = nxt_entry;
+                cur_used = 0u;
+                const uint32_t base = __shfl_sync(0xFFFFFFFFu, claim, 0);
+                const uint32_t i1 = base + lane;
+                nxt_entry = i1 < n ? (queue ? queue[i1] : i1) : NO_ENTRY;
+                if (lane == 0u && base < n) claim = atomicAdd(cursor, 32u);  // past the end it stays past the end
+                if (cur_entry != NO_ENTRY) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_o + cur_entry));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_d + cur_entry));
+                }
+                need = __ballot_sync(0xFFFFFFFFu, !have);
+            }
+        }
+#else
         if (!exhausted) {
             const unsigned need = __ballot_sync(0xFFFFFFFFu, !have);
             if (need) {
@@ -215,6 +279,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
                 if (base + cnt >= n) exhausted = true;
             }
         }
+#endif
         if (!__any_sync(0xFFFFFFFFu, have)) break;
         while (true) {
             if (have && tr.cur == SENTINEL) {

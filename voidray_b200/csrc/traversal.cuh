@@ -293,12 +293,22 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
 // through a neighbour's longer one.
 __device__ __forceinline__ void trav_leaf_step(Traversal& tr, const float4* __restrict__ tri_isect, int* sstack,
                                                int sstride VR_SPILL_PARAM) {
+#ifdef VR_LEAF_COMPACT
+    // Experiment (register pressure, used with -DVR_TRACE_CHUNK): nothing but tr.cur lives across the triangle test;
+    // (first + 1) << 3 | (count - 1) is the packed code plus 7.
+    if (((~tr.cur) & 7) > 0) intersect_triangle(tri_isect, (~tr.cur) >> 3, tr.o, tr.d, tr.best, tr.best_rank);
+    const int code = ~tr.cur;
+    int next = ~(code + 7);
+    if ((code & 7) <= 1) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
+    tr.cur = next;
+#else
     const int code = ~tr.cur;
     const int first = code >> 3, count = code & 7;
     if (count > 0) intersect_triangle(tri_isect, first, tr.o, tr.d, tr.best, tr.best_rank);
     int next = ~(((first + 1) << 3) | (count - 1));
     if (count <= 1) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
     tr.cur = next;
+#endif
 }
 
 __device__ __forceinline__ HitResult trav_finish(Traversal& tr, const DeviceScene& sc) {
