@@ -193,3 +193,13 @@ def test_shipped_builder_digest(name, want, nodes):
     assert runs[0][0] == want
     assert nodes is None or runs[0][1] == nodes
     assert runs[0][2] <= 32  # the traversal stack depth
+
+
+def test_chunked_refill_claim_logic_mirror():
+    # scripts/sim_chunk_refill.py: the claim / hand-out logic of the -DVR_TRACE_CHUNK refill, mirrored in scalar code
+    import subprocess
+    import sys
+    root = os.path.dirname(ASSETS)
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sim_chunk_refill.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
