@@ -1,7 +1,7 @@
 // traversal.cuh — closest-hit traversal of kernels.cu: Möller–Trumbore, analytic surfaces, the quantised-node slab
 // tests and the short stack. Device functions only, textually part of kernels.cu (the one place that includes it);
 // kept in a header of its own so that tests/c/trav_host.cpp can compile this very source for the CPU
-// (-DVR_HOST_SHIM: tests/c/host_shim.h stands in for the CUDA intrinsics) and check it against the oracle without a
+// (-DVR_HOST_SHIM: tests/c/host_shim.h stands in for the CUDA intrinsics) and check its hits bit for bit without a
 // GPU — in the shipped layout and in every experiment variant (-DVR_BVH4, -DVR_TRI48, -DVR_SMEM_STACK).
 #pragma once
 #include "device_math.cuh"
