@@ -1030,7 +1030,7 @@ struct TreeOptimizer {
 // a slot is free, replace the inner child with the largest surface area by its own two children. Nodes are numbered
 // in depth-first pre-order, node 0 is the root. A ray that enters a wide node parks at most (children - 1) entries
 // on the traversal stack; the collapse keeps the worst case over any root-to-leaf path within stack_limit by
-// leaving nodes narrower where a deep BVH2 path would not fit (never happens on the BASELINE scenes).
+// leaving nodes narrower on the way to the deepest BVH2 chains.
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct WideSlot {
@@ -1044,6 +1044,15 @@ struct WideCollapse {
     double cell[3];
     uint32_t bvh2_depth, stack_limit;
     uint32_t wide_depth = 0, max_stack = 0;
+    std::vector<uint8_t> height;  // per BVH2 node: inner levels of its subtree, itself included
+    uint8_t measure(uint32_t node) {
+        const Quad* q = &src[(size_t)node * 2];
+        const int32_t c0 = (int32_t)f_bits(q[1].z), c1 = (int32_t)f_bits(q[1].w);
+        uint8_t h = 0;
+        if (c0 >= 0) h = std::max(h, measure((uint32_t)c0));
+        if (c1 >= 0) h = std::max(h, measure((uint32_t)c1));
+        return height[node] = (uint8_t)(h + 1);
+    }
     static const uint32_t EMPTY_PAIR = (0x8000u | 32767u) | ((0x8000u | 0u) << 16);
 
     static uint32_t f_bits(float f) {
@@ -1075,11 +1084,15 @@ struct WideCollapse {
     uint32_t emit(uint32_t node, uint32_t depth, uint32_t used, uint32_t level) {
         WideSlot slots[5];
         int n = children(node, depth, slots, 0);
-        // widest node the remaining stack allows if every level below degrades to two children (one entry each)
-        const uint32_t below = bvh2_depth > depth + 1 ? bvh2_depth - depth - 1 : 0;
-        int width = 4;
-        while (width > 2 && used + (uint32_t)(width - 1) + below > stack_limit) --width;
-        while (n < width) {
+        // A child's subtree parks at most one entry per inner level if everything below stays binary, so a node may
+        // take one more child only while parked entries + (children - 1) + inner levels below every child stay within
+        // the stack. Only the few deepest chains of a tree are narrowed by this.
+        auto fits = [&](const WideSlot* sl, int count) {
+            for (int i = 0; i < count; ++i)
+                if (sl[i].code >= 0 && used + (uint32_t)(count - 1) + height[(uint32_t)sl[i].code] > stack_limit) return false;
+            return true;
+        };
+        while (n < 4) {
             int pick = -1;
             double best = -1.0;
             for (int i = 0; i < n; ++i)
@@ -1099,8 +1112,14 @@ struct WideCollapse {
                 slots[pick] = slots[--n];
                 continue;
             }
-            slots[pick] = kids[0];
-            if (nk == 2) slots[n++] = kids[1];
+            WideSlot trial[5];
+            for (int i = 0; i < n; ++i) trial[i] = slots[i];
+            trial[pick] = kids[0];
+            int nt = n;
+            if (nk == 2) trial[nt++] = kids[1];
+            if (!fits(trial, nt)) break;
+            for (int i = 0; i < nt; ++i) slots[i] = trial[i];
+            n = nt;
         }
         const uint32_t index = (uint32_t)(dst.size() / WIDE_NODE_QUADS);
         dst.resize(dst.size() + WIDE_NODE_QUADS);
@@ -1137,8 +1156,10 @@ void collapse_bvh4(const RawVector<Quad>& nodes2, const float grid_extent[3], ui
                    RawVector<Quad>& wide, uint32_t* wide_depth, uint32_t* max_stack) {
     wide.clear();
     wide.reserve(nodes2.size());
-    WideCollapse c{nodes2, wide, {}, bvh2_depth, stack_limit};
+    WideCollapse c{nodes2, wide, {0.0, 0.0, 0.0}, bvh2_depth, stack_limit, 0, 0, {}};
     for (int a = 0; a < 3; ++a) c.cell[a] = (double)grid_extent[a] / 32768.0;
+    c.height.assign(nodes2.size() / 2, 0);
+    c.measure(0);
     c.emit(0, 0, 0, 0);
     if (wide_depth) *wide_depth = c.wide_depth;
     if (max_stack) *max_stack = c.max_stack;
