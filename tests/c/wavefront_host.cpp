@@ -1,0 +1,146 @@
+// wavefront_host.cpp — test infrastructure: the CUDA kernels of voidray_b200/csrc/kernels.cu themselves (k_raygen,
+// k_trace, k_shade, k_accumulate — the very source nvcc compiles) built for the CPU through tests/c/host_shim.h with
+// -DVR_HOST_SHIM -DVR_HOST_SIMT: one OS thread per CUDA thread, warp-level intrinsics over a barrier per warp, real
+// atomics. Runs one wavefront batch of a small frame the way run_wavefront / vr_render_accumulate (csrc/abi.cu) drive
+// the device, and writes the accumulation buffer and the per-ray closest hits of depth 0 and 1.
+// tests/test_wavefront_host.py compares them with the oracle: the kernels' warp-level control flow (ray replacement,
+// vote stepping, queue compaction, the -DVR_TRACE_CHUNK claims, the -DVR_BVH4 step) checked without a GPU.
+//
+//   g++ -O2 -std=c++20 -pthread -ffp-contract=off -DVR_HOST_SHIM -DVR_HOST_SIMT -Itests/c -Ivoidray_b200/csrc -x c++
+//       voidray_b200/csrc/scene_build.cpp tests/c/wavefront_host.cpp -o wavefront_host
+//   wavefront_host <obj> <w> <h> <spp> <max_bounces> <seed> <eye xyz> <center xyz> <fov> <env rgb> <albedo rgb> <out.bin>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "scene_build.h"
+#include "../../voidray_b200/csrc/kernels.cu"
+
+using namespace vr;
+
+int main(int argc, char** argv) {
+    if (argc < 20) return 2;
+    int a = 1;
+    const char* obj = argv[a++];
+    const uint32_t w = (uint32_t)atoi(argv[a++]), h = (uint32_t)atoi(argv[a++]), spp = (uint32_t)atoi(argv[a++]);
+    const uint32_t max_bounces = (uint32_t)atoi(argv[a++]);
+    const uint64_t seed = strtoull(argv[a++], nullptr, 0);
+    float eye[3], center[3], env[3], albedo[3];
+    for (float& x : eye) x = (float)atof(argv[a++]);
+    for (float& x : center) x = (float)atof(argv[a++]);
+    const float fov = (float)atof(argv[a++]);
+    for (float& x : env) x = (float)atof(argv[a++]);
+    for (float& x : albedo) x = (float)atof(argv[a++]);
+    const char* out_path = argv[a++];
+
+    HostScene sc;
+    MaterialRec mat{};
+    mat.kind = 0;  // Lambertian
+    for (int k = 0; k < 3; ++k) mat.color[k] = albedo[k];
+    mat.albedo_tex = -1;
+    mat.normal_tex = -1;
+    sc.materials.push_back(mat);
+    std::string err;
+    HostMesh m;
+    if (!load_obj_file(obj, m, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    sc.meshes.push_back(std::move(m));
+    HostSurface sf;
+    sf.kind = 0;
+    sf.mesh = 0;
+    sc.surfaces.push_back(sf);
+    sc.objects.push_back(HostObject{0, 0});
+    const float up[3] = {0.0f, 1.0f, 0.0f};
+    for (int k = 0; k < 3; ++k) sc.camera.eye[k] = eye[k];
+    camera_look_at(eye, center, up, sc.camera.direction, sc.camera.up);
+    sc.camera.fov = fov;
+    sc.camera.has_dof = 0;
+    FlatScene flat;
+    if (!flatten_scene(sc, flat, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+
+    DeviceScene ds{};
+    ds.nodes = flat.nodes.data();
+    ds.tri_isect = flat.tri_isect.data();
+    ds.tri_shade = flat.tri_shade.data();
+    ds.tri_surface = flat.tri_surface.data();
+    ds.tri_prim = flat.tri_prim.data();
+    ds.materials = sc.materials.data();
+    ds.analytics = flat.analytics.data();
+    ds.n_analytics = (uint32_t)flat.analytics.size();
+    ds.n_tris = flat.n_tris;
+    for (int k = 0; k < 3; ++k) { ds.grid_min[k] = flat.grid_min[k]; ds.grid_extent[k] = flat.grid_extent[k]; ds.env_color[k] = env[k]; }
+    ds.env_kind = 1;
+    ds.camera = flat.camera;
+
+    const uint32_t n_pixels = w * h, n_paths = n_pixels * spp;
+    std::vector<float4> ray_o(n_paths), ray_d(n_paths), hit(n_paths), radiance(n_paths), att((size_t)max_bounces * n_paths);
+    std::vector<uint32_t> q0(n_paths), q1(n_paths), counts(2 * (max_bounces + 2), 0u);
+    unsigned long long segments = 0;
+    Wavefront wf{};
+    wf.ray_o = ray_o.data();
+    wf.ray_d = ray_d.data();
+    wf.hit = hit.data();
+    wf.att = att.data();
+    wf.radiance = radiance.data();
+    wf.queue[0] = q0.data();
+    wf.queue[1] = q1.data();
+    wf.counts = counts.data();
+    wf.cursors = counts.data() + (max_bounces + 2);
+    wf.segments = &segments;
+    wf.capacity = n_paths;
+    PathSource src{};
+    src.pixel = nullptr;
+    src.sample = nullptr;
+    src.n_pixels = n_pixels;
+    src.sample_base = 0;
+    src.width = w;
+    src.height = h;
+    FrameParams fp{};
+    fp.width = w;
+    fp.height = h;
+    fp.pixel_mapping = 0;
+    fp.max_bounces = max_bounces;
+    fp.firefly_clamp = 3.0f;
+    fp.render_mode = 0;
+    fp.integrator = 0;
+    fp.seed = seed;
+
+    // what run_wavefront does (csrc/abi.cu), with small grids: 2 blocks of ray generation, 2 persistent trace blocks
+    // (8 warps racing for the queue), 2 shade blocks
+    std::vector<float4> hits_depth0, hits_depth1;
+    std::vector<uint32_t> queue_depth1;
+    vr_host_launch(2, 256, [&] { k_raygen(ds, wf, src, fp, n_paths); });
+    const std::vector<float4> rays0_o = ray_o, rays0_d = ray_d;
+    std::vector<float4> rays1_o, rays1_d;
+    for (uint32_t depth = 0; depth < max_bounces; ++depth) {
+        if (depth == 1) { rays1_o = ray_o; rays1_d = ray_d; queue_depth1.assign(q1.begin(), q1.begin() + counts[1]); }
+        vr_host_launch(2, TRACE_THREADS, [&] { k_trace(ds, wf, depth); });
+        if (depth == 0) hits_depth0 = hit;
+        if (depth == 1) hits_depth1 = hit;
+        vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, false>(ds, wf, src, fp, depth); });
+    }
+    std::vector<float4> partial(n_pixels, float4{0, 0, 0, 0}), accum(n_pixels, float4{0, 0, 0, 0});
+    vr_host_launch(1, 256, [&] { k_accumulate(wf, partial.data(), accum.data(), w, h, spp, 1, 1.0f / (float)spp); });
+
+    // every ray of depth 0 and of depth 1 against the single-ray traversal (closest_hit, the gate kernels' path)
+    std::vector<int> stack(STACK_DEPTH + 8);
+    size_t wrong = 0, checked = 0;
+    auto check = [&](const std::vector<float4>& ro, const std::vector<float4>& rd, const std::vector<float4>& got, uint32_t slot) {
+        const HitResult hr = closest_hit(ds, xyz(ro[slot]), xyz(rd[slot]), stack.data(), 1);
+        const float4 g = got[slot];
+        ++checked;
+        if (__float_as_uint(g.x) != __float_as_uint(hr.t) || __float_as_int(g.y) != hr.prim || __float_as_uint(g.z) != __float_as_uint(hr.u) ||
+            __float_as_uint(g.w) != __float_as_uint(hr.v))
+            ++wrong;
+    };
+    for (uint32_t s = 0; s < n_paths; ++s) check(rays0_o, rays0_d, hits_depth0, s);
+    for (uint32_t s : queue_depth1) check(rays1_o, rays1_d, hits_depth1, s);
+    std::printf("%u paths, queue lengths", n_paths);
+    for (uint32_t d = 0; d <= max_bounces; ++d) std::printf(" %u", counts[d]);
+    std::printf(", %llu segments, %zu of %zu wavefront hits differ from the single-ray traversal\n", segments, wrong, checked);
+    FILE* of = std::fopen(out_path, "wb");
+    if (!of) return 1;
+    std::fwrite(accum.data(), sizeof(float4), n_pixels, of);
+    std::fclose(of);
+    return wrong ? 1 : 0;
+}

@@ -174,6 +174,18 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, Pa
 //     speculative traversal, no lane walks nodes that a pending leaf would have culled.
 static constexpr int REFILL_THRESHOLD = VR_REFILL_THRESHOLD;
 
+#ifdef VR_TRACE_CHUNK
+__device__ __forceinline__ void prefetch_ray(const Wavefront& wf, uint32_t slot) {
+#ifndef VR_HOST_SHIM
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_o + slot));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_d + slot));
+#else
+    (void)wf;
+    (void)slot;
+#endif
+}
+#endif
+
 __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
     __shared__ int s_stack[SMEM_STACK * TRACE_THREADS];
     const uint32_t n = wf.counts[depth];
@@ -211,10 +223,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
         cur_entry = i0 < n ? (queue ? queue[i0] : i0) : NO_ENTRY;
         nxt_entry = i1 < n ? (queue ? queue[i1] : i1) : NO_ENTRY;
         if (lane == 0u) claim = base + 64u < n ? atomicAdd(cursor, 32u) : n;
-        if (cur_entry != NO_ENTRY) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_o + cur_entry));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_d + cur_entry));
-        }
+        if (cur_entry != NO_ENTRY) prefetch_ray(wf, cur_entry);
     }
 #endif
 
@@ -250,10 +259,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
                 const uint32_t i1 = base + lane;
                 nxt_entry = i1 < n ? (queue ? queue[i1] : i1) : NO_ENTRY;
                 if (lane == 0u && base < n) claim = atomicAdd(cursor, 32u);  // past the end it stays past the end
-                if (cur_entry != NO_ENTRY) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_o + cur_entry));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_d + cur_entry));
-                }
+                if (cur_entry != NO_ENTRY) prefetch_ray(wf, cur_entry);
                 need = __ballot_sync(0xFFFFFFFFu, !have);
             }
         }
@@ -906,6 +912,7 @@ __global__ void k_environment_sample(DeviceScene sc, uint64_t n, const float* di
     }
 }
 
+#ifndef VR_HOST_SHIM  // (tests/c/ktrace_host.cpp compiles the kernels above for the CPU and launches them itself)
 // ------------------------------------------------------------------------------------------------
 // Launch wrappers. Grids are persistent-style: a multiple of the SM count x resident blocks, with
 // grid-stride loops; the live queue length is read on the device, so no host round trip per depth.
@@ -989,5 +996,7 @@ void launch_environment_sample(const DeviceScene& sc, uint64_t n, const float* d
     const uint32_t grid = (uint32_t)((n + 255) / 256);
     k_environment_sample<<<grid < 1 ? 1 : (grid > 4096 ? 4096 : grid), 256, 0, stream>>>(sc, n, dirs, rgb);
 }
+
+#endif  // VR_HOST_SHIM
 
 }  // namespace vr

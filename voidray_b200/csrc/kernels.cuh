@@ -1,6 +1,10 @@
 // kernels.cuh — launch interface of the wavefront integrator (kernels.cu) used by abi.cu.
 #pragma once
+#ifdef VR_HOST_SHIM  // tests only (tests/c/host_shim.h)
+#include "host_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "layout.h"
