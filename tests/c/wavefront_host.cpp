@@ -9,6 +9,7 @@
 //   g++ -O2 -std=c++20 -pthread -ffp-contract=off -DVR_HOST_SHIM -DVR_HOST_SIMT -Itests/c -Ivoidray_b200/csrc -x c++
 //       voidray_b200/csrc/scene_build.cpp tests/c/wavefront_host.cpp -o wavefront_host
 //   wavefront_host <obj> <w> <h> <spp> <max_bounces> <seed> <eye xyz> <center xyz> <fov> <env rgb> <albedo rgb> <out.bin>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -114,7 +115,26 @@ int main(int argc, char** argv) {
     std::vector<float4> rays1_o, rays1_d;
     for (uint32_t depth = 0; depth < max_bounces; ++depth) {
         if (depth == 1) { rays1_o = ray_o; rays1_d = ray_d; queue_depth1.assign(q1.begin(), q1.begin() + counts[1]); }
+#ifdef VR_HOST_STATS
+        g_trace_stats = TraceStats{};
+#endif
         vr_host_launch(2, TRACE_THREADS, [&] { k_trace(ds, wf, depth); });
+#ifdef VR_HOST_STATS
+        {
+            // lane occupancy of this depth's launch, and its cost in issue slots under a simple model: an executed
+            // step costs its instruction count once per warp whatever the number of active lanes
+            const TraceStats& st = g_trace_stats;
+            const double rays = (double)counts[depth];
+            const double c_node = atof(std::getenv("COST_NODE") ? std::getenv("COST_NODE") : "58"), c_leaf = 52, c_vote = 25, c_refill = 150;
+            const double slots = st.votes * c_vote + st.node_steps * c_node + st.leaf_steps * c_leaf + st.refills * c_refill;
+            if (rays > 0)
+                std::printf("depth %u: %.0f rays, %.2f node + %.2f leaf lane-steps per ray, live %.1f / vote, %.1f lanes per node step, "
+                            "%.1f per leaf step, %.1f rays per refill, model %.0f issue slots per ray\n", depth, rays,
+                            st.node_lanes / rays, st.leaf_lanes / rays, (double)st.live_lanes / std::max(1ull, st.votes),
+                            (double)st.node_lanes / std::max(1ull, st.node_steps), (double)st.leaf_lanes / std::max(1ull, st.leaf_steps),
+                            (double)st.refill_lanes / std::max(1ull, st.refills), slots / rays);
+        }
+#endif
         if (depth == 0) hits_depth0 = hit;
         if (depth == 1) hits_depth1 = hit;
         vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, false>(ds, wf, src, fp, depth); });

@@ -174,6 +174,27 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, Pa
 //     speculative traversal, no lane walks nodes that a pending leaf would have culled.
 static constexpr int REFILL_THRESHOLD = VR_REFILL_THRESHOLD;
 
+// tests/c/wavefront_host.cpp -DVR_HOST_STATS: lane occupancy of the vote loop when the kernel runs on the CPU shim
+// (votes, live lanes, lanes per executed node / leaf step, refills); compiles to nothing otherwise.
+#ifdef VR_HOST_STATS
+struct TraceStats {
+    unsigned long long votes, live_lanes, node_steps, node_lanes, leaf_steps, leaf_lanes, refills, refill_lanes;
+};
+static TraceStats g_trace_stats;
+#define VR_STAT_ADD(field, value) atomicAdd(&g_trace_stats.field, (unsigned long long)(value))
+#define VR_STAT_STEP(cond, steps, lanes)                                         \
+    {                                                                            \
+        const unsigned stat_m = __ballot_sync(0xFFFFFFFFu, (cond));              \
+        if (lane == 0u && stat_m) {                                              \
+            VR_STAT_ADD(steps, 1);                                               \
+            VR_STAT_ADD(lanes, __popc(stat_m));                                  \
+        }                                                                        \
+    }
+#else
+#define VR_STAT_ADD(field, value)
+#define VR_STAT_STEP(cond, steps, lanes)
+#endif
+
 #ifdef VR_TRACE_CHUNK
 __device__ __forceinline__ void prefetch_ray(const Wavefront& wf, uint32_t slot) {
 #ifndef VR_HOST_SHIM
@@ -250,6 +271,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
                     break;
                 }
                 const uint32_t wanted = (uint32_t)__popc(need);
+                if (lane == 0u) {
+                    VR_STAT_ADD(refills, 1);
+                    VR_STAT_ADD(refill_lanes, wanted < avail ? wanted : avail);
+                }
                 cur_used += wanted < avail ? wanted : avail;
                 if (cur_used < 32u) break;  // every lane is served
                 // open the next chunk
@@ -272,6 +297,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
                 uint32_t base = 0;
                 if ((int)lane == leader) base = atomicAdd(cursor, cnt);
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if ((int)lane == leader) {
+                    VR_STAT_ADD(refills, 1);
+                    VR_STAT_ADD(refill_lanes, cnt);
+                }
                 if (!have) {
                     const uint32_t i = base + (uint32_t)__popc(need & lt_mask);
                     if (i < n) {
@@ -300,6 +329,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
             const int live = __popc(m_node | m_leaf);
             if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
             const int n_node = __popc(m_node), n_leaf = __popc(m_leaf);
+            if (lane == 0u) {
+                VR_STAT_ADD(votes, 1);
+                VR_STAT_ADD(live_lanes, live);
+            }
 #ifndef VR_LEAF_VOTE_NUM
 #define VR_LEAF_VOTE_NUM 2
 #endif
@@ -315,12 +348,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
             // in profiles/README.md.
             if (n_node >= n_leaf * VR_LEAF_VOTE_NUM) {
 #pragma unroll
-                for (int step = 0; step < VR_NODE_STEPS; ++step)
+                for (int step = 0; step < VR_NODE_STEPS; ++step) {
+                    VR_STAT_STEP(have && is_inner(tr.cur), node_steps, node_lanes)
                     if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG);
+                }
             } else {
 #pragma unroll
-                for (int step = 0; step < VR_LEAF_STEPS; ++step)
+                for (int step = 0; step < VR_LEAF_STEPS; ++step) {
+                    VR_STAT_STEP(have && tr.cur < 0, leaf_steps, leaf_lanes)
                     if (have && tr.cur < 0) trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS VR_SPILL_ARG);
+                }
             }
         }
     }
