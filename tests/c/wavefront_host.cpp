@@ -9,6 +9,8 @@
 //   g++ -O2 -std=c++20 -pthread -ffp-contract=off -DVR_HOST_SHIM -DVR_HOST_SIMT -Itests/c -Ivoidray_b200/csrc -x c++
 //       voidray_b200/csrc/scene_build.cpp tests/c/wavefront_host.cpp -o wavefront_host
 //   wavefront_host <obj> <w> <h> <spp> <max_bounces> <seed> <eye xyz> <center xyz> <fov> <env rgb> <albedo rgb> <out.bin>
+//   wavefront_host <scene file of tests/scene_file.py> <w> <h> <spp> <max_bounces> <seed> <firefly_clamp> <render_mode>
+//                  <pixel_mapping> <out.bin>            (any scene the host API can describe)
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -17,61 +19,61 @@
 
 #include "scene_build.h"
 #include "../../voidray_b200/csrc/kernels.cu"
+#include "scene_file.h"
 
 using namespace vr;
 
 int main(int argc, char** argv) {
-    if (argc < 20) return 2;
+    if (argc < 11) return 2;
     int a = 1;
-    const char* obj = argv[a++];
+    const std::string first = argv[a++];
+    const bool scene_mode = first.size() > 8 && first.compare(first.size() - 8, 8, ".vrscene") == 0;
+    if (!scene_mode && argc < 20) return 2;
     const uint32_t w = (uint32_t)atoi(argv[a++]), h = (uint32_t)atoi(argv[a++]), spp = (uint32_t)atoi(argv[a++]);
     const uint32_t max_bounces = (uint32_t)atoi(argv[a++]);
     const uint64_t seed = strtoull(argv[a++], nullptr, 0);
-    float eye[3], center[3], env[3], albedo[3];
-    for (float& x : eye) x = (float)atof(argv[a++]);
-    for (float& x : center) x = (float)atof(argv[a++]);
-    const float fov = (float)atof(argv[a++]);
-    for (float& x : env) x = (float)atof(argv[a++]);
-    for (float& x : albedo) x = (float)atof(argv[a++]);
-    const char* out_path = argv[a++];
-
+    float firefly_clamp = 3.0f;
+    int32_t render_mode = 0, pixel_mapping = 0;
     HostScene sc;
-    MaterialRec mat{};
-    mat.kind = 0;  // Lambertian
-    for (int k = 0; k < 3; ++k) mat.color[k] = albedo[k];
-    mat.albedo_tex = -1;
-    mat.normal_tex = -1;
-    sc.materials.push_back(mat);
     std::string err;
-    HostMesh m;
-    if (!load_obj_file(obj, m, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
-    sc.meshes.push_back(std::move(m));
-    HostSurface sf;
-    sf.kind = 0;
-    sf.mesh = 0;
-    sc.surfaces.push_back(sf);
-    sc.objects.push_back(HostObject{0, 0});
-    const float up[3] = {0.0f, 1.0f, 0.0f};
-    for (int k = 0; k < 3; ++k) sc.camera.eye[k] = eye[k];
-    camera_look_at(eye, center, up, sc.camera.direction, sc.camera.up);
-    sc.camera.fov = fov;
-    sc.camera.has_dof = 0;
-    FlatScene flat;
-    if (!flatten_scene(sc, flat, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
-
-    DeviceScene ds{};
-    ds.nodes = flat.nodes.data();
-    ds.tri_isect = flat.tri_isect.data();
-    ds.tri_shade = flat.tri_shade.data();
-    ds.tri_surface = flat.tri_surface.data();
-    ds.tri_prim = flat.tri_prim.data();
-    ds.materials = sc.materials.data();
-    ds.analytics = flat.analytics.data();
-    ds.n_analytics = (uint32_t)flat.analytics.size();
-    ds.n_tris = flat.n_tris;
-    for (int k = 0; k < 3; ++k) { ds.grid_min[k] = flat.grid_min[k]; ds.grid_extent[k] = flat.grid_extent[k]; ds.env_color[k] = env[k]; }
-    ds.env_kind = 1;
-    ds.camera = flat.camera;
+    if (scene_mode) {
+        firefly_clamp = (float)atof(argv[a++]);
+        render_mode = atoi(argv[a++]);
+        pixel_mapping = atoi(argv[a++]);
+        if (!vr_test::read_scene(first.c_str(), sc)) { std::fprintf(stderr, "cannot read %s\n", first.c_str()); return 1; }
+    } else {
+        float eye[3], center[3], env[3], albedo[3];
+        for (float& x : eye) x = (float)atof(argv[a++]);
+        for (float& x : center) x = (float)atof(argv[a++]);
+        const float fov = (float)atof(argv[a++]);
+        for (float& x : env) x = (float)atof(argv[a++]);
+        for (float& x : albedo) x = (float)atof(argv[a++]);
+        MaterialRec mat{};
+        mat.kind = 0;  // Lambertian
+        for (int k = 0; k < 3; ++k) mat.color[k] = albedo[k];
+        mat.albedo_tex = -1;
+        mat.normal_tex = -1;
+        sc.materials.push_back(mat);
+        HostMesh m;
+        if (!load_obj_file(first.c_str(), m, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        sc.meshes.push_back(std::move(m));
+        HostSurface sf;
+        sf.kind = 0;
+        sf.mesh = 0;
+        sc.surfaces.push_back(sf);
+        sc.objects.push_back(HostObject{0, 0});
+        const float up[3] = {0.0f, 1.0f, 0.0f};
+        for (int k = 0; k < 3; ++k) sc.camera.eye[k] = eye[k];
+        camera_look_at(eye, center, up, sc.camera.direction, sc.camera.up);
+        sc.camera.fov = fov;
+        sc.camera.has_dof = 0;
+        sc.env_kind = 1;
+        for (int k = 0; k < 3; ++k) sc.env_color[k] = env[k];
+    }
+    const char* out_path = argv[a++];
+    vr_test::HostDeviceScene hds;
+    if (!hds.build(sc, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    const DeviceScene& ds = hds.ds;
 
     const uint32_t n_pixels = w * h, n_paths = n_pixels * spp;
     std::vector<float4> ray_o(n_paths), ray_d(n_paths), hit(n_paths), radiance(n_paths), att((size_t)max_bounces * n_paths);
@@ -99,10 +101,10 @@ int main(int argc, char** argv) {
     FrameParams fp{};
     fp.width = w;
     fp.height = h;
-    fp.pixel_mapping = 0;
+    fp.pixel_mapping = pixel_mapping;
     fp.max_bounces = max_bounces;
-    fp.firefly_clamp = 3.0f;
-    fp.render_mode = 0;
+    fp.firefly_clamp = firefly_clamp;
+    fp.render_mode = render_mode;
     fp.integrator = 0;
     fp.seed = seed;
 
@@ -137,7 +139,8 @@ int main(int argc, char** argv) {
 #endif
         if (depth == 0) hits_depth0 = hit;
         if (depth == 1) hits_depth1 = hit;
-        vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, false>(ds, wf, src, fp, depth); });
+        if (ds.has_microfacet) vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, true>(ds, wf, src, fp, depth); });
+        else vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, false>(ds, wf, src, fp, depth); });
     }
     std::vector<float4> partial(n_pixels, float4{0, 0, 0, 0}), accum(n_pixels, float4{0, 0, 0, 0});
     vr_host_launch(1, 256, [&] { k_accumulate(wf, partial.data(), accum.data(), w, h, spp, 1, 1.0f / (float)spp); });

@@ -76,3 +76,85 @@ def test_kernels_on_the_cpu_match_the_oracle(oracle, harness, tmp_path, variant)
     # same libm on both sides): the per-pixel means agree bit for bit
     assert np.array_equal(img[..., :3].view(np.uint32), ref[..., :3].astype(np.float32).view(np.uint32))
     assert np.all(img[..., 3] == 1.0)
+
+
+# ---- any scene the host API can describe (tests/scene_file.py -> tests/c/scene_file.h) -----------------------------
+def run_scene(harness, tmp_path, variant, scene, rs, w, h, spp):
+    from scene_file import write_scene
+    sp, out = str(tmp_path / "scene.vrscene"), str(tmp_path / "accum.bin")
+    write_scene(sp, scene)
+    r = subprocess.run([harness(variant), sp, str(w), str(h), str(spp), str(rs.max_bounces), hex(rs.seed),
+                        repr(float(rs.firefly_clamp)), str(int(rs.render_mode)), str(int(rs.pixel_mapping)), out],
+                       capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 of " in r.stdout
+    segments = int(r.stdout.split(" segments")[0].split()[-1])
+    return np.fromfile(out, np.float32).reshape(h, w, 4), segments
+
+
+def check_scene(oracle, harness, tmp_path, variant, scene, rs, w, h, spp, exact=True):
+    rs.total_samples = spp
+    img, segments = run_scene(harness, tmp_path, variant, scene, rs, w, h, spp)
+    ref, counters = oracle.OracleScene(scene).render(w, h, rs, spp)
+    ref = ref.astype(np.float32)
+    assert segments == counters.segments
+    if exact:
+        # both sides evaluate the same f32 operations in the same order and call the same libm here, so even the
+        # HDRI lookups (acosf / atan2f) and the 30-degree normal test agree bit for bit on the CPU
+        assert np.array_equal(img[..., :3].view(np.uint32), ref[..., :3].view(np.uint32)), \
+            float(np.abs(img[..., :3] - ref[..., :3]).max())
+    else:
+        assert float(np.abs(img[..., :3] - ref[..., :3]).max()) <= 2e-4
+    return img
+
+
+@pytest.mark.parametrize("variant", ["default", "bvh4_nosort_chunk"])
+def test_kernels_on_the_cpu_textured_hdri_dof(oracle, harness, tmp_path, variant):
+    from voidray_b200 import scenes
+    # configs[0]: albedo texture (bilinear), HDRI environment, thin-lens camera; then with the raw normal map
+    scene, st, _ = scenes.config1_mushroom(48, 36, 4)
+    img = check_scene(oracle, harness, tmp_path, variant, scene, st.render, 48, 36, 4)
+    assert float(img[..., :3].max()) > 0.5
+    scene, st, _ = scenes.config1_mushroom(48, 36, 4, normal_map=True)
+    check_scene(oracle, harness, tmp_path, variant, scene, st.render, 48, 36, 4)
+
+
+def test_kernels_on_the_cpu_all_material_kinds(oracle, harness, tmp_path):
+    from voidray_b200 import scenes
+    # lambertian, metal, dielectric, wood texture + nearest-sampled normal map, two meshes
+    scene, st, _ = scenes.config3_materials(48, 27, 4)
+    check_scene(oracle, harness, tmp_path, "default", scene, st.render, 48, 27, 4)
+    # emission, spheres, ground plane, quads, lambertian_bsdf (the reference's example scenes)
+    for fn in (scenes.example_cornell, scenes.example_spheres, scenes.example_material):
+        scene, st, _ = fn()
+        check_scene(oracle, harness, tmp_path, "default", scene, RenderSettings(total_samples=4, max_bounces=10), 40, 40, 4)
+
+
+def test_kernels_on_the_cpu_normal_mode_and_reference_pixel_mapping(oracle, harness, tmp_path):
+    from voidray_b200 import scenes
+    from voidray_b200.scene import PixelMapping, RenderMode
+    scene, st, _ = scenes.config1_mushroom(40, 40, 2, dof=False)
+    st.render.render_mode = RenderMode.Normal
+    check_scene(oracle, harness, tmp_path, "default", scene, st.render, 40, 40, 2)
+    st.render.render_mode = RenderMode.Full
+    st.render.pixel_mapping = PixelMapping.Reference
+    check_scene(oracle, harness, tmp_path, "default", scene, st.render, 40, 40, 2)
+
+
+@pytest.mark.parametrize("name", ["transparent", "clear", "metallic", "light"])
+def test_kernels_on_the_cpu_microfacet(oracle, harness, tmp_path, name):
+    # k_shade<false, true>: MicrofacetBSDF through the blanket BSDFMaterial impl (exp / ln / atan / sin / cos: the same
+    # libm on both sides here, unlike on the GPU, where tests/test_microfacet.py needs a tolerance)
+    from test_microfacet import MATERIALS
+    from test_oracle_shading import sphere_scene
+    scene = sphere_scene(MATERIALS[name], env=(0.5, 0.5, 0.5))
+    rs = RenderSettings(total_samples=8, max_bounces=8)
+    w = h = 32
+    img, segments = run_scene(harness, tmp_path, "default", scene, rs, w, h, 8)
+    ref, counters = oracle.OracleScene(scene).render(w, h, rs, 8)
+    ref = ref.astype(np.float32)
+    assert segments == counters.segments
+    fin = np.isfinite(ref[..., :3]).all(axis=2) & np.isfinite(img[..., :3]).all(axis=2)
+    assert fin.mean() > 0.99
+    assert np.array_equal(img[..., :3][fin].view(np.uint32), ref[..., :3][fin].view(np.uint32)), \
+        float(np.abs(img[..., :3][fin] - ref[..., :3][fin]).max())
