@@ -38,6 +38,9 @@ inline bool read_scene(const char* path, HostScene& sc) {
         t.h = r.get<uint32_t>();
         t.sample_type = r.get<int32_t>();
         r.floats(t.rgb, (size_t)3 * t.w * t.h);
+#ifdef VR_TEX8
+        pack_texture_rgba8(t);  // as vr_scene_add_texture_rgb32f does in the -DVR_TEX8 build
+#endif
         sc.textures.push_back(std::move(t));
     }
     const uint32_t n_surf = r.get<uint32_t>();
@@ -119,6 +122,16 @@ struct HostTexels {
 };
 inline void expand_texture(const HostTexture& t, HostTexels& out) {
     const size_t n = (size_t)t.w * t.h;
+#ifdef VR_TEX8
+    if (!t.rgba8.empty()) {  // upload_texture of the -DVR_TEX8 build: the RGBA8 form goes to the device
+        out.rec.texels = t.rgba8.data();
+        out.rec.width = t.w;
+        out.rec.height = t.h;
+        out.rec.sample_type = t.sample_type;
+        out.rec.pad = 1;
+        return;
+    }
+#endif
     out.texels.resize(n);
     for (size_t i = 0; i < n; ++i) out.texels[i] = Quad{t.rgb[3 * i], t.rgb[3 * i + 1], t.rgb[3 * i + 2], 0.0f};
     out.rec.texels = out.texels.data();

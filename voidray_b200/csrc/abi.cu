@@ -249,27 +249,6 @@ int32_t ensure_env_tables(vr_scene* scene) {
     return VR_OK;
 }
 
-#ifdef VR_TEX8
-// Experiment: a texture whose every value is exactly v / 255 (an 8-bit source through to_rgb32f) also keeps its
-// RGBA8 form; the kernel's conversion reproduces the same floats, so the lookups do not change by a bit.
-void pack_rgba8(HostTexture& t) {
-    const size_t n = (size_t)t.w * t.h;
-    std::vector<uint8_t> out(4 * n);
-    for (size_t i = 0; i < n; ++i) {
-        for (int c = 0; c < 3; ++c) {
-            const float f = t.rgb[3 * i + c];
-            const float scaled = f * 255.0f;
-            if (!(scaled >= 0.0f && scaled <= 255.0f)) return;
-            const int v = (int)(scaled + 0.5f);
-            const float back = (float)v / 255.0f;
-            if (std::memcmp(&back, &f, 4) != 0) return;  // bit for bit (-0.0 is not an 8-bit value)
-            out[4 * i + c] = (uint8_t)v;
-        }
-        out[4 * i + 3] = 0;
-    }
-    t.rgba8.swap(out);
-}
-#endif
 
 template <typename T>
 int32_t add_texture_int(vr_scene* scene, const T* pixels, uint32_t w, uint32_t h, uint32_t channels,
@@ -390,7 +369,7 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
     t.sample_type = sample_type;
     t.rgb.assign(rgb, rgb + (size_t)3 * w * h);
 #ifdef VR_TEX8
-    pack_rgba8(t);
+    pack_texture_rgba8(t);
 #endif
     scene->host.textures.push_back(std::move(t));
     cudaSetDevice(scene->ctx->device);

@@ -1165,6 +1165,28 @@ void collapse_bvh4(const RawVector<Quad>& nodes2, const float grid_extent[3], ui
     if (max_stack) *max_stack = c.max_stack;
 }
 
+#ifdef VR_TEX8
+// Experiment: a texture whose every value is exactly v / 255 (an 8-bit source through to_rgb32f) also keeps its
+// RGBA8 form; the kernel's conversion reproduces the same floats, so the lookups do not change by a bit.
+void pack_texture_rgba8(HostTexture& t) {
+    const size_t n = (size_t)t.w * t.h;
+    std::vector<uint8_t> out(4 * n);
+    for (size_t i = 0; i < n; ++i) {
+        for (int c = 0; c < 3; ++c) {
+            const float f = t.rgb[3 * i + c];
+            const float scaled = f * 255.0f;
+            if (!(scaled >= 0.0f && scaled <= 255.0f)) return;
+            const int v = (int)(scaled + 0.5f);
+            const float back = (float)v / 255.0f;
+            if (std::memcmp(&back, &f, 4) != 0) return;  // bit for bit (-0.0 is not an 8-bit value)
+            out[4 * i + c] = (uint8_t)v;
+        }
+        out[4 * i + 3] = 0;
+    }
+    t.rgba8.swap(out);
+}
+#endif
+
 namespace {
 // VOIDRAY_TIMING=1 prints the host phases of a commit to stderr
 struct PhaseTimer {

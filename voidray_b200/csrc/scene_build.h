@@ -109,6 +109,11 @@ void camera_look_at(const float eye[3], const float center[3], const float up_in
 
 bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err);
 
+#ifdef VR_TEX8
+// Experiment -DVR_TEX8: fills t.rgba8 when every float of t.rgb is exactly v / 255 (an 8-bit source), else leaves it empty.
+void pack_texture_rgba8(HostTexture& t);
+#endif
+
 // Collapses a finished BVH2 node array (layout.h, node 0 = root) into 4-wide nodes of WIDE_NODE_QUADS quads each
 // (experiment -DVR_BVH4, see scene_build.cpp). max_stack = the most entries a traversal can park on its stack.
 void collapse_bvh4(const RawVector<Quad>& nodes2, const float grid_extent[3], uint32_t bvh2_depth, uint32_t stack_limit,
