@@ -5,15 +5,15 @@
 # 1. the GPU gates on the default build (the commit path changed on the host since the last GPU run: same bytes, pinned
 #    by digests on CPU, but this is the first time the device sees them again)
 # 2. bench.py on all five configs (refreshes BASELINE.md §5: the host commit is 1.3-2x faster, e2e moves)
-# 3. the single-flag experiment variants (shared-memory stack, 48-byte triangles, RGBA8 textures, 4-wide nodes, chunked
-#    queue claims):
+# 3. the single-flag experiment variants (parked-leaf speculation first: the one the CPU lane model favours; shared-memory
+#    stack, 48-byte triangles, RGBA8 textures, 4-wide nodes, chunked queue claims):
 #    closest-hit + radiance gates, then the three-regime perf check
 # 4. launch list of the default build for profiles/
 mkdir -p gpurun_out
 echo "=== gates"; python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 echo "=== bench, all configs"; bash scripts/bench_all.sh r2
 # (the combined variants stack16_tri48*, bvh4_stack16* wait for the single-flag results)
-echo "=== variants"; PARITY=1 VARIANTS="stack16 stack12 tri48 tex8 bvh4 bvh4_steps1 bvh4_steps3 bvh4_nosort chunk chunk_r20 chunk_r24 chunk_r20_b7 bvh4_chunk_r20_b7" bash scripts/perf_variants.sh
+echo "=== variants"; PARITY=1 VARIANTS="spec spec_once spec_lv1_ls4 spec_stack16 bvh4_spec stack16 tri48 tex8 bvh4 bvh4_steps1 bvh4_nosort chunk chunk_r20 chunk_r20_b7" bash scripts/perf_variants.sh
 echo "=== launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_config2_r2.csv \
     python bench.py --workload config2_mossy_ground --spp 16 --steps 1 --warmup 3 --no-cpu --no-extra > gpurun_out/launches_config2_r2.log 2>&1

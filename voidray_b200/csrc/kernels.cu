@@ -225,6 +225,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
     bool have = false;
     bool exhausted = false;  // warp-uniform: the queue has no more rays
     uint32_t slot = 0;
+#ifdef VR_TRACE_SPEC
+    int pend = SENTINEL;  // a parked leaf (negative code) or SENTINEL
+#endif
 
 #ifdef VR_TRACE_CHUNK
     // Experiment -DVR_TRACE_CHUNK: a refill of the default kernel is three dependent long-latency operations
@@ -316,6 +319,74 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
         }
 #endif
         if (!__any_sync(0xFFFFFFFFu, have)) break;
+#ifdef VR_TRACE_SPEC
+        // Experiment -DVR_TRACE_SPEC: a lane that reaches a leaf while the warp is in a node phase does not wait: it
+        // parks the leaf (one per lane) and walks on from its stack, so its node steps ride in instruction slots that
+        // would have idled; parked leaves are tested first in the next leaf phase. Unlike postponing every leaf
+        // (profiles/r1_trace_v3_speculative.md: +31 % thread instructions), only waiting lanes speculate. The closest
+        // hit does not depend on the order in which candidates are tested, so the results are unchanged.
+        while (true) {
+            if (have && tr.cur == SENTINEL && pend == SENTINEL) {
+                const HitResult h = trav_finish(tr, sc);
+                wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+                have = false;
+            }
+            const bool can_park = have && tr.cur < 0 && pend == SENTINEL && tr.sp > 0;
+            const bool at_node = have && (is_inner(tr.cur) || can_park);
+            const bool at_leaf = have && (tr.cur < 0 || pend < 0);
+            const unsigned m_node = __ballot_sync(0xFFFFFFFFu, at_node);
+            const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, at_leaf);
+            const int live = __popc(m_node | m_leaf);
+            if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
+            const int n_node = __popc(m_node), n_leaf = __popc(m_leaf);
+            if (lane == 0u) {
+                VR_STAT_ADD(votes, 1);
+                VR_STAT_ADD(live_lanes, live);
+            }
+#ifndef VR_LEAF_VOTE_NUM
+#define VR_LEAF_VOTE_NUM 2
+#endif
+#ifndef VR_NODE_STEPS
+#define VR_NODE_STEPS 4
+#endif
+#ifndef VR_LEAF_STEPS
+#define VR_LEAF_STEPS 2
+#endif
+            if (n_node >= n_leaf * VR_LEAF_VOTE_NUM) {
+#pragma unroll
+                for (int step = 0; step < VR_NODE_STEPS; ++step) {
+#ifdef VR_SPEC_PARK_ONCE  // park only at the start of a node phase (one check per vote instead of one per step)
+                    if (step == 0)
+#endif
+                    if (have && tr.cur < 0 && pend == SENTINEL && tr.sp > 0) {
+                        pend = tr.cur;
+                        tr.cur = trav_pop(tr, sstack, TRACE_THREADS VR_SPILL_ARG);
+                    }
+                    VR_STAT_STEP(have && is_inner(tr.cur), node_steps, node_lanes)
+                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG);
+                }
+            } else {
+#pragma unroll
+                for (int step = 0; step < VR_LEAF_STEPS; ++step) {
+                    VR_STAT_STEP(have && (tr.cur < 0 || pend < 0), leaf_steps, leaf_lanes)
+                    // one triangle of the parked leaf if there is one, else of the current leaf — one copy of the
+                    // triangle test for both; (first + 1) << 3 | (count - 1) is the packed code plus 7
+                    const bool from_pend = pend < 0;
+                    if (have && (from_pend || tr.cur < 0)) {
+                        const int code = ~(from_pend ? pend : tr.cur);
+                        if ((code & 7) > 0) intersect_triangle(tri_isect, code >> 3, tr.o, tr.d, tr.best, tr.best_rank);
+                        const int code2 = ~(from_pend ? pend : tr.cur);  // re-derived: nothing else lives across the test
+                        const bool last = (code2 & 7) <= 1;
+                        const int next = ~(code2 + 7);
+                        if (from_pend) pend = last ? SENTINEL : next;
+                        else tr.cur = last ? trav_pop(tr, sstack, TRACE_THREADS VR_SPILL_ARG) : next;
+                    }
+                }
+            }
+        }
+    }
+}
+#else
         while (true) {
             if (have && tr.cur == SENTINEL) {
                 const HitResult h = trav_finish(tr, sc);
@@ -362,6 +433,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
         }
     }
 }
+
+#endif  // VR_TRACE_SPEC
 
 // ------------------------------------------------------------------------------------------------
 // Shading: core/tracer.rs:19-56 unrolled over the wavefront. The reference recursion
