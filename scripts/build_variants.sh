@@ -18,6 +18,8 @@ declare -A FLAGS=(
   [spec_b7]="-DVR_TRACE_SPEC -DVR_TRACE_MIN_BLOCKS=7"
   [spec_lv1_ls4]="-DVR_TRACE_SPEC -DVR_LEAF_VOTE_NUM=1 -DVR_LEAF_STEPS=4"
   [spec_stack16]="-DVR_TRACE_SPEC -DVR_SMEM_STACK=16"
+  [spec_stack16_tex8]="-DVR_TRACE_SPEC -DVR_SMEM_STACK=16 -DVR_TEX8"
+  [spec_stack16_tri48_tex8]="-DVR_TRACE_SPEC -DVR_SMEM_STACK=16 -DVR_TRI48 -DVR_TEX8"
   [bvh4_spec]="-DVR_BVH4 -DVR_NODE_STEPS=2 -DVR_TRACE_SPEC"
   [chunk]="-DVR_TRACE_CHUNK -DVR_LEAF_COMPACT"
   [chunk_r16]="-DVR_TRACE_CHUNK -DVR_LEAF_COMPACT -DVR_REFILL_THRESHOLD=16"
