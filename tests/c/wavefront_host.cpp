@@ -127,14 +127,18 @@ int main(int argc, char** argv) {
             // step costs its instruction count once per warp whatever the number of active lanes
             const TraceStats& st = g_trace_stats;
             const double rays = (double)counts[depth];
-            const double c_node = atof(std::getenv("COST_NODE") ? std::getenv("COST_NODE") : "58"), c_leaf = 52, c_vote = 25, c_refill = 150;
+            // instructions per executed node step / leaf step / vote / refill: defaults are the shipped kernel's SASS counts
+            // (distance between consecutive node / triangle loads in k_trace); scripts/lane_model.sh passes each variant's own
+            auto cost = [](const char* name, const char* dflt) { return atof(std::getenv(name) ? std::getenv(name) : dflt); };
+            const double c_node = cost("COST_NODE", "64"), c_leaf = cost("COST_LEAF", "104"), c_vote = cost("COST_VOTE", "24"),
+                         c_refill = cost("COST_REFILL", "170");
             const double slots = st.votes * c_vote + st.node_steps * c_node + st.leaf_steps * c_leaf + st.refills * c_refill;
             if (rays > 0)
                 std::printf("depth %u: %.0f rays, %.2f node + %.2f leaf lane-steps per ray, live %.1f / vote, %.1f lanes per node step, "
-                            "%.1f per leaf step, %.1f rays per refill, model %.0f issue slots per ray\n", depth, rays,
+                            "%.1f per leaf step, %.1f rays per refill, %.2f votes per ray, model %.0f issue slots per ray\n", depth, rays,
                             st.node_lanes / rays, st.leaf_lanes / rays, (double)st.live_lanes / std::max(1ull, st.votes),
                             (double)st.node_lanes / std::max(1ull, st.node_steps), (double)st.leaf_lanes / std::max(1ull, st.leaf_steps),
-                            (double)st.refill_lanes / std::max(1ull, st.refills), slots / rays);
+                            (double)st.refill_lanes / std::max(1ull, st.refills), st.votes / rays, slots / rays);
         }
 #endif
         if (depth == 0) hits_depth0 = hit;
