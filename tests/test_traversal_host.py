@@ -20,6 +20,7 @@ VARIANTS = {
     "bvh4_stack4": ["-DVR_BVH4", "-DVR_SMEM_STACK=4"],  # most pushes and pops go through the local tail
     "bvh4_nosort": ["-DVR_BVH4", "-DVR_BVH4_NOSORT"],
     "leaf_compact": ["-DVR_LEAF_COMPACT"],
+    "spec_arrival": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL"],  # the gate path passes no parking slot: must fold away
     "stack8": ["-DVR_SMEM_STACK=8"],
     "tri48": ["-DVR_TRI48"],
 }

@@ -26,6 +26,7 @@ VARIANTS = {
     "stack8_tri48": ["-DVR_SMEM_STACK=8", "-DVR_TRI48"],
     "tex8": ["-DVR_TEX8"],
     "spec": ["-DVR_TRACE_SPEC"],
+    "spec_arrival": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL"],
     "spec_r24_lv1": ["-DVR_TRACE_SPEC", "-DVR_REFILL_THRESHOLD=24", "-DVR_LEAF_VOTE_NUM=1", "-DVR_LEAF_STEPS=4"],
     "bvh4_spec_chunk": ["-DVR_BVH4", "-DVR_NODE_STEPS=2", "-DVR_TRACE_SPEC", "-DVR_TRACE_CHUNK", "-DVR_LEAF_COMPACT"],
 }
@@ -112,7 +113,7 @@ def check_scene(oracle, harness, tmp_path, variant, scene, rs, w, h, spp, exact=
     return img
 
 
-@pytest.mark.parametrize("variant", ["default", "bvh4_nosort_chunk", "tex8", "spec"])
+@pytest.mark.parametrize("variant", ["default", "bvh4_nosort_chunk", "tex8", "spec", "spec_arrival"])
 def test_kernels_on_the_cpu_textured_hdri_dof(oracle, harness, tmp_path, variant):
     from voidray_b200 import scenes
     # configs[0]: albedo texture (bilinear), HDRI environment, thin-lens camera; then with the raw normal map

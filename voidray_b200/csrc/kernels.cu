@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
             if (n_node >= n_leaf * VR_LEAF_VOTE_NUM) {
 #pragma unroll
                 for (int step = 0; step < VR_NODE_STEPS; ++step) {
-#ifdef VR_SPEC_PARK_ONCE  // park only at the start of a node phase (one check per vote instead of one per step)
+#if defined(VR_SPEC_PARK_ONCE) || defined(VR_SPEC_ARRIVAL)
+                    // park only at the start of a node phase (one check per vote instead of one per step); with
+                    // -DVR_SPEC_ARRIVAL the node step parks the leaves it arrives at itself
                     if (step == 0)
 #endif
                     if (have && tr.cur < 0 && pend == SENTINEL && tr.sp > 0) {
@@ -363,7 +365,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
                         tr.cur = trav_pop(tr, sstack, TRACE_THREADS VR_SPILL_ARG);
                     }
                     VR_STAT_STEP(have && is_inner(tr.cur), node_steps, node_lanes)
+#ifdef VR_SPEC_ARRIVAL
+                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG, &pend);
+#else
                     if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG);
+#endif
                 }
             } else {
 #pragma unroll

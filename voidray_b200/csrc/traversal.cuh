@@ -135,6 +135,15 @@ struct Traversal {
 #define VR_SPILL_ARG
 #define VR_SPILL_DECL
 #endif
+// Experiment -DVR_TRACE_SPEC -DVR_SPEC_ARRIVAL (kernels.cu): the node step itself parks a leaf it arrives at when the
+// caller passes a free parking slot; the gate kernels pass none and the parameter folds away.
+#if defined(VR_TRACE_SPEC) && defined(VR_SPEC_ARRIVAL)
+#define VR_PARK_PARAM , int* __restrict__ park
+#define VR_PARK_NONE , nullptr
+#else
+#define VR_PARK_PARAM
+#define VR_PARK_NONE
+#endif
 
 __device__ __forceinline__ void trav_axis(float o, float d, float gmin, float extent, float& a, float& bn, float& bf,
                                           uint32_t& sel) {
@@ -216,7 +225,10 @@ __device__ __forceinline__ void wide_push(Traversal& tr, int* sstack, int sstrid
 // One 4-wide node: two 256-bit loads, four slab tests, children that are hit sorted by entry distance (a 5-comparator
 // network, branch-free); the nearest is next, the others are parked farthest first. scripts/bvh_stats.cpp walks the
 // same node array with the same arithmetic on the CPU: half the node fetches of the BVH2 for the same triangle tests.
-__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride VR_SPILL_PARAM) {
+__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride VR_SPILL_PARAM VR_PARK_PARAM) {
+#if defined(VR_TRACE_SPEC) && defined(VR_SPEC_ARRIVAL)
+    (void)park;  // arrival parking is only built for the binary step
+#endif
     const float8 p0 = ldg8(nodes + WIDE_NODE_QUADS * tr.cur);
     const float8 p1 = ldg8(nodes + WIDE_NODE_QUADS * tr.cur + 2);
     float k0 = wide_child(tr, __float_as_uint(p0.lo.x), __float_as_uint(p0.lo.y), __float_as_uint(p0.lo.z));
@@ -250,7 +262,7 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
 }
 #else
 // One inner node: two slab tests from a single 32-byte record, near child first, far child pushed.
-__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride VR_SPILL_PARAM) {
+__device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride VR_SPILL_PARAM VR_PARK_PARAM) {
     const float8 n = ldg8(nodes + 2 * tr.cur);
     const uint32_t w0 = __float_as_uint(n.lo.x), w1 = __float_as_uint(n.lo.y), w2 = __float_as_uint(n.lo.z),
                    w3 = __float_as_uint(n.lo.w), w4 = __float_as_uint(n.hi.x), w5 = __float_as_uint(n.hi.y);
@@ -283,7 +295,14 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
 #endif
     tr.sp += both ? 1 : 0;
     int next = near_c;
+#if defined(VR_TRACE_SPEC) && defined(VR_SPEC_ARRIVAL)
+    // arrival at a leaf with a free parking slot and something left on the stack: park it and walk on (shares the pop)
+    const bool park_it = park != nullptr && any && near_c < 0 && *park == SENTINEL && tr.sp > 0;
+    if (park_it) *park = near_c;
+    if (!any || park_it) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
+#else
     if (!any) next = trav_pop(tr, sstack, sstride VR_SPILL_ARG);
+#endif
     tr.cur = next;
 }
 
@@ -325,7 +344,7 @@ __device__ __forceinline__ HitResult closest_hit(const DeviceScene& sc, f3 o, f3
     const float4* __restrict__ nodes = (const float4*)sc.nodes;
     const float4* __restrict__ tri_isect = (const float4*)sc.tri_isect;
     while (tr.cur != SENTINEL) {
-        if (is_inner(tr.cur)) trav_node(tr, nodes, sstack, sstride VR_SPILL_ARG);
+        if (is_inner(tr.cur)) trav_node(tr, nodes, sstack, sstride VR_SPILL_ARG VR_PARK_NONE);
         else trav_leaf_step(tr, tri_isect, sstack, sstride VR_SPILL_ARG);
     }
     return trav_finish(tr, sc);
