@@ -16,7 +16,7 @@ mkdir -p gpurun_out
 echo "=== gates"; python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 echo "=== bench, all configs"; bash scripts/bench_all.sh r2
 # (the combined variants stack16_tri48*, bvh4_stack16* wait for the single-flag results)
-echo "=== variants"; PARITY=1 VARIANTS="${VARIANTS:-stack16 tex8 tri48 bvh4_nosort bvh4 bvh4_steps1 spec_arrival spec_once spec bvh4_spec chunk chunk_r20_b7}" bash scripts/perf_variants.sh
+echo "=== variants"; PARITY=1 VARIANTS="${VARIANTS:-stack16 tex8 tri48 bvh4_nosort bvh4 bvh4_steps1 spec_arrival_unpark spec_arrival spec_once bvh4_spec chunk chunk_r20_b7}" bash scripts/perf_variants.sh
 echo "=== launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_config2_r2.csv \
     python bench.py --workload config2_mossy_ground --spp 16 --steps 1 --warmup 3 --no-cpu --no-extra > gpurun_out/launches_config2_r2.log 2>&1

@@ -372,6 +372,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
 #endif
                 }
             } else {
+#if defined(VR_SPEC_UNPARK) && !defined(VR_HAS_SPILL)
+                // the parked leaf becomes the current one for the leaf phase and what the lane was at goes back on the
+                // stack (the slot the parking freed), so the leaf steps are the shipped ones
+                if (have && pend < 0 && (tr.cur == SENTINEL || tr.sp < SMEM_STACK)) {
+                    if (tr.cur != SENTINEL) {
+                        sstack[tr.sp * TRACE_THREADS] = tr.cur;
+                        tr.sp += 1;
+                    }
+                    tr.cur = pend;
+                    pend = SENTINEL;
+                }
+#pragma unroll
+                for (int step = 0; step < VR_LEAF_STEPS; ++step) {
+                    VR_STAT_STEP(have && tr.cur < 0, leaf_steps, leaf_lanes)
+                    if (have && tr.cur < 0) trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS VR_SPILL_ARG);
+                }
+#else
 #pragma unroll
                 for (int step = 0; step < VR_LEAF_STEPS; ++step) {
                     VR_STAT_STEP(have && (tr.cur < 0 || pend < 0), leaf_steps, leaf_lanes)
@@ -388,6 +405,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
                         else tr.cur = last ? trav_pop(tr, sstack, TRACE_THREADS VR_SPILL_ARG) : next;
                     }
                 }
+#endif
             }
         }
     }
