@@ -16,6 +16,8 @@ declare -A FLAGS=(
   [spec]="-DVR_TRACE_SPEC"
   [spec_arrival]="-DVR_TRACE_SPEC -DVR_SPEC_ARRIVAL"
   [spec_arrival_unpark]="-DVR_TRACE_SPEC -DVR_SPEC_ARRIVAL -DVR_SPEC_UNPARK"
+  [spec_au_lv1]="-DVR_TRACE_SPEC -DVR_SPEC_ARRIVAL -DVR_SPEC_UNPARK -DVR_LEAF_VOTE_NUM=1"
+  [spec_au_lv1_stack16_tex8]="-DVR_TRACE_SPEC -DVR_SPEC_ARRIVAL -DVR_SPEC_UNPARK -DVR_LEAF_VOTE_NUM=1 -DVR_SMEM_STACK=16 -DVR_TEX8"
   [spec_once]="-DVR_TRACE_SPEC -DVR_SPEC_PARK_ONCE"
   [spec_b7]="-DVR_TRACE_SPEC -DVR_TRACE_MIN_BLOCKS=7"
   [spec_lv1_ls4]="-DVR_TRACE_SPEC -DVR_LEAF_VOTE_NUM=1 -DVR_LEAF_STEPS=4"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next session, one gpurun (~15 min of box time for parts 1, 2 and 4, ~3 min more per variant of
-# part 3: about 50 min with the 12 variants listed; VARIANTS="stack16 tex8" for a first short pass):
+# part 3: about 55 min with the 14 variants listed; VARIANTS="stack16 tex8" for a first short pass):
 #   bash scripts/build_variants.sh                      # here, before the call (the .so files travel with the snapshot;
 #                                                       # they are git-ignored, so a fresh container has to rebuild them)
 #   gpurun --timeout 4500 -- 'bash scripts/r2_first_call.sh > gpurun_out/r2_first.log 2>&1'   (in the background)
@@ -16,7 +16,7 @@ mkdir -p gpurun_out
 echo "=== gates"; python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 echo "=== bench, all configs"; bash scripts/bench_all.sh r2
 # (the combined variants stack16_tri48*, bvh4_stack16* wait for the single-flag results)
-echo "=== variants"; PARITY=1 VARIANTS="${VARIANTS:-stack16 tex8 tri48 bvh4_nosort bvh4 bvh4_steps1 spec_arrival_unpark spec_arrival spec_once bvh4_spec chunk chunk_r20_b7}" bash scripts/perf_variants.sh
+echo "=== variants"; PARITY=1 VARIANTS="${VARIANTS:-spec_au_lv1 stack16 tex8 tri48 bvh4_nosort bvh4 bvh4_steps1 spec_arrival_unpark spec_arrival spec_once bvh4_spec chunk chunk_r20_b7}" bash scripts/perf_variants.sh
 echo "=== launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_config2_r2.csv \
     python bench.py --workload config2_mossy_ground --spp 16 --steps 1 --warmup 3 --no-cpu --no-extra > gpurun_out/launches_config2_r2.log 2>&1

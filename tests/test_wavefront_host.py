@@ -27,7 +27,7 @@ VARIANTS = {
     "tex8": ["-DVR_TEX8"],
     "spec": ["-DVR_TRACE_SPEC"],
     "spec_arrival": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL"],
-    "spec_arrival_unpark": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL", "-DVR_SPEC_UNPARK"],
+    "spec_arrival_unpark": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL", "-DVR_SPEC_UNPARK", "-DVR_LEAF_VOTE_NUM=1"],
     "spec_r24_lv1": ["-DVR_TRACE_SPEC", "-DVR_REFILL_THRESHOLD=24", "-DVR_LEAF_VOTE_NUM=1", "-DVR_LEAF_STEPS=4"],
     "bvh4_spec_chunk": ["-DVR_BVH4", "-DVR_NODE_STEPS=2", "-DVR_TRACE_SPEC", "-DVR_TRACE_CHUNK", "-DVR_LEAF_COMPACT"],
 }
