@@ -16,9 +16,7 @@ from voidray_b200.scene import Camera, Environments, Materials, RenderSettings, 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "default": [],
-    "refill24": ["-DVR_REFILL_THRESHOLD=24"],
     "chunk": ["-DVR_TRACE_CHUNK", "-DVR_LEAF_COMPACT"],
-    "chunk_r24": ["-DVR_TRACE_CHUNK", "-DVR_LEAF_COMPACT", "-DVR_REFILL_THRESHOLD=24"],
     "chunk_r32": ["-DVR_TRACE_CHUNK", "-DVR_LEAF_COMPACT", "-DVR_REFILL_THRESHOLD=32"],
     "bvh4": ["-DVR_BVH4", "-DVR_NODE_STEPS=2"],
     "bvh4_nosort_chunk": ["-DVR_BVH4", "-DVR_BVH4_NOSORT", "-DVR_NODE_STEPS=1", "-DVR_TRACE_CHUNK", "-DVR_LEAF_COMPACT",
@@ -28,7 +26,6 @@ VARIANTS = {
     "spec": ["-DVR_TRACE_SPEC"],
     "spec_arrival": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL"],
     "spec_arrival_unpark": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL", "-DVR_SPEC_UNPARK", "-DVR_LEAF_VOTE_NUM=1"],
-    "spec_r24_lv1": ["-DVR_TRACE_SPEC", "-DVR_REFILL_THRESHOLD=24", "-DVR_LEAF_VOTE_NUM=1", "-DVR_LEAF_STEPS=4"],
     "bvh4_spec_chunk": ["-DVR_BVH4", "-DVR_NODE_STEPS=2", "-DVR_TRACE_SPEC", "-DVR_TRACE_CHUNK", "-DVR_LEAF_COMPACT"],
 }
 EYE, CENTER, FOV = (0.2, 2.8, -10.5), (0.2, 0.8, -0.5), 0.17  # the mushroom example's view (examples/mushroom.rs:27-30)
