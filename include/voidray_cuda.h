@@ -215,7 +215,9 @@ int32_t vr_render_clear(vr_render* render);
  * buffer (alpha += 1 per call). Blocking. */
 int32_t vr_render_accumulate(vr_render* render, uint32_t samples);
 /* RenderAction::Cancel (render/renderer.rs:101-106): thread-safe; the running accumulate returns
- * VR_ERR_CANCELLED after the wavefront batch in flight, leaving whole samples in the buffer. */
+ * VR_ERR_CANCELLED after the wavefront batch in flight, leaving whole samples in the buffer. Acts on the
+ * accumulate that is running when it is called: with none running it does nothing (no latch carries over
+ * into the next vr_render_accumulate). */
 int32_t vr_render_cancel(vr_render* render);
 
 typedef struct vr_stats {

@@ -911,8 +911,9 @@ struct Metal : Material {
         const V3 reflected = normalize(reflect(ray.direction, hit.normal));
         // The reference loop is unbounded (simple.rs:150-158). A path whose reflected direction lies
         // below the shading hemisphere with fuzz < 1 would spin forever; the oracle (and the CUDA
-        // path, identically) gives up after 64 rejected draws and terminates the path with the
-        // albedo as its value. Documented deviation, DESIGN.md "Reference quirks".
+        // path, identically) gives up after 64 rejected draws and terminates the path with BLACK
+        // (no light is injected where the reference would never return). Documented deviation,
+        // DESIGN.md "Reference quirks".
         for (int i = 0; i < 64; ++i) {
             scattered = Ray(hit.point, reflected + fuzz * rng.unit_sphere());
             if (dot(scattered.direction, hit.normal) > 0.0f) {
@@ -921,7 +922,7 @@ struct Metal : Material {
             }
         }
         has_scattered = false;
-        return albedo;
+        return Color{0.0f, 0.0f, 0.0f};
     }
 };
 // simple.rs:163-184

@@ -38,9 +38,7 @@ inline bool read_scene(const char* path, HostScene& sc) {
         t.h = r.get<uint32_t>();
         t.sample_type = r.get<int32_t>();
         r.floats(t.rgb, (size_t)3 * t.w * t.h);
-#ifdef VR_TEX8
         pack_texture_rgba8(t);  // as vr_scene_add_texture_rgb32f does in the -DVR_TEX8 build
-#endif
         sc.textures.push_back(std::move(t));
     }
     const uint32_t n_surf = r.get<uint32_t>();
@@ -122,7 +120,6 @@ struct HostTexels {
 };
 inline void expand_texture(const HostTexture& t, HostTexels& out) {
     const size_t n = (size_t)t.w * t.h;
-#ifdef VR_TEX8
     if (!t.rgba8.empty()) {  // upload_texture of the -DVR_TEX8 build: the RGBA8 form goes to the device
         out.rec.texels = t.rgba8.data();
         out.rec.width = t.w;
@@ -131,7 +128,6 @@ inline void expand_texture(const HostTexture& t, HostTexels& out) {
         out.rec.pad = 1;
         return;
     }
-#endif
     out.texels.resize(n);
     for (size_t i = 0; i < n; ++i) out.texels[i] = Quad{t.rgb[3 * i], t.rgb[3 * i + 1], t.rgb[3 * i + 2], 0.0f};
     out.rec.texels = out.texels.data();
@@ -165,6 +161,10 @@ struct HostDeviceScene {
         ds.analytics = flat.analytics.data();
         ds.n_analytics = (uint32_t)flat.analytics.size();
         ds.n_tris = flat.n_tris;
+        ds.scene_tree = flat.scene_tree.data();
+        ds.surface_node = flat.surface_node.data();
+        ds.n_scene_nodes = (uint32_t)flat.scene_tree.size();
+        ds.n_surfaces = (uint32_t)flat.surface_node.size();
         for (const MaterialRec& m : sc.materials)
             if (m.kind == 5) ds.has_microfacet = 1;
         for (int a = 0; a < 3; ++a) {

@@ -64,6 +64,10 @@ int main(int argc, char** argv) {
     ds.analytics = flat.analytics.data();
     ds.n_analytics = (uint32_t)flat.analytics.size();
     ds.n_tris = flat.n_tris;
+    ds.scene_tree = flat.scene_tree.data();
+    ds.surface_node = flat.surface_node.data();
+    ds.n_scene_nodes = (uint32_t)flat.scene_tree.size();
+    ds.n_surfaces = (uint32_t)flat.surface_node.size();
     for (int a = 0; a < 3; ++a) { ds.grid_min[a] = flat.grid_min[a]; ds.grid_extent[a] = flat.grid_extent[a]; }
 
     FILE* in = std::fopen(argv[1], "rb");

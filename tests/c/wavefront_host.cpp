@@ -117,37 +117,14 @@ int main(int argc, char** argv) {
     std::vector<float4> rays1_o, rays1_d;
     for (uint32_t depth = 0; depth < max_bounces; ++depth) {
         if (depth == 1) { rays1_o = ray_o; rays1_d = ray_d; queue_depth1.assign(q1.begin(), q1.begin() + counts[1]); }
-#ifdef VR_HOST_STATS
-        g_trace_stats = TraceStats{};
-#endif
         vr_host_launch(2, TRACE_THREADS, [&] { k_trace(ds, wf, depth); });
-#ifdef VR_HOST_STATS
-        {
-            // lane occupancy of this depth's launch, and its cost in issue slots under a simple model: an executed
-            // step costs its instruction count once per warp whatever the number of active lanes
-            const TraceStats& st = g_trace_stats;
-            const double rays = (double)counts[depth];
-            // instructions per executed node step / leaf step / vote / refill: defaults are the shipped kernel's SASS counts
-            // (distance between consecutive node / triangle loads in k_trace); scripts/lane_model.sh passes each variant's own
-            auto cost = [](const char* name, const char* dflt) { return atof(std::getenv(name) ? std::getenv(name) : dflt); };
-            const double c_node = cost("COST_NODE", "64"), c_leaf = cost("COST_LEAF", "104"), c_vote = cost("COST_VOTE", "24"),
-                         c_refill = cost("COST_REFILL", "170");
-            const double slots = st.votes * c_vote + st.node_steps * c_node + st.leaf_steps * c_leaf + st.refills * c_refill;
-            if (rays > 0)
-                std::printf("depth %u: %.0f rays, %.2f node + %.2f leaf lane-steps per ray, live %.1f / vote, %.1f lanes per node step, "
-                            "%.1f per leaf step, %.1f rays per refill, %.2f votes per ray, model %.0f issue slots per ray\n", depth, rays,
-                            st.node_lanes / rays, st.leaf_lanes / rays, (double)st.live_lanes / std::max(1ull, st.votes),
-                            (double)st.node_lanes / std::max(1ull, st.node_steps), (double)st.leaf_lanes / std::max(1ull, st.leaf_steps),
-                            (double)st.refill_lanes / std::max(1ull, st.refills), st.votes / rays, slots / rays);
-        }
-#endif
         if (depth == 0) hits_depth0 = hit;
         if (depth == 1) hits_depth1 = hit;
         if (ds.has_microfacet) vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, true>(ds, wf, src, fp, depth); });
         else vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, false>(ds, wf, src, fp, depth); });
     }
     std::vector<float4> partial(n_pixels, float4{0, 0, 0, 0}), accum(n_pixels, float4{0, 0, 0, 0});
-    vr_host_launch(1, 256, [&] { k_accumulate(wf, partial.data(), accum.data(), w, h, spp, 1, 1.0f / (float)spp); });
+    vr_host_launch(1, 256, [&] { k_accumulate(wf, partial.data(), accum.data(), w, h, spp, 1, 1.0f / (float)spp, 1.0f); });
 
     // every ray of depth 0 and of depth 1 against the single-ray traversal (closest_hit, the gate kernels' path)
     std::vector<int> stack(STACK_DEPTH + 8);

@@ -63,31 +63,22 @@ int main(int argc, char** argv) {
             }
         }
         for (uint32_t i = 0; i < flat.n_tris; ++i) if (seen[i] != 1) { printf("TRIANGLE %u seen %d times (n=%u)\n", i, seen[i], flat.n_tris); return 1; }
-        // the 4-wide collapse of the same tree (experiment -DVR_BVH4): same reachability, children in range, and the
-        // parked-entry bound within the kernel's stack
+        // the reference's scene-level tree (layout.h: SceneTreeNode): pre-order, every surface in exactly one leaf,
+        // skip links forward and inside the array, parents before their children
         {
-            RawVector<Quad> wide;
-            uint32_t wide_depth = 0, max_stack = 0;
-            collapse_bvh4(flat.nodes, flat.grid_extent, flat.bvh_depth, WIDE_STACK_LIMIT, wide, &wide_depth, &max_stack);
-            if (max_stack > (uint32_t)WIDE_STACK_LIMIT) { printf("WIDE STACK %u\n", max_stack); return 1; }
-            const size_t n_wide = wide.size() / WIDE_NODE_QUADS;
-            if (n_wide == 0 || n_wide > n_nodes + 1) { printf("WIDE NODE COUNT %zu\n", n_wide); return 1; }
-            std::vector<int> seen4(flat.n_tris, 0);
-            std::vector<size_t> st{0};
-            size_t visited4 = 0;
-            while (!st.empty()) {
-                size_t k = st.back(); st.pop_back();
-                if (++visited4 > n_wide) { printf("WIDE CYCLE\n"); return 1; }
-                for (int c = 0; c < 4; ++c) {
-                    const Quad& q = wide[k * WIDE_NODE_QUADS + 2 * (c / 2) + 1];
-                    uint32_t u; float f = (c & 1) == 0 ? q.z : q.w; memcpy(&u, &f, 4);
-                    int32_t code = (int32_t)u;
-                    if (code >= 0) { if ((size_t)code >= n_wide || (size_t)code <= k) { printf("WIDE CHILD OUT OF RANGE\n"); return 1; } st.push_back((size_t)code); }
-                    else { uint32_t v = ~u; uint32_t first = v >> 3, cnt = v & 7; if (first + cnt > flat.n_tris) { printf("WIDE LEAF OUT OF RANGE\n"); return 1; } for (uint32_t i = 0; i < cnt; ++i) seen4[first + i]++; }
-                }
+            const size_t n_surfaces = flat.surface_node.size(), n_st = flat.scene_tree.size();
+            if (n_st != (n_surfaces >= 2 ? 2 * n_surfaces - 1 : 0)) { printf("SCENE TREE SIZE %zu for %zu surfaces\n", n_st, n_surfaces); return 1; }
+            std::vector<int> leaf_seen(n_surfaces, 0);
+            for (size_t k = 0; k < n_st; ++k) {
+                const SceneTreeNode& nd = flat.scene_tree[k];
+                if (nd.parent >= (int32_t)k || (k == 0) != (nd.parent < 0)) { printf("SCENE TREE PARENT\n"); return 1; }
+                if (nd.a < 0) {
+                    const uint32_t sfc = (uint32_t)~nd.a;
+                    if (sfc >= n_surfaces || flat.surface_node[sfc] != k) { printf("SCENE TREE LEAF\n"); return 1; }
+                    leaf_seen[sfc]++;
+                } else if ((size_t)nd.a <= k + 2 || (size_t)nd.a > n_st) { printf("SCENE TREE SKIP\n"); return 1; }
             }
-            if (visited4 != n_wide) { printf("WIDE UNREACHABLE NODES\n"); return 1; }
-            for (uint32_t i = 0; i < flat.n_tris; ++i) if (seen4[i] != 1) { printf("WIDE TRIANGLE %u seen %d times\n", i, seen4[i]); return 1; }
+            if (n_st) for (size_t sfc = 0; sfc < n_surfaces; ++sfc) if (leaf_seen[sfc] != 1) { printf("SCENE TREE SURFACE %zu\n", sfc); return 1; }
         }
     }
     printf("ok\n");

@@ -130,49 +130,12 @@ def test_native_obj_loader_edge_cases(tmp_path):
         assets.load_obj_native(str(tmp_path / "missing.obj"))
 
 
-def test_bvh_quality_meter_builds_and_runs(tmp_path):
-    # scripts/bvh_stats.cpp: the offline meter behind the builder numbers in profiles/README.md
-    import subprocess
-    root = os.path.dirname(ASSETS)
-    exe = str(tmp_path / "bvh_stats")
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-I", os.path.join(root, "voidray_b200", "csrc"),
-                        "-x", "c++", os.path.join(root, "voidray_b200", "csrc", "scene_build.cpp"),
-                        os.path.join(root, "scripts", "bvh_stats.cpp"), "-o", exe], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-2000:]
-    out = subprocess.run([exe, os.path.join(ASSETS, "fancy_monkey.obj")], capture_output=True, text=True, timeout=300).stdout
-    assert "3936 triangles" in out and "nodes / ray" in out and "SAH cost" in out
-    assert "brute-force check: 0 of 3000 random rays differ" in out  # the quantised tree never culls a real hit
-    # what the device receives (nodes + triangle records) is the same bytes on every run although subtrees are built
-    # on several threads, and equal to the builder the GPU numbers in profiles/ were measured with
-    import re
-    digest = lambda o: re.search(r"flatten digest ([0-9a-f]{16})", o).group(1)  # noqa: E731
-    assert digest(out) == "cbf0e27fea44afdd"
-    runs = [subprocess.run([exe, os.path.join(ASSETS, "mossy_ground.obj")], capture_output=True, text=True, timeout=300).stdout
-            for _ in range(2)]
-    assert digest(runs[0]) == digest(runs[1]) == "8301c250a458b25e"
-    # the opt-in insertion-based optimiser (VOIDRAY_BVH_OPT) re-hangs subtrees: still no real hit culled, depth within
-    # the traversal stack, and a different tree than the default one
-    opt = subprocess.run([exe, os.path.join(ASSETS, "fancy_monkey.obj")], capture_output=True, text=True, timeout=300,
-                         env=dict(os.environ, VOIDRAY_BVH_OPT="2")).stdout
-    assert "brute-force check: 0 of 3000 random rays differ" in opt and digest(opt) != "cbf0e27fea44afdd"
-    assert int(re.search(r"depth (\d+)", opt).group(1)) <= 32
-    # experiment -DVR_BVH4: the 4-wide collapse of the same tree, walked with the kernel's own slab arithmetic next to
-    # the BVH2 — same closest hits bit for bit (also against brute force), about half the node fetches, stack bounded
-    wide = subprocess.run([exe, os.path.join(ASSETS, "fancy_monkey.obj")], capture_output=True, text=True, timeout=300,
-                          env=dict(os.environ, BVH_STATS_WIDE="1")).stdout
-    assert "kernel walks: 0 BVH2 / BVH4 differences, 0 of 3000 random rays differ from brute force" in wide
-    m = re.search(r"4-wide collapse: (\d+) nodes \(([\d.]+) children / node\), depth (\d+), stack bound (\d+)", wide)
-    assert m and int(m.group(4)) <= 64 and float(m.group(2)) > 2.5
-    g = re.search(r"generation 1, kernel walk: BVH2 ([\d.]+) nodes .* BVH4 ([\d.]+) nodes", wide)
-    assert float(g.group(2)) < 0.6 * float(g.group(1))
-
-
 def _library_digest(name):
     m = assets.load_obj_native(os.path.join(ASSETS, name))
     lib = _lib.load()
     n = len(m.positions)
     pos = np.ascontiguousarray(m.positions, F32)
-    uv = np.zeros((n, 2), F32)  # the same filler attributes scripts/bvh_stats.cpp uses
+    uv = np.zeros((n, 2), F32)  # filler attributes (the digest covers nodes and intersection records)
     nrm = np.tile(np.array([0, 1, 0], F32), (n, 1))
     idx = np.ascontiguousarray(m.indices, np.uint32).ravel()
     digest, nodes, depth, ms = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0), C.c_double(0)
@@ -193,13 +156,3 @@ def test_shipped_builder_digest(name, want, nodes):
     assert runs[0][0] == want
     assert nodes is None or runs[0][1] == nodes
     assert runs[0][2] <= 32  # the traversal stack depth
-
-
-def test_chunked_refill_claim_logic_mirror():
-    # scripts/sim_chunk_refill.py: the claim / hand-out logic of the -DVR_TRACE_CHUNK refill, mirrored in scalar code
-    import subprocess
-    import sys
-    root = os.path.dirname(ASSETS)
-    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sim_chunk_refill.py")], capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]

@@ -1,7 +1,6 @@
 """The closest-hit traversal source of the CUDA kernels (voidray_b200/csrc/traversal.cuh) compiled for the CPU
 (tests/c/trav_host.cpp + tests/c/host_shim.h) and compared with the oracle bit for bit: the k_trace_rays gate of
-tests/test_gpu_closest_hit.py without a GPU. Run for the shipped layout and for the experiment variants, whose
-kernels have not seen a GPU yet (-DVR_BVH4, -DVR_TRI48, -DVR_SMEM_STACK=n)."""
+tests/test_gpu_closest_hit.py without a GPU."""
 import os
 import subprocess
 
@@ -11,19 +10,11 @@ import pytest
 from voidray_b200.assets import asset_path, load_obj
 from voidray_b200.scene import Environments, Materials, Scene, Surfaces
 
-from util import F32, MISS, random_rays, scene_bounds
+from util import (F32, MISS, build_case_scene, flat_case_rays, flat_split_cases, quad_obj, random_rays, scene_bounds,
+                  write_obj)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = {
-    "default": [],
-    "bvh4": ["-DVR_BVH4"],
-    "bvh4_stack4": ["-DVR_BVH4", "-DVR_SMEM_STACK=4"],  # most pushes and pops go through the local tail
-    "bvh4_nosort": ["-DVR_BVH4", "-DVR_BVH4_NOSORT"],
-    "leaf_compact": ["-DVR_LEAF_COMPACT"],
-    "spec_arrival": ["-DVR_TRACE_SPEC", "-DVR_SPEC_ARRIVAL"],  # the gate path passes no parking slot: must fold away
-    "stack8": ["-DVR_SMEM_STACK=8"],
-    "tri48": ["-DVR_TRI48"],
-}
+VARIANTS = {"default": []}
 
 
 @pytest.fixture(scope="module")
@@ -78,11 +69,9 @@ def test_kernel_traversal_source_matches_oracle(oracle, harness, tmp_path, varia
     assert (s_ref != MISS).mean() > 0.1
     assert np.array_equal(out["surface"], s_ref) and np.array_equal(out["prim"], p_ref)
     assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))  # bit-equal distances, inf on a miss
-    if variant.startswith("bvh4"):
-        assert "of 4 quads" in log
 
 
-@pytest.mark.parametrize("variant", ["default", "bvh4", "bvh4_stack4", "bvh4_nosort"])
+@pytest.mark.parametrize("variant", ["default"])
 def test_kernel_traversal_source_two_meshes_and_analytic_surfaces(oracle, harness, tmp_path, variant):
     # two meshes, a sphere inside the scene and a ground plane: surface handles, the analytic pass after the BVH and
     # the tie ranks across surfaces
@@ -105,16 +94,7 @@ def test_kernel_traversal_source_two_meshes_and_analytic_surfaces(oracle, harnes
     assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))
 
 
-def _write_obj(path, positions, faces):
-    with open(path, "w") as f:
-        for p in positions:
-            f.write(f"v {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
-        f.write("vt 0 0\nvn 0 0 1\n")
-        for a, b, c in faces:
-            f.write(f"f {a + 1}/1/1 {b + 1}/1/1 {c + 1}/1/1\n")
-
-
-@pytest.mark.parametrize("variant", ["default", "bvh4", "bvh4_nosort", "tri48"])
+@pytest.mark.parametrize("variant", ["default"])
 def test_kernel_traversal_source_tie_rule_and_surface_starts(oracle, harness, tmp_path, variant):
     # (1) three coincident layers of an 8 x 8 quad grid (shared edges and vertices, every hit distance tied three to
     # eighteen ways): the winner is the reference's right-most leaf (bvh.rs:171), whatever order the traversal takes;
@@ -130,7 +110,7 @@ def test_kernel_traversal_source_tie_rule_and_surface_starts(oracle, harness, tm
     pos = np.concatenate([grid, grid, grid])
     faces = [(a + k * len(grid), b + k * len(grid), c + k * len(grid)) for k in range(3) for a, b, c in quads]
     obj = str(tmp_path / "layers.obj")
-    _write_obj(obj, pos, faces)
+    write_obj(obj, pos, faces)
     scene = Scene.empty()
     scene.add_object(scene.add_material(Materials.lambertian((0.5, 0.5, 0.5))), scene.add_mesh(load_obj(obj)))
     scene.environment = Environments.uniform((0.5, 0.5, 0.5))
@@ -157,3 +137,45 @@ def test_kernel_traversal_source_tie_rule_and_surface_starts(oracle, harness, tm
     out, _ = run_harness(harness(variant), tmp_path, o2, d2, ["obj", asset_path(name)])
     assert np.array_equal(out["surface"], s_ref) and np.array_equal(out["prim"], p_ref)
     assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))
+
+
+# ---- scene-level culling of the reference (core/scene.rs:182-185 over core/bvh.rs:132-160, util/aabb.rs:86-148) ----
+@pytest.mark.parametrize("case", ["two_coplanar_quads", "three_coplanar_quads", "five_coplanar_quads",
+                                  "flat_mesh_and_sphere", "flat_pair_inside_larger_scene", "two_coplanar_walls_x"])
+def test_scene_level_split_culling_matches_reference(oracle, harness, tmp_path, case):
+    scene, args = build_case_scene(flat_split_cases(tmp_path)[case])
+    o, d = flat_case_rays(scene, 3)
+    osc = oracle.OracleScene(scene)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d, oracle.MODE_FAITHFUL)
+    s_all, _, _, _ = osc.trace_rays(o, d, oracle.MODE_BRUTE)
+    out, _ = run_harness(harness("default"), tmp_path, o, d, args)
+    assert np.array_equal(out["surface"], s_ref)
+    tri = p_ref != MISS
+    assert np.array_equal(out["prim"][tri], p_ref[tri])
+    assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))
+    culled = (s_all != MISS) & (s_ref != s_all)
+    if case == "flat_mesh_and_sphere":
+        assert not culled.any() and (s_ref != MISS).mean() > 0.5
+    else:
+        # the case is not vacuous: the reference's flat Split drops hits that an un-culled closest hit finds
+        assert culled.sum() > 100, int(culled.sum())
+
+
+def test_scene_level_culling_beyond_the_mask_width(oracle, harness, tmp_path):
+    # 40 surfaces (> the 32 visibility bits a ray carries): candidates walk their ancestor chain instead.
+    # Coplanar tiles in rows of the plane y = 0 plus a second storey at y = 1, so flat and non-flat Splits mix.
+    surfaces = []
+    for k in range(40):
+        p = str(tmp_path / f"tile_{k}.obj")
+        x0, z0, y = 2.0 * (k % 8), 2.0 * ((k // 8) % 4), float(k // 32)
+        quad_obj(p, [(x0, y, z0), (x0, y, z0 + 1), (x0 + 1, y, z0 + 1), (x0 + 1, y, z0)])
+        surfaces.append(("obj", p))
+    scene, args = build_case_scene(surfaces)
+    o, d = flat_case_rays(scene, 9)
+    osc = oracle.OracleScene(scene)
+    s_ref, p_ref, t_ref, _ = osc.trace_rays(o, d, oracle.MODE_FAITHFUL)
+    s_all, _, _, _ = osc.trace_rays(o, d, oracle.MODE_BRUTE)
+    out, _ = run_harness(harness("default"), tmp_path, o, d, args)
+    assert np.array_equal(out["surface"], s_ref) and np.array_equal(out["prim"], p_ref)
+    assert np.array_equal(out["t"].view(np.uint32), t_ref.view(np.uint32))
+    assert ((s_all != MISS) & (s_ref != s_all)).sum() > 100 and (s_ref != MISS).sum() > 100

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/voidray_cuda.h"
@@ -60,6 +61,9 @@ struct vr_context {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     LaunchDims dims;
+    // vr_context_create_multi: the group's other devices (owned). This object is the group's first device.
+    std::vector<vr_context*> members;
+    std::vector<char> peer_ok;  // per member: the first device can load from it directly (cudaDeviceEnablePeerAccess)
 };
 
 // Device allocations of a scene are kept across commits and handed out again in the same order, so a
@@ -107,6 +111,10 @@ struct vr_scene {
     uint64_t commit_serial = 0;
     uint64_t h2d_bytes = 0;
     double flatten_ms = 0.0, upload_ms = 0.0;
+    // device group: the same scene on the group's other devices (owned). A replica has no host description of its
+    // own: commits upload the primary's (`source`).
+    std::vector<vr_scene*> replicas;
+    vr_scene* source = nullptr;
 };
 
 struct vr_render {
@@ -121,6 +129,7 @@ struct vr_render {
     uint32_t samples_per_batch = 1;
     uint32_t samples_done = 0;
     std::atomic<int> cancel{0};
+    std::atomic<int> running{0};  // an accumulate is in flight: only then does vr_render_cancel latch
     // statistics
     std::mutex stats_mutex;
     double seconds = 0.0, device_ms = 0.0, trace_ms = 0.0;
@@ -134,6 +143,12 @@ struct vr_render {
     uint32_t* dbg_surface = nullptr;
     uint32_t* dbg_prim = nullptr;
     float* dbg_t = nullptr;
+    // device group: this render's shards on the group's other devices (owned); `reduced` / `staged` live on the first
+    // device (the sum of all shards for read_accum; copies of the shards when a device cannot be peer-mapped)
+    std::vector<vr_render*> shards;
+    float4* reduced = nullptr;
+    std::vector<float4*> staged;
+    bool is_shard = false;
 };
 
 namespace {
@@ -201,7 +216,6 @@ void unpin_host(vr_scene* scene, const std::vector<float>& v) {
 int32_t upload_texture(vr_scene* scene, const HostTexture& t, void* stage, TextureRec* rec) {
     const size_t n = (size_t)t.w * t.h;
     void* d = nullptr;
-#ifdef VR_TEX8
     if (!t.rgba8.empty()) {  // 8-bit source: 4 B/texel over the bus and in HBM, widened per tap in the kernel
         VR_CUDA(scene->dev_mem.get(&d, 4 * n));
         VR_CUDA(cudaMemcpyAsync(d, t.rgba8.data(), 4 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
@@ -213,7 +227,6 @@ int32_t upload_texture(vr_scene* scene, const HostTexture& t, void* stage, Textu
         rec->pad = 1;
         return VR_OK;
     }
-#endif
     VR_CUDA(scene->dev_mem.get(&d, 16 * n));
     VR_CUDA(cudaMemcpyAsync(stage, t.rgb.data(), 12 * n, cudaMemcpyHostToDevice, scene->ctx->stream));
     launch_expand_rgb((const float*)stage, (float4*)d, n, scene->ctx->stream);
@@ -368,13 +381,10 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
     t.h = h;
     t.sample_type = sample_type;
     t.rgb.assign(rgb, rgb + (size_t)3 * w * h);
-#ifdef VR_TEX8
     pack_texture_rgba8(t);
-#endif
     scene->host.textures.push_back(std::move(t));
     cudaSetDevice(scene->ctx->device);
     pin_host(scene, scene->host.textures.back().rgb);
-#ifdef VR_TEX8
     {
         const std::vector<uint8_t>& p8 = scene->host.textures.back().rgba8;
         if (!p8.empty() && cudaHostRegister((void*)p8.data(), p8.size(), cudaHostRegisterDefault) == cudaSuccess)
@@ -382,7 +392,6 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
         else
             cudaGetLastError();
     }
-#endif
     scene->committed = false;
     if (texture) *texture = (uint32_t)scene->host.textures.size() - 1;
     return VR_OK;
@@ -679,6 +688,10 @@ int32_t vr_scene_commit(vr_scene* scene) try {
     if ((rc = upload_vector(scene, f.tri_prim, (const void**)&d.tri_prim))) return rc;
     if ((rc = upload_vector(scene, scene->host.materials, (const void**)&d.materials))) return rc;
     if ((rc = upload_vector(scene, f.analytics, (const void**)&d.analytics))) return rc;
+    if ((rc = upload_vector(scene, f.scene_tree, (const void**)&d.scene_tree))) return rc;
+    if ((rc = upload_vector(scene, f.surface_node, (const void**)&d.surface_node))) return rc;
+    d.n_scene_nodes = (uint32_t)f.scene_tree.size();
+    d.n_surfaces = (uint32_t)f.surface_node.size();
     size_t max_texels = scene->host.env_kind == 2 ? (size_t)scene->host.env_image.w * scene->host.env_image.h : 0;
     for (const HostTexture& t : scene->host.textures) max_texels = std::max(max_texels, (size_t)t.w * t.h);
     void* stage = nullptr;
@@ -839,6 +852,20 @@ int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
     if (samples == 0) return VR_OK;
     vr_context* ctx = r->scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
+    if (r->settings.integrator == 1) {
+        // a re-commit rewinds the scene's device memory and with it the sampling tables of integrator 1
+        const int32_t rc = ensure_env_tables(r->scene);
+        if (rc) return rc;
+    }
+    // Cancel acts on the accumulate that is running when it is issued (renderer.rs:101-106 polls between batches of
+    // the render in flight): a cancel that arrives while nothing runs is dropped, one that arrives after the last
+    // batch check is forgotten when the next accumulate starts.
+    r->cancel = 0;
+    r->running = 1;
+    struct Running {
+        std::atomic<int>& flag;
+        ~Running() { flag = 0; }
+    } running_guard{r->running};
     const auto t0 = std::chrono::steady_clock::now();
     const float inv_total = 1.0f / (float)r->settings.total_samples;  // iterative.rs:45
     VR_CUDA(cudaEventRecord(r->ev_begin, ctx->stream));
@@ -889,16 +916,13 @@ int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
         r->segments_host = seg;
         r->seconds += std::chrono::duration<double>(t1 - t0).count();
     }
-    if (cancelled) {
-        r->cancel = 0;
-        return fail(VR_ERR_CANCELLED, "accumulate cancelled");
-    }
+    if (cancelled) return fail(VR_ERR_CANCELLED, "accumulate cancelled");
     return VR_OK;
 } VR_CATCH
 
 int32_t vr_render_cancel(vr_render* r) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
-    r->cancel = 1;
+    if (r->running.load()) r->cancel = 1;
     return VR_OK;
 } VR_CATCH
 
@@ -1095,8 +1119,13 @@ int32_t vr_debug_trace_rays(vr_scene* scene, uint64_t n, const float* origins, c
 
 int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel, const uint32_t* sample, float* out) try {
     if (!r || !pixel || !sample || !out) return fail(VR_ERR_INVALID, "null argument");
+    if (!r->scene->committed) return fail(VR_ERR_INVALID, "scene was edited after commit");
     vr_context* ctx = r->scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
+    if (r->settings.integrator == 1) {
+        const int32_t rc = ensure_env_tables(r->scene);
+        if (rc) return rc;
+    }
     for (uint64_t i = 0; i < n; ++i)
         if (pixel[i] >= r->n_pixels) return fail(VR_ERR_INVALID, "pixel index out of range");
     DeviceBuffers tmp;

@@ -10,16 +10,8 @@
 
 namespace vr {
 
-#ifndef VR_TRACE_THREADS
-#define VR_TRACE_THREADS 128
-#endif
-#ifndef VR_TRACE_MIN_BLOCKS
-#define VR_TRACE_MIN_BLOCKS 8
-#endif
-#ifndef VR_REFILL_THRESHOLD
-#define VR_REFILL_THRESHOLD 12
-#endif
-static constexpr int TRACE_THREADS = VR_TRACE_THREADS;
+static constexpr int TRACE_THREADS = 128;
+static constexpr int TRACE_MIN_BLOCKS = 8;
 static constexpr int SHADE_THREADS = 128;
 }  // namespace vr
 #include "traversal.cuh"
@@ -28,7 +20,6 @@ namespace vr {
 // ------------------------------------------------------------------------------------------------
 // Textures and environment (core/texture.rs:52-98, voidray_common/src/environments.rs:57-86)
 // ------------------------------------------------------------------------------------------------
-#ifdef VR_TEX8
 // (float)v / 255.0f, correctly rounded, without the division: one Newton step on v * (1 / 255) recovers the exact
 // quotient for every v in 0..255 (checked exhaustively on the host: tests/c/unorm8_exact.c)
 __device__ __forceinline__ float unorm8(uint32_t v) {
@@ -36,15 +27,12 @@ __device__ __forceinline__ float unorm8(uint32_t v) {
     const float q = x * r;
     return __fmaf_rn(__fmaf_rn(-q, 255.0f, x), r, q);
 }
-#endif
 __device__ __forceinline__ f3 texel(const TextureRec& tex, uint32_t idx, uint32_t len) {
     if (idx >= len) idx -= len;  // `% len`: idx < 2*len always
-#ifdef VR_TEX8
     if (tex.pad == 1) {
         const uchar4 v = __ldg((const uchar4*)tex.texels + idx);
         return mk3(unorm8(v.x), unorm8(v.y), unorm8(v.z));
     }
-#endif
     return xyz(ldg4((const float4*)tex.texels + idx));
 }
 __device__ __forceinline__ f3 bilinear_sample(const TextureRec& tex, float x, float y) {
@@ -172,43 +160,14 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, Pa
 //     the state that holds more lanes (one vote each), the other lanes wait; waiting leaf lanes pile up
 //     until they outvote the node lanes. At least half of the live lanes work in every iteration and, unlike
 //     speculative traversal, no lane walks nodes that a pending leaf would have culled.
-static constexpr int REFILL_THRESHOLD = VR_REFILL_THRESHOLD;
+static constexpr int REFILL_THRESHOLD = 12;
 
-// tests/c/wavefront_host.cpp -DVR_HOST_STATS: lane occupancy of the vote loop when the kernel runs on the CPU shim
-// (votes, live lanes, lanes per executed node / leaf step, refills); compiles to nothing otherwise.
-#ifdef VR_HOST_STATS
-struct TraceStats {
-    unsigned long long votes, live_lanes, node_steps, node_lanes, leaf_steps, leaf_lanes, refills, refill_lanes;
-};
-static TraceStats g_trace_stats;
-#define VR_STAT_ADD(field, value) atomicAdd(&g_trace_stats.field, (unsigned long long)(value))
-#define VR_STAT_STEP(cond, steps, lanes)                                         \
-    {                                                                            \
-        const unsigned stat_m = __ballot_sync(0xFFFFFFFFu, (cond));              \
-        if (lane == 0u && stat_m) {                                              \
-            VR_STAT_ADD(steps, 1);                                               \
-            VR_STAT_ADD(lanes, __popc(stat_m));                                  \
-        }                                                                        \
-    }
-#else
-#define VR_STAT_ADD(field, value)
-#define VR_STAT_STEP(cond, steps, lanes)
-#endif
+// Vote parameters (measured sweep in profiles/README.md): the leaf step runs once the lanes waiting at a leaf exceed
+// 1 / LEAF_VOTE_NUM of the lanes at inner nodes; one vote buys NODE_STEPS node steps or LEAF_STEPS triangle tests.
+static constexpr int LEAF_VOTE_NUM = 2, NODE_STEPS = 4, LEAF_STEPS = 2;
 
-#ifdef VR_TRACE_CHUNK
-__device__ __forceinline__ void prefetch_ray(const Wavefront& wf, uint32_t slot) {
-#ifndef VR_HOST_SHIM
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_o + slot));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(wf.ray_d + slot));
-#else
-    (void)wf;
-    (void)slot;
-#endif
-}
-#endif
-
-__global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
-    __shared__ int s_stack[SMEM_STACK * TRACE_THREADS];
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
+    __shared__ int s_stack[(SMEM_STACK + 1) * TRACE_THREADS];  // + the rays' scene-level visibility words
     const uint32_t n = wf.counts[depth];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wf.segments, (unsigned long long)n);
     const uint32_t* __restrict__ queue = depth == 0 ? nullptr : wf.queue[depth & 1];
@@ -220,78 +179,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
     const unsigned lt_mask = (1u << lane) - 1u;
 
     Traversal tr;
-    VR_SPILL_DECL
     tr.cur = SENTINEL;
     bool have = false;
     bool exhausted = false;  // warp-uniform: the queue has no more rays
     uint32_t slot = 0;
-#ifdef VR_TRACE_SPEC
-    int pend = SENTINEL;  // a parked leaf (negative code) or SENTINEL
-#endif
 
-#ifdef VR_TRACE_CHUNK
-    // Experiment -DVR_TRACE_CHUNK: a refill of the default kernel is three dependent long-latency operations
-    // (atomicAdd on the cursor -> queue entry -> ray), during which the whole warp waits; that is why the refill
-    // threshold that measured best is as low as 12 lanes, and why a warp runs with about 22 live lanes on average
-    // (profiles/README.md). Here a warp claims the queue in chunks of 32 entries and keeps two of them in registers
-    // (one entry per lane, read with one coalesced load): the entries of the chunk after the current one are loaded
-    // and the chunk after that is claimed when the current one is opened, so both results are long there when they
-    // are needed; the rays of a freshly opened chunk are prefetched into L2. A refill then costs the ray loads only.
-    constexpr uint32_t NO_ENTRY = 0xFFFFFFFFu;
-    uint32_t cur_entry, nxt_entry, claim = 0u, cur_used = 0u;  // claim (lane 0): first index of the chunk after nxt
-    {
-        uint32_t base = 0u;
-        if (lane == 0u) base = atomicAdd(cursor, 64u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        const uint32_t i0 = base + lane, i1 = base + 32u + lane;
-        cur_entry = i0 < n ? (queue ? queue[i0] : i0) : NO_ENTRY;
-        nxt_entry = i1 < n ? (queue ? queue[i1] : i1) : NO_ENTRY;
-        if (lane == 0u) claim = base + 64u < n ? atomicAdd(cursor, 32u) : n;
-        if (cur_entry != NO_ENTRY) prefetch_ray(wf, cur_entry);
-    }
-#endif
 
     while (true) {
-#ifdef VR_TRACE_CHUNK
-        if (!exhausted) {
-            unsigned need = __ballot_sync(0xFFFFFFFFu, !have);
-            while (need) {  // at most two rounds: the rest of the current chunk, then the head of the next one
-                const uint32_t avail = 32u - cur_used;
-                const uint32_t r = (uint32_t)__popc(need & lt_mask);
-                const bool take = !have && r < avail;
-                const uint32_t e = __shfl_sync(0xFFFFFFFFu, cur_entry, (int)((cur_used + r) & 31u));
-                if (take && e != NO_ENTRY) {
-                    slot = e;
-                    const float4 ro = wf.ray_o[slot];
-                    const float4 rd = wf.ray_d[slot];
-                    trav_begin(tr, sc, xyz(ro), xyz(rd));
-                    have = true;
-                }
-                // entries are valid up to the end of the queue and a warp's chunks ascend: one missing entry means
-                // that nothing is left for this warp
-                if (__any_sync(0xFFFFFFFFu, take && e == NO_ENTRY)) {
-                    exhausted = true;
-                    break;
-                }
-                const uint32_t wanted = (uint32_t)__popc(need);
-                if (lane == 0u) {
-                    VR_STAT_ADD(refills, 1);
-                    VR_STAT_ADD(refill_lanes, wanted < avail ? wanted : avail);
-                }
-                cur_used += wanted < avail ? wanted : avail;
-                if (cur_used < 32u) break;  // every lane is served
-                // open the next chunk
-                cur_entry = nxt_entry;
-                cur_used = 0u;
-                const uint32_t base = __shfl_sync(0xFFFFFFFFu, claim, 0);
-                const uint32_t i1 = base + lane;
-                nxt_entry = i1 < n ? (queue ? queue[i1] : i1) : NO_ENTRY;
-                if (lane == 0u && base < n) claim = atomicAdd(cursor, 32u);  // past the end it stays past the end
-                if (cur_entry != NO_ENTRY) prefetch_ray(wf, cur_entry);
-                need = __ballot_sync(0xFFFFFFFFu, !have);
-            }
-        }
-#else
         if (!exhausted) {
             const unsigned need = __ballot_sync(0xFFFFFFFFu, !have);
             if (need) {
@@ -300,120 +194,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
                 uint32_t base = 0;
                 if ((int)lane == leader) base = atomicAdd(cursor, cnt);
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if ((int)lane == leader) {
-                    VR_STAT_ADD(refills, 1);
-                    VR_STAT_ADD(refill_lanes, cnt);
-                }
                 if (!have) {
                     const uint32_t i = base + (uint32_t)__popc(need & lt_mask);
                     if (i < n) {
                         slot = queue ? queue[i] : i;
                         const float4 ro = wf.ray_o[slot];
                         const float4 rd = wf.ray_d[slot];
-                        trav_begin(tr, sc, xyz(ro), xyz(rd));
+                        trav_begin(tr, sc, xyz(ro), xyz(rd), sstack, TRACE_THREADS);
                         have = true;
                     }
                 }
                 if (base + cnt >= n) exhausted = true;
             }
         }
-#endif
         if (!__any_sync(0xFFFFFFFFu, have)) break;
-#ifdef VR_TRACE_SPEC
-        // Experiment -DVR_TRACE_SPEC: a lane that reaches a leaf while the warp is in a node phase does not wait: it
-        // parks the leaf (one per lane) and walks on from its stack, so its node steps ride in instruction slots that
-        // would have idled; parked leaves are tested first in the next leaf phase. Unlike postponing every leaf
-        // (profiles/r1_trace_v3_speculative.md: +31 % thread instructions), only waiting lanes speculate. The closest
-        // hit does not depend on the order in which candidates are tested, so the results are unchanged.
-        while (true) {
-            if (have && tr.cur == SENTINEL && pend == SENTINEL) {
-                const HitResult h = trav_finish(tr, sc);
-                wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
-                have = false;
-            }
-            const bool can_park = have && tr.cur < 0 && pend == SENTINEL && tr.sp > 0;
-            const bool at_node = have && (is_inner(tr.cur) || can_park);
-            const bool at_leaf = have && (tr.cur < 0 || pend < 0);
-            const unsigned m_node = __ballot_sync(0xFFFFFFFFu, at_node);
-            const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, at_leaf);
-            const int live = __popc(m_node | m_leaf);
-            if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
-            const int n_node = __popc(m_node), n_leaf = __popc(m_leaf);
-            if (lane == 0u) {
-                VR_STAT_ADD(votes, 1);
-                VR_STAT_ADD(live_lanes, live);
-            }
-#ifndef VR_LEAF_VOTE_NUM
-#define VR_LEAF_VOTE_NUM 2
-#endif
-#ifndef VR_NODE_STEPS
-#define VR_NODE_STEPS 4
-#endif
-#ifndef VR_LEAF_STEPS
-#define VR_LEAF_STEPS 2
-#endif
-            if (n_node >= n_leaf * VR_LEAF_VOTE_NUM) {
-#pragma unroll
-                for (int step = 0; step < VR_NODE_STEPS; ++step) {
-#if defined(VR_SPEC_PARK_ONCE) || defined(VR_SPEC_ARRIVAL)
-                    // park only at the start of a node phase (one check per vote instead of one per step); with
-                    // -DVR_SPEC_ARRIVAL the node step parks the leaves it arrives at itself
-                    if (step == 0)
-#endif
-                    if (have && tr.cur < 0 && pend == SENTINEL && tr.sp > 0) {
-                        pend = tr.cur;
-                        tr.cur = trav_pop(tr, sstack, TRACE_THREADS VR_SPILL_ARG);
-                    }
-                    VR_STAT_STEP(have && is_inner(tr.cur), node_steps, node_lanes)
-#ifdef VR_SPEC_ARRIVAL
-                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG, &pend);
-#else
-                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG);
-#endif
-                }
-            } else {
-#if defined(VR_SPEC_UNPARK) && !defined(VR_HAS_SPILL)
-                // the parked leaf becomes the current one for the leaf phase and what the lane was at goes back on the
-                // stack (the slot the parking freed), so the leaf steps are the shipped ones
-                if (have && pend < 0 && (tr.cur == SENTINEL || tr.sp < SMEM_STACK)) {
-                    if (tr.cur != SENTINEL) {
-                        sstack[tr.sp * TRACE_THREADS] = tr.cur;
-                        tr.sp += 1;
-                    }
-                    tr.cur = pend;
-                    pend = SENTINEL;
-                }
-#pragma unroll
-                for (int step = 0; step < VR_LEAF_STEPS; ++step) {
-                    VR_STAT_STEP(have && tr.cur < 0, leaf_steps, leaf_lanes)
-                    if (have && tr.cur < 0) trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS VR_SPILL_ARG);
-                }
-#else
-#pragma unroll
-                for (int step = 0; step < VR_LEAF_STEPS; ++step) {
-                    VR_STAT_STEP(have && (tr.cur < 0 || pend < 0), leaf_steps, leaf_lanes)
-                    // one triangle of the parked leaf if there is one, else of the current leaf — one copy of the
-                    // triangle test for both; (first + 1) << 3 | (count - 1) is the packed code plus 7
-                    const bool from_pend = pend < 0;
-                    if (have && (from_pend || tr.cur < 0)) {
-                        const int code = ~(from_pend ? pend : tr.cur);
-                        if ((code & 7) > 0) intersect_triangle(tri_isect, code >> 3, tr.o, tr.d, tr.best, tr.best_rank);
-                        const int code2 = ~(from_pend ? pend : tr.cur);  // re-derived: nothing else lives across the test
-                        const bool last = (code2 & 7) <= 1;
-                        const int next = ~(code2 + 7);
-                        if (from_pend) pend = last ? SENTINEL : next;
-                        else tr.cur = last ? trav_pop(tr, sstack, TRACE_THREADS VR_SPILL_ARG) : next;
-                    }
-                }
-#endif
-            }
-        }
-    }
-}
-#else
         while (true) {
             if (have && tr.cur == SENTINEL) {
-                const HitResult h = trav_finish(tr, sc);
+                const HitResult h = trav_finish(tr, sc, sstack, TRACE_THREADS);
                 wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
                 have = false;
             }
@@ -424,41 +221,25 @@ __global__ void __launch_bounds__(TRACE_THREADS, VR_TRACE_MIN_BLOCKS) k_trace(De
             const int live = __popc(m_node | m_leaf);
             if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
             const int n_node = __popc(m_node), n_leaf = __popc(m_leaf);
-            if (lane == 0u) {
-                VR_STAT_ADD(votes, 1);
-                VR_STAT_ADD(live_lanes, live);
-            }
-#ifndef VR_LEAF_VOTE_NUM
-#define VR_LEAF_VOTE_NUM 2
-#endif
-#ifndef VR_NODE_STEPS
-#define VR_NODE_STEPS 4
-#endif
-#ifndef VR_LEAF_STEPS
-#define VR_LEAF_STEPS 2
-#endif
-            // Vote: the leaf step runs once the lanes waiting at a leaf exceed 1/VR_LEAF_VOTE_NUM of the lanes at
-            // inner nodes; otherwise every lane that is (still) at an inner node takes VR_NODE_STEPS node steps on
+            // Vote: the leaf step runs once the lanes waiting at a leaf exceed 1/LEAF_VOTE_NUM of the lanes at
+            // inner nodes; otherwise every lane that is (still) at an inner node takes NODE_STEPS node steps on
             // this one vote — the loop control costs ~25 full-width instructions, half a node step. Measured sweep
             // in profiles/README.md.
-            if (n_node >= n_leaf * VR_LEAF_VOTE_NUM) {
+            if (n_node >= n_leaf * LEAF_VOTE_NUM) {
 #pragma unroll
-                for (int step = 0; step < VR_NODE_STEPS; ++step) {
-                    VR_STAT_STEP(have && is_inner(tr.cur), node_steps, node_lanes)
-                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS VR_SPILL_ARG);
+                for (int step = 0; step < NODE_STEPS; ++step) {
+                    if (have && is_inner(tr.cur)) trav_node(tr, nodes, sstack, TRACE_THREADS);
                 }
             } else {
 #pragma unroll
-                for (int step = 0; step < VR_LEAF_STEPS; ++step) {
-                    VR_STAT_STEP(have && tr.cur < 0, leaf_steps, leaf_lanes)
-                    if (have && tr.cur < 0) trav_leaf_step(tr, tri_isect, sstack, TRACE_THREADS VR_SPILL_ARG);
+                for (int step = 0; step < LEAF_STEPS; ++step) {
+                    if (have && tr.cur < 0) trav_leaf_step(tr, sc, tri_isect, sstack, TRACE_THREADS);
                 }
             }
         }
     }
 }
 
-#endif  // VR_TRACE_SPEC
 
 // ------------------------------------------------------------------------------------------------
 // Shading: core/tracer.rs:19-56 unrolled over the wavefront. The reference recursion
@@ -780,6 +561,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
                             break;
                         }
                     }
+                    if (!scattered) attenuation = mk3(0.0f, 0.0f, 0.0f);  // gave up: the path ends BLACK
                 } else if (m.kind == 2) {
                     // Dielectric::scatter, simple.rs:201-231
                     const float ratio = front_face ? 1.0f / m.param : m.param;
@@ -867,7 +649,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_accumulate(Wavefront wf, float4* partial, float4* accum, uint32_t width,
                                                     uint32_t height, uint32_t samples_in_batch, int finish,
-                                                    float inv_total) {
+                                                    float inv_total, float alpha_inc) {
     const uint32_t n_pixels = width * height;
     // one thread per slot-in-sample j (coalesced radiance reads); it owns pixel tile_slot_to_pixel(j)
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pixels; j += gridDim.x * blockDim.x) {
@@ -884,7 +666,7 @@ __global__ void __launch_bounds__(256) k_accumulate(Wavefront wf, float4* partia
             a.x += p.x * inv_total;
             a.y += p.y * inv_total;
             a.z += p.z * inv_total;
-            a.w += 1.0f;  // Color::a() == 1.0 per call, util/color.rs:54 / iterative.rs:51
+            a.w += alpha_inc;  // Color::a() == 1.0 per call, util/color.rs:54 / iterative.rs:51 (0 on a group's other shards)
             accum[px] = a;
             p = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
@@ -990,7 +772,7 @@ __device__ __forceinline__ void export_hit(const DeviceScene& sc, const HitResul
 
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_rays(DeviceScene sc, const float* origins, const float* dirs,
                                                               uint64_t n, uint32_t* surface, uint32_t* prim, float* t) {
-    __shared__ int s_stack[SMEM_STACK * TRACE_THREADS];
+    __shared__ int s_stack[(SMEM_STACK + 1) * TRACE_THREADS];  // + the rays' scene-level visibility words
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const f3 o = mk3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         const f3 d = normalize(mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));  // Ray::new
@@ -1086,9 +868,10 @@ void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& 
     else k_shade<false, false><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
 }
 void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t width, uint32_t height,
-                       uint32_t samples_in_batch, int finish, float inv_total_samples, cudaStream_t stream) {
+                       uint32_t samples_in_batch, int finish, float inv_total_samples, float alpha_inc, cudaStream_t stream) {
     const uint32_t grid = (width * height + 255) / 256;
-    k_accumulate<<<grid, 256, 0, stream>>>(wf, partial, accum, width, height, samples_in_batch, finish, inv_total_samples);
+    k_accumulate<<<grid, 256, 0, stream>>>(wf, partial, accum, width, height, samples_in_batch, finish, inv_total_samples,
+                                           alpha_inc);
 }
 void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul, float inv_gamma,
                     int32_t tonemap, cudaStream_t stream) {

@@ -58,9 +58,9 @@ void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, ui
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
 // partial[pixel] += sum over the batch's samples (in sample order); when `finish`, fold
-// partial * (1/total_samples) into accum (alpha += 1) and clear partial.
+// partial * (1/total_samples) into accum (alpha += alpha_inc: 1 per iterative_render call) and clear partial.
 void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t width, uint32_t height,
-                       uint32_t samples_in_batch, int finish, float inv_total_samples, cudaStream_t stream);
+                       uint32_t samples_in_batch, int finish, float inv_total_samples, float alpha_inc, cudaStream_t stream);
 void launch_resolve(const float4* accum, float4* out, uint32_t n_pixels, float scale, float exposure_mul,
                     float inv_gamma, int32_t tonemap, cudaStream_t stream);
 

@@ -14,17 +14,7 @@ namespace vr {
 //   t = f * (extent * id) + ((grid_min - o) * id - extent * id),
 // with the near / far plane picked by the ray's sign (PRMT selector) instead of min / max.
 static const int NODE_QUADS = 2;
-// Experiment -DVR_BVH4 (every translation unit): 4-wide nodes, 64 B = two records of the format above back to back
-// (children 0, 1 | children 2, 3), child codes index wide nodes; an unused child is an inverted box with an empty
-// leaf code. The traversal parks up to three children per node; the collapse leaves nodes narrower where a path could
-// otherwise park more than WIDE_STACK_LIMIT entries (= the kernel's stack, the same 32 as for the BVH2).
-static const int WIDE_NODE_QUADS = 4;
-static const int WIDE_STACK_LIMIT = 32;
-#ifdef VR_BVH4
-static const int DEVICE_NODE_QUADS = WIDE_NODE_QUADS;
-#else
 static const int DEVICE_NODE_QUADS = NODE_QUADS;
-#endif
 static const int LEAF_MAX_TRIS = 4;
 
 // Intersection record, 64 B = 4 x float4 = two 256-bit loads (pre-subtracted edges: e1 = v1 - v0,
@@ -32,14 +22,9 @@ static const int LEAF_MAX_TRIS = 4;
 //   q0 = (v0.xyz, tie rank as uint bits)
 //   q1 = (e1.xyz, 0)
 //   q2 = (e2.xyz, 0)
-//   q3 = padding to the 32-byte alignment the 256-bit loads need
-// Experiment -DVR_TRI48 (every translation unit): 48-byte records, q3 dropped, three 128-bit loads; the L1 model of
-// scripts/bvh_stats.cpp gives it 2-3 points of sector hit rate. Not the shipped layout.
-#ifdef VR_TRI48
-static const int TRI_ISECT_QUADS = 3;
-#else
+//   q3 = (0, 0, 0, surface handle as uint bits): padding to the 32-byte alignment the 256-bit loads need; the
+//        surface handle is read only when a candidate would win and the scene has a scene-level tree (below)
 static const int TRI_ISECT_QUADS = 4;
-#endif
 
 // Shading record, 80 B = 5 x float4, fetched once per closest hit.
 //   q0 = (n0.xyz, uv0.x)   q1 = (n1.xyz, uv0.y)   q2 = (n2.xyz, uv1.x)
@@ -56,11 +41,11 @@ struct MaterialRec {  // 48 B
     float index, roughness, metallic, emittance;  // microfacet
 };
 
-struct TextureRec {  // texels are RGBA f32 (w unused) so one tap is one 16-byte load
+struct TextureRec {  // texels are RGBA f32 (w unused; one 16-byte load per tap) or RGBA8 for 8-bit sources (pad = 1)
     const void* texels;  // float4*
     uint32_t width, height;
     int32_t sample_type;
-    uint32_t pad;  // experiment -DVR_TEX8: 1 = texels are RGBA8 (4 B), converted on the device with the exact v / 255
+    uint32_t pad;  // 1 = texels are RGBA8 (4 B; an 8-bit source), widened on the device with the exact v / 255
 };
 
 struct AnalyticRec {  // 32 B; tested linearly after the triangle BVH (scenes have a handful)
@@ -71,6 +56,20 @@ struct AnalyticRec {  // 32 B; tested linearly after the triangle BVH (scenes ha
     uint32_t material;
     uint32_t surface;
 };
+
+// Scene-level tree of the reference (core/scene.rs:163-179: BvhNode::from_list over the surfaces), kept for its
+// culling semantics only: SceneAcceleration::hit (scene.rs:182-185) visits a surface iff every Split above it passes
+// AABB::hit (util/aabb.rs:86-148), and those boxes are unions of un-expanded Mesh::bounds() — a Split that is flat on
+// an axis rejects every ray with a component along it (t_max <= t_min). 32 B per node, pre-order:
+//   Split: lo, hi = its box; a = index of the first node after its subtree (>= 2); parent = its Split or -1
+//   leaf:  lo, hi unused;    a = ~surface handle (< 0);                         parent = its Split
+// Scenes with fewer than two surfaces have no Split and no nodes.
+struct SceneTreeNode {
+    float lo[3], hi[3];
+    int32_t a;
+    int32_t parent;
+};
+static const uint32_t SCENE_MASK_SURFACES = 32;  // up to here a ray carries one visibility bit per surface
 
 struct CameraRec {
     float origin[3];
@@ -92,6 +91,10 @@ struct DeviceScene {
     const MaterialRec* materials;
     const TextureRec* textures;
     const AnalyticRec* analytics;
+    const SceneTreeNode* scene_tree;  // reference scene-level tree (culling semantics), n_scene_nodes entries
+    const uint32_t* surface_node;     // surface handle -> its leaf in scene_tree
+    uint32_t n_scene_nodes;           // 0: fewer than two surfaces, nothing is culled at scene level
+    uint32_t n_surfaces;
     float grid_min[3];     // node quantisation grid: plane(q) = grid_min + grid_extent * q / 32768
     float grid_extent[3];
     uint32_t n_tris;

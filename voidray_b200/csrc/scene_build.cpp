@@ -776,397 +776,9 @@ struct Builder {
 };
 
 
-// ------------------------------------------------------------------------------------------------
-// Optional post-pass (VOIDRAY_BVH_OPT=<passes>, default off): insertion-based tree optimisation
-// (Bittner, Hapala, Havran, "Fast insertion-based optimization of bounding volume hierarchies", 2013) on the
-// finished, quantised tree. A subtree is cut out (its parent is replaced by its sibling) and re-inserted where the
-// summed area of the inner nodes grows least, found by branch and bound from the root. All boxes are the 15-bit grid
-// boxes of layout.h, so unions are exact and every node stays the union of its leaves: the tree remains conservative
-// for the same reason the input was. Leaves (triangle ranges) are never changed, only where they hang.
-// ------------------------------------------------------------------------------------------------
-struct QBox {
-    uint16_t lo[3], hi[3];
-    void grow(const QBox& b) {
-        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
-    }
-    bool operator==(const QBox& b) const { return !std::memcmp(this, &b, sizeof *this); }
-};
-
-struct TreeOptimizer {
-    struct Item {
-        QBox box;
-        int32_t parent, child[2];  // child[0] < 0: a leaf, leaf_code holds its code
-        int32_t leaf_code;
-        uint32_t height;           // 0 for a leaf
-    };
-    std::vector<Item> items;
-    double cell[3];
-    int32_t root = -1;
-
-    double area(const QBox& b) const {
-        const double dx = (double)(b.hi[0] - b.lo[0]) * cell[0], dy = (double)(b.hi[1] - b.lo[1]) * cell[1],
-                     dz = (double)(b.hi[2] - b.lo[2]) * cell[2];
-        return dx * dy + dy * dz + dz * dx;
-    }
-    static QBox child_qbox(const Quad* q, int c) {
-        uint32_t w[6];
-        const float src[6] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y};
-        std::memcpy(w, src, 24);
-        QBox b;
-        for (int a = 0; a < 3; ++a) {
-            b.lo[a] = (uint16_t)(w[3 * c + a] & 0x7FFF);
-            b.hi[a] = (uint16_t)((w[3 * c + a] >> 16) & 0x7FFF);
-        }
-        return b;
-    }
-    static bool empty_box(const QBox& b) { return b.lo[0] > b.hi[0] || b.lo[1] > b.hi[1] || b.lo[2] > b.hi[2]; }
-
-    // flat nodes -> items (iterative; node 1 is the root, node 0 its copy)
-    bool load(const FlatScene& f) {
-        for (int a = 0; a < 3; ++a) cell[a] = (double)f.grid_extent[a] / 32768.0;
-        const size_t n_nodes = f.nodes.size() / NODE_QUADS;
-        if (n_nodes < 2) return false;
-        items.reserve(2 * n_nodes + 1);
-        struct Todo {
-            int32_t node, item;
-        };
-        std::vector<Todo> todo;
-        items.push_back(Item{});
-        items[0].parent = -1;
-        root = 0;
-        todo.push_back(Todo{1, 0});
-        while (!todo.empty()) {
-            const Todo t = todo.back();
-            todo.pop_back();
-            const Quad* q = &f.nodes[(size_t)t.node * NODE_QUADS];
-            int32_t code[2];
-            std::memcpy(&code[0], &q[1].z, 4);
-            std::memcpy(&code[1], &q[1].w, 4);
-            for (int c = 0; c < 2; ++c) {
-                const int32_t id = (int32_t)items.size();
-                items.push_back(Item{});
-                Item& it = items[id];
-                it.box = child_qbox(q, c);
-                if (empty_box(it.box)) return false;  // a one-leaf tree carries an empty second child: nothing to optimise
-                it.parent = t.item;
-                it.leaf_code = code[c];
-                it.child[0] = it.child[1] = -1;
-                it.height = 0;
-                items[t.item].child[c] = id;
-                if (code[c] >= 0) todo.push_back(Todo{code[c], id});
-            }
-        }
-        refit_all();
-        return true;
-    }
-    bool is_leaf(int32_t i) const { return items[i].child[0] < 0; }
-    void refit_all() {
-        // children always have larger ids than their parents after load(); afterwards refit() keeps boxes current
-        for (int32_t i = (int32_t)items.size() - 1; i >= 0; --i) {
-            if (is_leaf(i)) continue;
-            Item& it = items[i];
-            it.box = items[it.child[0]].box;
-            it.box.grow(items[it.child[1]].box);
-            it.height = 1 + std::max(items[it.child[0]].height, items[it.child[1]].height);
-        }
-    }
-    void refit(int32_t i) {  // from inner node i upwards until nothing changes
-        while (i >= 0) {
-            Item& it = items[i];
-            QBox b = items[it.child[0]].box;
-            b.grow(items[it.child[1]].box);
-            const uint32_t h = 1 + std::max(items[it.child[0]].height, items[it.child[1]].height);
-            if (b == it.box && h == it.height) break;
-            it.box = b;
-            it.height = h;
-            i = it.parent;
-        }
-    }
-    uint32_t depth_of(int32_t i) const {  // the root has depth 1 (as in Builder::build)
-        uint32_t d = 1;
-        for (int32_t p = items[i].parent; p >= 0; p = items[p].parent) ++d;
-        return d;
-    }
-    double inner_area_sum() const {
-        double s = 0.0;
-        for (size_t i = 0; i < items.size(); ++i)
-            if (!is_leaf((int32_t)i)) s += area(items[i].box);
-        return s;
-    }
-
-    // Cuts n out and re-inserts it at the cheapest position. Returns true if the tree changed.
-    bool reinsert(int32_t n) {
-        const int32_t p = items[n].parent;
-        if (p < 0) return false;
-        const int32_t g = items[p].parent;
-        if (g < 0) return false;  // children of the root stay (the root node itself is not re-created)
-        const int32_t s = items[p].child[0] == n ? items[p].child[1] : items[p].child[0];
-        // remove: s takes p's place under g
-        items[g].child[items[g].child[0] == p ? 0 : 1] = s;
-        items[s].parent = g;
-        refit(g);
-        // branch and bound for the best sibling x: cost = area(x + n) + sum over x's ancestors of their growth
-        const QBox nb = items[n].box;
-        const double n_area = area(nb);
-        const uint32_t n_height = items[n].height;
-        std::vector<Cand>& heap = heap_;
-        heap.clear();
-        heap.push_back(Cand{0.0, root, 1});
-        double best_cost = 1e300;
-        int32_t best = -1;
-        while (!heap.empty()) {
-            std::pop_heap(heap.begin(), heap.end());
-            const Cand c = heap.back();
-            heap.pop_back();
-            if (c.induced + n_area >= best_cost) break;  // nothing left in the queue can do better
-            QBox u = items[c.item].box;
-            u.grow(nb);
-            const double direct = area(u);
-            // the new parent sits at c.depth, n below it: the deepest leaf of n lands at c.depth + 1 + n_height
-            const bool fits = c.depth + 1 + std::max(n_height, items[c.item].height) <= Builder::MAX_DEPTH;
-            if (fits && c.item != root && c.induced + direct < best_cost) {
-                best_cost = c.induced + direct;
-                best = c.item;
-            }
-            if (!is_leaf(c.item)) {
-                const double child_induced = c.induced + direct - area(items[c.item].box);
-                if (child_induced + n_area < best_cost) {
-                    for (int k = 0; k < 2; ++k) {
-                        heap.push_back(Cand{child_induced, items[c.item].child[k], c.depth + 1});
-                        std::push_heap(heap.begin(), heap.end());
-                    }
-                }
-            }
-        }
-        if (best < 0) best = s;  // cannot happen (s itself is a candidate), kept as a guard
-        // insert: p becomes the parent of {best, n} where best was
-        const int32_t bp = items[best].parent;
-        items[bp].child[items[bp].child[0] == best ? 0 : 1] = p;
-        items[p].parent = bp;
-        items[p].child[0] = best;
-        items[p].child[1] = n;
-        items[best].parent = p;
-        items[n].parent = p;
-        items[p].box = items[best].box;
-        items[p].box.grow(nb);
-        items[p].height = 1 + std::max(items[best].height, n_height);
-        refit(bp);
-        return best != s;
-    }
-    struct Cand {
-        double induced;
-        int32_t item;
-        uint32_t depth;
-        bool operator<(const Cand& o) const { return induced > o.induced; }  // min-heap on the induced cost
-    };
-    std::vector<Cand> heap_;
-
-    // `passes` sweeps over every item in order of decreasing area (large nodes first: they are visited most)
-    void run(int passes) {
-        std::vector<int32_t> order;
-        for (int pass = 0; pass < passes; ++pass) {
-            order.clear();
-            for (int32_t i = 1; i < (int32_t)items.size(); ++i) order.push_back(i);
-            std::vector<double> key(items.size());
-            for (size_t i = 0; i < items.size(); ++i) key[i] = area(items[i].box);
-            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] > key[b]; });
-            size_t changed = 0;
-            for (int32_t i : order) changed += reinsert(i) ? 1 : 0;
-            if (!changed) break;
-        }
-    }
-
-    // items -> flat nodes in depth-first pre-order (node 0 = copy of the root, node 1 = the root)
-    void store(FlatScene& f, uint32_t* depth_out) const {
-        size_t n_inner = 0;
-        for (size_t i = 0; i < items.size(); ++i) n_inner += is_leaf((int32_t)i) ? 0 : 1;
-        RawVector<Quad> out((n_inner + 1) * NODE_QUADS);
-        auto pair = [](const QBox& b, int a) { return (0x8000u | b.lo[a]) | ((0x8000u | (uint32_t)b.hi[a]) << 16); };
-        struct Todo {
-            int32_t item;
-            uint32_t node, depth;
-        };
-        std::vector<Todo> todo;
-        std::vector<uint32_t> inner_count(items.size(), 0);  // inner nodes in each subtree, for the pre-order numbers
-        for (int32_t i = (int32_t)items.size() - 1; i >= 0; --i) {
-            // parents no longer precede children after re-insertions: count by walking up instead
-            if (!is_leaf(i))
-                for (int32_t a = i; a >= 0; a = items[a].parent) inner_count[a]++;
-        }
-        uint32_t max_depth = 0;
-        todo.push_back(Todo{root, 1, 1});
-        while (!todo.empty()) {
-            const Todo t = todo.back();
-            todo.pop_back();
-            const Item& it = items[t.item];
-            const int32_t c0 = it.child[0], c1 = it.child[1];
-            const uint32_t left_node = t.node + 1, right_node = t.node + 1 + (is_leaf(c0) ? 0u : inner_count[c0]);
-            const uint32_t code0 = is_leaf(c0) ? (uint32_t)items[c0].leaf_code : left_node;
-            const uint32_t code1 = is_leaf(c1) ? (uint32_t)items[c1].leaf_code : right_node;
-            const QBox &b0 = items[c0].box, &b1 = items[c1].box;
-            Quad* q = &out[(size_t)t.node * NODE_QUADS];
-            q[0] = Quad{bits_f(pair(b0, 0)), bits_f(pair(b0, 1)), bits_f(pair(b0, 2)), bits_f(pair(b1, 0))};
-            q[1] = Quad{bits_f(pair(b1, 1)), bits_f(pair(b1, 2)), bits_f(code0), bits_f(code1)};
-            for (int c = 0; c < 2; ++c) {
-                const int32_t ch = it.child[c];
-                if (is_leaf(ch)) max_depth = std::max(max_depth, t.depth + 1);
-                else todo.push_back(Todo{ch, c == 0 ? left_node : right_node, t.depth + 1});
-            }
-        }
-        for (int k = 0; k < NODE_QUADS; ++k) out[k] = out[NODE_QUADS + k];
-        f.nodes.swap(out);
-        *depth_out = max_depth;
-    }
-};
-
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------
-// 4-wide nodes (experiment -DVR_BVH4; this pass is always compiled so that the CPU walk of scripts/bvh_stats.cpp
-// and the host tests can run it next to the shipped BVH2).
-// A wide node is 64 B = two records of the BVH2 format (layout.h): up to four children, each with the quantised box
-// its BVH2 parent already stored for it, so the wide tree culls with exactly the boxes of the BVH2 and stays
-// conservative for the same reason. Built by the usual greedy collapse: start from a node's two children and, while
-// a slot is free, replace the inner child with the largest surface area by its own two children. Nodes are numbered
-// in depth-first pre-order, node 0 is the root. A ray that enters a wide node parks at most (children - 1) entries
-// on the traversal stack; the collapse keeps the worst case over any root-to-leaf path within stack_limit by
-// leaving nodes narrower on the way to the deepest BVH2 chains.
-// ------------------------------------------------------------------------------------------------
-namespace {
-struct WideSlot {
-    uint32_t w[3];   // quantised (lo | hi << 16) pairs, x y z
-    int32_t code;    // BVH2 child code: >= 0 inner BVH2 node, < 0 leaf
-    uint32_t depth;  // BVH2 depth of the child (root = 0)
-};
-struct WideCollapse {
-    const RawVector<Quad>& src;
-    RawVector<Quad>& dst;
-    double cell[3];
-    uint32_t bvh2_depth, stack_limit;
-    uint32_t wide_depth = 0, max_stack = 0;
-    std::vector<uint8_t> height;  // per BVH2 node: inner levels of its subtree, itself included
-    uint8_t measure(uint32_t node) {
-        const Quad* q = &src[(size_t)node * 2];
-        const int32_t c0 = (int32_t)f_bits(q[1].z), c1 = (int32_t)f_bits(q[1].w);
-        uint8_t h = 0;
-        if (c0 >= 0) h = std::max(h, measure((uint32_t)c0));
-        if (c1 >= 0) h = std::max(h, measure((uint32_t)c1));
-        return height[node] = (uint8_t)(h + 1);
-    }
-    static const uint32_t EMPTY_PAIR = (0x8000u | 32767u) | ((0x8000u | 0u) << 16);
-
-    static uint32_t f_bits(float f) {
-        uint32_t u;
-        std::memcpy(&u, &f, 4);
-        return u;
-    }
-    static bool is_empty(const WideSlot& s) { return s.code < 0 && ((~(uint32_t)s.code) & 7u) == 0; }
-    double area(const WideSlot& s) const {
-        double e[3];
-        for (int a = 0; a < 3; ++a) {
-            const int lo = (int)(s.w[a] & 0x7FFFu), hi = (int)((s.w[a] >> 16) & 0x7FFFu);
-            e[a] = hi > lo ? (double)(hi - lo) * cell[a] : 0.0;
-        }
-        return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
-    }
-    // the (non-empty) children of BVH2 node `node` appended to slots[n..]
-    int children(uint32_t node, uint32_t depth, WideSlot* slots, int n) const {
-        const Quad* q = &src[(size_t)node * 2];
-        const uint32_t w[8] = {f_bits(q[0].x), f_bits(q[0].y), f_bits(q[0].z), f_bits(q[0].w),
-                               f_bits(q[1].x), f_bits(q[1].y), f_bits(q[1].z), f_bits(q[1].w)};
-        for (int c = 0; c < 2; ++c) {
-            WideSlot s{{w[3 * c], w[3 * c + 1], w[3 * c + 2]}, (int32_t)w[6 + c], depth + 1};
-            if (!is_empty(s)) slots[n++] = s;
-        }
-        return n;
-    }
-    // Emits the wide node that replaces BVH2 node `node`; `used` = stack entries that may be occupied on arrival.
-    uint32_t emit(uint32_t node, uint32_t depth, uint32_t used, uint32_t level) {
-        WideSlot slots[5];
-        int n = children(node, depth, slots, 0);
-        // A child's subtree parks at most one entry per inner level if everything below stays binary, so a node may
-        // take one more child only while parked entries + (children - 1) + inner levels below every child stay within
-        // the stack. Only the few deepest chains of a tree are narrowed by this.
-        auto fits = [&](const WideSlot* sl, int count) {
-            for (int i = 0; i < count; ++i)
-                if (sl[i].code >= 0 && used + (uint32_t)(count - 1) + height[(uint32_t)sl[i].code] > stack_limit) return false;
-            return true;
-        };
-        while (n < 4) {
-            int pick = -1;
-            double best = -1.0;
-            for (int i = 0; i < n; ++i)
-                if (slots[i].code >= 0) {
-                    const double a = area(slots[i]);
-                    if (a > best) {
-                        best = a;
-                        pick = i;
-                    }
-                }
-            if (pick < 0) break;
-            const WideSlot parent = slots[pick];
-            WideSlot kids[2];
-            const int nk = children((uint32_t)parent.code, parent.depth, kids, 0);
-            // the first child takes the parent's place, the second goes to the end
-            if (nk == 0) {
-                slots[pick] = slots[--n];
-                continue;
-            }
-            WideSlot trial[5];
-            for (int i = 0; i < n; ++i) trial[i] = slots[i];
-            trial[pick] = kids[0];
-            int nt = n;
-            if (nk == 2) trial[nt++] = kids[1];
-            if (!fits(trial, nt)) break;
-            for (int i = 0; i < nt; ++i) slots[i] = trial[i];
-            n = nt;
-        }
-        const uint32_t index = (uint32_t)(dst.size() / WIDE_NODE_QUADS);
-        dst.resize(dst.size() + WIDE_NODE_QUADS);
-        wide_depth = std::max(wide_depth, level + 1);
-        const uint32_t parked = n > 0 ? (uint32_t)(n - 1) : 0u;
-        max_stack = std::max(max_stack, used + parked);
-        uint32_t words[4][4];  // per slot: x y z code
-        for (int i = 0; i < 4; ++i) {
-            if (i < n) {
-                uint32_t code = (uint32_t)slots[i].code;
-                if (slots[i].code >= 0) code = emit((uint32_t)slots[i].code, slots[i].depth, used + parked, level + 1);
-                words[i][0] = slots[i].w[0];
-                words[i][1] = slots[i].w[1];
-                words[i][2] = slots[i].w[2];
-                words[i][3] = code;
-            } else {
-                words[i][0] = words[i][1] = words[i][2] = EMPTY_PAIR;
-                words[i][3] = 0xFFFFFFFFu;  // leaf code of an empty range
-            }
-        }
-        Quad* q = &dst[(size_t)index * WIDE_NODE_QUADS];
-        for (int p = 0; p < 2; ++p) {
-            const uint32_t* a = words[2 * p];
-            const uint32_t* b = words[2 * p + 1];
-            q[2 * p] = Quad{bits_f(a[0]), bits_f(a[1]), bits_f(a[2]), bits_f(b[0])};
-            q[2 * p + 1] = Quad{bits_f(b[1]), bits_f(b[2]), bits_f(a[3]), bits_f(b[3])};
-        }
-        return index;
-    }
-};
-}  // namespace
-
-void collapse_bvh4(const RawVector<Quad>& nodes2, const float grid_extent[3], uint32_t bvh2_depth, uint32_t stack_limit,
-                   RawVector<Quad>& wide, uint32_t* wide_depth, uint32_t* max_stack) {
-    wide.clear();
-    wide.reserve(nodes2.size());
-    WideCollapse c{nodes2, wide, {0.0, 0.0, 0.0}, bvh2_depth, stack_limit, 0, 0, {}};
-    for (int a = 0; a < 3; ++a) c.cell[a] = (double)grid_extent[a] / 32768.0;
-    c.height.assign(nodes2.size() / 2, 0);
-    c.measure(0);
-    c.emit(0, 0, 0, 0);
-    if (wide_depth) *wide_depth = c.wide_depth;
-    if (max_stack) *max_stack = c.max_stack;
-}
-
-#ifdef VR_TEX8
-// Experiment: a texture whose every value is exactly v / 255 (an 8-bit source through to_rgb32f) also keeps its
+// A texture whose every value is exactly v / 255 (an 8-bit source through to_rgb32f) also keeps its
 // RGBA8 form; the kernel's conversion reproduces the same floats, so the lookups do not change by a bit.
 void pack_texture_rgba8(HostTexture& t) {
     const size_t n = (size_t)t.w * t.h;
@@ -1185,7 +797,6 @@ void pack_texture_rgba8(HostTexture& t) {
     }
     t.rgba8.swap(out);
 }
-#endif
 
 namespace {
 // VOIDRAY_TIMING=1 prints the host phases of a commit to stderr
@@ -1344,6 +955,48 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         }
     }
 
+    // ---- the reference's scene-level tree, kept for its culling semantics (layout.h: SceneTreeNode) ----
+    // from_list cuts a sorted range at len / 2 (bvh.rs:111-120), so the in-order sequence determines the tree: a range
+    // of >= 2 surfaces is a Split whose box is the union of their bounds (bvh.rs:57-61), a single surface an Object.
+    out.scene_tree.clear();
+    out.surface_node.assign(n_surfaces, 0);
+    if (n_surfaces >= 2) {
+        out.scene_tree.reserve(2 * n_surfaces - 1);
+        struct Range {
+            size_t b, e;
+            int32_t parent;
+        };
+        std::vector<Range> todo;
+        todo.push_back(Range{0, n_surfaces, -1});
+        while (!todo.empty()) {  // pre-order: left subtree before right
+            const Range r = todo.back();
+            todo.pop_back();
+            SceneTreeNode node;
+            node.parent = r.parent;
+            const int32_t self = (int32_t)out.scene_tree.size();
+            if (r.e - r.b == 1) {
+                const uint32_t s = surface_order[r.b];
+                for (int a = 0; a < 3; ++a) { node.lo[a] = 0.0f; node.hi[a] = 0.0f; }
+                node.a = ~(int32_t)s;
+                out.surface_node[s] = (uint32_t)self;
+            } else {
+                for (int a = 0; a < 3; ++a) { node.lo[a] = INFINITY; node.hi[a] = -INFINITY; }
+                for (size_t i = r.b; i < r.e; ++i) {
+                    const float* b = &surface_boxes[6 * surface_order[i]];
+                    for (int a = 0; a < 3; ++a) {  // AABB::surround, util/aabb.rs:46-59
+                        node.lo[a] = fmin_(node.lo[a], b[a]);
+                        node.hi[a] = fmax_(node.hi[a], b[3 + a]);
+                    }
+                }
+                node.a = self + (int32_t)(2 * (r.e - r.b) - 1);  // a subtree over k surfaces has 2k - 1 nodes
+                const size_t mid = r.b + (r.e - r.b) / 2;
+                todo.push_back(Range{mid, r.e, self});
+                todo.push_back(Range{r.b, mid, self});
+            }
+            out.scene_tree.push_back(node);
+        }
+    }
+
     // ---- analytic surfaces ----
     for (size_t s = 0; s < n_surfaces; ++s) {
         const HostSurface& sf = in.surfaces[s];
@@ -1450,34 +1103,6 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
     out.nodes.resize((size_t)builder.next_node.load() * NODE_QUADS);
     out.bvh_depth = builder.max_depth.load();
     timer.lap("SAH build");
-    if (const char* e = std::getenv("VOIDRAY_BVH_OPT")) {  // experiment, default off (see TreeOptimizer)
-        TreeOptimizer opt;
-        if (atoi(e) > 0 && opt.load(out)) {
-            const double before = opt.inner_area_sum();
-            opt.run(atoi(e));
-            uint32_t depth = 0;
-            opt.store(out, &depth);
-            out.bvh_depth = depth;
-            if (timer.on) std::fprintf(stderr, "[voidray] flatten: inner-node area %.4g -> %.4g\n", before, opt.inner_area_sum());
-            timer.lap("insertion-based optimisation");
-        }
-    }
-
-#ifdef VR_BVH4
-    {
-        RawVector<Quad> wide;
-        uint32_t wide_depth = 0, max_stack = 0;
-        collapse_bvh4(out.nodes, out.grid_extent, out.bvh_depth, WIDE_STACK_LIMIT, wide, &wide_depth, &max_stack);
-        if (max_stack > (uint32_t)WIDE_STACK_LIMIT) {
-            err = "4-wide BVH too deep for the traversal stack";
-            return false;
-        }
-        out.nodes.swap(wide);
-        if (timer.on) std::fprintf(stderr, "[voidray] flatten: %zu wide nodes, depth %u, stack bound %u\n",
-                                   out.nodes.size() / WIDE_NODE_QUADS, wide_depth, max_stack);
-        timer.lap("4-wide collapse");
-    }
-#endif
 
     rank_join.join();
     if (rank_error) std::rethrow_exception(rank_error);
@@ -1499,7 +1124,7 @@ bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err) {
         qi[0] = Quad{p0.x, p0.y, p0.z, bits_f(rank)};
         qi[1] = Quad{e1.x, e1.y, e1.z, 0.0f};
         qi[2] = Quad{e2.x, e2.y, e2.z, 0.0f};
-        if (TRI_ISECT_QUADS > 3) qi[3] = Quad{0.0f, 0.0f, 0.0f, 0.0f};
+        if (TRI_ISECT_QUADS > 3) qi[3] = Quad{0.0f, 0.0f, 0.0f, bits_f(sp.surface)};
         // geometric normal, mesh.rs:80-84
         const V3 ng = normalize(cross(sub(p2, p1), sub(p0, p1)));
         const V3 n0 = ld3(&m.nrm[3 * i0]), n1 = ld3(&m.nrm[3 * i1]), n2 = ld3(&m.nrm[3 * i2]);

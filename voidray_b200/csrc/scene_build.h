@@ -54,9 +54,7 @@ struct HostSurface {
 
 struct HostTexture {
     std::vector<float> rgb;  // 3*w*h
-#ifdef VR_TEX8
-    std::vector<uint8_t> rgba8;  // experiment: 4*w*h when every float is exactly v / 255 (an 8-bit source), else empty
-#endif
+    std::vector<uint8_t> rgba8;  // 4*w*h when every float is exactly v / 255 (an 8-bit source), else empty
     uint32_t w = 0, h = 0;
     int32_t sample_type = 0;
 };
@@ -93,6 +91,8 @@ struct FlatScene {
     std::vector<AnalyticRec> analytics;
     std::vector<RawVector<uint32_t>> mesh_tie_rank;  // per surface (empty for analytic): rank inside the mesh
     std::vector<uint32_t> surface_rank_base;           // per surface: first global rank
+    std::vector<SceneTreeNode> scene_tree;             // reference scene-level tree in pre-order (layout.h)
+    std::vector<uint32_t> surface_node;                // per surface: its leaf in scene_tree (when the tree exists)
     CameraRec camera;
     float grid_min[3] = {0, 0, 0}, grid_extent[3] = {1, 1, 1};  // node quantisation grid
     uint32_t n_tris = 0;
@@ -109,15 +109,8 @@ void camera_look_at(const float eye[3], const float center[3], const float up_in
 
 bool flatten_scene(const HostScene& in, FlatScene& out, std::string& err);
 
-#ifdef VR_TEX8
-// Experiment -DVR_TEX8: fills t.rgba8 when every float of t.rgb is exactly v / 255 (an 8-bit source), else leaves it empty.
+// Fills t.rgba8 when every float of t.rgb is exactly v / 255 (an 8-bit source), else leaves it empty.
 void pack_texture_rgba8(HostTexture& t);
-#endif
-
-// Collapses a finished BVH2 node array (layout.h, node 0 = root) into 4-wide nodes of WIDE_NODE_QUADS quads each
-// (experiment -DVR_BVH4, see scene_build.cpp). max_stack = the most entries a traversal can park on its stack.
-void collapse_bvh4(const RawVector<Quad>& nodes2, const float grid_extent[3], uint32_t bvh2_depth, uint32_t stack_limit,
-                   RawVector<Quad>& wide, uint32_t* wide_depth, uint32_t* max_stack);
 
 // Wavefront OBJ with obj-rs 0.7.0 `load_obj::<TexturedVertex, u32>` semantics (core/mesh.rs:46-74).
 bool load_obj_file(const char* path, HostMesh& out, std::string& err);

@@ -402,6 +402,11 @@ class Renderer:
                     break
         except BaseException as e:  # surfaced by join()
             self._error = e
+            if isinstance(e, _lib.RenderCancelled) and self.target is not None:
+                # a cancelled accumulate keeps the whole batches it finished: the display scale total / done
+                # (post_process) must see them
+                with self._lock:
+                    self._samples = (int(self.target.stats().samples_done), self._samples[1] or self.settings.render.total_samples)
         finally:
             with self._lock:
                 self._currently_rendering = False
