@@ -202,6 +202,10 @@ struct ImageTexture {
 class Context {
 public:
     explicit Context(int device = 0, void* cuda_stream = nullptr) { check(vr_context_create(device, cuda_stream, &ctx_)); }
+    // a device group in this process: commit replicates, accumulate shards the samples, read / resolve sum over peer memory
+    explicit Context(const std::vector<int32_t>& devices) {
+        check(vr_context_create_multi(devices.data(), (uint32_t)devices.size(), &ctx_));
+    }
     ~Context() { vr_context_destroy(ctx_); }
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;

@@ -48,6 +48,22 @@ uint32_t vr_abi_version(void);
  * stream can bracket calls with its own CUDA events. */
 int32_t vr_context_create(int32_t device, void* cuda_stream, vr_context** out);
 int32_t vr_context_destroy(vr_context* ctx);
+/* A device group in ONE process (the Rust host of the reference is one process with one render thread,
+ * render/renderer.rs:35-125): `device_ids[0..n_devices)` are CUDA device ordinals, each with a library-owned
+ * stream. The returned context stands for the whole group and is used like any other:
+ *   vr_scene_commit        flattens once and uploads the scene to every device (one host thread per device);
+ *   vr_render_accumulate   cuts the call's sample range into n_devices contiguous pieces, one per device (the
+ *                          random streams are keyed by (pixel, global sample index), so the union is the sample
+ *                          set one device would draw); blocking until every device is done;
+ *   vr_render_read_accum / vr_render_resolve
+ *                          sum the devices' accumulation buffers on device_ids[0] — the other devices' buffers
+ *                          are read over peer memory (cudaDeviceEnablePeerAccess: NVLink / NVSwitch) inside the
+ *                          reduce(+tonemap) kernel, in device order; non-destructive, so progressive display works;
+ *   the vr_debug_* gates, vr_render_accum_device_ptr and the IPC reduce below see device_ids[0] only.
+ * The result equals a one-device render up to f32 summation order. A device may be listed more than once (several
+ * shards on one GPU; of use for testing on a one-GPU machine). At most 16 entries. */
+int32_t vr_context_create_multi(const int32_t* device_ids, uint32_t n_devices, vr_context** out);
+int32_t vr_context_device_count(vr_context* ctx, uint32_t* n_devices);
 
 /* ---- scene builder: core/scene.rs:94-161 --------------------------------------------------- */
 /* Scene::empty() (scene.rs:95-111): default camera look_at((1,0,10),(0,0,0),(0,1,0), PI/6), no

@@ -98,6 +98,9 @@ inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) {
     w.bar.arrive_and_wait();
     return r;
 }
+inline uint32_t __shfl_xor_sync(unsigned mask, uint32_t v, int lane_mask) {
+    return __shfl_sync(mask, v, (int)((threadIdx.x & 31u) ^ (unsigned)lane_mask));
+}
 inline void __syncwarp() {
     vr_warp->bar.arrive_and_wait();
 }

@@ -239,7 +239,7 @@ def tiled_floor_scene():
                          scene.add_mesh(Surfaces.quad((x0, 0, z0), (x0, 0, z0 + 2), (x0 + 2, 0, z0 + 2), (x0 + 2, 0, z0))))
     scene.add_object(scene.add_material(Materials.metal((0.8, 0.8, 0.8), 0.1)),
                      scene.add_analytic_surface(Surfaces.sphere((0.0, 0.75, 0.0), 0.75)))
-    scene.add_object(scene.add_material(Materials.emission((1.0, 0.9, 0.8), 4.0)),
+    scene.add_object(scene.add_material(Materials.colored_emissive((1.0, 0.9, 0.8), 4.0)),
                      scene.add_mesh(Surfaces.quad((-1, 3, -1), (-1, 3, 1), (1, 3, 1), (1, 3, -1))))
     scene.camera = Camera.look_at((3.0, 2.5, 5.0), (0.0, 0.5, 0.0), (0.0, 1.0, 0.0), 0.6)
     scene.environment = Environments.uniform((0.4, 0.5, 0.6))

@@ -59,6 +59,8 @@ _U32, _I32, _U64, _F = C.c_uint32, C.c_int32, C.c_uint64, C.c_float
 SIGNATURES = {
     "vr_context_create": [_I32, _P, C.POINTER(_P)],
     "vr_context_destroy": [_P],
+    "vr_context_create_multi": [C.POINTER(C.c_int32), _U32, C.POINTER(_P)],
+    "vr_context_device_count": [_P, _UP],
     "vr_scene_create": [_P, C.POINTER(_P)],
     "vr_scene_destroy": [_P],
     "vr_scene_add_texture_rgb32f": [_P, _FP, _U32, _U32, _I32, _UP],

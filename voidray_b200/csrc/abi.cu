@@ -128,6 +128,7 @@ struct vr_render {
     Wavefront wf;
     uint32_t samples_per_batch = 1;
     uint32_t samples_done = 0;
+    uint32_t tail_max = 256u << 10;  // queue length from which k_tail finishes a batch (VOIDRAY_TAIL_MAX; 0 = never)
     std::atomic<int> cancel{0};
     std::atomic<int> running{0};  // an accumulate is in flight: only then does vr_render_cancel latch
     // statistics
@@ -163,6 +164,7 @@ FrameParams frame_params(const vr_render* r) {
     fp.render_mode = r->settings.render_mode;
     fp.integrator = r->settings.integrator;
     fp.seed = r->settings.seed;
+    fp.tail_max = r->tail_max;
     return fp;
 }
 
@@ -184,9 +186,13 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
             }
             e0 = r->events[(*event_cursor)++];
             e1 = r->events[(*event_cursor)++];
-            cudaEventRecord(e0, ctx->stream);
         }
-        launch_trace(sc->dev, r->wf, depth, n_paths, ctx->dims, ctx->stream);
+        if (depth >= 1 && r->tail_max) {
+            launch_tail(sc->dev, r->wf, src, fp, depth, n_paths, ctx->dims, ctx->stream);
+            r->kernel_launches += 1;
+        }
+        if (time_trace) cudaEventRecord(e0, ctx->stream);
+        launch_trace(sc->dev, r->wf, depth, n_paths, r->tail_max, ctx->dims, ctx->stream);
         if (time_trace) cudaEventRecord(e1, ctx->stream);
         launch_shade(sc->dev, r->wf, src, fp, depth, n_paths, ctx->dims, ctx->stream);
         r->kernel_launches += 2;
@@ -197,7 +203,7 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
 // Page-lock the scene's own copy of a texture so that commits DMA straight from it.
 void pin_host(vr_scene* scene, const std::vector<float>& v) {
     if (v.empty()) return;
-    if (cudaHostRegister((void*)v.data(), v.size() * sizeof(float), cudaHostRegisterDefault) == cudaSuccess)
+    if (cudaHostRegister((void*)v.data(), v.size() * sizeof(float), cudaHostRegisterPortable) == cudaSuccess)
         scene->pinned.push_back(v.data());
     else
         cudaGetLastError();  // pageable copies still work, just slower
@@ -252,9 +258,10 @@ int32_t upload_vector(vr_scene* scene, const V& v, const void** out) {
 
 // Sampling tables of integrator 1, built and uploaded the first time a render asks for them after a commit.
 int32_t ensure_env_tables(vr_scene* scene) {
-    if (scene->host.env_kind != 2 || scene->dev.env_marginal) return VR_OK;
+    const HostScene& host = scene->source ? scene->source->host : scene->host;  // a group replica uploads the primary's
+    if (host.env_kind != 2 || scene->dev.env_marginal) return VR_OK;
     std::vector<float> marginal, cond;
-    build_env_tables(scene->host.env_image, marginal, cond);
+    build_env_tables(host.env_image, marginal, cond);
     int32_t rc;
     if ((rc = upload_vector(scene, marginal, (const void**)&scene->dev.env_marginal))) return rc;
     if ((rc = upload_vector(scene, cond, (const void**)&scene->dev.env_cond))) return rc;
@@ -336,9 +343,51 @@ int32_t vr_context_create(int32_t device, void* cuda_stream, vr_context** out) t
 
 int32_t vr_context_destroy(vr_context* ctx) try {
     if (!ctx) return VR_OK;
+    for (vr_context* m : ctx->members) vr_context_destroy(m);
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return VR_OK;
+} VR_CATCH
+
+// A device group in one process (vr_context_create(device_ids, n_devices)): the returned context is
+// the group's first device; scenes created on it are replicated to every device at commit, renders shard their
+// samples over the devices and read_accum / resolve sum the shards on the first device over peer memory.
+int32_t vr_context_create_multi(const int32_t* device_ids, uint32_t n_devices, vr_context** out) try {
+    if (!out) return fail(VR_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!device_ids || n_devices == 0) return fail(VR_ERR_INVALID, "empty device list");
+    if (n_devices > (uint32_t)MAX_PEERS + 1) return fail(VR_ERR_INVALID, "too many devices (max 16)");
+    vr_context* first = nullptr;
+    int32_t rc = vr_context_create(device_ids[0], nullptr, &first);
+    if (rc) return rc;
+    for (uint32_t i = 1; i < n_devices; ++i) {
+        vr_context* m = nullptr;
+        rc = vr_context_create(device_ids[i], nullptr, &m);
+        if (rc) {
+            const std::string why = g_error;
+            vr_context_destroy(first);
+            return fail(rc, why);
+        }
+        first->members.push_back(m);
+        // peer mapping first device <- member (NVLink / NVSwitch on a B200 box); without it the reduce stages copies
+        int can = 0;
+        cudaSetDevice(first->device);
+        char ok = m->device == first->device ? 1 : 0;  // (a device may be listed twice: two shards on one GPU)
+        if (!ok && cudaDeviceCanAccessPeer(&can, first->device, m->device) == cudaSuccess && can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(m->device, 0);
+            ok = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) ? 1 : 0;
+        }
+        cudaGetLastError();
+        first->peer_ok.push_back(ok);
+    }
+    *out = first;
+    return VR_OK;
+} VR_CATCH
+
+int32_t vr_context_device_count(vr_context* ctx, uint32_t* n_devices) try {
+    if (!ctx || !n_devices) return fail(VR_ERR_INVALID, "null argument");
+    *n_devices = 1u + (uint32_t)ctx->members.size();
     return VR_OK;
 } VR_CATCH
 
@@ -356,12 +405,23 @@ int32_t vr_scene_create(vr_context* ctx, vr_scene** out) try {
     c.has_dof = 0;
     c.aperture = 0.0f;
     c.focal_point[0] = c.focal_point[1] = c.focal_point[2] = 0.0f;
+    for (vr_context* m : ctx->members) {  // device group: one replica per further device
+        vr_scene* rep = new (std::nothrow) vr_scene();
+        if (!rep) {
+            vr_scene_destroy(s);
+            return fail(VR_ERR_OOM, "host allocation failed");
+        }
+        rep->ctx = m;
+        rep->source = s;
+        s->replicas.push_back(rep);
+    }
     *out = s;
     return VR_OK;
 } VR_CATCH
 
 int32_t vr_scene_destroy(vr_scene* scene) try {
     if (!scene) return VR_OK;
+    for (vr_scene* rep : scene->replicas) vr_scene_destroy(rep);
     cudaSetDevice(scene->ctx->device);
     cudaStreamSynchronize(scene->ctx->stream);
     scene->dev_mem.release();
@@ -387,7 +447,7 @@ int32_t vr_scene_add_texture_rgb32f(vr_scene* scene, const float* rgb, uint32_t 
     pin_host(scene, scene->host.textures.back().rgb);
     {
         const std::vector<uint8_t>& p8 = scene->host.textures.back().rgba8;
-        if (!p8.empty() && cudaHostRegister((void*)p8.data(), p8.size(), cudaHostRegisterDefault) == cudaSuccess)
+        if (!p8.empty() && cudaHostRegister((void*)p8.data(), p8.size(), cudaHostRegisterPortable) == cudaSuccess)
             scene->pinned.push_back(p8.data());
         else
             cudaGetLastError();
@@ -663,67 +723,109 @@ int32_t vr_scene_clear_environment(vr_scene* scene) try {
     return VR_OK;
 } VR_CATCH
 
-int32_t vr_scene_commit(vr_scene* scene) try {
-    if (check_scene(scene)) return VR_ERR_INVALID;
-    VR_CUDA(cudaSetDevice(scene->ctx->device));
-    scene->committed = false;  // a commit that fails half-way leaves no usable scene behind
-    std::string err;
-    const auto t_begin = std::chrono::steady_clock::now();
-    if (!flatten_scene(scene->host, scene->flat, err)) return fail(VR_ERR_INVALID, err);
-    const auto t_flat = std::chrono::steady_clock::now();
-    scene->h2d_bytes = 0;
-    if (scene->flat.bvh_depth > 32) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
-    VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
-    scene->dev_mem.rewind();
-    scene->dev_textures.clear();
+// The device half of a commit: everything `src` flattened (and its textures / environment) goes to dst's device.
+// dst == src for a single device; a group's replicas upload the primary's host data.
+static int32_t upload_scene(vr_scene* dst, const vr_scene* src) {
+    VR_CUDA(cudaSetDevice(dst->ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    dst->h2d_bytes = 0;
+    VR_CUDA(cudaStreamSynchronize(dst->ctx->stream));
+    dst->dev_mem.rewind();
+    dst->dev_textures.clear();
 
-    DeviceScene& d = scene->dev;
+    DeviceScene& d = dst->dev;
     std::memset(&d, 0, sizeof(d));
-    const FlatScene& f = scene->flat;
+    const FlatScene& f = src->flat;
+    const HostScene& host = src->host;
     int32_t rc;
-    if ((rc = upload_vector(scene, f.nodes, &d.nodes))) return rc;
-    if ((rc = upload_vector(scene, f.tri_isect, &d.tri_isect))) return rc;
-    if ((rc = upload_vector(scene, f.tri_shade, &d.tri_shade))) return rc;
-    if ((rc = upload_vector(scene, f.tri_surface, (const void**)&d.tri_surface))) return rc;
-    if ((rc = upload_vector(scene, f.tri_prim, (const void**)&d.tri_prim))) return rc;
-    if ((rc = upload_vector(scene, scene->host.materials, (const void**)&d.materials))) return rc;
-    if ((rc = upload_vector(scene, f.analytics, (const void**)&d.analytics))) return rc;
-    if ((rc = upload_vector(scene, f.scene_tree, (const void**)&d.scene_tree))) return rc;
-    if ((rc = upload_vector(scene, f.surface_node, (const void**)&d.surface_node))) return rc;
+    if ((rc = upload_vector(dst, f.nodes, &d.nodes))) return rc;
+    if ((rc = upload_vector(dst, f.tri_isect, &d.tri_isect))) return rc;
+    if ((rc = upload_vector(dst, f.tri_shade, &d.tri_shade))) return rc;
+    if ((rc = upload_vector(dst, f.tri_surface, (const void**)&d.tri_surface))) return rc;
+    if ((rc = upload_vector(dst, f.tri_prim, (const void**)&d.tri_prim))) return rc;
+    if ((rc = upload_vector(dst, host.materials, (const void**)&d.materials))) return rc;
+    if ((rc = upload_vector(dst, f.analytics, (const void**)&d.analytics))) return rc;
+    if ((rc = upload_vector(dst, f.scene_tree, (const void**)&d.scene_tree))) return rc;
+    if ((rc = upload_vector(dst, f.surface_node, (const void**)&d.surface_node))) return rc;
     d.n_scene_nodes = (uint32_t)f.scene_tree.size();
     d.n_surfaces = (uint32_t)f.surface_node.size();
-    size_t max_texels = scene->host.env_kind == 2 ? (size_t)scene->host.env_image.w * scene->host.env_image.h : 0;
-    for (const HostTexture& t : scene->host.textures) max_texels = std::max(max_texels, (size_t)t.w * t.h);
+    size_t max_texels = host.env_kind == 2 ? (size_t)host.env_image.w * host.env_image.h : 0;
+    for (const HostTexture& t : host.textures) max_texels = std::max(max_texels, (size_t)t.w * t.h);
     void* stage = nullptr;
-    VR_CUDA(scene->dev_mem.get(&stage, 12 * max_texels));
-    for (const HostTexture& t : scene->host.textures) {
+    VR_CUDA(dst->dev_mem.get(&stage, 12 * max_texels));
+    for (const HostTexture& t : host.textures) {
         TextureRec rec;
-        if ((rc = upload_texture(scene, t, stage, &rec))) return rc;
-        scene->dev_textures.push_back(rec);
+        if ((rc = upload_texture(dst, t, stage, &rec))) return rc;
+        dst->dev_textures.push_back(rec);
     }
-    if ((rc = upload_vector(scene, scene->dev_textures, (const void**)&d.textures))) return rc;
+    if ((rc = upload_vector(dst, dst->dev_textures, (const void**)&d.textures))) return rc;
     d.has_microfacet = 0;
-    for (const MaterialRec& m : scene->host.materials)
+    for (const MaterialRec& m : host.materials)
         if (m.kind == VR_MAT_MICROFACET) d.has_microfacet = 1;
     std::memcpy(d.grid_min, f.grid_min, 12);
     std::memcpy(d.grid_extent, f.grid_extent, 12);
     d.n_tris = f.n_tris;
     d.n_analytics = (uint32_t)f.analytics.size();
-    d.env_kind = scene->host.env_kind;
-    std::memcpy(d.env_color, scene->host.env_color, 12);
-    if (scene->host.env_kind == 2) {
-        if ((rc = upload_texture(scene, scene->host.env_image, stage, &d.env_tex))) return rc;
-        // the sampling tables of integrator 1 are built on demand by vr_render_begin (ensure_env_tables)
+    d.env_kind = host.env_kind;
+    std::memcpy(d.env_color, host.env_color, 12);
+    if (host.env_kind == 2) {
+        if ((rc = upload_texture(dst, host.env_image, stage, &d.env_tex))) return rc;
+        // the sampling tables of integrator 1 are built on demand (ensure_env_tables)
     }
     d.camera = f.camera;
-    VR_CUDA(cudaStreamSynchronize(scene->ctx->stream));
-    const auto t_up = std::chrono::steady_clock::now();
+    VR_CUDA(cudaStreamSynchronize(dst->ctx->stream));
+    dst->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return VR_OK;
+}
+
+int32_t vr_scene_commit(vr_scene* scene) try {
+    if (check_scene(scene)) return VR_ERR_INVALID;
+    if (scene->source) return fail(VR_ERR_INVALID, "a group replica is committed through its primary scene");
+    scene->committed = false;  // a commit that fails half-way leaves no usable scene behind
+    for (vr_scene* rep : scene->replicas) rep->committed = false;
+    std::string err;
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (!flatten_scene(scene->host, scene->flat, err)) return fail(VR_ERR_INVALID, err);
+    const auto t_flat = std::chrono::steady_clock::now();
+    if (scene->flat.bvh_depth > 32) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
+    int32_t rc = VR_OK;
+    if (scene->replicas.empty()) {
+        rc = upload_scene(scene, scene);
+    } else {
+        // one host thread per device: the copies of the pageable flat arrays block their thread, the devices' DMA
+        // engines run side by side
+        const size_t n = 1 + scene->replicas.size();
+        std::vector<int32_t> rcs(n, VR_OK);
+        std::vector<std::string> errs(n);
+        std::vector<std::thread> th;
+        auto work = [&](size_t i) {
+            vr_scene* dst = i == 0 ? scene : scene->replicas[i - 1];
+            try {
+                rcs[i] = upload_scene(dst, scene);
+            } catch (...) {
+                rcs[i] = translate_exception();
+            }
+            if (rcs[i]) errs[i] = g_error;  // thread-local on the worker
+        };
+        for (size_t i = 1; i < n; ++i) th.emplace_back(work, i);
+        work(0);
+        for (std::thread& t : th) t.join();
+        for (size_t i = 0; i < n; ++i)
+            if (rcs[i]) return fail(rcs[i], "device " + std::to_string(i) + " of the group: " + errs[i]);
+    }
+    if (rc) return rc;
     scene->flatten_ms = std::chrono::duration<double, std::milli>(t_flat - t_begin).count();
-    scene->upload_ms = std::chrono::duration<double, std::milli>(t_up - t_flat).count();
     scene->committed = true;
     scene->commit_serial++;
+    for (vr_scene* rep : scene->replicas) {
+        rep->committed = true;
+        rep->commit_serial++;
+        scene->h2d_bytes += rep->h2d_bytes;
+        scene->upload_ms = std::max(scene->upload_ms, rep->upload_ms);
+    }
     return VR_OK;
 } VR_CATCH
+
 
 int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
@@ -741,8 +843,8 @@ int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) try {
     return VR_OK;
 } VR_CATCH
 
-int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const vr_render_settings* settings,
-                        vr_render** out) try {
+static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t height, const vr_render_settings* settings,
+                                   vr_render** out) {
     if (check_scene(scene)) return VR_ERR_INVALID;
     if (!settings || !out) return fail(VR_ERR_INVALID, "null argument");
     if (!scene->committed) return fail(VR_ERR_INVALID, "vr_scene_commit must be called before vr_render_begin");
@@ -763,6 +865,7 @@ int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const 
     r->height = height;
     r->n_pixels = width * height;
     r->settings = *settings;
+    if (const char* e = std::getenv("VOIDRAY_TAIL_MAX")) r->tail_max = (uint32_t)std::max(0, atoi(e));  // experiments / tests
 
     // Paths in flight per wavefront batch. More is better for the deep, sparse depths (measured: +27 % on
     // config 1, +7 % on config 2 going from 8 Mi to 32 Mi); 32 Mi slots are 6.7 GB of the 180 GB of HBM at 8 bounces.
@@ -786,8 +889,10 @@ int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const 
     A((void**)&r->accum, 16ull * r->n_pixels);
     A((void**)&r->partial, 16ull * r->n_pixels);
     A((void**)&r->resolved, 16ull * r->n_pixels);
-    A((void**)&wf.ray_o, 16 * cap);
-    A((void**)&wf.ray_d, 16 * cap);
+    A((void**)&wf.ray_o[0], 16 * cap);
+    A((void**)&wf.ray_o[1], 16 * cap);
+    A((void**)&wf.ray_d[0], 16 * cap);
+    A((void**)&wf.ray_d[1], 16 * cap);
     A((void**)&wf.hit, 16 * cap);
     A((void**)&wf.radiance, 16 * cap);
     A((void**)&wf.att, 16 * cap * levels);
@@ -814,10 +919,49 @@ int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const 
     }
     *out = r;
     return VR_OK;
+}
+
+int32_t vr_render_begin(vr_scene* scene, uint32_t width, uint32_t height, const vr_render_settings* settings,
+                        vr_render** out) try {
+    if (!out) return fail(VR_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (scene && scene->source) return fail(VR_ERR_INVALID, "a group replica renders through its primary scene");
+    vr_render* r = nullptr;
+    int32_t rc = render_begin_single(scene, width, height, settings, &r);
+    if (rc) return rc;
+    // device group: one shard per further device (its own wavefront state and accumulation buffer), plus the buffer
+    // on the first device that receives the sum for vr_render_read_accum
+    for (size_t i = 0; i < scene->replicas.size(); ++i) {
+        vr_render* sh = nullptr;
+        rc = render_begin_single(scene->replicas[i], width, height, settings, &sh);
+        if (rc) {
+            const std::string why = g_error;
+            vr_render_end(r);
+            return fail(rc, why);
+        }
+        sh->is_shard = true;
+        r->shards.push_back(sh);
+    }
+    if (!r->shards.empty()) {
+        cudaSetDevice(scene->ctx->device);
+        cudaError_t e = r->dev_mem.alloc((void**)&r->reduced, 16ull * r->n_pixels);
+        for (size_t i = 0; i < r->shards.size() && e == cudaSuccess; ++i) {
+            float4* st = nullptr;
+            if (!scene->ctx->peer_ok[i]) e = r->dev_mem.alloc((void**)&st, 16ull * r->n_pixels);
+            r->staged.push_back(st);
+        }
+        if (e != cudaSuccess) {
+            vr_render_end(r);
+            return fail(e == cudaErrorMemoryAllocation ? VR_ERR_OOM : VR_ERR_CUDA, std::string("vr_render_begin: ") + cudaGetErrorString(e));
+        }
+    }
+    *out = r;
+    return VR_OK;
 } VR_CATCH
 
 int32_t vr_render_end(vr_render* r) try {
     if (!r) return VR_OK;
+    for (vr_render* sh : r->shards) vr_render_end(sh);
     cudaSetDevice(r->scene->ctx->device);
     cudaStreamSynchronize(r->scene->ctx->stream);
     for (auto& p : r->ipc_peers) cudaIpcCloseMemHandle(p.second);
@@ -831,6 +975,10 @@ int32_t vr_render_end(vr_render* r) try {
 
 int32_t vr_render_clear(vr_render* r) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
+    for (vr_render* sh : r->shards) {
+        const int32_t rc = vr_render_clear(sh);
+        if (rc) return rc;
+    }
     cudaStream_t st = r->scene->ctx->stream;
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
     VR_CUDA(cudaMemsetAsync(r->accum, 0, 16ull * r->n_pixels, st));
@@ -846,10 +994,10 @@ int32_t vr_render_clear(vr_render* r) try {
     return VR_OK;
 } VR_CATCH
 
-int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
-    if (!r) return fail(VR_ERR_INVALID, "null render");
-    if (!r->scene->committed) return fail(VR_ERR_INVALID, "scene was edited after commit");
-    if (samples == 0) return VR_OK;
+// `samples` camera samples per pixel starting at global sample index `first_sample`, on r's own device. Blocking.
+// alpha_inc: what the call adds to the alpha channel (1 per iterative_render call; 0 on a group's further shards).
+static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t samples, float alpha_inc, uint32_t* done_out) {
+    *done_out = 0;
     vr_context* ctx = r->scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
     if (r->settings.integrator == 1) {
@@ -857,15 +1005,6 @@ int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
         const int32_t rc = ensure_env_tables(r->scene);
         if (rc) return rc;
     }
-    // Cancel acts on the accumulate that is running when it is issued (renderer.rs:101-106 polls between batches of
-    // the render in flight): a cancel that arrives while nothing runs is dropped, one that arrives after the last
-    // batch check is forgotten when the next accumulate starts.
-    r->cancel = 0;
-    r->running = 1;
-    struct Running {
-        std::atomic<int>& flag;
-        ~Running() { flag = 0; }
-    } running_guard{r->running};
     const auto t0 = std::chrono::steady_clock::now();
     const float inv_total = 1.0f / (float)r->settings.total_samples;  // iterative.rs:45
     VR_CUDA(cudaEventRecord(r->ev_begin, ctx->stream));
@@ -884,14 +1023,15 @@ int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
         src.n_pixels = r->n_pixels;
         src.width = r->width;
         src.height = r->height;
-        src.sample_base = r->settings.sample_offset + r->samples_done + done;
+        src.sample_base = first_sample + done;
         run_wavefront(r, src, nb * r->n_pixels, true, &event_cursor);
         done += nb;
-        launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, nb, done == samples ? 1 : 0, inv_total, ctx->stream);
+        launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, nb, done == samples ? 1 : 0, inv_total, alpha_inc,
+                          ctx->stream);
         r->kernel_launches += 1;
     }
     if (cancelled && done > 0) {
-        launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, 0, 1, inv_total, ctx->stream);
+        launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, 0, 1, inv_total, alpha_inc, ctx->stream);
         r->kernel_launches += 1;
     }
     VR_CUDA(cudaEventRecord(r->ev_end, ctx->stream));
@@ -910,19 +1050,86 @@ int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
     const auto t1 = std::chrono::steady_clock::now();
     {
         std::lock_guard<std::mutex> lock(r->stats_mutex);
-        r->samples_done += done;
         r->device_ms += ms;
         r->trace_ms += trace_ms;
         r->segments_host = seg;
         r->seconds += std::chrono::duration<double>(t1 - t0).count();
     }
+    *done_out = done;
     if (cancelled) return fail(VR_ERR_CANCELLED, "accumulate cancelled");
     return VR_OK;
+}
+
+int32_t vr_render_accumulate(vr_render* r, uint32_t samples) try {
+    if (!r) return fail(VR_ERR_INVALID, "null render");
+    if (r->is_shard) return fail(VR_ERR_INVALID, "a group shard is driven through its primary render");
+    if (!r->scene->committed) return fail(VR_ERR_INVALID, "scene was edited after commit");
+    if (samples == 0) return VR_OK;
+    // Cancel acts on the accumulate that is running when it is issued (renderer.rs:101-106 polls between batches of
+    // the render in flight): a cancel that arrives while nothing runs is dropped, one that arrives after the last
+    // batch check is forgotten when the next accumulate starts.
+    r->cancel = 0;
+    for (vr_render* sh : r->shards) sh->cancel = 0;
+    r->running = 1;
+    struct Running {
+        std::atomic<int>& flag;
+        ~Running() { flag = 0; }
+    } running_guard{r->running};
+    const uint32_t first = r->settings.sample_offset + r->samples_done;
+    uint32_t done = 0;
+    int32_t rc = VR_OK;
+    if (r->shards.empty()) {
+        rc = accumulate_range(r, first, samples, 1.0f, &done);
+    } else {
+        // device group: the call's sample range is cut into contiguous pieces, one per device, each driven by its own
+        // host thread; the random streams are keyed by (pixel, global sample index), so the union of the shards is the
+        // sample set one device would have drawn. Only the first device counts the call in the alpha channel.
+        const uint32_t n = 1u + (uint32_t)r->shards.size();
+        std::vector<uint32_t> off(n), cnt(n), dn(n, 0);
+        for (uint32_t g = 0, o = 0; g < n; ++g) {
+            cnt[g] = samples / n + (g < samples % n ? 1u : 0u);
+            off[g] = o;
+            o += cnt[g];
+        }
+        std::vector<int32_t> rcs(n, VR_OK);
+        std::vector<std::string> errs(n);
+        auto work = [&](uint32_t g) {
+            vr_render* sh = g == 0 ? r : r->shards[g - 1];
+            if (cnt[g] == 0) return;
+            try {
+                rcs[g] = accumulate_range(sh, first + off[g], cnt[g], g == 0 ? 1.0f : 0.0f, &dn[g]);
+            } catch (...) {
+                rcs[g] = translate_exception();
+            }
+            if (rcs[g]) errs[g] = g_error;
+        };
+        std::vector<std::thread> th;
+        for (uint32_t g = 1; g < n; ++g) th.emplace_back(work, g);
+        work(0);
+        for (std::thread& t : th) t.join();
+        for (uint32_t g = 0; g < n; ++g) {
+            done += dn[g];
+            if (rcs[g] && (rc == VR_OK || rc == VR_ERR_CANCELLED)) {
+                rc = rcs[g];
+                g_error = errs[g];
+            }
+        }
+        // a cancelled group keeps whatever whole batches each device finished; the pieces are no longer one
+        // contiguous range, which only matters to a caller that resumes after a cancel (the reference does not)
+    }
+    {
+        std::lock_guard<std::mutex> lock(r->stats_mutex);
+        r->samples_done += done;
+    }
+    return rc;
 } VR_CATCH
 
 int32_t vr_render_cancel(vr_render* r) try {
     if (!r) return fail(VR_ERR_INVALID, "null render");
-    if (r->running.load()) r->cancel = 1;
+    if (r->running.load()) {
+        r->cancel = 1;
+        for (vr_render* sh : r->shards) sh->cancel = 1;
+    }
     return VR_OK;
 } VR_CATCH
 
@@ -938,15 +1145,54 @@ int32_t vr_render_stats(vr_render* r, vr_stats* out) try {
     out->trace_ms = r->trace_ms;
     out->trace_launches = r->trace_launches;
     out->kernel_launches = r->kernel_launches;
+    for (vr_render* sh : r->shards) {  // device group: work adds up, device time is the slowest shard's
+        std::lock_guard<std::mutex> shard_lock(sh->stats_mutex);
+        out->ray_segments += sh->segments_host;
+        out->device_ms = std::max(out->device_ms, sh->device_ms);
+        out->trace_ms += sh->trace_ms;
+        out->trace_launches += sh->trace_launches;
+        out->kernel_launches += sh->kernel_launches;
+    }
     return VR_OK;
 } VR_CATCH
+
+// Device group: own + shard 1 + shard 2 + ... (that order) per pixel on the first device, the shards read over peer
+// memory (NVLink / NVSwitch) inside the kernel, or from staged copies where a device cannot be mapped.
+// tonemap < 0: the plain sum goes to `out`; otherwise the resolved pixel (fused reduce + PostProcessingPass).
+static int32_t group_reduce(vr_render* r, float4* out, float scale, float gamma, float exposure, int32_t tonemap) {
+    vr_context* ctx = r->scene->ctx;
+    VR_CUDA(cudaSetDevice(ctx->device));
+    PeerList peers;
+    peers.n = (uint32_t)r->shards.size();
+    for (uint32_t k = 0; k < (uint32_t)MAX_PEERS; ++k) peers.ptr[k] = nullptr;
+    for (size_t i = 0; i < r->shards.size(); ++i) {
+        vr_render* sh = r->shards[i];
+        if (ctx->peer_ok[i]) {
+            peers.ptr[i] = sh->accum;
+        } else {
+            VR_CUDA(cudaMemcpyPeerAsync(r->staged[i], ctx->device, sh->accum, sh->scene->ctx->device, 16ull * r->n_pixels, ctx->stream));
+            peers.ptr[i] = r->staged[i];
+        }
+    }
+    launch_reduce_resolve_peers(r->accum, peers, out, r->n_pixels, scale, tonemap < 0 ? 1.0f : std::pow(2.0f, exposure),
+                                tonemap < 0 ? 1.0f : 1.0f / gamma, tonemap, ctx->stream);
+    r->kernel_launches += 1;
+    return VR_OK;
+}
 
 int32_t vr_render_read_accum(vr_render* r, float* rgba) try {
     if (!r || !rgba) return fail(VR_ERR_INVALID, "null argument");
     cudaStream_t st = r->scene->ctx->stream;
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
-    VR_CUDA(cudaMemcpyAsync(rgba, r->accum, 16ull * r->n_pixels, cudaMemcpyDeviceToHost, st));
+    const float4* src = r->accum;
+    if (!r->shards.empty()) {
+        const int32_t rc = group_reduce(r, r->reduced, 1.0f, 1.0f, 0.0f, -1);
+        if (rc) return rc;
+        src = r->reduced;
+    }
+    VR_CUDA(cudaMemcpyAsync(rgba, src, 16ull * r->n_pixels, cudaMemcpyDeviceToHost, st));
     VR_CUDA(cudaStreamSynchronize(st));
+    VR_CUDA(cudaGetLastError());
     return VR_OK;
 } VR_CATCH
 
@@ -961,8 +1207,13 @@ int32_t vr_render_resolve(vr_render* r, float scale, float gamma, float exposure
     if (tonemap < 0 || tonemap > 4) return fail(VR_ERR_INVALID, "unknown tonemap");
     cudaStream_t st = r->scene->ctx->stream;
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
-    launch_resolve(r->accum, r->resolved, r->n_pixels, scale, std::pow(2.0f, exposure), 1.0f / gamma, tonemap, st);
-    r->kernel_launches += 1;
+    if (!r->shards.empty()) {
+        const int32_t rc = group_reduce(r, r->resolved, scale, gamma, exposure, tonemap);
+        if (rc) return rc;
+    } else {
+        launch_resolve(r->accum, r->resolved, r->n_pixels, scale, std::pow(2.0f, exposure), 1.0f / gamma, tonemap, st);
+        r->kernel_launches += 1;
+    }
     VR_CUDA(cudaMemcpyAsync(rgba_out, r->resolved, 16ull * r->n_pixels, cudaMemcpyDeviceToHost, st));
     VR_CUDA(cudaStreamSynchronize(st));
     VR_CUDA(cudaGetLastError());
@@ -1076,7 +1327,7 @@ int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface,
     src.sample_base = sample;
     VR_CUDA(cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * 2 * (fp.max_bounces + 2), ctx->stream));
     launch_raygen(r->scene->dev, r->wf, src, fp, r->n_pixels, ctx->dims, ctx->stream);
-    launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, ctx->dims, ctx->stream);
+    launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, 0u, ctx->dims, ctx->stream);
     launch_primary_ids(r->scene->dev, r->wf, r->width, r->height, r->dbg_surface, r->dbg_prim, r->dbg_t, ctx->stream);
     VR_CUDA(cudaMemcpyAsync(surface, r->dbg_surface, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
     VR_CUDA(cudaMemcpyAsync(prim, r->dbg_prim, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));

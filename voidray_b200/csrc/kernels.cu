@@ -142,9 +142,10 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, Pa
             new_dir = focal_point - origin;
         }
         const f3 dir = normalize(normalize(new_dir));  // camera.rs:81 then Ray::new, util/ray.rs:15
-        wf.ray_o[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n));
-        wf.ray_d[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-        wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        wf.ray_o[0][slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n));
+        wf.ray_d[0][slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        // every path writes its radiance exactly once, when it ends in k_shade; with no bounce at all nothing does
+        if (fp.max_bounces == 0u) wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -166,11 +167,13 @@ static constexpr int REFILL_THRESHOLD = 12;
 // 1 / LEAF_VOTE_NUM of the lanes at inner nodes; one vote buys NODE_STEPS node steps or LEAF_STEPS triangle tests.
 static constexpr int LEAF_VOTE_NUM = 2, NODE_STEPS = 4, LEAF_STEPS = 2;
 
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth, uint32_t tail_max) {
     __shared__ int s_stack[(SMEM_STACK + 1) * TRACE_THREADS];  // + the rays' scene-level visibility words
     const uint32_t n = wf.counts[depth];
+    if (depth >= 1u && n <= tail_max) return;  // k_tail takes these paths to their end
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wf.segments, (unsigned long long)n);
-    const uint32_t* __restrict__ queue = depth == 0 ? nullptr : wf.queue[depth & 1];
+    const float4* __restrict__ ray_o = (depth & 1u ? wf.ray_o[1] : wf.ray_o[0]);
+    const float4* __restrict__ ray_d = (depth & 1u ? wf.ray_d[1] : wf.ray_d[0]);
     const float4* __restrict__ nodes = (const float4*)sc.nodes;
     const float4* __restrict__ tri_isect = (const float4*)sc.tri_isect;
     uint32_t* cursor = wf.cursors + depth;
@@ -182,8 +185,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
     tr.cur = SENTINEL;
     bool have = false;
     bool exhausted = false;  // warp-uniform: the queue has no more rays
-    uint32_t slot = 0;
-
+    uint32_t slot = 0;  // the ray's index in the depth's queue
 
     while (true) {
         if (!exhausted) {
@@ -197,9 +199,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
                 if (!have) {
                     const uint32_t i = base + (uint32_t)__popc(need & lt_mask);
                     if (i < n) {
-                        slot = queue ? queue[i] : i;
-                        const float4 ro = wf.ray_o[slot];
-                        const float4 rd = wf.ray_d[slot];
+                        slot = i;  // queue order: the lanes that refill together read consecutive rays
+                        const float4 ro = ray_o[i];
+                        const float4 rd = ray_d[i];
                         trav_begin(tr, sc, xyz(ro), xyz(rd), sstack, TRACE_THREADS);
                         have = true;
                     }
@@ -442,25 +444,18 @@ __device__ __forceinline__ f3 unwind(const Wavefront& wf, uint32_t slot, uint32_
 }
 
 // FAST = integrator 1 compiled in, MICROFACET = the scene has a MicrofacetBSDF material; the common
-// kernel (parity integrator, simple materials) carries neither code path
+// kernel (parity integrator, simple materials) carries neither code path.
+// One path at one depth: its ray (ro, rd: queue-order records) and closest hit hr. Either the path ends here — its
+// radiance is unwound and written, returns false — or it scatters: the level's attenuation is parked in wf.att, the
+// next ray is returned in next_o / next_d, returns true.
 template <bool FAST, bool MICROFACET>
-__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefront wf, PathSource src,
-                                                         FrameParams fp, uint32_t depth) {
-    const uint32_t n = wf.counts[depth];
-    const uint32_t* __restrict__ queue = depth == 0 ? nullptr : wf.queue[depth & 1];
-    uint32_t* __restrict__ queue_out = wf.queue[(depth + 1) & 1];
+__device__ __forceinline__ bool shade_path(const DeviceScene& sc, const Wavefront& wf, const PathSource& src,
+                                           const FrameParams& fp, uint32_t depth, uint32_t slot, float4 ro, float4 rd, float4 hr,
+                                           float4& next_o, float4& next_d) {
     const float4* __restrict__ tri_shade = (const float4*)sc.tri_shade;
-    const uint32_t lane = threadIdx.x & 31u;
-
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        bool alive = false;
-        uint32_t slot = 0;
-        if (i < n) {
-            slot = queue ? queue[i] : i;
-            const float4 ro = wf.ray_o[slot];
-            const float4 rd = wf.ray_d[slot];
-            const float4 hr = wf.hit[slot];
+    bool alive = false;
+    {
+        {
             const f3 o = xyz(ro), d = xyz(rd);
             const int prim = __float_as_int(hr.y);
 
@@ -625,11 +620,36 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
                     wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
                 } else {
                     wf.att[(size_t)depth * wf.capacity + slot] = make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f);
-                    wf.ray_o[slot] = make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng.n));
-                    wf.ray_d[slot] = make_float4(new_d.x, new_d.y, new_d.z, 0.0f);
+                    next_o = make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng.n));
+                    next_d = make_float4(new_d.x, new_d.y, new_d.z, 0.0f);
                     alive = true;
                 }
             }
+        }
+    }
+    return alive;
+}
+
+template <bool FAST, bool MICROFACET>
+__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefront wf, PathSource src,
+                                                         FrameParams fp, uint32_t depth) {
+    const uint32_t n = wf.counts[depth];
+    if (depth >= 1u && n <= fp.tail_max) return;  // k_tail took the rest of these paths (below)
+    const uint32_t* __restrict__ queue = depth == 0 ? nullptr : (depth & 1u ? wf.queue[1] : wf.queue[0]);
+    uint32_t* __restrict__ queue_out = depth & 1u ? wf.queue[0] : wf.queue[1];
+    const uint32_t lane = threadIdx.x & 31u;
+
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        bool alive = false;
+        uint32_t slot = 0;
+        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;  // the scattered ray of a surviving path
+        if (i < n) {
+            slot = queue ? queue[i] : i;
+            const float4 ro = (depth & 1u ? wf.ray_o[1] : wf.ray_o[0])[i];
+            const float4 rd = (depth & 1u ? wf.ray_d[1] : wf.ray_d[0])[i];
+            const float4 hr = wf.hit[i];
+            alive = shade_path<FAST, MICROFACET>(sc, wf, src, fp, depth, slot, ro, rd, hr, next_o, next_d);
         }
         // warp-aggregated compaction: one atomic per warp
         __syncwarp();
@@ -639,9 +659,54 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
             const int leader = __ffs(ballot) - 1;
             if ((int)lane == leader) warp_base = atomicAdd(&wf.counts[depth + 1], (uint32_t)__popc(ballot));
             warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, leader);
-            if (alive) queue_out[warp_base + __popc(ballot & ((1u << lane) - 1u))] = slot;
+            if (alive) {
+                // the next depth's ray goes to the path's place in the next queue (coalesced within the warp)
+                const uint32_t j = warp_base + __popc(ballot & ((1u << lane) - 1u));
+                queue_out[j] = slot;
+                (depth & 1u ? wf.ray_o[0] : wf.ray_o[1])[j] = next_o;
+                (depth & 1u ? wf.ray_d[0] : wf.ray_d[1])[j] = next_d;
+            }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The tail of a batch. Deep levels hold a few per cent of the paths, but as wavefront launches each of them costs the
+// latency of its longest ray plus a shade launch: on config 1 depths 3..7 are 3 % of the segments and 15 % of the step.
+// Once a depth's queue is down to fp.tail_max paths, one launch of this kernel takes every remaining path to its end —
+// closest hit, shade, next ray, in a loop per thread — and the wavefront kernels of that and all deeper depths return
+// at once (their queues stay empty: counts[] is only ever written by k_shade). Every decision is a pure function of
+// counts[depth], which nothing writes while these kernels run. Same path, same draws, same arithmetic: a path's
+// radiance does not depend on which kernel carried it.
+// ------------------------------------------------------------------------------------------------
+template <bool FAST, bool MICROFACET>
+__global__ void __launch_bounds__(TRACE_THREADS) k_tail(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp,
+                                                        uint32_t depth0) {
+    __shared__ int s_stack[(SMEM_STACK + 1) * TRACE_THREADS];
+    const uint32_t n = wf.counts[depth0];
+    if (n == 0u || n > fp.tail_max) return;
+    const uint32_t* __restrict__ queue = depth0 & 1u ? wf.queue[1] : wf.queue[0];
+    const float4* __restrict__ ray_o = depth0 & 1u ? wf.ray_o[1] : wf.ray_o[0];
+    const float4* __restrict__ ray_d = depth0 & 1u ? wf.ray_d[1] : wf.ray_d[0];
+    uint32_t segments = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue[i];
+        float4 ro = ray_o[i], rd = ray_d[i];
+        for (uint32_t depth = depth0;; ++depth) {
+            const HitResult h = closest_hit(sc, xyz(ro), xyz(rd), s_stack + threadIdx.x, TRACE_THREADS);
+            ++segments;
+            float4 next_o, next_d;
+            if (!shade_path<FAST, MICROFACET>(sc, wf, src, fp, depth, slot, ro, rd,
+                                              make_float4(h.t, __int_as_float(h.prim), h.u, h.v), next_o, next_d))
+                break;
+            ro = next_o;
+            rd = next_d;
+        }
+    }
+    // scene.hit calls of the tail (tracer.rs:29), one atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) segments += __shfl_xor_sync(0xFFFFFFFFu, segments, off);
+    if ((threadIdx.x & 31u) == 0u && segments) atomicAdd(wf.segments, (unsigned long long)segments);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -854,9 +919,21 @@ void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource&
                    uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream) {
     k_raygen<<<grid_for(n_paths, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, src, fp, n_paths);
 }
-void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, const LaunchDims& ld,
-                  cudaStream_t stream) {
-    k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(sc, wf, depth);
+void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, uint32_t tail_max,
+                  const LaunchDims& ld, cudaStream_t stream) {
+    k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(sc, wf, depth,
+                                                                                                                  tail_max);
+}
+void launch_tail(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp, uint32_t depth,
+                 uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {
+    if (depth == 0u || fp.tail_max == 0u) return;
+    const uint32_t bound = n_upper < fp.tail_max ? n_upper : fp.tail_max;
+    const uint32_t grid = grid_for(bound, TRACE_THREADS, ld.sm_count, 4);
+    const bool fast = fp.integrator == 1, mf = sc.has_microfacet != 0;
+    if (fast && mf) k_tail<true, true><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+    else if (fast) k_tail<true, false><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+    else if (mf) k_tail<false, true><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+    else k_tail<false, false><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
 }
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {

@@ -12,11 +12,15 @@
 namespace vr {
 
 // Wavefront state, structure-of-arrays over `capacity` path slots.
+// Rays and hits of depth d are stored in QUEUE ORDER: entry i of the depth's compacted list sits at ray_o[d & 1][i],
+// ray_d[d & 1][i], hit[i], and queue[d & 1][i] names the path slot it belongs to (depth 0: i itself). k_trace streams
+// its rays without an indirection and k_shade reads ray + hit coalesced; only the per-slot state (attenuation stack,
+// finished radiance) is addressed through the slot.
 struct Wavefront {
-    float4* ray_o;   // origin.xyz, draws consumed so far (uint bits)
-    float4* ray_d;   // direction.xyz (unit), unused
-    float4* hit;     // t, GPU primitive index (int bits, -1 miss), u, v
-    float4* att;     // [max_bounces][capacity] attenuation of every level (rgb, unused)
+    float4* ray_o[2];  // origin.xyz, draws consumed so far (uint bits); ping-pong by depth parity
+    float4* ray_d[2];  // direction.xyz (unit), unused
+    float4* hit;     // t, GPU primitive index (int bits, -1 miss), u, v — queue order of the depth being traced
+    float4* att;     // [max_bounces][capacity] attenuation of every level (rgb, unused), by slot
     float4* radiance;  // [capacity] finished radiance of the slot's camera sample
     uint32_t* queue[2];  // compacted slot lists, ping-pong by depth parity
     uint32_t* counts;    // [max_bounces + 1] queue lengths
@@ -41,6 +45,7 @@ struct FrameParams {
     float firefly_clamp;
     int32_t render_mode;
     int32_t integrator;
+    uint32_t tail_max;  // a depth >= 1 whose queue is down to this many paths is finished by k_tail (0: never)
     uint64_t seed;
 };
 
@@ -53,8 +58,12 @@ void query_launch_dims(LaunchDims* dims);
 
 void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                    uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream);
-void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper,
+void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, uint32_t tail_max,
                   const LaunchDims& ld, cudaStream_t stream);
+// depth >= 1: takes every remaining path to its end if the depth's queue holds at most fp.tail_max of them (decided on
+// the device); the wavefront kernels of that depth and below then return at once. A no-op launch otherwise.
+void launch_tail(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp, uint32_t depth,
+                 uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
 // partial[pixel] += sum over the batch's samples (in sample order); when `finish`, fold

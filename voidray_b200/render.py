@@ -38,6 +38,20 @@ class Context:
         self.handle = C.c_void_p()
         check(self._lib.vr_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.handle)))
         self.device = int(device)
+        self.devices = [int(device)]
+
+    @classmethod
+    def multi(cls, devices) -> "Context":
+        """A device group in this process (vr_context_create_multi): scenes are replicated to every device at commit,
+        accumulate shards its sample range over them, read / resolve sum the shards on devices[0] over peer memory."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self.handle = C.c_void_p()
+        ids = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        check(self._lib.vr_context_create_multi(ids, len(devices), C.byref(self.handle)))
+        self.device = int(devices[0])
+        self.devices = [int(d) for d in devices]
+        return self
 
     def close(self):
         if self.handle:
