@@ -533,7 +533,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="with --workload NAME: samples per pixel per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=5.0, help="--impl reference: CPU work per step")
-    ap.add_argument("--max-seconds", type=float, default=420.0,
+    ap.add_argument("--max-seconds", type=float, default=300.0,
                     help="budget of the timed loop; more than this and fewer steps are timed (strong series at N = 1)")
     ap.add_argument("--paths", type=int, default=0, help="wavefront capacity (paths in flight); 0 = library default")
     ap.add_argument("--launcher", default="ranks", choices=["ranks", "inproc"],

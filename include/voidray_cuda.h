@@ -195,7 +195,8 @@ typedef struct vr_scene_info {
     uint32_t reserved;
     uint64_t h2d_bytes;   /* bytes copied host -> device by the commit (geometry, BVH, textures, environment) */
     double flatten_ms;    /* host: tie ranks + BVH build + packing */
-    double upload_ms;     /* host -> device copies */
+    double upload_ms;     /* host -> device copies: what they add on top of the host build (the texture / environment
+                             copies are issued first and overlap it) */
 } vr_scene_info;
 int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out);
 

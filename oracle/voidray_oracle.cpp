@@ -13,11 +13,30 @@
 //
 // Third-party arithmetic that is absent from /root/reference (pinned in Cargo.lock) is restated
 // from the published algorithms:
-//   cgmath 0.18.0   dot = (x*x' + y*y') + z*z'; cross; normalize(v) = v * (1 / sqrt(dot(v,v)));
-//                   Vector3::angle(a,b) = atan2(|a x b|, a.b)
-//   rand 0.8.5      f32 gen_range(low..high): v01 = f32_from_bits((u32>>9)|0x3f800000) - 1;
-//                   res = v01*(high-low) + low, retry while res >= high; Standard f32 = (u32>>8)*2^-24
-//   rand_distr 0.4.3 UnitSphere (Marsaglia 1972), UnitDisc (rejection in the square), UnitCircle
+//   cgmath 0.18.0 (src/vector.rs, src/structure.rs), for Vector3<f32>:
+//     dot(a, b)      = Vector3::mul_element_wise(a, b).sum(), sum() = x + y + z          -> (ax*bx + ay*by) + az*bz
+//     cross(a, b)    = (ay*bz - az*by, az*bx - ax*bz, ax*by - ay*bx)
+//     magnitude(v)   = sqrt(dot(v, v));  normalize(v) = normalize_to(1) = v * (1 / magnitude(v))
+//     angle(a, b)    = Rad::atan2(a.cross(b).magnitude(), dot(a, b))   (the Vector3 specialisation; call site
+//                      core/mesh.rs:179 compares `.0 > degrees_to_radians(30.0)` = 30 * PI / 180, util/math.rs:32-34;
+//                      known answers around the threshold: tests/test_oracle_geometry.py)
+//     Matrix3::new(c0r0, c0r1, c0r2, c1r0, ...) is column-major; Matrix3 * Vector3 = c0 * v.x + c1 * v.y + c2 * v.z
+//   rand 0.8.5 (src/distributions/{float,uniform,bernoulli}.rs):
+//     f32 from 23 bits   into_float_with_exponent(0): f32::from_bits((u32 >> 9) | 0x3f80_0000) in [1, 2)
+//     gen_range(low..high) = UniformFloat::sample_single: scale = high - low; loop { res = (value1_2 - 1.0) * scale + low;
+//                          if res < high { return res } }
+//     Uniform::new(-1., 1.).sample (rand_distr's samplers): value0_1 * scale + low with scale = 2, low = -1
+//     gen::<f32>()       = Standard: (u32 >> 8) as f32 * 2^-24
+//     gen_bool(p)        = Bernoulli::new(p): p == 1 -> always true (no draw); p_int = (p * 2^64) as u64; next_u64() < p_int;
+//                          BlockRng::next_u64 takes two consecutive u32 words, low word first
+//   rand_distr 0.4.3 (src/unit_sphere.rs, unit_disc.rs, unit_circle.rs):
+//     UnitSphere  Marsaglia 1972: loop { x1, x2 ~ U(-1, 1); sum = x1*x1 + x2*x2; if sum >= 1 { continue }
+//                 factor = 2 * sqrt(1 - sum); return [x1*factor, x2*factor, 1 - 2*sum] }
+//     UnitDisc    loop { x1, x2 ~ U(-1, 1); if x1*x1 + x2*x2 <= 1 { return [x1, x2] } }
+//     UnitCircle  loop { x1, x2 ~ U(-1, 1); sum = x1*x1 + x2*x2; if sum < 1 { break } };
+//                 return [(x1*x1 - x2*x2) / sum, 2*x1*x2 / sum]
+//   These are restated from the published crate sources, which are not under /root/reference; the call sites, not the
+//   crates, are what the reference pins (iterative.rs:29,39-40, camera.rs:76, simple.rs:77,116,153,220, microfacet.rs:243-266).
 //   The reference draws from rand::thread_rng() (OS-seeded ChaCha12, unseedable through the API,
 //   voidray_renderer/src/render/iterative.rs:29), so only the *distributions* can be matched. The
 //   oracle replaces the generator by Philox4x32-10 keyed by (seed) with counter

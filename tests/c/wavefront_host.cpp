@@ -110,8 +110,6 @@ int main(int argc, char** argv) {
     fp.render_mode = render_mode;
     fp.integrator = 0;
     fp.seed = seed;
-    // VR_TEST_TAIL_MAX: queue length from which k_tail finishes the batch (0: the wavefront kernels do every depth)
-    fp.tail_max = std::getenv("VR_TEST_TAIL_MAX") ? (uint32_t)atoi(std::getenv("VR_TEST_TAIL_MAX")) : 0u;
 
     // what run_wavefront does (csrc/abi.cu), with small grids: 2 blocks of ray generation, 2 persistent trace blocks
     // (8 warps racing for the queue), 2 shade blocks
@@ -122,11 +120,7 @@ int main(int argc, char** argv) {
     std::vector<float4> rays1_o, rays1_d;
     for (uint32_t depth = 0; depth < max_bounces; ++depth) {
         if (depth == 1) { rays1_o = ray_o1; rays1_d = ray_d1; queue_depth1.assign(q1.begin(), q1.begin() + counts[1]); }
-        if (depth >= 1 && fp.tail_max) {
-            if (ds.has_microfacet) vr_host_launch(2, TRACE_THREADS, [&] { k_tail<false, true>(ds, wf, src, fp, depth); });
-            else vr_host_launch(2, TRACE_THREADS, [&] { k_tail<false, false>(ds, wf, src, fp, depth); });
-        }
-        vr_host_launch(2, TRACE_THREADS, [&] { k_trace(ds, wf, depth, fp.tail_max); });
+        vr_host_launch(2, TRACE_THREADS, [&] { k_trace(ds, wf, depth); });
         if (depth == 0) hits_depth0 = hit;
         if (depth == 1) hits_depth1 = hit;
         if (ds.has_microfacet) vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, true>(ds, wf, src, fp, depth); });
@@ -147,8 +141,7 @@ int main(int argc, char** argv) {
             ++wrong;
     };
     for (uint32_t s = 0; s < n_paths; ++s) check(rays0_o, rays0_d, hits_depth0, s);
-    if (!(fp.tail_max && queue_depth1.size() <= fp.tail_max))  // (depth 1 went through k_trace, not through k_tail)
-        for (uint32_t i = 0; i < (uint32_t)queue_depth1.size(); ++i) check(rays1_o, rays1_d, hits_depth1, i);  // queue order
+    for (uint32_t i = 0; i < (uint32_t)queue_depth1.size(); ++i) check(rays1_o, rays1_d, hits_depth1, i);  // queue order
     std::printf("%u paths, queue lengths", n_paths);
     for (uint32_t d = 0; d <= max_bounces; ++d) std::printf(" %u", counts[d]);
     std::printf(", %llu segments, %zu of %zu wavefront hits differ from the single-ray traversal\n", segments, wrong, checked);

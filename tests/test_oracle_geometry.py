@@ -102,3 +102,35 @@ def test_hit_record_details_on_cube(oracle):
     ang = np.degrees(np.arctan2(np.linalg.norm(np.cross(n[1], [0, 0, 1])), n[1, 2]))
     assert ang <= 30.0
     assert np.all((uv >= 0.0) & (uv <= 1.0))
+
+
+def test_thirty_degree_normal_threshold(oracle):
+    # core/mesh.rs:176-181: the interpolated normal is replaced by the geometric one when
+    # cgmath 0.18 Vector3::angle(n, n_geo) = atan2(|n x n_geo|, n . n_geo) exceeds degrees_to_radians(30) = 30 * PI / 180
+    # (util/math.rs:32-34), strictly. Known answers around the threshold: vertex normals tilted from the geometric normal
+    # (0, 0, -1 for this winding seen from -z ... the hit record flips it towards the ray) by a known angle in the xz plane.
+    from voidray_b200.scene import MeshData
+    base = np.array([[-1, -1, 2], [1, -1, 2], [0, 1, 2]], F32)
+    thr = F32(30.0) * F32(np.pi) / F32(180.0)
+    flipped = []
+    for deg in (0.0, 10.0, 29.0, 29.99, 29.999, 30.001, 30.01, 31.0, 60.0, 89.0):
+        a = np.deg2rad(deg)
+        # geometric normal of this triangle: ((v2 - v1) x (v0 - v1)) normalised (mesh.rs:80-84)
+        ng = np.cross(base[2] - base[1], base[0] - base[1]).astype(F32)
+        ng = ng / np.linalg.norm(ng)
+        tilt = np.array([np.sin(a), 0.0, np.cos(a) * ng[2]], np.float64).astype(F32)  # same hemisphere as ng, tilted in x
+        mesh = MeshData.from_buffers(base, [0, 1, 2], normals=np.tile(tilt, (3, 1)))
+        osc = oracle.OracleScene(single_mesh_scene(mesh))
+        s, p, t, normal, uv, front, _ = osc.trace_rays(np.array([[0.1, -0.2, 0]], F32), np.array([[0, 0, 1]], F32), details=True)
+        assert s[0] == 0 and t[0] == F32(2.0)
+        # the oracle's decision against an independent f32 evaluation of the same expression
+        cr = np.cross(tilt.astype(F32), ng.astype(F32)).astype(F32)
+        mag = np.sqrt(((cr[0] * cr[0] + cr[1] * cr[1]) + cr[2] * cr[2]).astype(F32)).astype(F32)
+        dt = ((tilt[0] * ng[0] + tilt[1] * ng[1]) + tilt[2] * ng[2]).astype(F32)
+        ang = np.arctan2(mag, dt).astype(F32)
+        is_geo = bool(np.allclose(np.abs(normal[0]), np.abs(ng), atol=1e-6))
+        is_tilt = bool(np.allclose(np.abs(normal[0]), np.abs(tilt), atol=1e-6))  # (u + v + w) * tilt, a rounding off
+        if abs(float(ang) - float(thr)) > 1e-5:  # away from the last ulps of atan2 the answer is known
+            assert (is_geo if ang > thr else is_tilt), (deg, ang, thr, normal[0])
+        flipped.append(is_geo and not is_tilt)
+    assert flipped[1:3] == [False, False] and flipped[-3:] == [True, True, True]

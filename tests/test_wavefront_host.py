@@ -46,21 +46,15 @@ def oracle_render(oracle, name, w, h, spp, bounces, seed):
     return img, counters
 
 
-# tail: the queue length from which k_tail takes every remaining path to its end (kernels.cu): never, from depth 1 on,
-# and from somewhere in the middle of the batch
-@pytest.mark.parametrize("tail", ["0", "1000000", "600"])
-def test_kernels_on_the_cpu_match_the_oracle(oracle, harness, tmp_path, tail, variant="default"):
+def test_kernels_on_the_cpu_match_the_oracle(oracle, harness, tmp_path, variant="default"):
     name, w, h, spp, bounces, seed = "mushroom.obj", 64, 48, 4, 6, 0x5EED0001
     out = str(tmp_path / "accum.bin")
     args = [harness(variant), asset_path(name), str(w), str(h), str(spp), str(bounces), hex(seed),
             *[repr(float(x)) for x in EYE], *[repr(float(x)) for x in CENTER], repr(FOV),
             *[repr(float(x)) for x in ENV], *[repr(float(x)) for x in ALBEDO], out]
-    r = subprocess.run(args, capture_output=True, text=True, timeout=900, env=dict(os.environ, VR_TEST_TAIL_MAX=tail))
+    r = subprocess.run(args, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 of " in r.stdout and "wavefront hits differ" in r.stdout
-    lengths = [int(x) for x in r.stdout.split("queue lengths")[1].split(",")[0].split()]
-    if tail == "600":  # the wavefront carried the first depths, the tail kernel the rest
-        assert lengths[1] > 600 and 0 in lengths[2:] and any(0 < n <= 600 for n in lengths[2:])
     img = np.fromfile(out, np.float32).reshape(h, w, 4)
     ref, counters = oracle_render(oracle, name, w, h, spp, bounces, seed)
     # the same number of scene.hit calls as the reference recursion makes, and at least a third of the camera rays hit
@@ -73,13 +67,13 @@ def test_kernels_on_the_cpu_match_the_oracle(oracle, harness, tmp_path, tail, va
 
 
 # ---- any scene the host API can describe (tests/scene_file.py -> tests/c/scene_file.h) -----------------------------
-def run_scene(harness, tmp_path, variant, scene, rs, w, h, spp, tail="400"):
+def run_scene(harness, tmp_path, variant, scene, rs, w, h, spp):
     from scene_file import write_scene
     sp, out = str(tmp_path / "scene.vrscene"), str(tmp_path / "accum.bin")
     write_scene(sp, scene)
     r = subprocess.run([harness(variant), sp, str(w), str(h), str(spp), str(rs.max_bounces), hex(rs.seed),
                         repr(float(rs.firefly_clamp)), str(int(rs.render_mode)), str(int(rs.pixel_mapping)), out],
-                       capture_output=True, text=True, timeout=1800, env=dict(os.environ, VR_TEST_TAIL_MAX=tail))
+                       capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 of " in r.stdout
     segments = int(r.stdout.split(" segments")[0].split()[-1])

@@ -128,7 +128,6 @@ struct vr_render {
     Wavefront wf;
     uint32_t samples_per_batch = 1;
     uint32_t samples_done = 0;
-    uint32_t tail_max = 256u << 10;  // queue length from which k_tail finishes a batch (VOIDRAY_TAIL_MAX; 0 = never)
     std::atomic<int> cancel{0};
     std::atomic<int> running{0};  // an accumulate is in flight: only then does vr_render_cancel latch
     // statistics
@@ -164,7 +163,6 @@ FrameParams frame_params(const vr_render* r) {
     fp.render_mode = r->settings.render_mode;
     fp.integrator = r->settings.integrator;
     fp.seed = r->settings.seed;
-    fp.tail_max = r->tail_max;
     return fp;
 }
 
@@ -187,12 +185,8 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
             e0 = r->events[(*event_cursor)++];
             e1 = r->events[(*event_cursor)++];
         }
-        if (depth >= 1 && r->tail_max) {
-            launch_tail(sc->dev, r->wf, src, fp, depth, n_paths, ctx->dims, ctx->stream);
-            r->kernel_launches += 1;
-        }
         if (time_trace) cudaEventRecord(e0, ctx->stream);
-        launch_trace(sc->dev, r->wf, depth, n_paths, r->tail_max, ctx->dims, ctx->stream);
+        launch_trace(sc->dev, r->wf, depth, n_paths, ctx->dims, ctx->stream);
         if (time_trace) cudaEventRecord(e1, ctx->stream);
         launch_shade(sc->dev, r->wf, src, fp, depth, n_paths, ctx->dims, ctx->stream);
         r->kernel_launches += 2;
@@ -723,18 +717,42 @@ int32_t vr_scene_clear_environment(vr_scene* scene) try {
     return VR_OK;
 } VR_CATCH
 
-// The device half of a commit: everything `src` flattened (and its textures / environment) goes to dst's device.
-// dst == src for a single device; a group's replicas upload the primary's host data.
-static int32_t upload_scene(vr_scene* dst, const vr_scene* src) {
+// The device half of a commit, in two steps so that the large copies overlap the host's BVH build: the textures and
+// the environment do not depend on the flatten, so their copies (from page-locked host memory) are put on the stream
+// first and run while the host flattens; the geometry follows. dst == src for a single device; a group's replicas upload
+// the primary's host data.
+static int32_t upload_textures(vr_scene* dst, const vr_scene* src) {
     VR_CUDA(cudaSetDevice(dst->ctx->device));
-    const auto t0 = std::chrono::steady_clock::now();
     dst->h2d_bytes = 0;
     VR_CUDA(cudaStreamSynchronize(dst->ctx->stream));
     dst->dev_mem.rewind();
     dst->dev_textures.clear();
-
     DeviceScene& d = dst->dev;
     std::memset(&d, 0, sizeof(d));
+    const HostScene& host = src->host;
+    int32_t rc;
+    size_t max_texels = host.env_kind == 2 ? (size_t)host.env_image.w * host.env_image.h : 0;
+    for (const HostTexture& t : host.textures) max_texels = std::max(max_texels, (size_t)t.w * t.h);
+    void* stage = nullptr;
+    VR_CUDA(dst->dev_mem.get(&stage, 12 * max_texels));
+    for (const HostTexture& t : host.textures) {
+        TextureRec rec;
+        if ((rc = upload_texture(dst, t, stage, &rec))) return rc;
+        dst->dev_textures.push_back(rec);
+    }
+    if ((rc = upload_vector(dst, dst->dev_textures, (const void**)&d.textures))) return rc;
+    d.env_kind = host.env_kind;
+    std::memcpy(d.env_color, host.env_color, 12);
+    if (host.env_kind == 2) {
+        if ((rc = upload_texture(dst, host.env_image, stage, &d.env_tex))) return rc;
+        // the sampling tables of integrator 1 are built on demand (ensure_env_tables)
+    }
+    return VR_OK;
+}
+
+static int32_t upload_geometry(vr_scene* dst, const vr_scene* src) {
+    VR_CUDA(cudaSetDevice(dst->ctx->device));
+    DeviceScene& d = dst->dev;
     const FlatScene& f = src->flat;
     const HostScene& host = src->host;
     int32_t rc;
@@ -749,16 +767,6 @@ static int32_t upload_scene(vr_scene* dst, const vr_scene* src) {
     if ((rc = upload_vector(dst, f.surface_node, (const void**)&d.surface_node))) return rc;
     d.n_scene_nodes = (uint32_t)f.scene_tree.size();
     d.n_surfaces = (uint32_t)f.surface_node.size();
-    size_t max_texels = host.env_kind == 2 ? (size_t)host.env_image.w * host.env_image.h : 0;
-    for (const HostTexture& t : host.textures) max_texels = std::max(max_texels, (size_t)t.w * t.h);
-    void* stage = nullptr;
-    VR_CUDA(dst->dev_mem.get(&stage, 12 * max_texels));
-    for (const HostTexture& t : host.textures) {
-        TextureRec rec;
-        if ((rc = upload_texture(dst, t, stage, &rec))) return rc;
-        dst->dev_textures.push_back(rec);
-    }
-    if ((rc = upload_vector(dst, dst->dev_textures, (const void**)&d.textures))) return rc;
     d.has_microfacet = 0;
     for (const MaterialRec& m : host.materials)
         if (m.kind == VR_MAT_MICROFACET) d.has_microfacet = 1;
@@ -766,15 +774,8 @@ static int32_t upload_scene(vr_scene* dst, const vr_scene* src) {
     std::memcpy(d.grid_extent, f.grid_extent, 12);
     d.n_tris = f.n_tris;
     d.n_analytics = (uint32_t)f.analytics.size();
-    d.env_kind = host.env_kind;
-    std::memcpy(d.env_color, host.env_color, 12);
-    if (host.env_kind == 2) {
-        if ((rc = upload_texture(dst, host.env_image, stage, &d.env_tex))) return rc;
-        // the sampling tables of integrator 1 are built on demand (ensure_env_tables)
-    }
     d.camera = f.camera;
     VR_CUDA(cudaStreamSynchronize(dst->ctx->stream));
-    dst->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return VR_OK;
 }
 
@@ -783,25 +784,31 @@ int32_t vr_scene_commit(vr_scene* scene) try {
     if (scene->source) return fail(VR_ERR_INVALID, "a group replica is committed through its primary scene");
     scene->committed = false;  // a commit that fails half-way leaves no usable scene behind
     for (vr_scene* rep : scene->replicas) rep->committed = false;
-    std::string err;
+    const size_t n = 1 + scene->replicas.size();
+    auto device_scene = [&](size_t i) { return i == 0 ? scene : scene->replicas[i - 1]; };
     const auto t_begin = std::chrono::steady_clock::now();
+    // textures / environment: asynchronous copies from page-locked memory, issued before the host work they overlap
+    for (size_t i = 0; i < n; ++i) {
+        const int32_t rc = upload_textures(device_scene(i), scene);
+        if (rc) return rc;
+    }
+    const auto t_issued = std::chrono::steady_clock::now();
+    std::string err;
     if (!flatten_scene(scene->host, scene->flat, err)) return fail(VR_ERR_INVALID, err);
     const auto t_flat = std::chrono::steady_clock::now();
     if (scene->flat.bvh_depth > 32) return fail(VR_ERR_INVALID, "BVH too deep for the traversal stack");
-    int32_t rc = VR_OK;
-    if (scene->replicas.empty()) {
-        rc = upload_scene(scene, scene);
+    if (n == 1) {
+        const int32_t rc = upload_geometry(scene, scene);
+        if (rc) return rc;
     } else {
         // one host thread per device: the copies of the pageable flat arrays block their thread, the devices' DMA
         // engines run side by side
-        const size_t n = 1 + scene->replicas.size();
         std::vector<int32_t> rcs(n, VR_OK);
         std::vector<std::string> errs(n);
         std::vector<std::thread> th;
         auto work = [&](size_t i) {
-            vr_scene* dst = i == 0 ? scene : scene->replicas[i - 1];
             try {
-                rcs[i] = upload_scene(dst, scene);
+                rcs[i] = upload_geometry(device_scene(i), scene);
             } catch (...) {
                 rcs[i] = translate_exception();
             }
@@ -813,19 +820,21 @@ int32_t vr_scene_commit(vr_scene* scene) try {
         for (size_t i = 0; i < n; ++i)
             if (rcs[i]) return fail(rcs[i], "device " + std::to_string(i) + " of the group: " + errs[i]);
     }
-    if (rc) return rc;
-    scene->flatten_ms = std::chrono::duration<double, std::milli>(t_flat - t_begin).count();
+    const auto t_end = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    scene->flatten_ms = ms(t_issued, t_flat);
+    scene->upload_ms = ms(t_begin, t_issued) + ms(t_flat, t_end);  // what the copies add on top of the host build
     scene->committed = true;
     scene->commit_serial++;
     for (vr_scene* rep : scene->replicas) {
         rep->committed = true;
         rep->commit_serial++;
         scene->h2d_bytes += rep->h2d_bytes;
-        scene->upload_ms = std::max(scene->upload_ms, rep->upload_ms);
     }
     return VR_OK;
 } VR_CATCH
-
 
 int32_t vr_scene_get_info(vr_scene* scene, vr_scene_info* out) try {
     if (check_scene(scene)) return VR_ERR_INVALID;
@@ -865,7 +874,6 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     r->height = height;
     r->n_pixels = width * height;
     r->settings = *settings;
-    if (const char* e = std::getenv("VOIDRAY_TAIL_MAX")) r->tail_max = (uint32_t)std::max(0, atoi(e));  // experiments / tests
 
     // Paths in flight per wavefront batch. More is better for the deep, sparse depths (measured: +27 % on
     // config 1, +7 % on config 2 going from 8 Mi to 32 Mi); 32 Mi slots are 6.7 GB of the 180 GB of HBM at 8 bounces.
@@ -1327,7 +1335,7 @@ int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface,
     src.sample_base = sample;
     VR_CUDA(cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * 2 * (fp.max_bounces + 2), ctx->stream));
     launch_raygen(r->scene->dev, r->wf, src, fp, r->n_pixels, ctx->dims, ctx->stream);
-    launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, 0u, ctx->dims, ctx->stream);
+    launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, ctx->dims, ctx->stream);
     launch_primary_ids(r->scene->dev, r->wf, r->width, r->height, r->dbg_surface, r->dbg_prim, r->dbg_t, ctx->stream);
     VR_CUDA(cudaMemcpyAsync(surface, r->dbg_surface, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
     VR_CUDA(cudaMemcpyAsync(prim, r->dbg_prim, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));

@@ -167,10 +167,9 @@ static constexpr int REFILL_THRESHOLD = 12;
 // 1 / LEAF_VOTE_NUM of the lanes at inner nodes; one vote buys NODE_STEPS node steps or LEAF_STEPS triangle tests.
 static constexpr int LEAF_VOTE_NUM = 2, NODE_STEPS = 4, LEAF_STEPS = 2;
 
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth, uint32_t tail_max) {
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
     __shared__ int s_stack[(SMEM_STACK + 1) * TRACE_THREADS];  // + the rays' scene-level visibility words
     const uint32_t n = wf.counts[depth];
-    if (depth >= 1u && n <= tail_max) return;  // k_tail takes these paths to their end
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wf.segments, (unsigned long long)n);
     const float4* __restrict__ ray_o = (depth & 1u ? wf.ray_o[1] : wf.ray_o[0]);
     const float4* __restrict__ ray_d = (depth & 1u ? wf.ray_d[1] : wf.ray_d[0]);
@@ -634,7 +633,6 @@ template <bool FAST, bool MICROFACET>
 __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefront wf, PathSource src,
                                                          FrameParams fp, uint32_t depth) {
     const uint32_t n = wf.counts[depth];
-    if (depth >= 1u && n <= fp.tail_max) return;  // k_tail took the rest of these paths (below)
     const uint32_t* __restrict__ queue = depth == 0 ? nullptr : (depth & 1u ? wf.queue[1] : wf.queue[0]);
     uint32_t* __restrict__ queue_out = depth & 1u ? wf.queue[0] : wf.queue[1];
     const uint32_t lane = threadIdx.x & 31u;
@@ -668,45 +666,6 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefro
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The tail of a batch. Deep levels hold a few per cent of the paths, but as wavefront launches each of them costs the
-// latency of its longest ray plus a shade launch: on config 1 depths 3..7 are 3 % of the segments and 15 % of the step.
-// Once a depth's queue is down to fp.tail_max paths, one launch of this kernel takes every remaining path to its end —
-// closest hit, shade, next ray, in a loop per thread — and the wavefront kernels of that and all deeper depths return
-// at once (their queues stay empty: counts[] is only ever written by k_shade). Every decision is a pure function of
-// counts[depth], which nothing writes while these kernels run. Same path, same draws, same arithmetic: a path's
-// radiance does not depend on which kernel carried it.
-// ------------------------------------------------------------------------------------------------
-template <bool FAST, bool MICROFACET>
-__global__ void __launch_bounds__(TRACE_THREADS) k_tail(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp,
-                                                        uint32_t depth0) {
-    __shared__ int s_stack[(SMEM_STACK + 1) * TRACE_THREADS];
-    const uint32_t n = wf.counts[depth0];
-    if (n == 0u || n > fp.tail_max) return;
-    const uint32_t* __restrict__ queue = depth0 & 1u ? wf.queue[1] : wf.queue[0];
-    const float4* __restrict__ ray_o = depth0 & 1u ? wf.ray_o[1] : wf.ray_o[0];
-    const float4* __restrict__ ray_d = depth0 & 1u ? wf.ray_d[1] : wf.ray_d[0];
-    uint32_t segments = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = queue[i];
-        float4 ro = ray_o[i], rd = ray_d[i];
-        for (uint32_t depth = depth0;; ++depth) {
-            const HitResult h = closest_hit(sc, xyz(ro), xyz(rd), s_stack + threadIdx.x, TRACE_THREADS);
-            ++segments;
-            float4 next_o, next_d;
-            if (!shade_path<FAST, MICROFACET>(sc, wf, src, fp, depth, slot, ro, rd,
-                                              make_float4(h.t, __int_as_float(h.prim), h.u, h.v), next_o, next_d))
-                break;
-            ro = next_o;
-            rd = next_d;
-        }
-    }
-    // scene.hit calls of the tail (tracer.rs:29), one atomic per warp
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) segments += __shfl_xor_sync(0xFFFFFFFFu, segments, off);
-    if ((threadIdx.x & 31u) == 0u && segments) atomicAdd(wf.segments, (unsigned long long)segments);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -919,21 +878,9 @@ void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource&
                    uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream) {
     k_raygen<<<grid_for(n_paths, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, src, fp, n_paths);
 }
-void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, uint32_t tail_max,
-                  const LaunchDims& ld, cudaStream_t stream) {
-    k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(sc, wf, depth,
-                                                                                                                  tail_max);
-}
-void launch_tail(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp, uint32_t depth,
-                 uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {
-    if (depth == 0u || fp.tail_max == 0u) return;
-    const uint32_t bound = n_upper < fp.tail_max ? n_upper : fp.tail_max;
-    const uint32_t grid = grid_for(bound, TRACE_THREADS, ld.sm_count, 4);
-    const bool fast = fp.integrator == 1, mf = sc.has_microfacet != 0;
-    if (fast && mf) k_tail<true, true><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
-    else if (fast) k_tail<true, false><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
-    else if (mf) k_tail<false, true><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
-    else k_tail<false, false><<<grid, TRACE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, const LaunchDims& ld,
+                  cudaStream_t stream) {
+    k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(sc, wf, depth);
 }
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {

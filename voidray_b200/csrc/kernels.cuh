@@ -45,7 +45,6 @@ struct FrameParams {
     float firefly_clamp;
     int32_t render_mode;
     int32_t integrator;
-    uint32_t tail_max;  // a depth >= 1 whose queue is down to this many paths is finished by k_tail (0: never)
     uint64_t seed;
 };
 
@@ -58,12 +57,8 @@ void query_launch_dims(LaunchDims* dims);
 
 void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                    uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream);
-void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, uint32_t tail_max,
+void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper,
                   const LaunchDims& ld, cudaStream_t stream);
-// depth >= 1: takes every remaining path to its end if the depth's queue holds at most fp.tail_max of them (decided on
-// the device); the wavefront kernels of that depth and below then return at once. A no-op launch otherwise.
-void launch_tail(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp, uint32_t depth,
-                 uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
 // partial[pixel] += sum over the batch's samples (in sample order); when `finish`, fold
