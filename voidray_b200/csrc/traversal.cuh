@@ -188,7 +188,10 @@ __device__ __forceinline__ void trav_axis(float o, float d, float gmin, float ex
     a = extent * id;
     const float g = (gmin - o) * id;
     const float b = g - a;
-    const float err = 2.4e-7f * (fabsf(g) + fabsf(a)) + 1e-30f;
+    // 2.4e-7 (|g| + |a|) bounds the rounding of b = g - a and of g itself; the plane's own FFMA t = f * a + b (f in
+    // [1, 2)) rounds by at most 2^-24 (2 |a| + |b|) <= 6e-8 (|g| + 3 |a|): both are folded into the addends, so the
+    // node step compares near <= far directly, with no widening multiply
+    const float err = 4.5e-7f * (fabsf(g) + fabsf(a)) + 1e-30f;
     bn = b - err;
     bf = b + err;
     sel = id >= 0.0f ? 0x7104u : 0x7324u;  // bytes (0x00, q.b0, q.b1, 0x3F) of the low / high half-word
@@ -243,10 +246,10 @@ __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restric
                            fmaxf(plane_t(w5, tr.selz, tr.az, tr.bnz), 0.0f));
     const float bf = fminf(fminf(plane_t(w3, fx, tr.ax, tr.bfx), plane_t(w4, fy, tr.ay, tr.bfy)),
                            fminf(plane_t(w5, fz, tr.az, tr.bfz), tr.best.t));
-    // conservative: the boxes carry a guard cell, bn / bf carry the addend's rounding, and the exit is widened
-    // by a few ulps for the FFMA's own rounding (Ize, "Robust BVH ray traversal", 2013)
-    const bool hit_a = an <= af * 1.0000005f;
-    const bool hit_b = bn <= bf * 1.0000005f;
+    // conservative: the boxes carry a guard cell, and bn / bf carry the rounding of the addend and of the FFMA
+    // itself (trav_axis; Ize, "Robust BVH ray traversal", 2013)
+    const bool hit_a = an <= af;
+    const bool hit_b = bn <= bf;
     const int ca = __float_as_int(n.hi.z), cb = __float_as_int(n.hi.w);
     // branch-free child selection: the divergent if/else ladder ran at 2-3 lanes per instruction
     const bool b_first = hit_b && (!hit_a || bn < an);
