@@ -7,7 +7,7 @@ M=smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dr
 CONFIGS=${CONFIGS:-"config1_mushroom:64 config2_mossy_ground:16 config3_materials:16 config5_combined:4 config4_field:8"}
 for cfg in $CONFIGS; do
   name=${cfg%%:*}; spp=${cfg##*:}
-  ncu --metrics $M --clock-control none -k regex:'k_trace|k_shade' --csv --log-file gpurun_out/inst_${name}.csv \
+  ncu --metrics $M --clock-control none -k regex:'k_trace|k_shade|k_miss|k_raygen|k_accumulate' --csv --log-file gpurun_out/inst_${name}.csv \
       python scripts/render_once.py $name $spp > gpurun_out/inst_${name}.json 2> gpurun_out/inst_${name}.err
   tail -1 gpurun_out/inst_${name}.json | cut -c1-200
 done

@@ -39,7 +39,7 @@ for jp in sorted(glob.glob(os.path.join(src, "inst_*.json"))):
         dram = m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
         md.append(f"| {lid} | {kn} | {m.get('gpu__time_duration.sum', 0):.1f} | {wi:.0f} | {ti / wi if wi else 0:.2f} | "
                   f"{m.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.1f} | {dram / 1e6:.1f} |")
-        k = "trace" if "k_trace" in kn else "shade"
+        k = "trace" if "k_trace" in kn else ("shade" if ("k_shade" in kn or "k_miss" in kn) else "other")
         tot[k + "_warp"] += wi
         tot[k + "_thread"] += ti
         tot[k + "_dram"] += dram
@@ -49,12 +49,13 @@ for jp in sorted(glob.glob(os.path.join(src, "inst_*.json"))):
                  "dram_bytes_per_segment": tot["trace_dram"] / seg,
                  "shade_warp_inst_per_segment": tot["shade_warp"] / seg, "shade_thread_inst_per_segment": tot["shade_thread"] / seg,
                  "shade_dram_bytes_per_segment": tot["shade_dram"] / seg,
-                 "trace_us_under_ncu": tot["trace_us"], "shade_us_under_ncu": tot["shade_us"], "segments": seg,
+                 "trace_us_under_ncu": tot["trace_us"], "shade_us_under_ncu": tot["shade_us"],
+                 "other_us_under_ncu": tot["other_us"], "segments": seg,
                  "source": f"ncu smsp__inst_executed.sum / smsp__thread_inst_executed.sum / dram__bytes over every k_trace launch of "
                            f"one accumulate, {meta['width']}x{meta['height']} x {meta['spp']} spp (scripts/ncu_trace_inst.sh)"}
     md.append(f"\nper segment: k_trace {out[name]['warp_inst_per_segment']:.1f} warp instructions "
               f"({out[name]['thread_inst_per_segment'] / 32 / out[name]['warp_inst_per_segment']:.3f} lane efficiency), "
-              f"{out[name]['dram_bytes_per_segment']:.1f} DRAM bytes; k_shade {out[name]['shade_warp_inst_per_segment']:.1f} warp "
+              f"{out[name]['dram_bytes_per_segment']:.1f} DRAM bytes; k_shade + k_miss {out[name]['shade_warp_inst_per_segment']:.1f} warp "
               f"instructions, {out[name]['shade_dram_bytes_per_segment']:.1f} DRAM bytes")
 json.dump(out, open(os.path.join(ROOT, "profiles", "r2_trace_inst.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "r2_trace_inst.md"), "w").write("\n".join(md) + "\n")

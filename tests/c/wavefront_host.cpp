@@ -78,7 +78,8 @@ int main(int argc, char** argv) {
     const uint32_t n_pixels = w * h, n_paths = n_pixels * spp;
     std::vector<float4> ray_o(n_paths), ray_d(n_paths), ray_o1(n_paths), ray_d1(n_paths), hit(n_paths), radiance(n_paths),
         att((size_t)max_bounces * n_paths);
-    std::vector<uint32_t> q0(n_paths), q1(n_paths), counts(2 * (max_bounces + 2), 0u);
+    std::vector<uint32_t> q0(n_paths), q1(n_paths), counts(2 * (max_bounces + 2) + 1, 0u);
+    std::vector<float4> miss(n_paths);
     unsigned long long segments = 0;
     Wavefront wf{};
     wf.ray_o[0] = ray_o.data();
@@ -92,15 +93,11 @@ int main(int argc, char** argv) {
     wf.queue[1] = q1.data();
     wf.counts = counts.data();
     wf.cursors = counts.data() + (max_bounces + 2);
+    wf.miss = miss.data();
+    wf.miss_count = counts.data() + 2 * (max_bounces + 2);
     wf.segments = &segments;
     wf.capacity = n_paths;
-    PathSource src{};
-    src.pixel = nullptr;
-    src.sample = nullptr;
-    src.n_pixels = n_pixels;
-    src.sample_base = 0;
-    src.width = w;
-    src.height = h;
+    const PathSource src = make_path_source(nullptr, nullptr, w, h, 0);
     FrameParams fp{};
     fp.width = w;
     fp.height = h;
@@ -115,17 +112,21 @@ int main(int argc, char** argv) {
     // (8 warps racing for the queue), 2 shade blocks
     std::vector<float4> hits_depth0, hits_depth1;
     std::vector<uint32_t> queue_depth1;
-    vr_host_launch(2, 256, [&] { k_raygen(ds, wf, src, fp, n_paths); });
+    vr_host_launch(2, 256, [&] { k_raygen(ds, wf, src, fp, n_paths, spp > 1 ? 2u : 1u); });
     const std::vector<float4> rays0_o = ray_o, rays0_d = ray_d;
     std::vector<float4> rays1_o, rays1_d;
     for (uint32_t depth = 0; depth < max_bounces; ++depth) {
         if (depth == 1) { rays1_o = ray_o1; rays1_d = ray_d1; queue_depth1.assign(q1.begin(), q1.begin() + counts[1]); }
-        vr_host_launch(2, TRACE_THREADS, [&] { k_trace(ds, wf, depth); });
+        vr_host_launch(2, TRACE_THREADS, [&] { k_trace(ds, wf, depth, REFILL_THRESHOLD); });
         if (depth == 0) hits_depth0 = hit;
         if (depth == 1) hits_depth1 = hit;
-        if (ds.has_microfacet) vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, true>(ds, wf, src, fp, depth); });
+        if (depth == 0) {
+            if (ds.has_microfacet) vr_host_launch(2, SHADE_THREADS, [&] { k_shade_first<false, true>(ds, wf, src, fp); });
+            else vr_host_launch(2, SHADE_THREADS, [&] { k_shade_first<false, false>(ds, wf, src, fp); });
+        } else if (ds.has_microfacet) vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, true>(ds, wf, src, fp, depth); });
         else vr_host_launch(2, SHADE_THREADS, [&] { k_shade<false, false>(ds, wf, src, fp, depth); });
     }
+    if (max_bounces > 1) vr_host_launch(2, 256, [&] { k_miss(ds, wf, fp.firefly_clamp); });
     std::vector<float4> partial(n_pixels, float4{0, 0, 0, 0}), accum(n_pixels, float4{0, 0, 0, 0});
     vr_host_launch(1, 256, [&] { k_accumulate(wf, partial.data(), accum.data(), w, h, spp, 1, 1.0f / (float)spp, 1.0f); });
 

@@ -146,3 +146,14 @@ def test_kernels_on_the_cpu_microfacet(oracle, harness, tmp_path, name):
     assert fin.mean() > 0.99
     assert np.array_equal(img[..., :3][fin].view(np.uint32), ref[..., :3][fin].view(np.uint32)), \
         float(np.abs(img[..., :3][fin] - ref[..., :3][fin]).max())
+
+
+def test_fast_division_by_launch_invariants(tmp_path):
+    # k_raygen / k_shade divide slots by the pixel count and the tiles per row with a multiply-high (kernels.cuh)
+    exe = str(tmp_path / "fastdiv_check")
+    csrc = os.path.join(ROOT, "voidray_b200", "csrc")
+    r = subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-DVR_HOST_SHIM", "-DVR_HOST_SIMT", "-I", os.path.join(ROOT, "tests", "c"),
+                        "-I", csrc, os.path.join(ROOT, "tests", "c", "fastdiv_check.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and ", 0 wrong" in r.stdout, r.stdout

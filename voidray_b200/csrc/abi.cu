@@ -171,7 +171,7 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
     vr_scene* sc = r->scene;
     vr_context* ctx = sc->ctx;
     const FrameParams fp = frame_params(r);
-    cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * 2 * (fp.max_bounces + 2), ctx->stream);  // counts + cursors
+    cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * (2 * (fp.max_bounces + 2) + 1), ctx->stream);  // counts + cursors + miss_count
     launch_raygen(sc->dev, r->wf, src, fp, n_paths, ctx->dims, ctx->stream);
     r->kernel_launches += 1;
     for (uint32_t depth = 0; depth < fp.max_bounces; ++depth) {
@@ -191,6 +191,10 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
         launch_shade(sc->dev, r->wf, src, fp, depth, n_paths, ctx->dims, ctx->stream);
         r->kernel_launches += 2;
         r->trace_launches += 1;
+    }
+    if (fp.max_bounces > 1) {  // the misses of depth >= 1 that k_shade parked
+        launch_miss(sc->dev, r->wf, fp, n_paths, ctx->dims, ctx->stream);
+        r->kernel_launches += 1;
     }
 }
 
@@ -882,7 +886,7 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     if (capacity < r->n_pixels) capacity = r->n_pixels;
     r->samples_per_batch = (uint32_t)(capacity / r->n_pixels);
     capacity = (uint64_t)r->samples_per_batch * r->n_pixels;
-    if (capacity >= (1ull << 31)) {
+    if (capacity >= (1ull << 26)) {  // a miss record packs slot | depth << 26 (kernels.cu)
         delete r;
         return fail(VR_ERR_INVALID, "max_paths_in_flight too large");
     }
@@ -906,12 +910,14 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     A((void**)&wf.att, 16 * cap * levels);
     A((void**)&wf.queue[0], 4 * cap);
     A((void**)&wf.queue[1], 4 * cap);
-    A((void**)&wf.counts, 4 * 2 * (settings->max_bounces + 2));
+    A((void**)&wf.miss, 16 * cap);
+    A((void**)&wf.counts, 4 * (2 * (settings->max_bounces + 2) + 1));
     A((void**)&wf.segments, 8);
     A((void**)&r->dbg_surface, 4ull * r->n_pixels);
     A((void**)&r->dbg_prim, 4ull * r->n_pixels);
     A((void**)&r->dbg_t, 4ull * r->n_pixels);
     wf.cursors = wf.counts ? wf.counts + (settings->max_bounces + 2) : nullptr;
+    wf.miss_count = wf.counts ? wf.counts + 2 * (settings->max_bounces + 2) : nullptr;
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_end);
     cudaStream_t st = scene->ctx->stream;
@@ -1025,13 +1031,7 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
             break;
         }
         const uint32_t nb = std::min(samples - done, r->samples_per_batch);
-        PathSource src;
-        src.pixel = nullptr;
-        src.sample = nullptr;
-        src.n_pixels = r->n_pixels;
-        src.width = r->width;
-        src.height = r->height;
-        src.sample_base = first_sample + done;
+        const PathSource src = make_path_source(nullptr, nullptr, r->width, r->height, first_sample + done);
         run_wavefront(r, src, nb * r->n_pixels, true, &event_cursor);
         done += nb;
         launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, nb, done == samples ? 1 : 0, inv_total, alpha_inc,
@@ -1326,13 +1326,7 @@ int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface,
     vr_context* ctx = r->scene->ctx;
     VR_CUDA(cudaSetDevice(ctx->device));
     const FrameParams fp = frame_params(r);
-    PathSource src;
-    src.pixel = nullptr;
-    src.sample = nullptr;
-    src.n_pixels = r->n_pixels;
-    src.width = r->width;
-    src.height = r->height;
-    src.sample_base = sample;
+    const PathSource src = make_path_source(nullptr, nullptr, r->width, r->height, sample);
     VR_CUDA(cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * 2 * (fp.max_bounces + 2), ctx->stream));
     launch_raygen(r->scene->dev, r->wf, src, fp, r->n_pixels, ctx->dims, ctx->stream);
     launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, ctx->dims, ctx->stream);
@@ -1398,13 +1392,7 @@ int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel
         e = cudaMemcpyAsync(d_px, pixel + base, 4ull * m, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_sm, sample + base, 4ull * m, cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) break;
-        PathSource src;
-        src.pixel = d_px;
-        src.sample = d_sm;
-        src.n_pixels = r->n_pixels;
-        src.width = r->width;
-        src.height = r->height;
-        src.sample_base = 0;
+        const PathSource src = make_path_source(d_px, d_sm, r->width, r->height, 0);
         size_t cursor = 0;
         run_wavefront(r, src, m, false, &cursor);
         e = cudaMemcpyAsync(host.data(), r->wf.radiance, 16ull * m, cudaMemcpyDeviceToHost, ctx->stream);

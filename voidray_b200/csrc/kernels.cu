@@ -7,12 +7,18 @@
 // environments.rs -> shaders/post_process.glsl.
 #include "device_math.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace vr {
 
 static constexpr int TRACE_THREADS = 128;
 static constexpr int TRACE_MIN_BLOCKS = 8;
 static constexpr int SHADE_THREADS = 128;
+#ifndef VR_SHADE_MIN_BLOCKS
+#define VR_SHADE_MIN_BLOCKS 8
+#endif
+static constexpr int SHADE_MIN_BLOCKS = VR_SHADE_MIN_BLOCKS;  // <= 64 registers: k_shade is bound by memory latency x resident warps
 }  // namespace vr
 #include "traversal.cuh"
 namespace vr {
@@ -79,20 +85,42 @@ __device__ __forceinline__ f3 environment_sample(const DeviceScene& sc, f3 dir) 
 // cover a compact screen tile instead of a 32x1 strip (coherent node fetches at depth 0). Pixels right of
 // the last full tile column / below the last full tile row follow in row order. Pure enumeration: the
 // pixel index itself (and with it the camera mapping and the random stream) is unchanged.
-__device__ __forceinline__ uint32_t tile_slot_to_pixel(uint32_t j, uint32_t W, uint32_t H) {
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, const FastDiv& f) {  // x < 2^31, see kernels.cuh
+    if (f.m == 0u) return f.d <= 1u ? x : x / f.d;  // d == 1, or no magic number prepared
+    return __umulhi(x, f.m) >> f.s;
+}
+// (x, y) of slot-in-sample j; by_tpr divides by the tiles per row, (W & ~7) >> 3
+__device__ __forceinline__ void tile_slot_to_xy(uint32_t j, uint32_t W, uint32_t H, const FastDiv& by_tpr, uint32_t& x, uint32_t& y) {
     const uint32_t W8 = W & ~7u, H4 = H & ~3u;
     const uint32_t n_tiled = W8 * H4;
     if (j < n_tiled) {
         const uint32_t tile = j >> 5, within = j & 31u;
-        const uint32_t tiles_per_row = W8 >> 3;
-        const uint32_t tx = tile % tiles_per_row, ty = tile / tiles_per_row;
-        return (ty * 4 + (within >> 3)) * W + tx * 8 + (within & 7u);
+        const uint32_t ty = fast_div(tile, by_tpr), tx = tile - ty * by_tpr.d;
+        x = tx * 8 + (within & 7u);
+        y = ty * 4 + (within >> 3);
+        return;
     }
     uint32_t r = j - n_tiled;
     const uint32_t RW = W - W8;
-    if (r < RW * H4) return (r / RW) * W + W8 + r % RW;
+    if (r < RW * H4) {
+        y = r / RW;
+        x = W8 + r % RW;
+        return;
+    }
     r -= RW * H4;
-    return (H4 + r / W) * W + r % W;
+    y = H4 + r / W;
+    x = r % W;
+}
+__device__ __forceinline__ uint32_t tile_slot_to_pixel(uint32_t j, uint32_t W, uint32_t H, const FastDiv& by_tpr) {
+    uint32_t x, y;
+    tile_slot_to_xy(j, W, H, by_tpr, x, y);
+    return y * W + x;
+}
+// once per pixel (k_accumulate, gate kernels): the plain division
+__device__ __forceinline__ uint32_t tile_slot_to_pixel(uint32_t j, uint32_t W, uint32_t H) {
+    uint32_t x, y;
+    tile_slot_to_xy(j, W, H, FastDiv{(W & ~7u) >> 3, 0u, 0u}, x, y);
+    return y * W + x;
 }
 __device__ __forceinline__ uint32_t tile_pixel_to_slot(uint32_t pixel, uint32_t W, uint32_t H) {
     const uint32_t W8 = W & ~7u, H4 = H & ~3u;
@@ -108,44 +136,72 @@ __device__ __forceinline__ void slot_source(const PathSource& src, uint32_t slot
         pixel = src.pixel[slot];
         sample = src.sample[slot];
     } else {
-        pixel = tile_slot_to_pixel(slot % src.n_pixels, src.width, src.height);
-        sample = src.sample_base + slot / src.n_pixels;
+        const uint32_t s = fast_div(slot, src.by_pixels);
+        pixel = tile_slot_to_pixel(slot - s * src.n_pixels, src.width, src.height, src.by_tiles_per_row);
+        sample = src.sample_base + s;
     }
 }
 
-__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp,
-                                                uint32_t n_paths) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[0] = n_paths;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
-        uint32_t pixel, sample;
-        slot_source(src, slot, pixel, sample);
-        const uint32_t W = fp.width, H = fp.height;
-        const uint32_t px = pixel % W;
-        const uint32_t py = fp.pixel_mapping == 1 ? pixel / H : pixel / W;
-        const float dd = (float)(W > H ? W : H);
-        const float x = ((float)(2u * px + 1u) - (float)W) / dd;
-        const float y = ((float)(2u * (H - py) - 1u) - (float)H) / dd;
-        Rng rng(fp.seed, pixel, sample, 0);
-        const float dx = rng.gen_range(-1.0f / dd, 1.0f / dd);
-        const float dy = rng.gen_range(-1.0f / dd, 1.0f / dd);
-        const float cx = x + dx, cy = y + dy;
+// One camera sample: render/iterative.rs:25-33 + core/camera.rs:58-82. (x, y) = the pixel centre on the film, dd = the
+// longer image side, jitter = 1 / dd.
+__device__ __forceinline__ void raygen_sample(const DeviceScene& sc, const Wavefront& wf, const FrameParams& fp, uint32_t slot,
+                                              uint32_t pixel, uint32_t sample, float x, float y, float jitter) {
+    Rng rng(fp.seed, pixel, sample, 0);
+    const float dx = rng.gen_range(-jitter, jitter);
+    const float dy = rng.gen_range(-jitter, jitter);
+    const float cx = x + dx, cy = y + dy;
 
-        const CameraRec& cam = sc.camera;
-        const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
-        const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
-        f3 origin = mk3(cam.origin[0], cam.origin[1], cam.origin[2]);
-        f3 new_dir = cam.d * mk3(cam.direction[0], cam.direction[1], cam.direction[2]) + cx * right + cy * up;
-        if (cam.has_dof) {
-            const f3 focal_point = origin + normalize(new_dir) * cam.focal_length;
-            const f2 s = rng.unit_disc();
-            origin = origin + (s.x * right + s.y * up) * cam.aperture;
-            new_dir = focal_point - origin;
+    const CameraRec& cam = sc.camera;
+    const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
+    const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
+    f3 origin = mk3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    f3 new_dir = cam.d * mk3(cam.direction[0], cam.direction[1], cam.direction[2]) + cx * right + cy * up;
+    if (cam.has_dof) {
+        const f3 focal_point = origin + normalize(new_dir) * cam.focal_length;
+        const f2 s = rng.unit_disc();
+        origin = origin + (s.x * right + s.y * up) * cam.aperture;
+        new_dir = focal_point - origin;
+    }
+    const f3 dir = normalize(normalize(new_dir));  // camera.rs:81 then Ray::new, util/ray.rs:15
+    st_stream(&wf.ray_o[0][slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n)));
+    st_stream(&wf.ray_d[0][slot], make_float4(dir.x, dir.y, dir.z, 0.0f));
+    // every path writes its radiance exactly once, when it ends; with no bounce at all nothing does
+    if (fp.max_bounces == 0u) wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+__device__ __forceinline__ void film_point(const FrameParams& fp, uint32_t px, uint32_t py, float dd, float& x, float& y) {
+    x = ((float)(2u * px + 1u) - (float)fp.width) / dd;
+    y = ((float)(2u * (fp.height - py) - 1u) - (float)fp.height) / dd;
+}
+
+// Implicit source: a thread owns one pixel (slot-in-sample j, 8x4 tiles) and every `groups`-th sample of the batch, so
+// the tile decode, the film point and their divisions are paid once per thread, not once per ray (the per-ray kernel
+// was 12 % of config 1's step at 2.6x its own store bandwidth bound). Consecutive threads write consecutive slots.
+__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp,
+                                                uint32_t n_paths, uint32_t groups) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[0] = n_paths;
+    const uint32_t W = fp.width, H = fp.height;
+    const float dd = (float)(W > H ? W : H);
+    const float jitter = 1.0f / dd;
+    if (src.pixel) {  // explicit (pixel, sample) lists: one ray per thread
+        for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+            const uint32_t pixel = src.pixel[slot], sample = src.sample[slot];
+            float x, y;
+            film_point(fp, pixel % W, fp.pixel_mapping == 1 ? pixel / H : pixel / W, dd, x, y);
+            raygen_sample(sc, wf, fp, slot, pixel, sample, x, y, jitter);
         }
-        const f3 dir = normalize(normalize(new_dir));  // camera.rs:81 then Ray::new, util/ray.rs:15
-        wf.ray_o[0][slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n));
-        wf.ray_d[0][slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-        // every path writes its radiance exactly once, when it ends in k_shade; with no bounce at all nothing does
-        if (fp.max_bounces == 0u) wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    const uint32_t n_pixels = src.n_pixels, samples = n_paths / n_pixels;
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_pixels * groups; id += gridDim.x * blockDim.x) {
+        const uint32_t g = fast_div(id, src.by_pixels), j = id - g * n_pixels;
+        uint32_t px, py;
+        tile_slot_to_xy(j, W, H, src.by_tiles_per_row, px, py);
+        const uint32_t pixel = py * W + px;
+        if (fp.pixel_mapping == 1) py = pixel / H;  // PixelMapping::Stretch quirk of the reference (iterative.rs:26)
+        float x, y;
+        film_point(fp, px, py, dd, x, y);
+        for (uint32_t s = g; s < samples; s += groups)
+            raygen_sample(sc, wf, fp, s * n_pixels + j, pixel, src.sample_base + s, x, y, jitter);
     }
 }
 
@@ -167,7 +223,7 @@ static constexpr int REFILL_THRESHOLD = 12;
 // 1 / LEAF_VOTE_NUM of the lanes at inner nodes; one vote buys NODE_STEPS node steps or LEAF_STEPS triangle tests.
 static constexpr int LEAF_VOTE_NUM = 2, NODE_STEPS = 4, LEAF_STEPS = 2;
 
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth) {
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, Wavefront wf, uint32_t depth, int refill_below) {
     __shared__ int s_stack[(SMEM_STACK + 1) * TRACE_THREADS];  // + the rays' scene-level visibility words
     const uint32_t n = wf.counts[depth];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(wf.segments, (unsigned long long)n);
@@ -199,8 +255,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
                     const uint32_t i = base + (uint32_t)__popc(need & lt_mask);
                     if (i < n) {
                         slot = i;  // queue order: the lanes that refill together read consecutive rays
-                        const float4 ro = ray_o[i];
-                        const float4 rd = ray_d[i];
+                        const float4 ro = ld_stream(ray_o + i);
+                        const float4 rd = ld_stream(ray_d + i);
                         trav_begin(tr, sc, xyz(ro), xyz(rd), sstack, TRACE_THREADS);
                         have = true;
                     }
@@ -212,7 +268,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
         while (true) {
             if (have && tr.cur == SENTINEL) {
                 const HitResult h = trav_finish(tr, sc, sstack, TRACE_THREADS);
-                wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
+                st_stream(&wf.hit[slot], make_float4(h.t, __int_as_float(h.prim), h.u, h.v));
                 have = false;
             }
             const bool at_node = have && is_inner(tr.cur);
@@ -220,7 +276,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
             const unsigned m_node = __ballot_sync(0xFFFFFFFFu, at_node);
             const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, at_leaf);
             const int live = __popc(m_node | m_leaf);
-            if (live == 0 || (!exhausted && live < REFILL_THRESHOLD)) break;
+            if (live == 0 || (!exhausted && live < refill_below)) break;
             const int n_node = __popc(m_node), n_leaf = __popc(m_leaf);
             // Vote: the leaf step runs once the lanes waiting at a leaf exceed 1/LEAF_VOTE_NUM of the lanes at
             // inner nodes; otherwise every lane that is (still) at an inner node takes NODE_STEPS node steps on
@@ -436,7 +492,7 @@ __device__ __forceinline__ f3 clamp_color(f3 c, float mx) { return mk3(fminf(c.x
 // L_level = value; fold levels level-1 .. 0
 __device__ __forceinline__ f3 unwind(const Wavefront& wf, uint32_t slot, uint32_t level, f3 value, float clampv) {
     for (uint32_t d = level; d-- > 0;) {
-        const f3 att = xyz(wf.att[(size_t)d * wf.capacity + slot]);
+        const f3 att = xyz(ld_stream(&wf.att[(size_t)d * wf.capacity + slot]));
         value = mk3(0.0f, 0.0f, 0.0f) + clamp_color(mul_elem(att, value), clampv);
     }
     return value;
@@ -444,26 +500,27 @@ __device__ __forceinline__ f3 unwind(const Wavefront& wf, uint32_t slot, uint32_
 
 // FAST = integrator 1 compiled in, MICROFACET = the scene has a MicrofacetBSDF material; the common
 // kernel (parity integrator, simple materials) carries neither code path.
-// One path at one depth: its ray (ro, rd: queue-order records) and closest hit hr. Either the path ends here — its
-// radiance is unwound and written, returns false — or it scatters: the level's attenuation is parked in wf.att, the
-// next ray is returned in next_o / next_d, returns true.
+// A miss: tracer.rs:30-33 returns the environment sample unclamped at this level; the path ends.
+__device__ __forceinline__ void shade_miss(const DeviceScene& sc, const Wavefront& wf, float firefly_clamp, uint32_t depth,
+                                           uint32_t slot, f3 d) {
+    const f3 env = environment_sample(sc, d);
+    const f3 L = unwind(wf, slot, depth, env, firefly_clamp);
+    st_stream(&wf.radiance[slot], make_float4(L.x, L.y, L.z, 0.0f));
+}
+// One path at one depth that hit something: its ray (ro, rd: queue-order records) and closest hit hr. Either the path
+// ends here — its radiance is unwound and written, returns false — or it scatters: the level's attenuation is parked in
+// wf.att, the next ray is returned in next_o / next_d, returns true.
 template <bool FAST, bool MICROFACET>
-__device__ __forceinline__ bool shade_path(const DeviceScene& sc, const Wavefront& wf, const PathSource& src,
-                                           const FrameParams& fp, uint32_t depth, uint32_t slot, float4 ro, float4 rd, float4 hr,
-                                           float4& next_o, float4& next_d) {
+__device__ __forceinline__ bool shade_hit(const DeviceScene& sc, const Wavefront& wf, const PathSource& src,
+                                          const FrameParams& fp, uint32_t depth, uint32_t slot, float4 ro, float4 rd, float4 hr,
+                                          float4& next_o, float4& next_d) {
     const float4* __restrict__ tri_shade = (const float4*)sc.tri_shade;
     bool alive = false;
     {
         {
             const f3 o = xyz(ro), d = xyz(rd);
             const int prim = __float_as_int(hr.y);
-
-            if (prim < 0) {
-                // tracer.rs:30-33: a miss returns the environment sample unclamped at this level
-                const f3 env = environment_sample(sc, d);
-                const f3 L = unwind(wf, slot, depth, env, fp.firefly_clamp);
-                wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
-            } else {
+            {
                 const float t = hr.x;
                 const f3 point = o + d * t;  // Ray::at, util/ray.rs:19-21
                 f3 outward;
@@ -610,15 +667,15 @@ __device__ __forceinline__ bool shade_path(const DeviceScene& sc, const Wavefron
                     // tracer.rs:44-50 with no scattered ray: delta = attenuation
                     const f3 Lk = mk3(0.0f, 0.0f, 0.0f) + clamp_color(attenuation, fp.firefly_clamp);
                     const f3 L = unwind(wf, slot, depth, Lk, fp.firefly_clamp);
-                    wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+                    st_stream(&wf.radiance[slot], make_float4(L.x, L.y, L.z, 0.0f));
                 } else if (killed || depth + 1 >= fp.max_bounces) {
                     // the scattered ray would be traced at depth == max_bounces and return BLACK (tracer.rs:28)
                     const f3 Lk = mk3(0.0f, 0.0f, 0.0f) +
                                   clamp_color(mul_elem(attenuation, mk3(0.0f, 0.0f, 0.0f)), fp.firefly_clamp);
                     const f3 L = unwind(wf, slot, depth, Lk, fp.firefly_clamp);
-                    wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+                    st_stream(&wf.radiance[slot], make_float4(L.x, L.y, L.z, 0.0f));
                 } else {
-                    wf.att[(size_t)depth * wf.capacity + slot] = make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f);
+                    st_stream(&wf.att[(size_t)depth * wf.capacity + slot], make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f));
                     next_o = make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng.n));
                     next_d = make_float4(new_d.x, new_d.y, new_d.z, 0.0f);
                     alive = true;
@@ -629,42 +686,149 @@ __device__ __forceinline__ bool shade_path(const DeviceScene& sc, const Wavefron
     return alive;
 }
 
+// Shading kernel. After the first bounce a warp's 32 queue entries are a mix of misses (environment lookup + unwind)
+// and hits (triangle record, material, textures, scatter) — measured 27 miss / 5 hit lanes per instruction on config 1,
+// 14 of 32 lanes overall (profiles/r2_trace_inst.md) — so the two are separated:
+//  * a miss of depth >= 1 only appends {direction, slot, depth} to the batch's miss list; k_miss shades the whole list
+//    after the last depth with every lane on the same code and, the list being in depth order, the same unwind length;
+//  * hits are compacted per warp: a warp scans SHADE_SPAN consecutive 32-entry chunks at a time (all their loads in
+//    flight together, one miss-list atomic per span), parks the indices of the hits in a ring in shared memory and runs
+//    the material code on full groups of 32 (the rays and hit records it re-reads were touched a moment ago: L1 / L2).
+// Depth 0 runs k_shade_first instead.
+#ifndef VR_SHADE_SPAN
+#define VR_SHADE_SPAN 4
+#endif
+static constexpr int SHADE_SPAN = VR_SHADE_SPAN;   // chunks a warp scans at a time
+static constexpr uint32_t SHADE_RING = VR_SHADE_SPAN > 4 ? 512 : 256;  // >= 31 + 32 * SHADE_SPAN, power of two
+static constexpr uint32_t MISS_SLOT_BITS = 26;  // miss record: slot | depth << 26 (capacity < 2^26, max_bounces <= 64)
+
 template <bool FAST, bool MICROFACET>
-__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, Wavefront wf, PathSource src,
+__device__ __forceinline__ void shade_group(const DeviceScene& sc, const Wavefront& wf, const PathSource& src,
+                                            const FrameParams& fp, uint32_t depth, const uint32_t* __restrict__ queue,
+                                            uint32_t* __restrict__ queue_out, bool active, uint32_t i, uint32_t lane) {
+    bool alive = false;
+    uint32_t slot = 0;
+    float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;  // the scattered ray of a surviving path
+    if (active) {
+        slot = queue ? ld_stream(queue + i) : i;
+        const float4 ro = ld_stream((depth & 1u ? wf.ray_o[1] : wf.ray_o[0]) + i);
+        const float4 rd = ld_stream((depth & 1u ? wf.ray_d[1] : wf.ray_d[0]) + i);
+        const float4 hr = ld_stream(wf.hit + i);
+        if (__float_as_int(hr.y) < 0) shade_miss(sc, wf, fp.firefly_clamp, depth, slot, xyz(rd));  // depth 0 only
+        else alive = shade_hit<FAST, MICROFACET>(sc, wf, src, fp, depth, slot, ro, rd, hr, next_o, next_d);
+    }
+    // warp-aggregated compaction: one atomic per warp
+    __syncwarp();
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, alive);
+    if (ballot) {
+        uint32_t warp_base = 0;
+        const int leader = __ffs(ballot) - 1;
+        if ((int)lane == leader) warp_base = atomicAdd(&wf.counts[depth + 1], (uint32_t)__popc(ballot));
+        warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, leader);
+        if (alive) {
+            // the next depth's ray goes to the path's place in the next queue (coalesced within the warp)
+            const uint32_t j = warp_base + __popc(ballot & ((1u << lane) - 1u));
+            st_stream(queue_out + j, slot);
+            st_stream((depth & 1u ? wf.ray_o[0] : wf.ray_o[1]) + j, next_o);
+            st_stream((depth & 1u ? wf.ray_d[0] : wf.ray_d[1]) + j, next_d);
+        }
+    }
+}
+
+// Depth 0: primary rays are coherent (hits and misses come in screen tiles) and a miss has nothing to unwind, so the
+// first depth keeps the plain shape: one queue entry per thread, misses shaded in place.
+template <bool FAST, bool MICROFACET>
+__global__ void __launch_bounds__(SHADE_THREADS) k_shade_first(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp) {
+    const uint32_t n = wf.counts[0];
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        shade_group<FAST, MICROFACET>(sc, wf, src, fp, 0u, nullptr, wf.queue[1], i < n, i, lane);
+    }
+}
+
+template <bool FAST, bool MICROFACET>
+__global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, Wavefront wf, PathSource src,
                                                          FrameParams fp, uint32_t depth) {
+    __shared__ uint32_t s_pending[SHADE_THREADS / 32][SHADE_RING];
     const uint32_t n = wf.counts[depth];
     const uint32_t* __restrict__ queue = depth == 0 ? nullptr : (depth & 1u ? wf.queue[1] : wf.queue[0]);
     uint32_t* __restrict__ queue_out = depth & 1u ? wf.queue[0] : wf.queue[1];
+    const float4* __restrict__ ray_d = depth & 1u ? wf.ray_d[1] : wf.ray_d[0];
     const uint32_t lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t* pending = s_pending[threadIdx.x >> 5];
+    uint32_t head = 0, count = 0;  // warp-uniform: the ring holds `count` indices from `head` on
 
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        bool alive = false;
-        uint32_t slot = 0;
-        float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;  // the scattered ray of a surviving path
-        if (i < n) {
-            slot = queue ? queue[i] : i;
-            const float4 ro = (depth & 1u ? wf.ray_o[1] : wf.ray_o[0])[i];
-            const float4 rd = (depth & 1u ? wf.ray_d[1] : wf.ray_d[0])[i];
-            const float4 hr = wf.hit[i];
-            alive = shade_path<FAST, MICROFACET>(sc, wf, src, fp, depth, slot, ro, rd, hr, next_o, next_d);
-        }
-        // warp-aggregated compaction: one atomic per warp
-        __syncwarp();
-        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, alive);
-        if (ballot) {
-            uint32_t warp_base = 0;
-            const int leader = __ffs(ballot) - 1;
-            if ((int)lane == leader) warp_base = atomicAdd(&wf.counts[depth + 1], (uint32_t)__popc(ballot));
-            warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, leader);
-            if (alive) {
-                // the next depth's ray goes to the path's place in the next queue (coalesced within the warp)
-                const uint32_t j = warp_base + __popc(ballot & ((1u << lane) - 1u));
-                queue_out[j] = slot;
-                (depth & 1u ? wf.ray_o[0] : wf.ray_o[1])[j] = next_o;
-                (depth & 1u ? wf.ray_d[0] : wf.ray_d[1])[j] = next_d;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t n_chunks = (n + 31u) >> 5;
+    // the warp's spans: SHADE_SPAN consecutive chunks, then the span a whole grid further on
+    uint32_t chunk = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * SHADE_SPAN;
+    const uint32_t chunk_stride = gridDim.x * warps_per_block * SHADE_SPAN;
+    while (true) {
+        while (count < 32u && chunk < n_chunks) {
+            // every chunk's hit record of the span in flight at once
+            int prim[SHADE_SPAN];
+            unsigned miss_ballot[SHADE_SPAN];
+            uint32_t n_miss = 0;
+#pragma unroll
+            for (int c = 0; c < SHADE_SPAN; ++c) {
+                const uint32_t i = (chunk + c) * 32u + lane;
+                prim[c] = i < n ? __float_as_int(wf.hit[i].y) : 0x7FFFFFFF;  // 0x7FFFFFFF: past the end
             }
+#pragma unroll
+            for (int c = 0; c < SHADE_SPAN; ++c) {
+                const bool is_miss = prim[c] < 0;
+                const bool is_hit = prim[c] != 0x7FFFFFFF && !is_miss;
+                miss_ballot[c] = __ballot_sync(0xFFFFFFFFu, is_miss);
+                n_miss += (uint32_t)__popc(miss_ballot[c]);
+                const unsigned hit_ballot = __ballot_sync(0xFFFFFFFFu, is_hit);
+                if (is_hit) pending[(head + count + (uint32_t)__popc(hit_ballot & lt_mask)) & (SHADE_RING - 1u)] = (chunk + c) * 32u + lane;
+                count += (uint32_t)__popc(hit_ballot);
+            }
+            if (n_miss) {  // warp-uniform; one atomic for the span, the records in (chunk, lane) order
+                uint32_t base = 0;
+                if (lane == 0u) base = atomicAdd(wf.miss_count, n_miss);
+                float4 rd[SHADE_SPAN];
+                uint32_t sl[SHADE_SPAN];
+#pragma unroll
+                for (int c = 0; c < SHADE_SPAN; ++c) {
+                    if ((miss_ballot[c] >> lane) & 1u) {
+                        const uint32_t i = (chunk + c) * 32u + lane;
+                        rd[c] = ld_stream(ray_d + i);
+                        sl[c] = ld_stream(queue + i);
+                    }
+                }
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+                for (int c = 0; c < SHADE_SPAN; ++c) {
+                    if ((miss_ballot[c] >> lane) & 1u)
+                        st_stream(&wf.miss[base + (uint32_t)__popc(miss_ballot[c] & lt_mask)],
+                                  make_float4(rd[c].x, rd[c].y, rd[c].z, __uint_as_float(sl[c] | (depth << MISS_SLOT_BITS))));
+                    base += (uint32_t)__popc(miss_ballot[c]);
+                }
+            }
+            chunk += chunk_stride;
         }
+        if (count == 0u) break;  // the queue is exhausted and nothing is parked
+        __syncwarp();
+        const uint32_t take = count < 32u ? count : 32u;  // a partial group only at the very end
+        const bool active = lane < take;
+        const uint32_t idx = active ? pending[(head + lane) & (SHADE_RING - 1u)] : 0u;
+        __syncwarp();
+        shade_group<FAST, MICROFACET>(sc, wf, src, fp, depth, queue, queue_out, active, idx, lane);
+        head = (head + take) & (SHADE_RING - 1u);
+        count -= take;
+    }
+}
+
+// The batch's misses of depth >= 1, in one launch after the last depth (see k_shade).
+__global__ void __launch_bounds__(256) k_miss(DeviceScene sc, Wavefront wf, float firefly_clamp) {
+    const uint32_t n = *wf.miss_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 rec = ld_stream(wf.miss + i);
+        const uint32_t w = __float_as_uint(rec.w);
+        shade_miss(sc, wf, firefly_clamp, w >> MISS_SLOT_BITS, w & ((1u << MISS_SLOT_BITS) - 1u), xyz(rec));
     }
 }
 
@@ -680,7 +844,7 @@ __global__ void __launch_bounds__(256) k_accumulate(Wavefront wf, float4* partia
         const uint32_t px = tile_slot_to_pixel(j, width, height);
         float4 p = partial[px];
         for (uint32_t s = 0; s < samples_in_batch; ++s) {
-            const float4 L = wf.radiance[(size_t)s * n_pixels + j];
+            const float4 L = ld_stream(&wf.radiance[(size_t)s * n_pixels + j]);
             p.x += L.x;
             p.y += L.y;
             p.z += L.z;
@@ -865,8 +1029,20 @@ void query_launch_dims(LaunchDims* dims) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_blocks_per_sm, k_shade<false, false>, SHADE_THREADS, 0);
     if (dims->trace_blocks_per_sm < 1) dims->trace_blocks_per_sm = 1;
     if (dims->shade_blocks_per_sm < 1) dims->shade_blocks_per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_first_blocks_per_sm, k_shade_first<false, false>, SHADE_THREADS, 0);
+    if (dims->shade_first_blocks_per_sm < 1) dims->shade_first_blocks_per_sm = 1;
 }
 
+static int env_int(const char* name, int index, int fallback) {  // "a,b,c" -> the index-th integer
+    const char* v = std::getenv(name);
+    if (!v) return fallback;
+    for (int i = 0; i < index; ++i) {
+        v = std::strchr(v, ',');
+        if (!v) return fallback;
+        ++v;
+    }
+    return std::atoi(v);
+}
 static inline uint32_t grid_for(uint64_t n, int threads, int sm_count, int blocks_per_sm) {
     const uint64_t need = (n + threads - 1) / threads;
     const uint64_t cap = (uint64_t)sm_count * blocks_per_sm;
@@ -876,20 +1052,45 @@ static inline uint32_t grid_for(uint64_t n, int threads, int sm_count, int block
 
 void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                    uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream) {
-    k_raygen<<<grid_for(n_paths, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, src, fp, n_paths);
+    // enough threads for ~4 blocks of 256 per SM, at most one per ray
+    uint32_t groups = 1;
+    if (!src.pixel) {
+        const uint32_t samples = n_paths / src.n_pixels;
+        const uint64_t want = (uint64_t)ld.sm_count * 8 * 256;
+        groups = (uint32_t)((want + src.n_pixels - 1) / src.n_pixels);
+        groups = groups < 1 ? 1 : (groups > samples ? samples : groups);
+        if (groups < 1) groups = 1;
+    }
+    const uint64_t threads = src.pixel ? n_paths : (uint64_t)src.n_pixels * groups;
+    k_raygen<<<grid_for(threads, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, src, fp, n_paths, groups);
 }
 void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, const LaunchDims& ld,
                   cudaStream_t stream) {
-    k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(sc, wf, depth);
+    // experiment knob (scripts only): VOIDRAY_REFILL="<depth 0>,<deeper>" overrides the refill threshold
+    static const int refill[2] = {env_int("VOIDRAY_REFILL", 0, REFILL_THRESHOLD), env_int("VOIDRAY_REFILL", 1, REFILL_THRESHOLD)};
+    k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(
+        sc, wf, depth, refill[depth ? 1 : 0]);
 }
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {
-    const uint32_t grid = grid_for(n_upper, SHADE_THREADS, ld.sm_count, ld.shade_blocks_per_sm);
     const bool fast = fp.integrator == 1, mf = sc.has_microfacet != 0;
+    if (depth == 0) {
+        const uint32_t grid = grid_for(n_upper, SHADE_THREADS, ld.sm_count, ld.shade_first_blocks_per_sm);
+        if (fast && mf) k_shade_first<true, true><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp);
+        else if (fast) k_shade_first<true, false><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp);
+        else if (mf) k_shade_first<false, true><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp);
+        else k_shade_first<false, false><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp);
+        return;
+    }
+    const uint32_t grid = grid_for(n_upper, SHADE_THREADS, ld.sm_count, ld.shade_blocks_per_sm);
     if (fast && mf) k_shade<true, true><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
     else if (fast) k_shade<true, false><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
     else if (mf) k_shade<false, true><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
     else k_shade<false, false><<<grid, SHADE_THREADS, 0, stream>>>(sc, wf, src, fp, depth);
+}
+void launch_miss(const DeviceScene& sc, const Wavefront& wf, const FrameParams& fp, uint32_t n_upper, const LaunchDims& ld,
+                 cudaStream_t stream) {
+    k_miss<<<grid_for(n_upper, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, fp.firefly_clamp);
 }
 void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t width, uint32_t height,
                        uint32_t samples_in_batch, int finish, float inv_total_samples, float alpha_inc, cudaStream_t stream) {

@@ -20,14 +20,33 @@ struct Wavefront {
     float4* ray_o[2];  // origin.xyz, draws consumed so far (uint bits); ping-pong by depth parity
     float4* ray_d[2];  // direction.xyz (unit), unused
     float4* hit;     // t, GPU primitive index (int bits, -1 miss), u, v — queue order of the depth being traced
-    float4* att;     // [max_bounces][capacity] attenuation of every level (rgb, unused), by slot
+    float4* att;     // [max_bounces][capacity] attenuation of every level (rgb, unused), by slot (level-major: the
+                     // writes of depth 0, where slot == queue index, coalesce; slot-major measured +40 % DRAM traffic)
     float4* radiance;  // [capacity] finished radiance of the slot's camera sample
     uint32_t* queue[2];  // compacted slot lists, ping-pong by depth parity
-    uint32_t* counts;    // [max_bounces + 1] queue lengths
-    uint32_t* cursors;   // [max_bounces + 1] next unclaimed queue entry (dynamic ray fetch)
+    uint32_t* counts;    // [max_bounces + 2] queue lengths
+    uint32_t* cursors;   // [max_bounces + 2] next unclaimed queue entry (dynamic ray fetch); then miss_count
     unsigned long long* segments;  // scene.hit calls, whole render
-    uint32_t capacity;
+    float4* miss;          // [capacity] misses of depth >= 1 waiting for k_miss: direction.xyz, slot | depth << 26
+    uint32_t* miss_count;  // entries in `miss`, zeroed with the counts
+    uint32_t capacity;     // < 2^26
 };
+
+// Division by a launch-invariant divisor without the ~25-instruction software divide: q = umulhi(x, m) >> s, exact for
+// every x < 2^31 (m = floor(2^(31 + L) / d) + 1, L = ceil(log2 d), s = L - 1; d == 1 passes x through).
+// tests/c/fastdiv_check.cpp sweeps it against the plain division.
+struct FastDiv {
+    uint32_t d, m, s;
+};
+inline FastDiv make_fast_div(uint32_t d) {
+    FastDiv f{d, 0u, 0u};
+    if (d <= 1u) return f;
+    uint32_t L = 0;
+    while ((1ull << L) < d) ++L;
+    f.m = (uint32_t)((1ull << (31u + L)) / d) + 1u;
+    f.s = L - 1u;
+    return f;
+}
 
 // slot -> (pixel, global sample): implicit (slot % n_pixels, sample_base + slot / n_pixels) or explicit lists
 struct PathSource {
@@ -36,7 +55,21 @@ struct PathSource {
     uint32_t n_pixels;
     uint32_t sample_base;
     uint32_t width, height;  // implicit mode enumerates pixels in 8x4 tiles
+    FastDiv by_pixels, by_tiles_per_row;
 };
+inline PathSource make_path_source(const uint32_t* pixel, const uint32_t* sample, uint32_t width, uint32_t height,
+                                   uint32_t sample_base) {
+    PathSource src{};
+    src.pixel = pixel;
+    src.sample = sample;
+    src.n_pixels = width * height;
+    src.sample_base = sample_base;
+    src.width = width;
+    src.height = height;
+    src.by_pixels = make_fast_div(src.n_pixels);
+    src.by_tiles_per_row = make_fast_div((width & ~7u) >> 3);
+    return src;
+}
 
 struct FrameParams {
     uint32_t width, height;
@@ -52,6 +85,7 @@ struct LaunchDims {
     int sm_count;
     int trace_blocks_per_sm;
     int shade_blocks_per_sm;
+    int shade_first_blocks_per_sm;
 };
 void query_launch_dims(LaunchDims* dims);
 
@@ -61,6 +95,9 @@ void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, ui
                   const LaunchDims& ld, cudaStream_t stream);
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream);
+// after the last depth: the environment lookups + unwinds that k_shade parked in wf.miss
+void launch_miss(const DeviceScene& sc, const Wavefront& wf, const FrameParams& fp, uint32_t n_upper, const LaunchDims& ld,
+                 cudaStream_t stream);
 // partial[pixel] += sum over the batch's samples (in sample order); when `finish`, fold
 // partial * (1/total_samples) into accum (alpha += alpha_inc: 1 per iterative_render call) and clear partial.
 void launch_accumulate(const Wavefront& wf, float4* partial, float4* accum, uint32_t width, uint32_t height,
