@@ -2,6 +2,7 @@
 // progressive wavefront driver behind vr_render_accumulate, resolve, and the gate entry points.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -126,6 +127,13 @@ struct vr_render {
     float4* partial = nullptr;
     float4* resolved = nullptr;
     Wavefront wf;
+    // Second wavefront on a stream of its own: consecutive batches alternate between the two, so that the sparse deep
+    // levels and the ramp-down of every kernel of one batch (a persistent grid ends with a few long rays on an almost
+    // empty GPU) are filled by the other batch's kernels. Accumulation stays in batch order (ev_acc).
+    Wavefront wf_b;
+    cudaStream_t stream_b = nullptr;
+    cudaEvent_t ev_acc[2] = {nullptr, nullptr};
+    bool dual = false;
     uint32_t samples_per_batch = 1;
     uint32_t samples_done = 0;
     std::atomic<int> cancel{0};
@@ -167,12 +175,13 @@ FrameParams frame_params(const vr_render* r) {
 }
 
 // One wavefront batch: ray generation, then per depth closest-hit + shade/compact. No host sync.
-void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool time_trace, size_t* event_cursor) {
+void run_wavefront(vr_render* r, const Wavefront& wf, cudaStream_t stream, const PathSource& src, uint32_t n_paths,
+                   bool time_trace, size_t* event_cursor) {
     vr_scene* sc = r->scene;
     vr_context* ctx = sc->ctx;
     const FrameParams fp = frame_params(r);
-    cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * (2 * (fp.max_bounces + 2) + 1), ctx->stream);  // counts + cursors + miss_count
-    launch_raygen(sc->dev, r->wf, src, fp, n_paths, ctx->dims, ctx->stream);
+    cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (2 * (fp.max_bounces + 2) + 1), stream);  // counts + cursors + miss_count
+    launch_raygen(sc->dev, wf, src, fp, n_paths, ctx->dims, stream);
     r->kernel_launches += 1;
     for (uint32_t depth = 0; depth < fp.max_bounces; ++depth) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -185,15 +194,15 @@ void run_wavefront(vr_render* r, const PathSource& src, uint32_t n_paths, bool t
             e0 = r->events[(*event_cursor)++];
             e1 = r->events[(*event_cursor)++];
         }
-        if (time_trace) cudaEventRecord(e0, ctx->stream);
-        launch_trace(sc->dev, r->wf, depth, n_paths, ctx->dims, ctx->stream);
-        if (time_trace) cudaEventRecord(e1, ctx->stream);
-        launch_shade(sc->dev, r->wf, src, fp, depth, n_paths, ctx->dims, ctx->stream);
+        if (time_trace) cudaEventRecord(e0, stream);
+        launch_trace(sc->dev, wf, depth, n_paths, ctx->dims, stream);
+        if (time_trace) cudaEventRecord(e1, stream);
+        launch_shade(sc->dev, wf, src, fp, depth, n_paths, ctx->dims, stream);
         r->kernel_launches += 2;
         r->trace_launches += 1;
     }
     if (fp.max_bounces > 1) {  // the misses of depth >= 1 that k_shade parked
-        launch_miss(sc->dev, r->wf, fp, n_paths, ctx->dims, ctx->stream);
+        launch_miss(sc->dev, wf, fp, n_paths, ctx->dims, stream);
         r->kernel_launches += 1;
     }
 }
@@ -880,9 +889,18 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     r->settings = *settings;
 
     // Paths in flight per wavefront batch. More is better for the deep, sparse depths (measured: +27 % on
-    // config 1, +7 % on config 2 going from 8 Mi to 32 Mi); 32 Mi slots are 6.7 GB of the 180 GB of HBM at 8 bounces.
+    // config 1, +7 % on config 2 going from 8 Mi to 32 Mi); 32 Mi slots are 7.8 GB of the 180 GB of HBM at 8 bounces.
+    // Two wavefronts (see vr_render::wf_b) share max_paths_in_flight when the caller sets it; VOIDRAY_STREAMS=1
+    // (experiment knob) keeps a single one.
+    const char* streams_env = std::getenv("VOIDRAY_STREAMS");
+    bool dual = !(streams_env && std::atoi(streams_env) == 1) && settings->total_samples >= 2;
     uint64_t capacity = settings->max_paths_in_flight ? settings->max_paths_in_flight : (32ull << 20);
-    capacity = std::min<uint64_t>(capacity, (uint64_t)r->n_pixels * settings->total_samples);
+    if (dual && settings->max_paths_in_flight) {
+        if (capacity / 2 >= r->n_pixels) capacity /= 2;
+        else dual = false;
+    }
+    const uint64_t samples_each = dual ? (settings->total_samples + 1) / 2 : settings->total_samples;
+    capacity = std::min<uint64_t>(capacity, (uint64_t)r->n_pixels * samples_each);
     if (capacity < r->n_pixels) capacity = r->n_pixels;
     r->samples_per_batch = (uint32_t)(capacity / r->n_pixels);
     capacity = (uint64_t)r->samples_per_batch * r->n_pixels;
@@ -890,8 +908,7 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
         delete r;
         return fail(VR_ERR_INVALID, "max_paths_in_flight too large");
     }
-    Wavefront& wf = r->wf;
-    wf.capacity = (uint32_t)capacity;
+    r->dual = dual;
     const size_t cap = capacity;
     const uint32_t levels = settings->max_bounces ? settings->max_bounces : 1;
     cudaError_t e = cudaSuccess;
@@ -901,23 +918,36 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     A((void**)&r->accum, 16ull * r->n_pixels);
     A((void**)&r->partial, 16ull * r->n_pixels);
     A((void**)&r->resolved, 16ull * r->n_pixels);
-    A((void**)&wf.ray_o[0], 16 * cap);
-    A((void**)&wf.ray_o[1], 16 * cap);
-    A((void**)&wf.ray_d[0], 16 * cap);
-    A((void**)&wf.ray_d[1], 16 * cap);
-    A((void**)&wf.hit, 16 * cap);
-    A((void**)&wf.radiance, 16 * cap);
-    A((void**)&wf.att, 16 * cap * levels);
-    A((void**)&wf.queue[0], 4 * cap);
-    A((void**)&wf.queue[1], 4 * cap);
-    A((void**)&wf.miss, 16 * cap);
-    A((void**)&wf.counts, 4 * (2 * (settings->max_bounces + 2) + 1));
-    A((void**)&wf.segments, 8);
+    unsigned long long* segments = nullptr;
+    A((void**)&segments, 8);
+    auto alloc_wavefront = [&](Wavefront& w) {
+        w.capacity = (uint32_t)capacity;
+        A((void**)&w.ray_o[0], 16 * cap);
+        A((void**)&w.ray_o[1], 16 * cap);
+        A((void**)&w.ray_d[0], 16 * cap);
+        A((void**)&w.ray_d[1], 16 * cap);
+        A((void**)&w.hit, 16 * cap);
+        A((void**)&w.radiance, 16 * cap);
+        A((void**)&w.att, 16 * cap * levels);
+        A((void**)&w.queue[0], 4 * cap);
+        A((void**)&w.queue[1], 4 * cap);
+        A((void**)&w.miss, 16 * cap);
+        A((void**)&w.counts, 4 * (2 * (settings->max_bounces + 2) + 1));
+        w.segments = segments;  // one counter for the whole render
+        w.cursors = w.counts ? w.counts + (settings->max_bounces + 2) : nullptr;
+        w.miss_count = w.counts ? w.counts + 2 * (settings->max_bounces + 2) : nullptr;
+    };
+    Wavefront& wf = r->wf;
+    alloc_wavefront(wf);
+    if (dual) {
+        alloc_wavefront(r->wf_b);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream_b, cudaStreamNonBlocking);
+        for (cudaEvent_t& ev : r->ev_acc)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    }
     A((void**)&r->dbg_surface, 4ull * r->n_pixels);
     A((void**)&r->dbg_prim, 4ull * r->n_pixels);
     A((void**)&r->dbg_t, 4ull * r->n_pixels);
-    wf.cursors = wf.counts ? wf.counts + (settings->max_bounces + 2) : nullptr;
-    wf.miss_count = wf.counts ? wf.counts + 2 * (settings->max_bounces + 2) : nullptr;
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_end);
     cudaStream_t st = scene->ctx->stream;
@@ -927,6 +957,9 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         r->dev_mem.release();
+        if (r->stream_b) cudaStreamDestroy(r->stream_b);
+        for (cudaEvent_t ev : r->ev_acc)
+            if (ev) cudaEventDestroy(ev);
         delete r;
         return fail(e == cudaErrorMemoryAllocation ? VR_ERR_OOM : VR_ERR_CUDA,
                     std::string("vr_render_begin: ") + cudaGetErrorString(e));
@@ -982,6 +1015,12 @@ int32_t vr_render_end(vr_render* r) try {
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     if (r->ev_begin) cudaEventDestroy(r->ev_begin);
     if (r->ev_end) cudaEventDestroy(r->ev_end);
+    if (r->stream_b) {
+        cudaStreamSynchronize(r->stream_b);
+        cudaStreamDestroy(r->stream_b);
+    }
+    for (cudaEvent_t ev : r->ev_acc)
+        if (ev) cudaEventDestroy(ev);
     r->dev_mem.release();
     delete r;
     return VR_OK;
@@ -1022,22 +1061,34 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
     const auto t0 = std::chrono::steady_clock::now();
     const float inv_total = 1.0f / (float)r->settings.total_samples;  // iterative.rs:45
     VR_CUDA(cudaEventRecord(r->ev_begin, ctx->stream));
+    if (r->dual) VR_CUDA(cudaStreamWaitEvent(r->stream_b, r->ev_begin, 0));  // after whatever the caller queued before
     uint32_t done = 0;
     size_t event_cursor = 0;
     bool cancelled = false;
-    while (done < samples) {
+    // with two wavefronts a call of >= 2 samples is cut into at least two batches, so that there is something to overlap
+    const uint32_t per_batch = r->dual ? std::min(r->samples_per_batch, std::max(1u, (samples + 1) / 2)) : r->samples_per_batch;
+    int last = -1;  // the wavefront of the previous batch
+    for (uint32_t batch = 0; done < samples; ++batch) {
         if (r->cancel.load()) {
             cancelled = true;
             break;
         }
-        const uint32_t nb = std::min(samples - done, r->samples_per_batch);
+        const int w = r->dual ? (int)(batch & 1u) : 0;
+        const Wavefront& wf = w ? r->wf_b : r->wf;
+        cudaStream_t stream = w ? r->stream_b : ctx->stream;
+        const uint32_t nb = std::min(samples - done, per_batch);
         const PathSource src = make_path_source(nullptr, nullptr, r->width, r->height, first_sample + done);
-        run_wavefront(r, src, nb * r->n_pixels, true, &event_cursor);
+        run_wavefront(r, wf, stream, src, nb * r->n_pixels, true, &event_cursor);
         done += nb;
-        launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, nb, done == samples ? 1 : 0, inv_total, alpha_inc,
-                          ctx->stream);
+        // the per-pixel sums run in batch order whatever the streams do: bit-identical to a single wavefront
+        if (r->dual && last >= 0) VR_CUDA(cudaStreamWaitEvent(stream, r->ev_acc[last], 0));
+        launch_accumulate(wf, r->partial, r->accum, r->width, r->height, nb, done == samples ? 1 : 0, inv_total, alpha_inc,
+                          stream);
+        if (r->dual) VR_CUDA(cudaEventRecord(r->ev_acc[w], stream));
+        last = w;
         r->kernel_launches += 1;
     }
+    if (r->dual && last >= 0) VR_CUDA(cudaStreamWaitEvent(ctx->stream, r->ev_acc[last], 0));
     if (cancelled && done > 0) {
         launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, 0, 1, inv_total, alpha_inc, ctx->stream);
         r->kernel_launches += 1;
@@ -1047,11 +1098,29 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
     VR_CUDA(cudaGetLastError());
     float ms = 0.0f;
     VR_CUDA(cudaEventElapsedTime(&ms, r->ev_begin, r->ev_end));
+    // time during which a closest-hit kernel was running: the union of the launches' [start, end] intervals (with two
+    // wavefronts the launches of the two streams overlap each other and the other stream's shading)
     double trace_ms = 0.0;
-    for (size_t i = 0; i + 1 < event_cursor; i += 2) {
-        float t = 0.0f;
-        cudaEventElapsedTime(&t, r->events[i], r->events[i + 1]);
-        trace_ms += t;
+    {
+        std::vector<std::pair<float, float>> spans;
+        for (size_t i = 0; i + 1 < event_cursor; i += 2) {
+            float a = 0.0f, b = 0.0f;
+            cudaEventElapsedTime(&a, r->ev_begin, r->events[i]);
+            cudaEventElapsedTime(&b, r->ev_begin, r->events[i + 1]);
+            spans.emplace_back(a, b);
+        }
+        std::sort(spans.begin(), spans.end());
+        float lo = 0.0f, hi = -1.0f;
+        for (const auto& sp : spans) {
+            if (hi < lo || sp.first > hi) {
+                if (hi >= lo) trace_ms += hi - lo;
+                lo = sp.first;
+                hi = sp.second;
+            } else if (sp.second > hi) {
+                hi = sp.second;
+            }
+        }
+        if (hi >= lo) trace_ms += hi - lo;
     }
     unsigned long long seg = 0;
     VR_CUDA(cudaMemcpy(&seg, r->wf.segments, 8, cudaMemcpyDeviceToHost));
@@ -1394,7 +1463,7 @@ int32_t vr_debug_sample_radiance(vr_render* r, uint64_t n, const uint32_t* pixel
         if (e != cudaSuccess) break;
         const PathSource src = make_path_source(d_px, d_sm, r->width, r->height, 0);
         size_t cursor = 0;
-        run_wavefront(r, src, m, false, &cursor);
+        run_wavefront(r, r->wf, ctx->stream, src, m, false, &cursor);
         e = cudaMemcpyAsync(host.data(), r->wf.radiance, 16ull * m, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e == cudaSuccess) e = cudaGetLastError();

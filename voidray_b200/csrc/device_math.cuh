@@ -62,21 +62,6 @@ __device__ __forceinline__ float8 ldg8(const float4* p) {
     return r;
 }
 
-// Path state (rays, hits, queues, attenuation, radiance) streams through the L2 once per depth, ~1 GB a batch; with
-// -DVR_STREAM_HINTS those accesses carry the evict-first policy so that they do not push the scene's nodes, triangles
-// and textures out of the 126 MB L2.
-#if defined(VR_STREAM_HINTS) && !defined(VR_HOST_SHIM)
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
-__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
-__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
-#else
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return *p; }
-__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return *p; }
-__device__ __forceinline__ void st_stream(float4* p, float4 v) { *p = v; }
-__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { *p = v; }
-#endif
-
 #define VR_PI_F 3.14159265358979323846f
 
 // compiler-rt __powisf2 (what f32::powi lowers to), specialised for exponent 5: a * (a^2)^2

@@ -163,8 +163,8 @@ __device__ __forceinline__ void raygen_sample(const DeviceScene& sc, const Wavef
         new_dir = focal_point - origin;
     }
     const f3 dir = normalize(normalize(new_dir));  // camera.rs:81 then Ray::new, util/ray.rs:15
-    st_stream(&wf.ray_o[0][slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n)));
-    st_stream(&wf.ray_d[0][slot], make_float4(dir.x, dir.y, dir.z, 0.0f));
+    wf.ray_o[0][slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n));
+    wf.ray_d[0][slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
     // every path writes its radiance exactly once, when it ends; with no bounce at all nothing does
     if (fp.max_bounces == 0u) wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
                     const uint32_t i = base + (uint32_t)__popc(need & lt_mask);
                     if (i < n) {
                         slot = i;  // queue order: the lanes that refill together read consecutive rays
-                        const float4 ro = ld_stream(ray_o + i);
-                        const float4 rd = ld_stream(ray_d + i);
+                        const float4 ro = ray_o[i];
+                        const float4 rd = ray_d[i];
                         trav_begin(tr, sc, xyz(ro), xyz(rd), sstack, TRACE_THREADS);
                         have = true;
                     }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
         while (true) {
             if (have && tr.cur == SENTINEL) {
                 const HitResult h = trav_finish(tr, sc, sstack, TRACE_THREADS);
-                st_stream(&wf.hit[slot], make_float4(h.t, __int_as_float(h.prim), h.u, h.v));
+                wf.hit[slot] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
                 have = false;
             }
             const bool at_node = have && is_inner(tr.cur);
@@ -492,7 +492,7 @@ __device__ __forceinline__ f3 clamp_color(f3 c, float mx) { return mk3(fminf(c.x
 // L_level = value; fold levels level-1 .. 0
 __device__ __forceinline__ f3 unwind(const Wavefront& wf, uint32_t slot, uint32_t level, f3 value, float clampv) {
     for (uint32_t d = level; d-- > 0;) {
-        const f3 att = xyz(ld_stream(&wf.att[(size_t)d * wf.capacity + slot]));
+        const f3 att = xyz(wf.att[(size_t)d * wf.capacity + slot]);
         value = mk3(0.0f, 0.0f, 0.0f) + clamp_color(mul_elem(att, value), clampv);
     }
     return value;
@@ -505,7 +505,7 @@ __device__ __forceinline__ void shade_miss(const DeviceScene& sc, const Wavefron
                                            uint32_t slot, f3 d) {
     const f3 env = environment_sample(sc, d);
     const f3 L = unwind(wf, slot, depth, env, firefly_clamp);
-    st_stream(&wf.radiance[slot], make_float4(L.x, L.y, L.z, 0.0f));
+    wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
 }
 // One path at one depth that hit something: its ray (ro, rd: queue-order records) and closest hit hr. Either the path
 // ends here — its radiance is unwound and written, returns false — or it scatters: the level's attenuation is parked in
@@ -667,15 +667,15 @@ __device__ __forceinline__ bool shade_hit(const DeviceScene& sc, const Wavefront
                     // tracer.rs:44-50 with no scattered ray: delta = attenuation
                     const f3 Lk = mk3(0.0f, 0.0f, 0.0f) + clamp_color(attenuation, fp.firefly_clamp);
                     const f3 L = unwind(wf, slot, depth, Lk, fp.firefly_clamp);
-                    st_stream(&wf.radiance[slot], make_float4(L.x, L.y, L.z, 0.0f));
+                    wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
                 } else if (killed || depth + 1 >= fp.max_bounces) {
                     // the scattered ray would be traced at depth == max_bounces and return BLACK (tracer.rs:28)
                     const f3 Lk = mk3(0.0f, 0.0f, 0.0f) +
                                   clamp_color(mul_elem(attenuation, mk3(0.0f, 0.0f, 0.0f)), fp.firefly_clamp);
                     const f3 L = unwind(wf, slot, depth, Lk, fp.firefly_clamp);
-                    st_stream(&wf.radiance[slot], make_float4(L.x, L.y, L.z, 0.0f));
+                    wf.radiance[slot] = make_float4(L.x, L.y, L.z, 0.0f);
                 } else {
-                    st_stream(&wf.att[(size_t)depth * wf.capacity + slot], make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f));
+                    wf.att[(size_t)depth * wf.capacity + slot] = make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f);
                     next_o = make_float4(new_o.x, new_o.y, new_o.z, __uint_as_float(rng.n));
                     next_d = make_float4(new_d.x, new_d.y, new_d.z, 0.0f);
                     alive = true;
@@ -710,10 +710,10 @@ __device__ __forceinline__ void shade_group(const DeviceScene& sc, const Wavefro
     uint32_t slot = 0;
     float4 next_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), next_d = next_o;  // the scattered ray of a surviving path
     if (active) {
-        slot = queue ? ld_stream(queue + i) : i;
-        const float4 ro = ld_stream((depth & 1u ? wf.ray_o[1] : wf.ray_o[0]) + i);
-        const float4 rd = ld_stream((depth & 1u ? wf.ray_d[1] : wf.ray_d[0]) + i);
-        const float4 hr = ld_stream(wf.hit + i);
+        slot = queue ? queue[i] : i;
+        const float4 ro = (depth & 1u ? wf.ray_o[1] : wf.ray_o[0])[i];
+        const float4 rd = (depth & 1u ? wf.ray_d[1] : wf.ray_d[0])[i];
+        const float4 hr = wf.hit[i];
         if (__float_as_int(hr.y) < 0) shade_miss(sc, wf, fp.firefly_clamp, depth, slot, xyz(rd));  // depth 0 only
         else alive = shade_hit<FAST, MICROFACET>(sc, wf, src, fp, depth, slot, ro, rd, hr, next_o, next_d);
     }
@@ -728,9 +728,9 @@ __device__ __forceinline__ void shade_group(const DeviceScene& sc, const Wavefro
         if (alive) {
             // the next depth's ray goes to the path's place in the next queue (coalesced within the warp)
             const uint32_t j = warp_base + __popc(ballot & ((1u << lane) - 1u));
-            st_stream(queue_out + j, slot);
-            st_stream((depth & 1u ? wf.ray_o[0] : wf.ray_o[1]) + j, next_o);
-            st_stream((depth & 1u ? wf.ray_d[0] : wf.ray_d[1]) + j, next_d);
+            queue_out[j] = slot;
+            (depth & 1u ? wf.ray_o[0] : wf.ray_o[1])[j] = next_o;
+            (depth & 1u ? wf.ray_d[0] : wf.ray_d[1])[j] = next_d;
         }
     }
 }
@@ -795,16 +795,16 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(Devic
                 for (int c = 0; c < SHADE_SPAN; ++c) {
                     if ((miss_ballot[c] >> lane) & 1u) {
                         const uint32_t i = (chunk + c) * 32u + lane;
-                        rd[c] = ld_stream(ray_d + i);
-                        sl[c] = ld_stream(queue + i);
+                        rd[c] = ray_d[i];
+                        sl[c] = queue[i];
                     }
                 }
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
 #pragma unroll
                 for (int c = 0; c < SHADE_SPAN; ++c) {
                     if ((miss_ballot[c] >> lane) & 1u)
-                        st_stream(&wf.miss[base + (uint32_t)__popc(miss_ballot[c] & lt_mask)],
-                                  make_float4(rd[c].x, rd[c].y, rd[c].z, __uint_as_float(sl[c] | (depth << MISS_SLOT_BITS))));
+                        wf.miss[base + (uint32_t)__popc(miss_ballot[c] & lt_mask)] =
+                            make_float4(rd[c].x, rd[c].y, rd[c].z, __uint_as_float(sl[c] | (depth << MISS_SLOT_BITS)));
                     base += (uint32_t)__popc(miss_ballot[c]);
                 }
             }
@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(Devic
 __global__ void __launch_bounds__(256) k_miss(DeviceScene sc, Wavefront wf, float firefly_clamp) {
     const uint32_t n = *wf.miss_count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 rec = ld_stream(wf.miss + i);
+        const float4 rec = wf.miss[i];
         const uint32_t w = __float_as_uint(rec.w);
         shade_miss(sc, wf, firefly_clamp, w >> MISS_SLOT_BITS, w & ((1u << MISS_SLOT_BITS) - 1u), xyz(rec));
     }
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(256) k_accumulate(Wavefront wf, float4* partia
         const uint32_t px = tile_slot_to_pixel(j, width, height);
         float4 p = partial[px];
         for (uint32_t s = 0; s < samples_in_batch; ++s) {
-            const float4 L = ld_stream(&wf.radiance[(size_t)s * n_pixels + j]);
+            const float4 L = wf.radiance[(size_t)s * n_pixels + j];
             p.x += L.x;
             p.y += L.y;
             p.z += L.z;
