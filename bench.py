@@ -314,6 +314,36 @@ def issue_roofline(name, acc, dev_ms, sm_count, sm_mhz):
     return out
 
 
+def kernel_alone_roofline(torch, name, total, spp, device, stream, paths, sm_count, sm_mhz, steps):
+    """The same roofline with ONE wavefront (VOIDRAY_STREAMS=1, read by vr_render_begin): no other kernel shares the GPU
+    with a k_trace launch, so launch duration = the kernel's own. A side measurement after the timed loop; the headline
+    numbers come from the shipped two-wavefront path, whose k_trace launches overlap the other wavefront's kernels."""
+    old = os.environ.get("VOIDRAY_STREAMS")
+    os.environ["VOIDRAY_STREAMS"] = "1"
+    try:
+        job = Job(torch, name, total, 0, spp, device, stream, paths=paths)
+    finally:
+        if old is None:
+            os.environ.pop("VOIDRAY_STREAMS", None)
+        else:
+            os.environ["VOIDRAY_STREAMS"] = old
+    try:
+        for _ in range(2):
+            job.target.clear()
+            job.target.accumulate(spp)
+        d_ms, _, acc = timed_loop(torch, job, steps, lambda: None, torch.cuda.synchronize, True)
+        out = issue_roofline(name, acc, d_ms, sm_count, sm_mhz)
+        if out is not None:
+            out = {k: out[k] for k in ("achieved", "frac", "avg_launch_ms", "segments_per_launch", "gsegments_per_s",
+                                       "trace_share_of_step") if k in out}
+            out["msamples_per_s"] = float(job.w) * job.h * spp * steps / (d_ms * 1e-3) / 1e6
+            out["spp_per_step"] = spp
+            out["steps"] = steps
+        return out
+    finally:
+        job.close()
+
+
 def run_ours(args):
     import torch
     from voidray_b200.distributed import env_rank, init_process_group, shard_samples
@@ -445,6 +475,17 @@ def run_ours(args):
 
     sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
     roofline = issue_roofline(name, acc, dev_ms, props.multi_processor_count, sm_mhz)
+    if roofline is not None:
+        roofline["note_overlap"] = ("timed region of the shipped path: consecutive batches run on two wavefronts / two streams, so a "
+                                    "k_trace launch shares the GPU with the other wavefront's kernels; launch time = the union of "
+                                    "the launches' [start, end] intervals. kernel_alone = the same measurement with one wavefront")
+        if world_eff == 1:
+            try:
+                alone_spp = my_spp if (t_first or 0.0) < 1.0 else min(my_spp, 16)
+                roofline["kernel_alone"] = kernel_alone_roofline(torch, name, total, alone_spp, local, stream, args.paths,
+                                                                 props.multi_processor_count, sm_mhz, min(steps, 5))
+            except Exception as e:  # a side measurement must not take the headline line with it
+                roofline["kernel_alone"] = {"error": repr(e)}
 
     cpu = None
     extra = {}
@@ -478,6 +519,9 @@ def run_ours(args):
                                 "roofline": issue_roofline(other, o_acc, d_ms, props.multi_processor_count, sm_mhz),
                                 "clocks": o_clocks}
                 oj.close()
+                if extra[other]["roofline"] is not None:
+                    extra[other]["roofline"]["kernel_alone"] = kernel_alone_roofline(
+                        torch, other, o_spp, min(o_spp, 32), local, stream, args.paths, props.multi_processor_count, sm_mhz, 2)
             except Exception as e:  # a side measurement must not take the headline line with it
                 extra[other] = {"error": repr(e)}
 

@@ -59,9 +59,11 @@ def kernel(path, out, title):
     h, units, data = rows[0], rows[1], rows[2:]
     with open(out, "w") as f:
         f.write(f"{title}\n\nSource: `ncu --set full --clock-control none --import-source on`, raw page `{path}`; "
-                f"one column per captured launch (wavefront depths 0,1,2,3 of one batch).\n\n")
+                f"one column per captured launch.\n\n")
         f.write("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n")
         f.write("|---|---|" + "---:|" * len(data) + "\n")
+        if "Kernel Name" in h:
+            f.write("| kernel | | " + " | ".join(d[h.index("Kernel Name")].split("(")[0].replace("void ", "") for d in data) + " |\n")
         for key, label in KEYS:
             if key in h:
                 i = h.index(key)

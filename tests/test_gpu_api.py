@@ -65,7 +65,8 @@ def test_accumulation_semantics_match_iterative_render(oracle, ctx):
     assert np.abs(img - ref).max() <= 2e-4
     st_ = tgt.stats()
     assert (st_.samples_done, st_.total_samples, st_.camera_samples) == (8, 8, 96 * 72 * 8)
-    assert st_.kernel_launches > 0 and st_.trace_launches == 16 and st_.device_ms > 0 and st_.trace_ms > 0
+    # one closest-hit launch per depth and batch; a call of >= 2 samples is cut into two batches (one per wavefront)
+    assert st_.kernel_launches > 0 and st_.trace_launches == 2 * 2 * rs.max_bounces and st_.device_ms > 0 and st_.trace_ms > 0
     tgt.clear()
     assert not tgt.read().any() and tgt.stats().samples_done == 0
 
@@ -85,6 +86,26 @@ def test_wavefront_batching_is_invisible(ctx):
     tgt = RenderTarget(accel, (128, 72), RenderSettings(total_samples=12, max_bounces=8))
     tgt.accumulate(12)
     assert np.array_equal(tgt.read(), imgs[0])
+
+
+def test_two_wavefronts_are_invisible(ctx, monkeypatch):
+    # consecutive batches alternate between two wavefronts on two streams; the per-pixel sums still run in batch order,
+    # so the image is bit-identical to a single wavefront's (VOIDRAY_STREAMS=1, read when the render begins)
+    scene, st, _ = scenes.config5_combined(160, 96, 24)
+    accel = scene.build_acceleration(ctx)
+    imgs, launches = [], []
+    for streams in ("1", "2"):
+        monkeypatch.setenv("VOIDRAY_STREAMS", streams)
+        for cap in (160 * 96 * 4, 0):
+            tgt = RenderTarget(accel, (160, 96), RenderSettings(total_samples=24, max_bounces=8, max_paths_in_flight=cap))
+            tgt.accumulate(7)   # 7 + 17: odd batch counts, a last short batch
+            tgt.accumulate(17)
+            imgs.append(tgt.read())
+            launches.append(tgt.stats().trace_launches)
+            tgt.close()
+    for img in imgs[1:]:
+        assert np.array_equal(img, imgs[0])
+    assert launches[0] != launches[2] or launches[1] != launches[3]  # the two settings really cut the work differently
 
 
 def test_sample_range_sharding_on_one_device(ctx):

@@ -127,13 +127,14 @@ struct vr_render {
     float4* partial = nullptr;
     float4* resolved = nullptr;
     Wavefront wf;
-    // Second wavefront on a stream of its own: consecutive batches alternate between the two, so that the sparse deep
+    // Further wavefronts on streams of their own: consecutive batches rotate through them, so that the sparse deep
     // levels and the ramp-down of every kernel of one batch (a persistent grid ends with a few long rays on an almost
     // empty GPU) are filled by the other batch's kernels. Accumulation stays in batch order (ev_acc).
-    Wavefront wf_b;
-    cudaStream_t stream_b = nullptr;
-    cudaEvent_t ev_acc[2] = {nullptr, nullptr};
-    bool dual = false;
+    static constexpr int MAX_WAVEFRONTS = 4;
+    Wavefront wf_more[MAX_WAVEFRONTS - 1];                 // wavefronts 1 .. n_wavefronts - 1
+    cudaStream_t stream_more[MAX_WAVEFRONTS - 1] = {};     // their streams (wavefront 0 runs on the context's stream)
+    cudaEvent_t ev_acc[MAX_WAVEFRONTS] = {};
+    int n_wavefronts = 1;
     uint32_t samples_per_batch = 1;
     uint32_t samples_done = 0;
     std::atomic<int> cancel{0};
@@ -890,16 +891,18 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
 
     // Paths in flight per wavefront batch. More is better for the deep, sparse depths (measured: +27 % on
     // config 1, +7 % on config 2 going from 8 Mi to 32 Mi); 32 Mi slots are 7.8 GB of the 180 GB of HBM at 8 bounces.
-    // Two wavefronts (see vr_render::wf_b) share max_paths_in_flight when the caller sets it; VOIDRAY_STREAMS=1
-    // (experiment knob) keeps a single one.
+    // Two wavefronts (see vr_render::wf_more) share max_paths_in_flight when the caller sets it; VOIDRAY_STREAMS=n
+    // (experiment knob, 1 .. 4) sets their number.
     const char* streams_env = std::getenv("VOIDRAY_STREAMS");
-    bool dual = !(streams_env && std::atoi(streams_env) == 1) && settings->total_samples >= 2;
+    int n_wf = streams_env ? std::atoi(streams_env) : 2;
+    n_wf = std::max(1, std::min(n_wf, (int)vr_render::MAX_WAVEFRONTS));
+    n_wf = (int)std::min<uint64_t>((uint64_t)n_wf, settings->total_samples);
     uint64_t capacity = settings->max_paths_in_flight ? settings->max_paths_in_flight : (32ull << 20);
-    if (dual && settings->max_paths_in_flight) {
-        if (capacity / 2 >= r->n_pixels) capacity /= 2;
-        else dual = false;
+    if (settings->max_paths_in_flight) {
+        while (n_wf > 1 && capacity / n_wf < r->n_pixels) --n_wf;
+        capacity /= n_wf;
     }
-    const uint64_t samples_each = dual ? (settings->total_samples + 1) / 2 : settings->total_samples;
+    const uint64_t samples_each = (settings->total_samples + n_wf - 1) / n_wf;
     capacity = std::min<uint64_t>(capacity, (uint64_t)r->n_pixels * samples_each);
     if (capacity < r->n_pixels) capacity = r->n_pixels;
     r->samples_per_batch = (uint32_t)(capacity / r->n_pixels);
@@ -908,7 +911,7 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
         delete r;
         return fail(VR_ERR_INVALID, "max_paths_in_flight too large");
     }
-    r->dual = dual;
+    r->n_wavefronts = n_wf;
     const size_t cap = capacity;
     const uint32_t levels = settings->max_bounces ? settings->max_bounces : 1;
     cudaError_t e = cudaSuccess;
@@ -939,12 +942,12 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     };
     Wavefront& wf = r->wf;
     alloc_wavefront(wf);
-    if (dual) {
-        alloc_wavefront(r->wf_b);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream_b, cudaStreamNonBlocking);
-        for (cudaEvent_t& ev : r->ev_acc)
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (int k = 1; k < n_wf; ++k) {
+        alloc_wavefront(r->wf_more[k - 1]);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream_more[k - 1], cudaStreamNonBlocking);
     }
+    for (int k = 0; k < n_wf && n_wf > 1; ++k)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_acc[k], cudaEventDisableTiming);
     A((void**)&r->dbg_surface, 4ull * r->n_pixels);
     A((void**)&r->dbg_prim, 4ull * r->n_pixels);
     A((void**)&r->dbg_t, 4ull * r->n_pixels);
@@ -957,7 +960,8 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         r->dev_mem.release();
-        if (r->stream_b) cudaStreamDestroy(r->stream_b);
+        for (cudaStream_t sm : r->stream_more)
+            if (sm) cudaStreamDestroy(sm);
         for (cudaEvent_t ev : r->ev_acc)
             if (ev) cudaEventDestroy(ev);
         delete r;
@@ -1015,10 +1019,11 @@ int32_t vr_render_end(vr_render* r) try {
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     if (r->ev_begin) cudaEventDestroy(r->ev_begin);
     if (r->ev_end) cudaEventDestroy(r->ev_end);
-    if (r->stream_b) {
-        cudaStreamSynchronize(r->stream_b);
-        cudaStreamDestroy(r->stream_b);
-    }
+    for (cudaStream_t sm : r->stream_more)
+        if (sm) {
+            cudaStreamSynchronize(sm);
+            cudaStreamDestroy(sm);
+        }
     for (cudaEvent_t ev : r->ev_acc)
         if (ev) cudaEventDestroy(ev);
     r->dev_mem.release();
@@ -1061,34 +1066,35 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
     const auto t0 = std::chrono::steady_clock::now();
     const float inv_total = 1.0f / (float)r->settings.total_samples;  // iterative.rs:45
     VR_CUDA(cudaEventRecord(r->ev_begin, ctx->stream));
-    if (r->dual) VR_CUDA(cudaStreamWaitEvent(r->stream_b, r->ev_begin, 0));  // after whatever the caller queued before
+    const int n_wf = r->n_wavefronts;
+    for (int k = 1; k < n_wf; ++k) VR_CUDA(cudaStreamWaitEvent(r->stream_more[k - 1], r->ev_begin, 0));  // after whatever the caller queued before
     uint32_t done = 0;
     size_t event_cursor = 0;
     bool cancelled = false;
-    // with two wavefronts a call of >= 2 samples is cut into at least two batches, so that there is something to overlap
-    const uint32_t per_batch = r->dual ? std::min(r->samples_per_batch, std::max(1u, (samples + 1) / 2)) : r->samples_per_batch;
+    // with n wavefronts a call of >= n samples is cut into at least n batches, so that there is something to overlap
+    const uint32_t per_batch = std::min(r->samples_per_batch, std::max(1u, (samples + (uint32_t)n_wf - 1u) / (uint32_t)n_wf));
     int last = -1;  // the wavefront of the previous batch
     for (uint32_t batch = 0; done < samples; ++batch) {
         if (r->cancel.load()) {
             cancelled = true;
             break;
         }
-        const int w = r->dual ? (int)(batch & 1u) : 0;
-        const Wavefront& wf = w ? r->wf_b : r->wf;
-        cudaStream_t stream = w ? r->stream_b : ctx->stream;
+        const int w = (int)(batch % (uint32_t)n_wf);
+        const Wavefront& wf = w ? r->wf_more[w - 1] : r->wf;
+        cudaStream_t stream = w ? r->stream_more[w - 1] : ctx->stream;
         const uint32_t nb = std::min(samples - done, per_batch);
         const PathSource src = make_path_source(nullptr, nullptr, r->width, r->height, first_sample + done);
         run_wavefront(r, wf, stream, src, nb * r->n_pixels, true, &event_cursor);
         done += nb;
         // the per-pixel sums run in batch order whatever the streams do: bit-identical to a single wavefront
-        if (r->dual && last >= 0) VR_CUDA(cudaStreamWaitEvent(stream, r->ev_acc[last], 0));
+        if (n_wf > 1 && last >= 0) VR_CUDA(cudaStreamWaitEvent(stream, r->ev_acc[last], 0));
         launch_accumulate(wf, r->partial, r->accum, r->width, r->height, nb, done == samples ? 1 : 0, inv_total, alpha_inc,
                           stream);
-        if (r->dual) VR_CUDA(cudaEventRecord(r->ev_acc[w], stream));
+        if (n_wf > 1) VR_CUDA(cudaEventRecord(r->ev_acc[w], stream));
         last = w;
         r->kernel_launches += 1;
     }
-    if (r->dual && last >= 0) VR_CUDA(cudaStreamWaitEvent(ctx->stream, r->ev_acc[last], 0));
+    if (n_wf > 1 && last >= 0) VR_CUDA(cudaStreamWaitEvent(ctx->stream, r->ev_acc[last], 0));
     if (cancelled && done > 0) {
         launch_accumulate(r->wf, r->partial, r->accum, r->width, r->height, 0, 1, inv_total, alpha_inc, ctx->stream);
         r->kernel_launches += 1;

@@ -1021,18 +1021,6 @@ __global__ void k_environment_sample(DeviceScene sc, uint64_t n, const float* di
 // Launch wrappers. Grids are persistent-style: a multiple of the SM count x resident blocks, with
 // grid-stride loops; the live queue length is read on the device, so no host round trip per depth.
 // ------------------------------------------------------------------------------------------------
-void query_launch_dims(LaunchDims* dims) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&dims->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->trace_blocks_per_sm, k_trace, TRACE_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_blocks_per_sm, k_shade<false, false>, SHADE_THREADS, 0);
-    if (dims->trace_blocks_per_sm < 1) dims->trace_blocks_per_sm = 1;
-    if (dims->shade_blocks_per_sm < 1) dims->shade_blocks_per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_first_blocks_per_sm, k_shade_first<false, false>, SHADE_THREADS, 0);
-    if (dims->shade_first_blocks_per_sm < 1) dims->shade_first_blocks_per_sm = 1;
-}
-
 static int env_int(const char* name, int index, int fallback) {  // "a,b,c" -> the index-th integer
     const char* v = std::getenv(name);
     if (!v) return fallback;
@@ -1043,6 +1031,22 @@ static int env_int(const char* name, int index, int fallback) {  // "a,b,c" -> t
     }
     return std::atoi(v);
 }
+void query_launch_dims(LaunchDims* dims) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&dims->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->trace_blocks_per_sm, k_trace, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_blocks_per_sm, k_shade<false, false>, SHADE_THREADS, 0);
+    if (dims->trace_blocks_per_sm < 1) dims->trace_blocks_per_sm = 1;
+    {  // experiment knob (scripts only): fewer persistent closest-hit blocks per SM leave room for the other stream's kernels
+        const int want = env_int("VOIDRAY_TRACE_BLOCKS", 0, 0);
+        if (want > 0 && want < dims->trace_blocks_per_sm) dims->trace_blocks_per_sm = want;
+    }
+    if (dims->shade_blocks_per_sm < 1) dims->shade_blocks_per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_first_blocks_per_sm, k_shade_first<false, false>, SHADE_THREADS, 0);
+    if (dims->shade_first_blocks_per_sm < 1) dims->shade_first_blocks_per_sm = 1;
+}
+
 static inline uint32_t grid_for(uint64_t n, int threads, int sm_count, int blocks_per_sm) {
     const uint64_t need = (n + threads - 1) / threads;
     const uint64_t cap = (uint64_t)sm_count * blocks_per_sm;
