@@ -7,8 +7,6 @@
 // environments.rs -> shaders/post_process.glsl.
 #include "device_math.cuh"
 #include "kernels.cuh"
-#include <cstdlib>
-#include <cstring>
 
 namespace vr {
 
@@ -1021,16 +1019,6 @@ __global__ void k_environment_sample(DeviceScene sc, uint64_t n, const float* di
 // Launch wrappers. Grids are persistent-style: a multiple of the SM count x resident blocks, with
 // grid-stride loops; the live queue length is read on the device, so no host round trip per depth.
 // ------------------------------------------------------------------------------------------------
-static int env_int(const char* name, int index, int fallback) {  // "a,b,c" -> the index-th integer
-    const char* v = std::getenv(name);
-    if (!v) return fallback;
-    for (int i = 0; i < index; ++i) {
-        v = std::strchr(v, ',');
-        if (!v) return fallback;
-        ++v;
-    }
-    return std::atoi(v);
-}
 void query_launch_dims(LaunchDims* dims) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1038,11 +1026,6 @@ void query_launch_dims(LaunchDims* dims) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->trace_blocks_per_sm, k_trace, TRACE_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_blocks_per_sm, k_shade<false, false>, SHADE_THREADS, 0);
     if (dims->trace_blocks_per_sm < 1) dims->trace_blocks_per_sm = 1;
-    {  // experiment knob (scripts only): fewer persistent closest-hit blocks per SM leave room for the other stream's kernels
-        const int want = env_int("VOIDRAY_TRACE_BLOCKS", 0, 0);
-        if (want > 0 && want < dims->trace_blocks_per_sm) dims->trace_blocks_per_sm = want;
-    }
-    if (dims->shade_blocks_per_sm < 1) dims->shade_blocks_per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dims->shade_first_blocks_per_sm, k_shade_first<false, false>, SHADE_THREADS, 0);
     if (dims->shade_first_blocks_per_sm < 1) dims->shade_first_blocks_per_sm = 1;
 }
@@ -1070,10 +1053,8 @@ void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource&
 }
 void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, const LaunchDims& ld,
                   cudaStream_t stream) {
-    // experiment knob (scripts only): VOIDRAY_REFILL="<depth 0>,<deeper>" overrides the refill threshold
-    static const int refill[2] = {env_int("VOIDRAY_REFILL", 0, REFILL_THRESHOLD), env_int("VOIDRAY_REFILL", 1, REFILL_THRESHOLD)};
     k_trace<<<grid_for(n_upper, TRACE_THREADS, ld.sm_count, ld.trace_blocks_per_sm), TRACE_THREADS, 0, stream>>>(
-        sc, wf, depth, refill[depth ? 1 : 0]);
+        sc, wf, depth, REFILL_THRESHOLD);
 }
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
                   uint32_t depth, uint32_t n_upper, const LaunchDims& ld, cudaStream_t stream) {
