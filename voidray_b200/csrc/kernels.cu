@@ -10,8 +10,8 @@
 
 namespace vr {
 
-static constexpr int TRACE_THREADS = 128;
-static constexpr int TRACE_MIN_BLOCKS = 8;
+static constexpr int TRACE_THREADS = 128;  // 64 x 16 and 256 x 4 measured level (profiles/r2_variants.md)
+static constexpr int TRACE_MIN_BLOCKS = 8;  // 1024 threads x 64 registers = the SM's register file
 static constexpr int SHADE_THREADS = 128;
 #ifndef VR_SHADE_MIN_BLOCKS
 #define VR_SHADE_MIN_BLOCKS 8
