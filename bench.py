@@ -10,7 +10,7 @@ Workload (`--workload auto`, the default; `config.workload` / `config.series` in
   * several GPUs visible (the 1 -> 8 scaling series, every N including N = 1) -> config5_combined: configs[4], the 4K
     scene north_star's ">= 85 % at 8 GPUs" target is quoted on. STRONG scaling: a step = the whole job, 4096 spp of the
     3840x2160 frame, sample-range sharded over the N ranks (4096 / N spp each, total_samples = 4096), then one sum of
-    the accumulation buffers onto rank 0. At N = 1 a step is ~20 s: if K steps do not fit --max-seconds the run
+    the accumulation buffers onto rank 0. At N = 1 a step is ~27 s: if K steps do not fit --max-seconds (150 s) the run
     times fewer steps (never fewer spp) and says so ("steps", "steps_requested").
   `--workload NAME [--spp S]` picks any config by hand (weak scaling: S spp per GPU).
 
@@ -577,7 +577,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="with --workload NAME: samples per pixel per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=5.0, help="--impl reference: CPU work per step")
-    ap.add_argument("--max-seconds", type=float, default=300.0,
+    ap.add_argument("--max-seconds", type=float, default=150.0,
                     help="budget of the timed loop; more than this and fewer steps are timed (strong series at N = 1)")
     ap.add_argument("--paths", type=int, default=0, help="wavefront capacity (paths in flight); 0 = library default")
     ap.add_argument("--launcher", default="ranks", choices=["ranks", "inproc"],

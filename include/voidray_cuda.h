@@ -216,7 +216,8 @@ typedef struct vr_render_settings {
     uint64_t seed;          /* Philox4x32-10 key. The reference's thread_rng() is unseedable (iterative.rs:29) */
     uint32_t sample_offset; /* global index of this render's first camera sample: rank r of an N-GPU job
                                renders [sample_offset, sample_offset + its share) of every pixel */
-    uint32_t max_paths_in_flight; /* wavefront capacity; 0 = library default (32 Mi paths, 248 B each at 8 bounces); < 64 Mi */
+    uint32_t max_paths_in_flight; /* paths in flight, shared by the two wavefronts consecutive batches alternate between;
+                                     0 = library default (2 x 32 Mi paths, 248 B each at 8 bounces); < 64 Mi per wavefront */
 } vr_render_settings;
 
 /* CpuRenderTarget::new + clear (render/target.rs:90-131,284-290): allocates the zeroed W*H RGBA f32

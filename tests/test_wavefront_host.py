@@ -157,3 +157,4 @@ def test_fast_division_by_launch_invariants(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and ", 0 wrong" in r.stdout, r.stdout
+

@@ -234,7 +234,7 @@ __device__ __forceinline__ float plane_t(uint32_t pair, uint32_t sel, float a, f
 
 // One inner node: two slab tests from a single 32-byte record, near child first, far child pushed.
 __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride) {
-    const float8 n = ldg8(nodes + 2 * tr.cur);
+    const float8 n = ldg8((const float4*)((const char*)nodes + (size_t)(uint32_t)tr.cur * 32u));  // one IMAD.WIDE
     const uint32_t w0 = __float_as_uint(n.lo.x), w1 = __float_as_uint(n.lo.y), w2 = __float_as_uint(n.lo.z),
                    w3 = __float_as_uint(n.lo.w), w4 = __float_as_uint(n.hi.x), w5 = __float_as_uint(n.hi.y);
     const uint32_t fx = tr.selx ^ 0x0220u, fy = tr.sely ^ 0x0220u, fz = tr.selz ^ 0x0220u;
