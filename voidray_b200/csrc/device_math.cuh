@@ -62,6 +62,33 @@ __device__ __forceinline__ float8 ldg8(const float4* p) {
     return r;
 }
 
+// The same load with an L1 eviction priority (experiment, -DVR_L1_HINTS): nodes are re-used by every ray of the SM,
+// a triangle record by few — keep the former, do not let the latter push them out.
+__device__ __forceinline__ float8 ldg8_keep(const float4* p) {
+#if defined(VR_L1_HINTS) && !defined(VR_HOST_SHIM)
+    float8 r;
+    asm volatile("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
+                   "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+#else
+    return ldg8(p);
+#endif
+}
+__device__ __forceinline__ float8 ldg8_once(const float4* p) {
+#if defined(VR_L1_HINTS) && !defined(VR_HOST_SHIM)
+    float8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
+                   "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+#else
+    return ldg8(p);
+#endif
+}
+
 #define VR_PI_F 3.14159265358979323846f
 
 // compiler-rt __powisf2 (what f32::powi lowers to), specialised for exponent 5: a * (a^2)^2

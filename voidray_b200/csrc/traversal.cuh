@@ -100,8 +100,8 @@ __device__ __forceinline__ bool candidate_visible(const DeviceScene& sc, const i
 __device__ __forceinline__ void intersect_triangle(const DeviceScene& sc, const int* vis_row,
                                                    const float4* __restrict__ tri_isect, int tri, f3 o, f3 d,
                                                    HitResult& best, uint32_t& best_rank) {
-    const float8 r0 = ldg8(tri_isect + TRI_ISECT_QUADS * tri);      // v0 | e1
-    const float8 r1 = ldg8(tri_isect + TRI_ISECT_QUADS * tri + 2);  // e2 | -
+    const float8 r0 = ldg8_once(tri_isect + TRI_ISECT_QUADS * tri);      // v0 | e1
+    const float8 r1 = ldg8_once(tri_isect + TRI_ISECT_QUADS * tri + 2);  // e2 | -
     const float4 q0 = r0.lo;
     const f3 v0 = xyz(r0.lo), e1 = xyz(r0.hi), e2 = xyz(r1.lo);
     // core/mesh.rs:153-175, same operation order
@@ -249,7 +249,7 @@ __device__ __forceinline__ float plane_t(uint32_t pair, uint32_t sel, float a, f
 
 // One inner node: two slab tests from a single 32-byte record, near child first, far child pushed.
 __device__ __forceinline__ void trav_node(Traversal& tr, const float4* __restrict__ nodes, int* sstack, int sstride) {
-    const float8 n = ldg8((const float4*)((const char*)nodes + (size_t)(uint32_t)tr.cur * 32u));  // one IMAD.WIDE
+    const float8 n = ldg8_keep((const float4*)((const char*)nodes + (size_t)(uint32_t)tr.cur * 32u));  // one IMAD.WIDE
     const uint32_t w0 = __float_as_uint(n.lo.x), w1 = __float_as_uint(n.lo.y), w2 = __float_as_uint(n.lo.z),
                    w3 = __float_as_uint(n.lo.w), w4 = __float_as_uint(n.hi.x), w5 = __float_as_uint(n.hi.y);
     const uint32_t fx = tr.selx ^ 0x0220u, fy = tr.sely ^ 0x0220u, fz = tr.selz ^ 0x0220u;
