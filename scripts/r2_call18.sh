@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round 2, eighteenth GPU call: which half of the L1 eviction priorities pays — nodes evict_last only (l1keep), + triangles
+# evict_first (l1ef), + triangles no_allocate (l1hints) — against the default build; two runs each.
+mkdir -p gpurun_out
+one() {  # one <workload> <spp> <steps>
+  timeout -k 10 300 python bench.py --workload $1 --spp $2 --steps $3 --no-cpu --no-extra 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+ka=(d['roofline'] or {}).get('kernel_alone') or {}
+print('$1 spp $2: %.1f | %.1f  trace share %.3f  frac %.3f alone %.3f' % (d['value'], d['e2e']['value'], d['roofline']['trace_share_of_step'], d['roofline']['frac'] or 0, ka.get('frac') or 0))"
+}
+ab() { one config1_mushroom 64 10; one config2_mossy_ground 64 3; one config3_materials 64 3; one config5_combined 16 3; one config4_field 16 3; }
+for rep in 1 2; do
+echo "=== default build"; ab
+for v in l1keep l1ef l1hints; do echo "=== $v"; VOIDRAY_CUDA_LIB=$PWD/gpurun_variants/$v.so ab; done
+done

@@ -62,10 +62,12 @@ __device__ __forceinline__ float8 ldg8(const float4* p) {
     return r;
 }
 
-// The same load with an L1 eviction priority (experiment, -DVR_L1_HINTS): nodes are re-used by every ray of the SM,
-// a triangle record by few — keep the former, do not let the latter push them out.
+// The same 256-bit load with an L1 policy. The SM's L1 (what the eight blocks' stacks leave of 256 KB) cannot hold a
+// scene's nodes and triangles, so what it keeps matters: a node is re-used by every ray of the SM (evict_last), a
+// triangle record by few (no_allocate: it does not push nodes out). Measured +1.2 ... +1.9 % on every config, with
+// the rays' own loads bypassing the L1 as well +1.0 ... +2.3 % (profiles/r2_variants.md, calls 16-19).
 __device__ __forceinline__ float8 ldg8_keep(const float4* p) {
-#if defined(VR_L1_HINTS) && !defined(VR_HOST_SHIM)
+#ifndef VR_HOST_SHIM
     float8 r;
     asm volatile("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
@@ -77,7 +79,7 @@ __device__ __forceinline__ float8 ldg8_keep(const float4* p) {
 #endif
 }
 __device__ __forceinline__ float8 ldg8_once(const float4* p) {
-#if defined(VR_L1_HINTS) && !defined(VR_HOST_SHIM)
+#ifndef VR_HOST_SHIM
     float8 r;
     asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z),
@@ -86,6 +88,17 @@ __device__ __forceinline__ float8 ldg8_once(const float4* p) {
     return r;
 #else
     return ldg8(p);
+#endif
+}
+
+// A ray is read once by k_trace: its two quads bypass the L1
+__device__ __forceinline__ float4 ld_once4(const float4* p) {
+#ifndef VR_HOST_SHIM
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
+    return *p;
 #endif
 }
 

@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Devic
                     const uint32_t i = base + (uint32_t)__popc(need & lt_mask);
                     if (i < n) {
                         slot = i;  // queue order: the lanes that refill together read consecutive rays
-                        const float4 ro = ray_o[i];
-                        const float4 rd = ray_d[i];
+                        const float4 ro = ld_once4(ray_o + i);
+                        const float4 rd = ld_once4(ray_d + i);
                         trav_begin(tr, sc, xyz(ro), xyz(rd), sstack, TRACE_THREADS);
                         have = true;
                     }

@@ -105,20 +105,6 @@ __device__ __forceinline__ void intersect_triangle(const DeviceScene& sc, const 
     const float4 q0 = r0.lo;
     const f3 v0 = xyz(r0.lo), e1 = xyz(r0.hi), e2 = xyz(r1.lo);
     // core/mesh.rs:153-175, same operation order
-#ifdef VR_LEAF_BRANCHLESS
-    // the reference's early returns as one predicate: in a warp some lane nearly always survives each test, so the
-    // branches only cost their own instructions; a rejected lane's u / v / t are garbage (possibly inf / NaN) and unused
-    const f3 h = cross(d, e2);
-    const float a = dot(e1, h);
-    const float f = 1.0f / a;
-    const f3 s = o - v0;
-    const float u = f * dot(s, h);
-    const f3 q = cross(s, e1);
-    const float v = f * dot(d, q);
-    const float t = f * dot(e2, q);
-    const bool ok = !(a > -T_MIN && a < T_MIN) && !(u < 0.0f || u > 1.0f) && !(v < 0.0f || u + v > 1.0f) && t > T_MIN;
-    if (ok) {
-#else
     const f3 h = cross(d, e2);
     const float a = dot(e1, h);
     if (a > -T_MIN && a < T_MIN) return;
@@ -131,13 +117,11 @@ __device__ __forceinline__ void intersect_triangle(const DeviceScene& sc, const 
     if (v < 0.0f || u + v > 1.0f) return;
     const float t = f * dot(e2, q);
     if (t > T_MIN) {
-#endif
         const uint32_t rank = __float_as_uint(q0.w);
         if (t < best.t || (t == best.t && rank > best_rank)) {
-            // would win: was its surface reached by the reference's scene tree? (re-read from the record just
-            // fetched — nothing extra lives across the test)
+            // would win: was its surface reached by the reference's scene tree?
             if (sc.n_scene_nodes != 0u) {
-                const uint32_t surface = __float_as_uint(ldg4(tri_isect + TRI_ISECT_QUADS * tri + 3).w);
+                const uint32_t surface = __float_as_uint(r1.hi.w);  // (the record bypassed the L1: no cheap re-read)
                 if (!candidate_visible(sc, vis_row, surface, o, d)) return;
             }
             best.t = t;
