@@ -158,3 +158,15 @@ def test_fast_division_by_launch_invariants(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and ", 0 wrong" in r.stdout, r.stdout
 
+
+
+def test_rejection_samplers_up_front_equal_the_plain_loops(tmp_path):
+    # UnitSphere / UnitCircle / UnitDisc evaluate their first three candidate pairs up front (device_math.cuh
+    # Rng::accepted_pair): same values, same draws consumed, same stream afterwards as rand_distr's plain loops
+    exe = str(tmp_path / "rng_pairs_check")
+    csrc = os.path.join(ROOT, "voidray_b200", "csrc")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-DVR_HOST_SHIM", "-I", os.path.join(ROOT, "tests", "c"),
+                        "-I", csrc, os.path.join(ROOT, "tests", "c", "rng_pairs_check.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and ", 0 wrong" in r.stdout, r.stdout

@@ -165,16 +165,58 @@ struct Rng {
     }
     // Uniform::new(-1.0, 1.0).sample
     __device__ __forceinline__ float uniform_m1_1() { return v01() * 2.0f + -1.0f; }
+    __device__ __forceinline__ static float m1_1(uint32_t w) {  // uniform_m1_1 of one word
+        return (__uint_as_float((w >> 9) | 0x3f800000u) - 1.0f) * 2.0f + -1.0f;
+    }
+    // The first accepted pair of rand_distr's rejection loops — loop { x1, x2 = Uniform(-1, 1); accept on x1^2 + x2^2 } —
+    // with the acceptance INCLUSIVE (UnitDisc: <= 1) or not (UnitSphere, UnitCircle: < 1). A warp that loops until its
+    // unluckiest lane is accepted runs ~3 iterations at a third of its lanes, each with a lazily computed Philox block
+    // (40 % of k_raygen's instructions with a thin lens), so the first three candidates — the words n .. n + 5, which
+    // live in the current block and the next — are evaluated up front at full width and the first accepted one is picked
+    // without a branch; only a lane that rejects all three (1 % for the disc and the sphere) enters the loop. Same draws,
+    // same count consumed.
+    template <bool INCLUSIVE>
+    __device__ __forceinline__ void accepted_pair(float& x1, float& x2, float& sum) {
+        if ((n & 1u) == 0u) {
+            const uint32_t blk = n >> 2;
+            if (blk != block) {
+                uint32_t o[4];
+                philox4x32_10(pixel, sample, blk, 0u, k0, k1, o);
+                b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+                block = blk;
+            }
+            uint32_t c[4];
+            philox4x32_10(pixel, sample, blk + 1u, 0u, k0, k1, c);
+            const bool upper = (n & 2u) != 0u;  // the first pair is words 2, 3 of the current block
+            const uint32_t w0 = upper ? b2 : b0, w1 = upper ? b3 : b1, w2 = upper ? c[0] : b2, w3 = upper ? c[1] : b3,
+                           w4 = upper ? c[2] : c[0], w5 = upper ? c[3] : c[1];
+            const float p1 = m1_1(w0), p2 = m1_1(w1), q1 = m1_1(w2), q2 = m1_1(w3), r1 = m1_1(w4), r2 = m1_1(w5);
+            const float sp = p1 * p1 + p2 * p2, sq = q1 * q1 + q2 * q2, sr = r1 * r1 + r2 * r2;
+            const bool okp = INCLUSIVE ? sp <= 1.0f : sp < 1.0f, okq = INCLUSIVE ? sq <= 1.0f : sq < 1.0f,
+                       okr = INCLUSIVE ? sr <= 1.0f : sr < 1.0f;
+            n += okp ? 2u : (okq ? 4u : 6u);
+            if ((n >> 2) != blk) {  // the next draw is in the block just computed (or the one after it: computed when drawn)
+                b0 = c[0]; b1 = c[1]; b2 = c[2]; b3 = c[3];
+                block = blk + 1u;
+            }
+            x1 = okp ? p1 : (okq ? q1 : r1);
+            x2 = okp ? p2 : (okq ? q2 : r2);
+            sum = okp ? sp : (okq ? sq : sr);
+            if (okp || okq || okr) return;
+        }
+        while (true) {
+            x1 = uniform_m1_1();
+            x2 = uniform_m1_1();
+            sum = x1 * x1 + x2 * x2;
+            if (INCLUSIVE ? sum <= 1.0f : sum < 1.0f) return;
+        }
+    }
     // rand_distr 0.4.3 UnitSphere (Marsaglia 1972)
     __device__ __forceinline__ f3 unit_sphere() {
-        while (true) {
-            const float x1 = uniform_m1_1();
-            const float x2 = uniform_m1_1();
-            const float sum = x1 * x1 + x2 * x2;
-            if (sum >= 1.0f) continue;
-            const float factor = 2.0f * sqrtf(1.0f - sum);
-            return f3{x1 * factor, x2 * factor, 1.0f - 2.0f * sum};
-        }
+        float x1, x2, sum;
+        accepted_pair<false>(x1, x2, sum);
+        const float factor = 2.0f * sqrtf(1.0f - sum);
+        return f3{x1 * factor, x2 * factor, 1.0f - 2.0f * sum};
     }
     // rand 0.8.5 Standard f32: 24 random bits * 2^-24
     __device__ __forceinline__ float gen_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
@@ -194,22 +236,15 @@ struct Rng {
     // rand_distr 0.4.3 UnitCircle
     __device__ __forceinline__ f2 unit_circle() {
         float x1, x2, sum;
-        while (true) {
-            x1 = uniform_m1_1();
-            x2 = uniform_m1_1();
-            sum = x1 * x1 + x2 * x2;
-            if (sum < 1.0f) break;
-        }
+        accepted_pair<false>(x1, x2, sum);
         const float diff = x1 * x1 - x2 * x2;
         return f2{diff / sum, 2.0f * x1 * x2 / sum};
     }
     // rand_distr 0.4.3 UnitDisc
     __device__ __forceinline__ f2 unit_disc() {
-        while (true) {
-            const float x1 = uniform_m1_1();
-            const float x2 = uniform_m1_1();
-            if (x1 * x1 + x2 * x2 <= 1.0f) return f2{x1, x2};
-        }
+        float x1, x2, sum;
+        accepted_pair<true>(x1, x2, sum);
+        return f2{x1, x2};
     }
 };
 
