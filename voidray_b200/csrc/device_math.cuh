@@ -173,11 +173,12 @@ struct Rng {
     // unluckiest lane is accepted runs ~3 iterations at a third of its lanes, each with a lazily computed Philox block
     // (40 % of k_raygen's instructions with a thin lens), so the first three candidates — the words n .. n + 5, which
     // live in the current block and the next — are evaluated up front at full width and the first accepted one is picked
-    // without a branch; only a lane that rejects all three (1 % for the disc and the sphere) enters the loop. Same draws,
-    // same count consumed.
-    template <bool INCLUSIVE>
+    // without a branch; only a lane that rejects all three (1 %) enters the loop. Same draws, same count consumed.
+    // UP_FRONT is the thin lens of k_raygen only (+1.1 % on config 1): in the shade kernels, which are not bound by
+    // issue slots, the extra Philox block of every scatter costs more than the loop (-1.2 % on config 3).
+    template <bool INCLUSIVE, bool UP_FRONT>
     __device__ __forceinline__ void accepted_pair(float& x1, float& x2, float& sum) {
-        if ((n & 1u) == 0u) {
+        if (UP_FRONT && (n & 1u) == 0u) {
             const uint32_t blk = n >> 2;
             if (blk != block) {
                 uint32_t o[4];
@@ -214,7 +215,7 @@ struct Rng {
     // rand_distr 0.4.3 UnitSphere (Marsaglia 1972)
     __device__ __forceinline__ f3 unit_sphere() {
         float x1, x2, sum;
-        accepted_pair<false>(x1, x2, sum);
+        accepted_pair<false, false>(x1, x2, sum);
         const float factor = 2.0f * sqrtf(1.0f - sum);
         return f3{x1 * factor, x2 * factor, 1.0f - 2.0f * sum};
     }
@@ -236,14 +237,14 @@ struct Rng {
     // rand_distr 0.4.3 UnitCircle
     __device__ __forceinline__ f2 unit_circle() {
         float x1, x2, sum;
-        accepted_pair<false>(x1, x2, sum);
+        accepted_pair<false, false>(x1, x2, sum);
         const float diff = x1 * x1 - x2 * x2;
         return f2{diff / sum, 2.0f * x1 * x2 / sum};
     }
     // rand_distr 0.4.3 UnitDisc
     __device__ __forceinline__ f2 unit_disc() {
         float x1, x2, sum;
-        accepted_pair<true>(x1, x2, sum);
+        accepted_pair<true, true>(x1, x2, sum);
         return f2{x1, x2};
     }
 };
