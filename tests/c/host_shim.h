@@ -79,6 +79,8 @@ struct vr_warp_ctx {
     uint32_t vals[32];
 };
 inline thread_local vr_warp_ctx* vr_warp = nullptr;
+inline thread_local std::barrier<>* vr_block = nullptr;
+inline void __syncthreads() { vr_block->arrive_and_wait(); }  // block-uniform control flow only, as on the device
 
 inline unsigned __ballot_sync(unsigned, bool p) {
     vr_warp_ctx& w = *vr_warp;
@@ -114,6 +116,7 @@ template <class Kernel>
 inline void vr_host_launch(unsigned grid, unsigned block, Kernel&& kernel) {
     std::vector<vr_warp_ctx> warps((block + 31) / 32);
     for (unsigned b = 0; b < grid; ++b) {
+        std::barrier<> block_bar(block);
         std::vector<std::thread> threads;
         threads.reserve(block);
         for (unsigned t = 0; t < block; ++t)
@@ -123,6 +126,7 @@ inline void vr_host_launch(unsigned grid, unsigned block, Kernel&& kernel) {
                 blockDim = vr_uint3{block, 1, 1};
                 gridDim = vr_uint3{grid, 1, 1};
                 vr_warp = &warps[t / 32];
+                vr_block = &block_bar;
                 kernel();
             });
         for (std::thread& th : threads) th.join();

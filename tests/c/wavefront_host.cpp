@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -80,7 +81,7 @@ int main(int argc, char** argv) {
         att((size_t)max_bounces * n_paths);
     std::vector<uint32_t> q0(n_paths), q1(n_paths), counts(2 * (max_bounces + 2) + 1, 0u);
     std::vector<float4> miss(n_paths);
-    unsigned long long segments = 0;
+    unsigned long long segments = 0, culled = 0;
     Wavefront wf{};
     wf.ray_o[0] = ray_o.data();
     wf.ray_d[0] = ray_d.data();
@@ -96,6 +97,7 @@ int main(int argc, char** argv) {
     wf.miss = miss.data();
     wf.miss_count = counts.data() + 2 * (max_bounces + 2);
     wf.segments = &segments;
+    wf.culled = &culled;
     wf.capacity = n_paths;
     const PathSource src = make_path_source(nullptr, nullptr, w, h, 0);
     FrameParams fp{};
@@ -112,8 +114,17 @@ int main(int argc, char** argv) {
     // (8 warps racing for the queue), 2 shade blocks
     std::vector<float4> hits_depth0, hits_depth1;
     std::vector<uint32_t> queue_depth1;
-    vr_host_launch(2, 256, [&] { k_raygen(ds, wf, src, fp, n_paths, spp > 1 ? 2u : 1u); });
-    const std::vector<float4> rays0_o = ray_o, rays0_d = ray_d;
+    // every camera ray in slot order first (cull = 0, what the gate kernels use): the reference for the compacted run
+    vr_host_launch(2, 256, [&] { k_raygen(ds, wf, src, fp, n_paths, spp > 1 ? 2u : 1u, 0); });
+    const std::vector<float4> all_o = ray_o, all_d = ray_d;
+    std::fill(counts.begin(), counts.end(), 0u);
+    segments = 0;
+    culled = 0;
+    // the shipped path: rays that miss the scene's bounds are finished by k_raygen, the rest compacted into queue 0
+    vr_host_launch(2, 256, [&] { k_raygen(ds, wf, src, fp, n_paths, spp > 1 ? 2u : 1u, 1); });
+    const uint32_t n_queued = counts[0];
+    const std::vector<uint32_t> queue0(q0.begin(), q0.begin() + n_queued);
+    const std::vector<float4> rays0_o(ray_o.begin(), ray_o.begin() + n_queued), rays0_d(ray_d.begin(), ray_d.begin() + n_queued);
     std::vector<float4> rays1_o, rays1_d;
     for (uint32_t depth = 0; depth < max_bounces; ++depth) {
         if (depth == 1) { rays1_o = ray_o1; rays1_d = ray_d1; queue_depth1.assign(q1.begin(), q1.begin() + counts[1]); }
@@ -130,7 +141,9 @@ int main(int argc, char** argv) {
     std::vector<float4> partial(n_pixels, float4{0, 0, 0, 0}), accum(n_pixels, float4{0, 0, 0, 0});
     vr_host_launch(1, 256, [&] { k_accumulate(wf, partial.data(), accum.data(), w, h, spp, 1, 1.0f / (float)spp, 1.0f); });
 
-    // every ray of depth 0 and of depth 1 against the single-ray traversal (closest_hit, the gate kernels' path)
+    // every ray of depth 0 and of depth 1 against the single-ray traversal (closest_hit, the gate kernels' path); the
+    // depth-0 queue holds each slot at most once with the ray k_raygen generates for it, and every slot it does not
+    // hold is a certain miss
     std::vector<int> stack(STACK_DEPTH + 8);
     size_t wrong = 0, checked = 0;
     auto check = [&](const std::vector<float4>& ro, const std::vector<float4>& rd, const std::vector<float4>& got, uint32_t slot) {
@@ -141,7 +154,25 @@ int main(int argc, char** argv) {
             __float_as_uint(g.w) != __float_as_uint(hr.v))
             ++wrong;
     };
-    for (uint32_t s = 0; s < n_paths; ++s) check(rays0_o, rays0_d, hits_depth0, s);
+    std::vector<char> queued(n_paths, 0);
+    for (uint32_t i = 0; i < n_queued; ++i) {
+        const uint32_t slot = queue0[i];
+        ++checked;
+        if (slot >= n_paths || queued[slot] || std::memcmp(&rays0_o[i], &all_o[slot], 16) != 0 || std::memcmp(&rays0_d[i], &all_d[slot], 16) != 0) {
+            ++wrong;
+            continue;
+        }
+        queued[slot] = 1;
+        check(rays0_o, rays0_d, hits_depth0, i);  // queue order
+    }
+    unsigned long long n_culled = 0;
+    for (uint32_t slot = 0; slot < n_paths; ++slot) {
+        if (queued[slot]) continue;
+        ++checked;
+        ++n_culled;
+        if (closest_hit(ds, xyz(all_o[slot]), xyz(all_d[slot]), stack.data(), 1).prim >= 0) ++wrong;  // culled, but it hits
+    }
+    if (n_culled != culled) ++wrong;
     for (uint32_t i = 0; i < (uint32_t)queue_depth1.size(); ++i) check(rays1_o, rays1_d, hits_depth1, i);  // queue order
     std::printf("%u paths, queue lengths", n_paths);
     for (uint32_t d = 0; d <= max_bounces; ++d) std::printf(" %u", counts[d]);

@@ -144,6 +144,12 @@ struct vr_render {
     double seconds = 0.0, device_ms = 0.0, trace_ms = 0.0;
     std::atomic<uint64_t> trace_launches{0}, kernel_launches{0};  // bumped by the render thread, read by vr_render_stats
     unsigned long long segments_host = 0;
+    // camera rays that miss the scene's bounds are finished by k_raygen (kernels.cu): on while it pays. A call that
+    // culled less than 15 % of its camera rays switches it off; every 16th call after that probes again (the scene or
+    // the camera may have changed: the state survives clears and commits)
+    unsigned long long culled_host = 0;
+    bool cull_camera_rays = true;
+    uint32_t calls_without_cull = 0;
     std::vector<cudaEvent_t> events;  // pairs around trace launches, reused call to call
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // peer accumulation buffers opened through CUDA IPC: (handle bytes, mapped pointer)
@@ -182,7 +188,7 @@ void run_wavefront(vr_render* r, const Wavefront& wf, cudaStream_t stream, const
     vr_context* ctx = sc->ctx;
     const FrameParams fp = frame_params(r);
     cudaMemsetAsync(wf.counts, 0, sizeof(uint32_t) * (2 * (fp.max_bounces + 2) + 1), stream);  // counts + cursors + miss_count
-    launch_raygen(sc->dev, wf, src, fp, n_paths, ctx->dims, stream);
+    launch_raygen(sc->dev, wf, src, fp, n_paths, r->cull_camera_rays, ctx->dims, stream);
     r->kernel_launches += 1;
     for (uint32_t depth = 0; depth < fp.max_bounces; ++depth) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -922,7 +928,7 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     A((void**)&r->partial, 16ull * r->n_pixels);
     A((void**)&r->resolved, 16ull * r->n_pixels);
     unsigned long long* segments = nullptr;
-    A((void**)&segments, 8);
+    A((void**)&segments, 16);  // + the culled camera rays
     auto alloc_wavefront = [&](Wavefront& w) {
         w.capacity = (uint32_t)capacity;
         A((void**)&w.ray_o[0], 16 * cap);
@@ -937,6 +943,7 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
         A((void**)&w.miss, 16 * cap);
         A((void**)&w.counts, 4 * (2 * (settings->max_bounces + 2) + 1));
         w.segments = segments;  // one counter for the whole render
+        w.culled = segments ? segments + 1 : nullptr;
         w.cursors = w.counts ? w.counts + (settings->max_bounces + 2) : nullptr;
         w.miss_count = w.counts ? w.counts + 2 * (settings->max_bounces + 2) : nullptr;
     };
@@ -956,7 +963,7 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
     cudaStream_t st = scene->ctx->stream;
     if (e == cudaSuccess) e = cudaMemsetAsync(r->accum, 0, 16ull * r->n_pixels, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(r->partial, 0, 16ull * r->n_pixels, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(wf.segments, 0, 8, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(wf.segments, 0, 16, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         r->dev_mem.release();
@@ -1041,13 +1048,14 @@ int32_t vr_render_clear(vr_render* r) try {
     VR_CUDA(cudaSetDevice(r->scene->ctx->device));
     VR_CUDA(cudaMemsetAsync(r->accum, 0, 16ull * r->n_pixels, st));
     VR_CUDA(cudaMemsetAsync(r->partial, 0, 16ull * r->n_pixels, st));
-    VR_CUDA(cudaMemsetAsync(r->wf.segments, 0, 8, st));
+    VR_CUDA(cudaMemsetAsync(r->wf.segments, 0, 16, st));
     VR_CUDA(cudaStreamSynchronize(st));
     std::lock_guard<std::mutex> lock(r->stats_mutex);
     r->samples_done = 0;
     r->seconds = r->device_ms = r->trace_ms = 0.0;
     r->trace_launches = r->kernel_launches = 0;
     r->segments_host = 0;
+    r->culled_host = 0;
     r->cancel = 0;
     return VR_OK;
 } VR_CATCH
@@ -1062,6 +1070,10 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
         // a re-commit rewinds the scene's device memory and with it the sampling tables of integrator 1
         const int32_t rc = ensure_env_tables(r->scene);
         if (rc) return rc;
+    }
+    if (!r->cull_camera_rays && ++r->calls_without_cull >= 16u) {
+        r->cull_camera_rays = true;
+        r->calls_without_cull = 0;
     }
     const auto t0 = std::chrono::steady_clock::now();
     const float inv_total = 1.0f / (float)r->settings.total_samples;  // iterative.rs:45
@@ -1128,8 +1140,14 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
         }
         if (hi >= lo) trace_ms += hi - lo;
     }
-    unsigned long long seg = 0;
-    VR_CUDA(cudaMemcpy(&seg, r->wf.segments, 8, cudaMemcpyDeviceToHost));
+    unsigned long long counters[2] = {0, 0};  // segments, culled camera rays (both since the last clear)
+    VR_CUDA(cudaMemcpy(counters, r->wf.segments, 16, cudaMemcpyDeviceToHost));
+    const unsigned long long seg = counters[0];
+    if (r->cull_camera_rays && done > 0) {
+        const double culled_now = (double)(counters[1] - r->culled_host), camera_rays = (double)r->n_pixels * done;
+        if (culled_now < 0.15 * camera_rays) r->cull_camera_rays = false;
+    }
+    r->culled_host = counters[1];
     const auto t1 = std::chrono::steady_clock::now();
     {
         std::lock_guard<std::mutex> lock(r->stats_mutex);
@@ -1403,7 +1421,7 @@ int32_t vr_debug_trace_primary(vr_render* r, uint32_t sample, uint32_t* surface,
     const FrameParams fp = frame_params(r);
     const PathSource src = make_path_source(nullptr, nullptr, r->width, r->height, sample);
     VR_CUDA(cudaMemsetAsync(r->wf.counts, 0, sizeof(uint32_t) * 2 * (fp.max_bounces + 2), ctx->stream));
-    launch_raygen(r->scene->dev, r->wf, src, fp, r->n_pixels, ctx->dims, ctx->stream);
+    launch_raygen(r->scene->dev, r->wf, src, fp, r->n_pixels, false, ctx->dims, ctx->stream);
     launch_trace(r->scene->dev, r->wf, 0, r->n_pixels, ctx->dims, ctx->stream);
     launch_primary_ids(r->scene->dev, r->wf, r->width, r->height, r->dbg_surface, r->dbg_prim, r->dbg_t, ctx->stream);
     VR_CUDA(cudaMemcpyAsync(surface, r->dbg_surface, 4ull * r->n_pixels, cudaMemcpyDeviceToHost, ctx->stream));

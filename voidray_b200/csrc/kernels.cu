@@ -140,69 +140,6 @@ __device__ __forceinline__ void slot_source(const PathSource& src, uint32_t slot
     }
 }
 
-// One camera sample: render/iterative.rs:25-33 + core/camera.rs:58-82. (x, y) = the pixel centre on the film, dd = the
-// longer image side, jitter = 1 / dd.
-__device__ __forceinline__ void raygen_sample(const DeviceScene& sc, const Wavefront& wf, const FrameParams& fp, uint32_t slot,
-                                              uint32_t pixel, uint32_t sample, float x, float y, float jitter) {
-    Rng rng(fp.seed, pixel, sample, 0);
-    const float dx = rng.gen_range(-jitter, jitter);
-    const float dy = rng.gen_range(-jitter, jitter);
-    const float cx = x + dx, cy = y + dy;
-
-    const CameraRec& cam = sc.camera;
-    const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
-    const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
-    f3 origin = mk3(cam.origin[0], cam.origin[1], cam.origin[2]);
-    f3 new_dir = cam.d * mk3(cam.direction[0], cam.direction[1], cam.direction[2]) + cx * right + cy * up;
-    if (cam.has_dof) {
-        const f3 focal_point = origin + normalize(new_dir) * cam.focal_length;
-        const f2 s = rng.unit_disc();
-        origin = origin + (s.x * right + s.y * up) * cam.aperture;
-        new_dir = focal_point - origin;
-    }
-    const f3 dir = normalize(normalize(new_dir));  // camera.rs:81 then Ray::new, util/ray.rs:15
-    wf.ray_o[0][slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n));
-    wf.ray_d[0][slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-    // every path writes its radiance exactly once, when it ends; with no bounce at all nothing does
-    if (fp.max_bounces == 0u) wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-}
-__device__ __forceinline__ void film_point(const FrameParams& fp, uint32_t px, uint32_t py, float dd, float& x, float& y) {
-    x = ((float)(2u * px + 1u) - (float)fp.width) / dd;
-    y = ((float)(2u * (fp.height - py) - 1u) - (float)fp.height) / dd;
-}
-
-// Implicit source: a thread owns one pixel (slot-in-sample j, 8x4 tiles) and every `groups`-th sample of the batch, so
-// the tile decode, the film point and their divisions are paid once per thread, not once per ray (the per-ray kernel
-// was 12 % of config 1's step at 2.6x its own store bandwidth bound). Consecutive threads write consecutive slots.
-__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp,
-                                                uint32_t n_paths, uint32_t groups) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[0] = n_paths;
-    const uint32_t W = fp.width, H = fp.height;
-    const float dd = (float)(W > H ? W : H);
-    const float jitter = 1.0f / dd;
-    if (src.pixel) {  // explicit (pixel, sample) lists: one ray per thread
-        for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
-            const uint32_t pixel = src.pixel[slot], sample = src.sample[slot];
-            float x, y;
-            film_point(fp, pixel % W, fp.pixel_mapping == 1 ? pixel / H : pixel / W, dd, x, y);
-            raygen_sample(sc, wf, fp, slot, pixel, sample, x, y, jitter);
-        }
-        return;
-    }
-    const uint32_t n_pixels = src.n_pixels, samples = n_paths / n_pixels;
-    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_pixels * groups; id += gridDim.x * blockDim.x) {
-        const uint32_t g = fast_div(id, src.by_pixels), j = id - g * n_pixels;
-        uint32_t px, py;
-        tile_slot_to_xy(j, W, H, src.by_tiles_per_row, px, py);
-        const uint32_t pixel = py * W + px;
-        if (fp.pixel_mapping == 1) py = pixel / H;  // PixelMapping::Stretch quirk of the reference (iterative.rs:26)
-        float x, y;
-        film_point(fp, px, py, dd, x, y);
-        for (uint32_t s = g; s < samples; s += groups)
-            raygen_sample(sc, wf, fp, s * n_pixels + j, pixel, src.sample_base + s, x, y, jitter);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Closest-hit kernel: one ray per thread, queue of slots
 // ------------------------------------------------------------------------------------------------
@@ -684,6 +621,164 @@ __device__ __forceinline__ bool shade_hit(const DeviceScene& sc, const Wavefront
     return alive;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ray generation
+// ------------------------------------------------------------------------------------------------
+// One camera sample: render/iterative.rs:25-33 + core/camera.rs:58-82. (x, y) = the pixel centre on the film, jitter =
+// 1 / the longer image side. Returns the ray and the draws consumed.
+__device__ __forceinline__ void raygen_sample(const DeviceScene& sc, const FrameParams& fp, uint32_t pixel, uint32_t sample,
+                                              float x, float y, float jitter, float4& ray_o, float4& ray_d) {
+    Rng rng(fp.seed, pixel, sample, 0);
+    const float dx = rng.gen_range(-jitter, jitter);
+    const float dy = rng.gen_range(-jitter, jitter);
+    const float cx = x + dx, cy = y + dy;
+
+    const CameraRec& cam = sc.camera;
+    const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
+    const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
+    f3 origin = mk3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    f3 new_dir = cam.d * mk3(cam.direction[0], cam.direction[1], cam.direction[2]) + cx * right + cy * up;
+    if (cam.has_dof) {
+        const f3 focal_point = origin + normalize(new_dir) * cam.focal_length;
+        const f2 s = rng.unit_disc();
+        origin = origin + (s.x * right + s.y * up) * cam.aperture;
+        new_dir = focal_point - origin;
+    }
+    const f3 dir = normalize(normalize(new_dir));  // camera.rs:81 then Ray::new, util/ray.rs:15
+    ray_o = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.n));
+    ray_d = make_float4(dir.x, dir.y, dir.z, 0.0f);
+}
+__device__ __forceinline__ void film_point(const FrameParams& fp, uint32_t px, uint32_t py, float dd, float& x, float& y) {
+    x = ((float)(2u * px + 1u) - (float)fp.width) / dd;
+    y = ((float)(2u * (fp.height - py) - 1u) - (float)fp.height) / dd;
+}
+// Does the ray miss everything for certain? The first step of k_trace's own traversal — the root record's two child
+// boxes, same conservative slab test — so a ray culled here is a ray k_trace would have finished after one node step
+// with no hit. Scenes with analytic surfaces (tested outside the tree) are never culled.
+__device__ __forceinline__ bool misses_the_scene(const DeviceScene& sc, f3 o, f3 d) {
+    if (sc.n_analytics != 0u) return false;
+    if (sc.n_tris == 0u) return true;
+    int stack[2];  // one push at most
+    Traversal tr;
+    trav_axis(o.x, d.x, sc.grid_min[0], sc.grid_extent[0], tr.ax, tr.bnx, tr.bfx, tr.selx);
+    trav_axis(o.y, d.y, sc.grid_min[1], sc.grid_extent[1], tr.ay, tr.bny, tr.bfy, tr.sely);
+    trav_axis(o.z, d.z, sc.grid_min[2], sc.grid_extent[2], tr.az, tr.bnz, tr.bfz, tr.selz);
+    tr.best.t = INFINITY;
+    tr.sp = 0;
+    tr.cur = 0;
+    trav_node(tr, (const float4*)sc.nodes, stack, 1);
+    return tr.cur == SENTINEL;  // neither child box entered, nothing pushed
+}
+
+// Implicit source: a thread owns one pixel (slot-in-sample j, 8x4 tiles) and every `groups`-th sample of the batch, so
+// the tile decode, the film point and their divisions are paid once per thread, not once per ray (the per-ray kernel
+// was 12 % of config 1's step at 2.6x its own store bandwidth bound).
+// cull != 0: a camera ray that misses the scene for certain (misses_the_scene) never enters the wavefront — its
+// environment sample is its radiance (tracer.rs:30-33 at level 0), written here; the others are compacted into the
+// depth-0 queue, one atomic per block and round. Such a ray skips a ray write, a k_trace refill, a hit record and a
+// k_shade_first entry (+5.9 % / +4.8 % on configs 3 / 4, where about half of the frame is background); where nearly
+// every camera ray enters the bounds the test and the block barriers only cost (-1.2 % on configs 2 / 5), so the host
+// switches it off when a call culled less than 15 % of its camera rays (abi.cu). cull == 0 (and the gate kernels):
+// every ray is queued, entry i = slot i.
+__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp,
+                                                uint32_t n_paths, uint32_t groups, int cull) {
+    __shared__ uint32_t s_warp_count[8], s_block_base;
+    const uint32_t W = fp.width, H = fp.height;
+    const float dd = (float)(W > H ? W : H);
+    const float jitter = 1.0f / dd;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (src.pixel || !cull || fp.max_bounces == 0u) {  // every ray queued in slot order
+        if (blockIdx.x == 0 && threadIdx.x == 0) wf.counts[0] = n_paths;
+        const uint32_t samples = src.pixel ? 0u : n_paths / src.n_pixels;
+        const uint32_t n_threads = src.pixel ? n_paths : src.n_pixels * groups;
+        for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_threads; id += gridDim.x * blockDim.x) {
+            uint32_t pixel, px, py, g = 0, j = 0;
+            if (src.pixel) {
+                pixel = src.pixel[id];
+                px = pixel % W;
+                py = pixel / W;
+            } else {
+                g = fast_div(id, src.by_pixels);
+                j = id - g * src.n_pixels;
+                tile_slot_to_xy(j, W, H, src.by_tiles_per_row, px, py);
+                pixel = py * W + px;
+            }
+            if (fp.pixel_mapping == 1) py = pixel / H;  // PixelMapping::Stretch quirk of the reference (iterative.rs:26)
+            float x, y;
+            film_point(fp, px, py, dd, x, y);
+            for (uint32_t s = g; s < (src.pixel ? 1u : samples); s += groups) {
+                const uint32_t slot = src.pixel ? id : s * src.n_pixels + j;
+                float4 ro, rd;
+                raygen_sample(sc, fp, pixel, src.pixel ? src.sample[id] : src.sample_base + s, x, y, jitter, ro, rd);
+                wf.queue[0][slot] = slot;
+                wf.ray_o[0][slot] = ro;
+                wf.ray_d[0][slot] = rd;
+                // every path writes its radiance exactly once, when it ends; with no bounce at all nothing does
+                if (fp.max_bounces == 0u) wf.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        return;
+    }
+    const uint32_t n_pixels = src.n_pixels, samples = n_paths / n_pixels;
+    const uint32_t n_threads = n_pixels * groups, rounds = (samples + groups - 1u) / groups;
+    unsigned long long culled = 0;  // thread 0 of the block: camera rays answered here (they are segments all the same)
+    // block-uniform loops: every thread of the block meets every __syncthreads
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_threads; base += gridDim.x * blockDim.x) {
+        const uint32_t id = base + threadIdx.x;
+        const bool owner = id < n_threads;
+        uint32_t g = 0, j = 0, px = 0, py = 0, pixel = 0;
+        float x = 0.0f, y = 0.0f;
+        if (owner) {
+            g = fast_div(id, src.by_pixels);
+            j = id - g * n_pixels;
+            tile_slot_to_xy(j, W, H, src.by_tiles_per_row, px, py);
+            pixel = py * W + px;
+            if (fp.pixel_mapping == 1) py = pixel / H;  // PixelMapping::Stretch quirk of the reference (iterative.rs:26)
+            film_point(fp, px, py, dd, x, y);
+        }
+        for (uint32_t k = 0; k < rounds; ++k) {
+            const uint32_t s = g + k * groups;
+            const bool active = owner && s < samples;
+            const uint32_t slot = s * n_pixels + j;
+            float4 ro = make_float4(0.0f, 0.0f, 0.0f, 0.0f), rd = ro;
+            bool keep = false;
+            if (active) {
+                raygen_sample(sc, fp, pixel, src.sample_base + s, x, y, jitter, ro, rd);
+                keep = !misses_the_scene(sc, xyz(ro), xyz(rd));
+                if (!keep) shade_miss(sc, wf, fp.firefly_clamp, 0u, slot, xyz(rd));
+            }
+            // block-aggregated compaction into the depth-0 queue
+            const unsigned keep_ballot = __ballot_sync(0xFFFFFFFFu, keep);
+            const unsigned active_ballot = __ballot_sync(0xFFFFFFFFu, active);
+            if (lane == 0u) s_warp_count[warp] = (uint32_t)__popc(keep_ballot) | ((uint32_t)__popc(active_ballot) << 16);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t kept = 0, seen = 0;
+                for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+                    const uint32_t c = s_warp_count[w];
+                    s_warp_count[w] = kept;  // the warp's offset inside the block's range
+                    kept += c & 0xFFFFu;
+                    seen += c >> 16;
+                }
+                culled += seen - kept;
+                s_block_base = kept ? atomicAdd(&wf.counts[0], kept) : 0u;
+            }
+            __syncthreads();
+            if (keep) {
+                const uint32_t at = s_block_base + s_warp_count[warp] + (uint32_t)__popc(keep_ballot & ((1u << lane) - 1u));
+                wf.queue[0][at] = slot;
+                wf.ray_o[0][at] = ro;
+                wf.ray_d[0][at] = rd;
+            }
+            __syncthreads();  // the counters are rewritten in the next round
+        }
+    }
+    if (threadIdx.x == 0 && culled) {
+        atomicAdd(wf.segments, culled);
+        atomicAdd(wf.culled, culled);
+    }
+}
+
 // Shading kernel. After the first bounce a warp's 32 queue entries are a mix of misses (environment lookup + unwind)
 // and hits (triangle record, material, textures, scatter) — measured 27 miss / 5 hit lanes per instruction on config 1,
 // 14 of 32 lanes overall (profiles/r2_trace_inst.md) — so the two are separated:
@@ -734,14 +829,15 @@ __device__ __forceinline__ void shade_group(const DeviceScene& sc, const Wavefro
 }
 
 // Depth 0: primary rays are coherent (hits and misses come in screen tiles) and a miss has nothing to unwind, so the
-// first depth keeps the plain shape: one queue entry per thread, misses shaded in place.
+// first depth keeps the plain shape: one queue entry per thread, misses shaded in place (camera rays that miss the
+// scene's bounds altogether may never get here: k_raygen).
 template <bool FAST, bool MICROFACET>
 __global__ void __launch_bounds__(SHADE_THREADS) k_shade_first(DeviceScene sc, Wavefront wf, PathSource src, FrameParams fp) {
     const uint32_t n = wf.counts[0];
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        shade_group<FAST, MICROFACET>(sc, wf, src, fp, 0u, nullptr, wf.queue[1], i < n, i, lane);
+        shade_group<FAST, MICROFACET>(sc, wf, src, fp, 0u, wf.queue[0], wf.queue[1], i < n, i, lane);
     }
 }
 
@@ -1038,7 +1134,7 @@ static inline uint32_t grid_for(uint64_t n, int threads, int sm_count, int block
 }
 
 void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
-                   uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream) {
+                   uint32_t n_paths, bool cull, const LaunchDims& ld, cudaStream_t stream) {
     // enough threads for ~4 blocks of 256 per SM, at most one per ray
     uint32_t groups = 1;
     if (!src.pixel) {
@@ -1049,7 +1145,7 @@ void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource&
         if (groups < 1) groups = 1;
     }
     const uint64_t threads = src.pixel ? n_paths : (uint64_t)src.n_pixels * groups;
-    k_raygen<<<grid_for(threads, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, src, fp, n_paths, groups);
+    k_raygen<<<grid_for(threads, 256, ld.sm_count, 8), 256, 0, stream>>>(sc, wf, src, fp, n_paths, groups, cull ? 1 : 0);
 }
 void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper, const LaunchDims& ld,
                   cudaStream_t stream) {

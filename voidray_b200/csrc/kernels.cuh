@@ -13,7 +13,7 @@ namespace vr {
 
 // Wavefront state, structure-of-arrays over `capacity` path slots.
 // Rays and hits of depth d are stored in QUEUE ORDER: entry i of the depth's compacted list sits at ray_o[d & 1][i],
-// ray_d[d & 1][i], hit[i], and queue[d & 1][i] names the path slot it belongs to (depth 0: i itself). k_trace streams
+// ray_d[d & 1][i], hit[i], and queue[d & 1][i] names the path slot it belongs to (depth 0 too: k_raygen may compact). k_trace streams
 // its rays without an indirection and k_shade reads ray + hit coalesced; only the per-slot state (attenuation stack,
 // finished radiance) is addressed through the slot.
 struct Wavefront {
@@ -27,6 +27,7 @@ struct Wavefront {
     uint32_t* counts;    // [max_bounces + 2] queue lengths
     uint32_t* cursors;   // [max_bounces + 2] next unclaimed queue entry (dynamic ray fetch); then miss_count
     unsigned long long* segments;  // scene.hit calls, whole render
+    unsigned long long* culled;    // of those, camera rays k_raygen answered itself (they missed the scene's bounds)
     float4* miss;          // [capacity] misses of depth >= 1 waiting for k_miss: direction.xyz, slot | depth << 26
     uint32_t* miss_count;  // entries in `miss`, zeroed with the counts
     uint32_t capacity;     // < 2^26
@@ -89,8 +90,10 @@ struct LaunchDims {
 };
 void query_launch_dims(LaunchDims* dims);
 
+// cull: camera rays that miss the scene's bounds are finished by k_raygen itself and the depth-0 queue is compacted;
+// without it entry i of the queue is slot i (gate kernels read hits by slot)
 void launch_raygen(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
-                   uint32_t n_paths, const LaunchDims& ld, cudaStream_t stream);
+                   uint32_t n_paths, bool cull, const LaunchDims& ld, cudaStream_t stream);
 void launch_trace(const DeviceScene& sc, const Wavefront& wf, uint32_t depth, uint32_t n_upper,
                   const LaunchDims& ld, cudaStream_t stream);
 void launch_shade(const DeviceScene& sc, const Wavefront& wf, const PathSource& src, const FrameParams& fp,
