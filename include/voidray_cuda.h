@@ -219,7 +219,8 @@ typedef struct vr_render_settings {
     uint32_t max_paths_in_flight; /* paths in flight, shared by the two wavefronts consecutive batches alternate between;
                                      0 = library default (2 x 32 Mi paths, 248 B each at 8 bounces); < 64 Mi per wavefront.
                                      Diagnostic: the environment variable VOIDRAY_STREAMS=n (1..4, read by vr_render_begin)
-                                     sets the number of wavefronts; the image does not depend on it */
+                                     sets the number of wavefronts, VOIDRAY_CAMERA_CULL=0 / 1 pins the camera-ray culling
+                                     of the ray generation off / on; the image depends on neither */
 } vr_render_settings;
 
 /* CpuRenderTarget::new + clear (render/target.rs:90-131,284-290): allocates the zeroed W*H RGBA f32

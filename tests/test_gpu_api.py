@@ -108,6 +108,30 @@ def test_two_wavefronts_are_invisible(ctx, monkeypatch):
     assert launches[0] != launches[2] or launches[1] != launches[3]  # the two settings really cut the work differently
 
 
+def test_camera_ray_culling_is_invisible(ctx, monkeypatch):
+    # k_raygen finishes the camera rays that miss the scene's bounds itself while the host sees that pay (a call that
+    # culled less than 15 % of its camera rays switches it off for the calls that follow). Same image, same segment count
+    # with it pinned off, pinned on (VOIDRAY_CAMERA_CULL, read when the render begins) and left to the host — on a scene
+    # whose ground fills the frame (switched off after the first call) and on the mushroom alone (stays on)
+    for recipe in (scenes.config5_combined, scenes.config1_mushroom):
+        scene, st, _ = recipe(160, 96, 24)
+        accel = scene.build_acceleration(ctx)
+        imgs, segments = [], []
+        for mode in ("0", "1", None):
+            if mode is None:
+                monkeypatch.delenv("VOIDRAY_CAMERA_CULL", raising=False)
+            else:
+                monkeypatch.setenv("VOIDRAY_CAMERA_CULL", mode)
+            tgt = RenderTarget(accel, (160, 96), RenderSettings(total_samples=24, max_bounces=8))
+            tgt.accumulate(1)
+            tgt.accumulate(23)
+            imgs.append(tgt.read())
+            segments.append(tgt.stats().ray_segments)
+            tgt.close()
+        assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+        assert segments[0] == segments[1] == segments[2]  # culled camera rays are segments all the same
+
+
 def test_sample_range_sharding_on_one_device(ctx):
     # N renders owning disjoint sample ranges, summed, equal one render of all samples (up to f32 summation order)
     w, h, spp = 128, 72, 16

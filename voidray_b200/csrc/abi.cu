@@ -150,6 +150,7 @@ struct vr_render {
     unsigned long long culled_host = 0;
     bool cull_camera_rays = true;
     uint32_t calls_without_cull = 0;
+    int cull_forced = -1;  // diagnostic: VOIDRAY_CAMERA_CULL=0 / 1 (read by vr_render_begin) pins it off / on
     std::vector<cudaEvent_t> events;  // pairs around trace launches, reused call to call
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // peer accumulation buffers opened through CUDA IPC: (handle bytes, mapped pointer)
@@ -918,6 +919,7 @@ static int32_t render_begin_single(vr_scene* scene, uint32_t width, uint32_t hei
         return fail(VR_ERR_INVALID, "max_paths_in_flight too large");
     }
     r->n_wavefronts = n_wf;
+    if (const char* v = std::getenv("VOIDRAY_CAMERA_CULL")) r->cull_forced = std::atoi(v) != 0 ? 1 : 0;
     const size_t cap = capacity;
     const uint32_t levels = settings->max_bounces ? settings->max_bounces : 1;
     cudaError_t e = cudaSuccess;
@@ -1071,7 +1073,8 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
         const int32_t rc = ensure_env_tables(r->scene);
         if (rc) return rc;
     }
-    if (!r->cull_camera_rays && ++r->calls_without_cull >= 16u) {
+    if (r->cull_forced >= 0) r->cull_camera_rays = r->cull_forced != 0;
+    else if (!r->cull_camera_rays && ++r->calls_without_cull >= 16u) {
         r->cull_camera_rays = true;
         r->calls_without_cull = 0;
     }
@@ -1143,7 +1146,7 @@ static int32_t accumulate_range(vr_render* r, uint32_t first_sample, uint32_t sa
     unsigned long long counters[2] = {0, 0};  // segments, culled camera rays (both since the last clear)
     VR_CUDA(cudaMemcpy(counters, r->wf.segments, 16, cudaMemcpyDeviceToHost));
     const unsigned long long seg = counters[0];
-    if (r->cull_camera_rays && done > 0) {
+    if (r->cull_forced < 0 && r->cull_camera_rays && done > 0) {
         const double culled_now = (double)(counters[1] - r->culled_host), camera_rays = (double)r->n_pixels * done;
         if (culled_now < 0.15 * camera_rays) r->cull_camera_rays = false;
     }

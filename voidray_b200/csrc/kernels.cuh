@@ -21,7 +21,7 @@ struct Wavefront {
     float4* ray_d[2];  // direction.xyz (unit), unused
     float4* hit;     // t, GPU primitive index (int bits, -1 miss), u, v — queue order of the depth being traced
     float4* att;     // [max_bounces][capacity] attenuation of every level (rgb, unused), by slot (level-major: the
-                     // writes of depth 0, where slot == queue index, coalesce; slot-major measured +40 % DRAM traffic)
+                     // writes of depth 0, whose queue is in slot order, coalesce; slot-major measured +40 % DRAM traffic)
     float4* radiance;  // [capacity] finished radiance of the slot's camera sample
     uint32_t* queue[2];  // compacted slot lists, ping-pong by depth parity
     uint32_t* counts;    // [max_bounces + 2] queue lengths
