@@ -12,6 +12,7 @@ import ctypes as C
 import enum
 import threading
 import time
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -39,6 +40,7 @@ class Context:
         check(self._lib.vr_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.handle)))
         self.device = int(device)
         self.devices = [int(device)]
+        self._children = weakref.WeakSet()  # live SceneAccelerations: closed before the context is (any close order)
 
     @classmethod
     def multi(cls, devices) -> "Context":
@@ -51,10 +53,13 @@ class Context:
         check(self._lib.vr_context_create_multi(ids, len(devices), C.byref(self.handle)))
         self.device = int(devices[0])
         self.devices = [int(d) for d in devices]
+        self._children = weakref.WeakSet()
         return self
 
     def close(self):
         if self.handle:
+            for child in list(self._children):
+                child.close()
             self._lib.vr_context_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -84,6 +89,8 @@ class SceneAcceleration:
         lib = self._lib
         self.handle = C.c_void_p()
         check(lib.vr_scene_create(self.ctx.handle, C.byref(self.handle)))
+        self._children = weakref.WeakSet()  # live RenderTargets: ended before the scene is destroyed
+        self.ctx._children.add(self)
         self.scene = scene
         out = C.c_uint32()
         for tex in scene.textures:
@@ -170,6 +177,8 @@ class SceneAcceleration:
 
     def close(self):
         if self.handle:
+            for child in list(self._children):
+                child.close()
             self._lib.vr_scene_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -209,6 +218,7 @@ class RenderTarget:
         self.handle = C.c_void_p()
         check(self._lib.vr_render_begin(scene.handle, self.dimensions[0], self.dimensions[1], C.byref(cs),
                                         C.byref(self.handle)))
+        scene._children.add(self)
 
     @property
     def n_pixels(self) -> int:
